@@ -1,0 +1,158 @@
+/*
+ * pct_b200 -- C ABI of the B200-native curvature hot path.
+ *
+ * The reference (masnottuh/point-cloud-toolbox) has no FFI, plugin or operator
+ * interface: its hot path is five pure-Python methods of one class,
+ * `PointCloud` in pointCloudToolbox.py, calling scipy/numpy.  The drop-in
+ * boundary is therefore that class's surface; this header is what a Python
+ * `PointCloud` binds through `ctypes` (see INTEGRATION.md for the stub) and
+ * every entry point below names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ exceptions cross the boundary; return 0 (PCT_OK) or a
+ *     negative PCT_ERR_* code, `pct_last_error()` gives a thread-local message
+ *   - every pointer except `pct_index*` and the `*_host` entry is a DEVICE
+ *     pointer owned by the caller (PyTorch allocates), 16-byte aligned
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream);
+ *     calls are asynchronous on it unless stated otherwise
+ *   - the library owns only `pct_index` (opaque; immutable after build)
+ *   - per-point failures are reported in `status[]` bits, never as an error
+ *     code; outputs of a failed point are NaN
+ *
+ * Query ranges and output layout
+ *   The index keeps the cloud Morton-sorted.  Queries are addressed by SORTED
+ *   position [q_begin, q_end) so that ranks of a multi-GPU job take contiguous,
+ *   spatially coherent slices.  `layout` selects where row r of an output goes:
+ *     PCT_LAYOUT_ORIGINAL  row = original index of the query point; outputs are
+ *                          sized for all N points (single-GPU drop-in)
+ *     PCT_LAYOUT_SLICE     row = sorted position - q_begin; outputs are sized
+ *                          (q_end - q_begin) (multi-GPU shard, gathered later)
+ *   Neighbour indices written to `idx` are always ORIGINAL point indices.
+ */
+#ifndef PCT_B200_H
+#define PCT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCT_VERSION 100
+
+#define PCT_OK 0
+#define PCT_ERR_INVALID_ARGUMENT (-1)
+#define PCT_ERR_CUDA (-2)
+#define PCT_ERR_NONFINITE (-3)   /* cloud holds NaN/Inf: ref :273-274 ValueError */
+#define PCT_ERR_K_TOO_LARGE (-4) /* k + 1 > N: ref :640 IndexError */
+#define PCT_ERR_NO_DEVICE (-5)
+
+#define PCT_LAYOUT_ORIGINAL 0
+#define PCT_LAYOUT_SLICE 1
+
+/* status[] bits */
+#define PCT_STATUS_OK 0u
+#define PCT_STATUS_EXACT_PATH 1u     /* informational: resolved by the exact tie/expansion path */
+#define PCT_STATUS_FEW_NEIGHBORS 2u  /* < 2 neighbours (no covariance) -> NaN */
+#define PCT_STATUS_RANK_DEFICIENT 4u /* 6x6 normal equations not positive definite -> NaN */
+#define PCT_STATUS_NONFINITE 8u      /* non-finite intermediate: ref :318-319 / :356-357 ValueError */
+
+typedef struct pct_index pct_index;
+
+typedef struct pct_index_info {
+    int64_t num_points;
+    float cell_size;      /* level-0 cell edge */
+    float origin[3];      /* bounding-box minimum */
+    float extent[3];      /* bounding-box size */
+    int32_t dims[3];      /* level-0 grid dimensions */
+    int32_t bits_per_axis;
+    int32_t num_levels;
+    int64_t cells_level0; /* occupied cells */
+    int64_t device_bytes; /* HBM held by the index */
+    float est_dimension;  /* intrinsic dimension seen by the density pilot */
+} pct_index_info;
+
+typedef struct pct_query_stats {
+    int64_t queries;
+    int64_t level1_retries; /* queries whose k-th neighbour left the level-0 stencil */
+    int64_t exact_path;     /* queries resolved by the exact (tie / expansion) kernel */
+    int64_t kernel_launches;
+} pct_query_stats;
+
+int pct_version(void);
+const char* pct_last_error(void);
+
+/* Spatial index: replaces `sp.spatial.cKDTree(points)` (ref :74).
+ * xyz: N rows of `stride` floats (3 = packed xyz, 4 = padded), fp32.
+ * cell_hint > 0 fixes the level-0 cell edge; otherwise it is chosen from a
+ * density pilot so that a cell holds about 0.5 * k_hint points (k_hint <= 0: 20).
+ * Synchronises `stream` (the grid shape is needed on the host).
+ * PCT_ERR_NONFINITE if any coordinate is NaN/Inf. */
+int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, int k_hint,
+                    void* stream, pct_index** out);
+int pct_index_destroy(pct_index* index);
+int pct_index_get_info(const pct_index* index, pct_index_info* info);
+/* perm[sorted position] = original index, int32 x N */
+int pct_index_permutation(const pct_index* index, int32_t* perm, void* stream);
+/* counters of the most recent query call on this index (synchronises `stream`) */
+int pct_index_last_stats(const pct_index* index, void* stream, pct_query_stats* stats);
+
+/* kNN lists: replaces the `kdtree.query(point, k+1)` loop of plant_kdtree (ref :81-85).
+ * Row = the k nearest OTHER entries of the (k+1)-list ordered by (fp64 squared
+ * distance, index) with the first entry dropped, exactly like the reference.
+ * idx: rows x k int32 (original indices), dist: rows x k fp32 (either may be NULL). */
+int pct_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
+            int32_t* idx, float* dist, int layout, void* stream);
+
+/* epsilon-ball (advertised README.md:8, absent in the reference; semantics of
+ * scipy `query_ball_point`: d2 <= radius*radius in fp64, self excluded).
+ * count: rows x int32.  fill: CSR rows given exclusive `offsets` (rows + 1, int64),
+ * each row ordered by (d2, index). */
+int pct_ball_count(const pct_index* index, int64_t q_begin, int64_t q_end, double radius,
+                   int32_t* counts, int layout, void* stream);
+int pct_ball_fill(const pct_index* index, int64_t q_begin, int64_t q_end, double radius,
+                  const int64_t* offsets, int32_t* idx, float* dist, int layout, void* stream);
+
+/* Fit from given neighbour lists: replaces fit_explicit_quadratic_surfaces_to_neighborhoods
+ * (ref :635-647) + calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points
+ * (ref :657-674) for rows of `idx` (nq x k, original indices, reference order:
+ * first = nearest, last = farthest).  query_ids (nq, may be NULL = 0..nq-1) names
+ * the cloud point each row belongs to.  xyz: N x 3 packed fp32, original order.
+ * normals nq x 3, coeffs nq x 6 [A,B,C,D,E,F], curv nq x 5 [K,H,k1,k2,H^2],
+ * status nq (any output may be NULL). */
+int pct_fit_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k,
+                           const int32_t* query_ids, float* normals, float* coeffs, float* curv,
+                           uint8_t* status, void* stream);
+/* same for variable-size rows (CSR offsets nq + 1 int64) */
+int pct_fit_from_csr(const float* xyz, int64_t n, const int64_t* offsets, const int32_t* idx,
+                     int64_t nq, const int32_t* query_ids, float* normals, float* coeffs,
+                     float* curv, uint8_t* status, void* stream);
+
+/* Fused search + fit, neighbourhoods never leave the SM: the throughput path of
+ * plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() (ref :69-89, :505-509). */
+int pct_curvature_fused_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
+                            float* normals, float* coeffs, float* curv, uint8_t* status,
+                            int layout, void* stream);
+int pct_curvature_fused_ball(const pct_index* index, int64_t q_begin, int64_t q_end, double radius,
+                             int32_t* counts, float* normals, float* coeffs, float* curv,
+                             uint8_t* status, int layout, void* stream);
+
+/* Batched forms of the three static methods.
+ * pct_plane_rotate: get_best_fit_plane_and_rotate (ref :270-321) on nq neighbourhoods of
+ *   k centred points (fp32, nq x k x 3) -> rotated fp64 (nq x k x 3), unit normals fp64 (nq x 3).
+ * pct_quadric_fit: fit_quadratic_surface (ref :331-360) on nq x k x 3 fp64 -> coeffs fp32 nq x 6.
+ * pct_quadric_curvature: calculate_explicit_quadratic_curvatures (ref :398-431), nq x 6 -> nq x 5. */
+int pct_plane_rotate(const float* centered, int64_t nq, int k, double* rotated, double* normals,
+                     uint8_t* status, void* stream);
+int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uint8_t* status,
+                    void* stream);
+int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream);
+
+/* Host-buffer convenience for callers without PyTorch: H2D + build + fused kNN
+ * curvature + D2H, synchronous.  K, H: N fp32 host arrays. */
+int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_host, float* H_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCT_B200_H */

@@ -1,0 +1,401 @@
+// Per-neighbourhood arithmetic of the curvature path, register resident.
+//
+// Everything here is what ONE thread does for ONE query point once it can
+// enumerate the neighbourhood: moments -> covariance -> smallest eigenvector
+// (cyclic Jacobi) -> orientation -> Rodrigues frame -> fp32 quantisation ->
+// 6x6 normal equations -> Cholesky -> Monge curvature.  The precision of every
+// step is chosen to land on the reference's numbers, not merely near them
+// (reference = /root/reference/pointCloudToolbox.py, cited as "ref :line"):
+//
+//   ref :641      neighbours are centred on the query point in fp32
+//   ref :277      covariance in fp64 (np.cov promotes), ddof = 1
+//   ref :280-283  normal = singular vector of the smallest singular value
+//   ref :286-297  flip so that normal . (last - first) >= 0
+//   ref :300-315  rotation I + [v]x + [v]x^2 (1-c)/s^2 in fp64 (identity if s == 0)
+//   ref :350,:358 rotated points and the design matrix are quantised to fp32
+//   ref :359      least squares solved in fp64, coefficients rounded to fp32
+//   ref :403-431  curvature formulas in fp32
+//
+// The functions are __host__ __device__ so that tests/host_harness can run the
+// same code on the CPU against the oracle before any GPU time is spent.  The
+// shipped library only ever calls them from kernels.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PCT_HD __host__ __device__ __forceinline__
+#define PCT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PCT_HD inline
+#define PCT_HD_NOINLINE inline
+#endif
+
+namespace pct {
+
+// ---- arithmetic with the rounding pinned (no FMA contraction) -------------
+// The host build of the harness uses -ffp-contract=off, so plain operators are
+// already uncontracted there.
+PCT_HD float fsub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+PCT_HD float fadd_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+PCT_HD float fmul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+PCT_HD double dadd_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+PCT_HD double dmul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
+// fp32 squared distance used for culling.  The SAME function is used by the
+// selection pass and the collection pass, so both see identical bits.
+PCT_HD float dist2_f32(float qx, float qy, float qz, float px, float py, float pz) {
+    const float dx = fsub_rn(px, qx), dy = fsub_rn(py, qy), dz = fsub_rn(pz, qz);
+    return fmaf(dz, dz, fmaf(dy, dy, fmul_rn(dx, dx)));
+}
+
+// The ranking key of scipy's cKDTree (p = 2, three coordinates):
+// ((dx*dx + dy*dy) + dz*dz) on the fp64 images of the fp32 coordinates, separate
+// multiplies and adds (ckdtree/src/distance.h sqeuclidean_distance_double).
+PCT_HD double dist2_f64(float qx, float qy, float qz, float px, float py, float pz) {
+    const double dx = (double)px - (double)qx;
+    const double dy = (double)py - (double)qy;
+    const double dz = (double)pz - (double)qz;
+    return dadd_rn(dadd_rn(dmul_rn(dx, dx), dmul_rn(dy, dy)), dmul_rn(dz, dz));
+}
+
+// (d2, index) lexicographic order -- the canonical tie rule.
+PCT_HD bool key_less(double da, uint32_t ia, double db, uint32_t ib) {
+    return (da < db) || (da == db && ia < ib);
+}
+
+// ---- first pass over a neighbourhood: raw moments about the query point ----
+struct Moments {
+    double sx, sy, sz, sxx, sxy, sxz, syy, syz, szz;
+    float max_abs;
+    int n;
+    bool finite;
+    PCT_HD void reset() {
+        sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0.0;
+        max_abs = 0.f;
+        n = 0;
+        finite = true;
+    }
+    // (cx, cy, cz) = neighbour - query, already rounded to fp32 (ref :641)
+    PCT_HD void add(float cx, float cy, float cz) {
+        const double x = cx, y = cy, z = cz;
+        sx += x; sy += y; sz += z;
+        sxx = fma(x, x, sxx); sxy = fma(x, y, sxy); sxz = fma(x, z, sxz);
+        syy = fma(y, y, syy); syz = fma(y, z, syz); szz = fma(z, z, szz);
+        max_abs = fmaxf(max_abs, fmaxf(fabsf(cx), fmaxf(fabsf(cy), fabsf(cz))));
+        finite = finite && (fabsf(cx) <= 3.0e38f) && (fabsf(cy) <= 3.0e38f) && (fabsf(cz) <= 3.0e38f);
+        ++n;
+    }
+};
+
+// ---- smallest eigenvector of a symmetric 3x3 (fp64 cyclic Jacobi) ----------
+// a = [a00 a01 a02; . a11 a12; . . a22].  The matrix is a covariance, i.e. PSD,
+// so the smallest eigenvalue is also the smallest singular value (ref :280-283).
+PCT_HD void jacobi_rotate(double& app, double& aqq, double& apq, double& arp, double& arq,
+                          double& v0p, double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
+    if (apq == 0.0) return;
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = 1.0 / sqrt(t * t + 1.0);
+    const double s = t * c;
+    const double tau = s / (1.0 + c);
+    app -= t * apq;
+    aqq += t * apq;
+    apq = 0.0;
+    // the remaining row/column r (the third index)
+    const double rp = arp, rq = arq;
+    arp = rp - s * (rq + tau * rp);
+    arq = rq + s * (rp - tau * rq);
+    double a, b;
+    a = v0p; b = v0q; v0p = a - s * (b + tau * a); v0q = b + s * (a - tau * b);
+    a = v1p; b = v1q; v1p = a - s * (b + tau * a); v1q = b + s * (a - tau * b);
+    a = v2p; b = v2q; v2p = a - s * (b + tau * a); v2q = b + s * (a - tau * b);
+}
+
+PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double a11, double a12, double a22,
+                                      double n[3]) {
+    // scale by the trace: eigenvectors are unchanged, fp range issues vanish
+    const double tr = a00 + a11 + a22;
+    if (!(tr > 0.0)) {  // all neighbours coincide with their mean (or NaN): any unit vector
+        n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
+        return;
+    }
+    const double inv = 1.0 / tr;
+    a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        const double off = a01 * a01 + a02 * a02 + a12 * a12;
+        if (off < 1e-36) break;  // relative to trace^2 == 1
+        jacobi_rotate(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21);  // (p,q) = (0,1), r = 2
+        jacobi_rotate(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22);  // (0,2), r = 1
+        jacobi_rotate(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22);  // (1,2), r = 0
+    }
+    if (a00 <= a11 && a00 <= a22) { n[0] = v00; n[1] = v10; n[2] = v20; }
+    else if (a11 <= a22)          { n[0] = v01; n[1] = v11; n[2] = v21; }
+    else                          { n[0] = v02; n[1] = v12; n[2] = v22; }
+}
+
+// ---- tangent frame ---------------------------------------------------------
+struct Frame {
+    double r00, r01, r02, r10, r11, r12, r20, r21, r22;  // Rodrigues matrix, row major
+    double nx, ny, nz;                                   // oriented unit normal
+};
+
+// moments -> covariance -> normal, oriented by ref = c_last - c_first (fp32, ref :286)
+PCT_HD void plane_frame(const Moments& m, float rfx, float rfy, float rfz, Frame& f) {
+    const double invn = 1.0 / (double)m.n;
+    const double denom = 1.0 / (double)(m.n - 1);  // ddof = 1 (ref :277); scale does not move eigenvectors
+    const double mx = m.sx * invn, my = m.sy * invn, mz = m.sz * invn;
+    const double c00 = (m.sxx - m.sx * mx) * denom, c01 = (m.sxy - m.sx * my) * denom, c02 = (m.sxz - m.sx * mz) * denom;
+    const double c11 = (m.syy - m.sy * my) * denom, c12 = (m.syz - m.sy * mz) * denom, c22 = (m.szz - m.sz * mz) * denom;
+    double n[3];
+    smallest_eigenvector_sym3(c00, c01, c02, c11, c12, c22, n);
+    // ref :289-297: only the SIGN of normal.ref matters; a zero-length ref gives NaN -> no flip
+    const double dot = n[0] * (double)rfx + n[1] * (double)rfy + n[2] * (double)rfz;
+    if (dot < 0.0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    const double nn = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);  // ref :301
+    const double ax = n[0] * nn, ay = n[1] * nn, az = n[2] * nn;
+    f.nx = ax; f.ny = ay; f.nz = az;
+    // v = a x z = (ay, -ax, 0); c = az; s = |v|  (ref :303-305)
+    const double s = sqrt(ay * ay + ax * ax);
+    if (s == 0.0) {  // ref :308-309, also taken for a == -z
+        f.r00 = 1; f.r01 = 0; f.r02 = 0; f.r10 = 0; f.r11 = 1; f.r12 = 0; f.r20 = 0; f.r21 = 0; f.r22 = 1;
+        return;
+    }
+    const double fac = (1.0 - az) / (s * s);  // ref :312
+    f.r00 = 1.0 - fac * ax * ax; f.r01 = -fac * ax * ay;      f.r02 = -ax;
+    f.r10 = -fac * ax * ay;      f.r11 = 1.0 - fac * ay * ay; f.r12 = -ay;
+    f.r20 = ax;                  f.r21 = ay;                  f.r22 = 1.0 - fac * (ax * ax + ay * ay);
+}
+
+PCT_HD void rotate_point(const Frame& f, float cx, float cy, float cz, double& x, double& y, double& z) {
+    const double a = cx, b = cy, c = cz;
+    x = f.r00 * a + f.r01 * b + f.r02 * c;
+    y = f.r10 * a + f.r11 * b + f.r12 * c;
+    z = f.r20 * a + f.r21 * b + f.r22 * c;
+}
+
+// ---- second pass: normal equations of z = A a^2 + B b^2 + C ab + D a + E b + F
+// Coordinates are pre-multiplied by a power of two `scale` (about 1/r_k).  This
+// is exact in binary floating point, so the fp32 products below are exactly the
+// reference's fp32 design-matrix entries times a power of two, while the 6x6
+// system becomes well conditioned (unscaled it reaches cond ~ 1e11 on bunny).
+struct Quadric {
+    double g[21];  // upper triangle of X^T X, row major: (0,0) (0,1) .. (0,5) (1,1) ..
+    double r[6];   // X^T z
+    bool finite;
+    PCT_HD void reset() {
+#pragma unroll
+        for (int i = 0; i < 21; ++i) g[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) r[i] = 0.0;
+        finite = true;
+    }
+    // rotated coordinates in fp64, quantised here to fp32 like ref :350
+    PCT_HD void add(double xr, double yr, double zr, float scale) {
+        const float a = (float)xr * scale, b = (float)yr * scale, z = (float)zr * scale;
+        finite = finite && (fabsf(a) <= 3.0e38f) && (fabsf(b) <= 3.0e38f) && (fabsf(z) <= 3.0e38f);
+        double x[6];
+        x[0] = (double)fmul_rn(a, a);  // ref :358, fp32 products
+        x[1] = (double)fmul_rn(b, b);
+        x[2] = (double)fmul_rn(a, b);
+        x[3] = (double)a;
+        x[4] = (double)b;
+        x[5] = 1.0;
+        const double zd = (double)z;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = i; j < 6; ++j) { g[t] = fma(x[i], x[j], g[t]); ++t; }
+            r[i] = fma(x[i], zd, r[i]);
+        }
+    }
+};
+
+// power of two close to 1 / max_abs (exact scaling)
+PCT_HD float pow2_scale(float max_abs) {
+    if (!(max_abs > 0.f) || !(max_abs < 3.0e38f)) return 1.f;
+    int e = ilogbf(max_abs);
+    if (e > 100) e = 100;
+    if (e < -100) e = -100;
+    return ldexpf(1.f, -e);
+}
+
+// In-place Cholesky of the 6x6 normal matrix + two triangular solves.
+// Returns false when a pivot is not safely positive (rank-deficient design).
+PCT_HD bool solve_normal_equations(Quadric& q, double w[6]) {
+    // unpack to a full lower triangle with compile-time indices (stays in registers)
+    double L[6][6];
+    {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { L[j][i] = q.g[t]; ++t; }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = L[j][j];
+        const double d0 = d;
+#pragma unroll
+        for (int p = 0; p < j; ++p) d -= L[j][p] * L[j][p];
+        if (!(d > 1e-13 * d0) || !(d0 > 0.0)) { ok = false; d = 1.0; }
+        const double inv = 1.0 / sqrt(d);
+        L[j][j] = d * inv;  // sqrt(d)
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double s = L[i][j];
+#pragma unroll
+            for (int p = 0; p < j; ++p) s -= L[i][p] * L[j][p];
+            L[i][j] = s * inv;
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = q.r[i];
+#pragma unroll
+        for (int p = 0; p < i; ++p) s -= L[i][p] * y[p];
+        y[i] = s / L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int p = i + 1; p < 6; ++p) s -= L[p][i] * w[p];
+        w[i] = s / L[i][i];
+    }
+    return ok;
+}
+
+// scaled solution -> reference coefficients [A,B,C,D,E,F] in fp32 (ref :359 result dtype)
+PCT_HD void unscale_coefficients(const double w[6], float scale, float c[6]) {
+    const double s = (double)scale;
+    c[0] = (float)(w[0] * s);
+    c[1] = (float)(w[1] * s);
+    c[2] = (float)(w[2] * s);
+    c[3] = (float)w[3];
+    c[4] = (float)w[4];
+    c[5] = (float)(w[5] / s);
+}
+
+// ref :403-431 in fp32, operation by operation
+PCT_HD void monge_curvature(const float c[6], float out[5]) {
+    const float A = c[0], B = c[1], C = c[2], D = c[3], E = c[4];
+    const float fx2 = fmul_rn(D, D), fy2 = fmul_rn(E, E);
+    const float fxx = fmul_rn(2.f, A), fyy = fmul_rn(2.f, B), fxy = C;
+    const float g = fadd_rn(fadd_rn(1.f, fx2), fy2);
+    const float den_g = fmul_rn(g, g);
+    const float den_m = fmul_rn(g, sqrtf(g));  // g ** 1.5
+    const float K = fsub_rn(fmul_rn(fxx, fyy), fmul_rn(fxy, fxy)) / den_g;
+    const float t1 = fmul_rn(fadd_rn(1.f, fx2), fyy);
+    const float t2 = fmul_rn(fmul_rn(fmul_rn(2.f, D), E), fxy);
+    const float t3 = fmul_rn(fadd_rn(1.f, fy2), fxx);
+    const float H = fadd_rn(fsub_rn(t1, t2), t3) / fmul_rn(2.f, den_m);
+    const float H2 = fmul_rn(H, H);
+    const float disc = fmaxf(fsub_rn(H2, K), 0.f);
+    const float root = sqrtf(disc);
+    out[0] = K;
+    out[1] = H;
+    out[2] = fadd_rn(H, root);
+    out[3] = fsub_rn(H, root);
+    out[4] = H2;
+}
+
+struct FitResult {
+    float normal[3];
+    float coeffs[6];
+    float curv[5];
+    uint32_t status;
+};
+
+PCT_HD void fit_fail(FitResult& o, uint32_t status) {
+    const float nanv = nanf("");
+    o.normal[0] = o.normal[1] = o.normal[2] = nanv;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o.coeffs[i] = nanv;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) o.curv[i] = nanv;
+    o.status |= status;
+}
+
+// status bits (mirrors include/pct_b200.h)
+enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u };
+
+// Whole per-point pipeline over an abstract neighbourhood.
+//   nb.pass(fn)  calls fn(cx, cy, cz) for every neighbour (fp32, centred)
+//   nb.reference(rx, ry, rz) gives c_last - c_first in fp32, valid after the first pass
+template <class Nbr>
+PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
+    Moments mom;
+    mom.reset();
+    nb.pass(mom);
+    if (mom.n < 2) { fit_fail(out, ST_FEW); return; }
+    if (!mom.finite) { fit_fail(out, ST_NONFINITE); return; }
+    float rx, ry, rz;
+    nb.reference(rx, ry, rz);
+    Frame fr;
+    plane_frame(mom, rx, ry, rz, fr);
+    struct Second {
+        const Frame* f;
+        Quadric q;
+        float scale;
+        PCT_HD void add(float cx, float cy, float cz) {
+            double x, y, z;
+            rotate_point(*f, cx, cy, cz, x, y, z);
+            q.add(x, y, z, scale);
+        }
+    } sec;
+    sec.f = &fr;
+    sec.q.reset();
+    sec.scale = pow2_scale(mom.max_abs);
+    nb.pass(sec);
+    out.normal[0] = (float)fr.nx; out.normal[1] = (float)fr.ny; out.normal[2] = (float)fr.nz;
+    if (!sec.q.finite) { fit_fail(out, ST_NONFINITE); return; }
+    double w[6];
+    const bool ok = solve_normal_equations(sec.q, w);
+    if (!ok) {
+        const float nx = out.normal[0], ny = out.normal[1], nz = out.normal[2];
+        fit_fail(out, ST_RANK);
+        out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;
+        return;
+    }
+    unscale_coefficients(w, sec.scale, out.coeffs);
+    monge_curvature(out.coeffs, out.curv);
+}
+
+}  // namespace pct

@@ -1,0 +1,147 @@
+"""The oracle against the reference's own outputs (tests/golden, made by oracle/make_golden.py)."""
+import io
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import datasets
+from conftest import load_golden
+
+CASES = [("bunny", 20), ("bunny", 30), ("egg_carton", 20), ("torus_c1", 20)]
+
+
+def _cloud(name):
+    return load_golden(name + "_points")["points"]
+
+
+@pytest.mark.parametrize("name,k", CASES)
+def test_ranking_key_is_scipys(name, k):
+    """dists stored by the reference == sqrt of the restated fp64 key, bit for bit."""
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name).astype(np.float64)
+    d2 = oracle.squared_distance_key(pts[g["neighbor_indices"]], pts[g["rows"]][:, None, :])
+    assert np.array_equal(np.sqrt(d2).astype(np.float32), g["dists"])
+
+
+@pytest.mark.parametrize("name,k", CASES)
+def test_knn_canonical_matches_reference_up_to_ties(name, k):
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name)
+    idx, dist, d2 = oracle.knn_canonical(pts, k, rows=g["rows"])
+    # distances are tie-independent: must be bit-equal row by row
+    assert np.array_equal(dist, g["dists"])
+    ref_idx = g["neighbor_indices"]
+    differs = (idx != ref_idx).any(axis=1)
+    # every difference must sit inside a group of exactly equal keys
+    p64 = pts.astype(np.float64)
+    d2_ref = oracle.squared_distance_key(p64[ref_idx], p64[g["rows"]][:, None, :])
+    assert np.array_equal(d2_ref, d2)
+    for r in np.nonzero(differs)[0]:
+        bad = idx[r] != ref_idx[r]
+        for c in np.nonzero(bad)[0]:
+            same_key = d2[r] == d2[r, c]
+            boundary = c == k - 1 or same_key.sum() > 1 or d2[r, c] == d2[r, -1]
+            assert boundary, (name, k, r, c)
+    # rows without any exact tie are identical, order included
+    no_tie = np.array([len(np.unique(row)) == k for row in d2]) & (d2[:, -1] < np.inf)
+    strict = no_tie & ~differs
+    assert strict.sum() >= 0.9 * no_tie.sum()
+    if name == "bunny":
+        assert not differs.any()  # no boundary ties on bunny
+
+
+@pytest.mark.parametrize("name,k", CASES)
+def test_per_point_functions_reproduce_reference_bitwise(name, k):
+    """Fed the reference's own neighbour rows, the restatement gives the reference's numbers exactly."""
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name)
+    sel = np.arange(0, len(g["rows"]), 4)
+    res = oracle.curvature_from_neighbors(pts, g["neighbor_indices"][sel], g["rows"][sel])
+    assert np.array_equal(res["coeffs"], g["quadratic_coefficients"][sel])
+    assert np.array_equal(res["K"], g["K_quadratic"][sel])
+    assert np.array_equal(res["H"], g["H_quadratic"][sel])
+    assert np.array_equal(res["H2"], g["K_H_sq_quadratic"][sel])
+
+
+@pytest.mark.parametrize("name,k", [("bunny", 20), ("egg_carton", 20)])
+def test_static_rotation_reproduces_reference_bitwise(name, k):
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name)
+    pos = {int(r): j for j, r in enumerate(g["rows"])}
+    for j, i in enumerate(g["static_rows"]):
+        nb = g["neighbor_indices"][pos[int(i)]]
+        rot, normal = oracle.best_fit_plane_and_rotate(pts[nb] - pts[i], return_normal=True)
+        assert np.array_equal(rot, g["static_rotated"][j])
+        # the rotation takes the oriented normal to +z (or is the identity)
+        assert abs(np.linalg.norm(normal) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("name,k", [("bunny", 30), ("torus_c1", 20)])
+def test_batched_equals_per_point(name, k):
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name)
+    sel = np.arange(0, len(g["rows"]), 2)
+    a = oracle.curvature_from_neighbors(pts, g["neighbor_indices"][sel], g["rows"][sel])
+    b = oracle.curvature_from_neighbors_batched(pts, g["neighbor_indices"][sel], g["rows"][sel])
+    r_k = g["dists"][sel, -1].astype(np.float64)
+    rep = oracle.compare.curvature_report(b, a, r_k)
+    assert rep["violations"] == 0, rep
+    assert rep["tight_fraction"] > 0.99, rep
+    assert np.allclose(a["margin"], b["margin"], atol=1e-9)
+
+
+def test_loader_matches_reference():
+    g = load_golden("loader_case")
+    buf = io.StringIO()
+    np.savetxt(buf, g["table"], fmt="%.5f")
+    buf.seek(0)
+    pts, nrm = oracle.load_points(buf)
+    assert pts.dtype == np.float32 and np.array_equal(pts, g["points"])
+    assert np.array_equal(nrm, g["normals"])
+    assert pts[:, 0].max() == 0 and pts[:, 1].max() == 0
+
+
+def test_torus_c1_is_regenerable(torus_c1):
+    pts, K, H = datasets.torus_c1()
+    assert np.array_equal(pts, torus_c1)
+    assert len(pts) == 317 * 317
+
+
+def test_ball_membership_is_inclusive_squared_radius(bunny):
+    pts = bunny[:6000]
+    r = 3.8e-3
+    rows = np.arange(0, 6000, 7)
+    off, idx, dist = oracle.ball_canonical(pts, r, rows=rows)
+    p64 = pts.astype(np.float64)
+    for j, i in enumerate(rows[:200]):
+        d2 = oracle.squared_distance_key(p64, p64[i])
+        want = np.nonzero((d2 <= r * r) & (np.arange(len(pts)) != i))[0]
+        got = idx[off[j]:off[j + 1]]
+        assert set(got.tolist()) == set(want.tolist())
+        key = list(zip(d2[got].tolist(), got.tolist()))
+        assert key == sorted(key)
+    # a radius that hits a neighbour distance exactly: boundary is inclusive
+    i = 17
+    d2 = oracle.squared_distance_key(p64, p64[i])
+    target = np.sort(d2)[10]
+    r_exact = float(np.sqrt(target))
+    if r_exact * r_exact == target:
+        off, idx, _ = oracle.ball_canonical(pts, r_exact, rows=[i])
+        assert np.count_nonzero(d2 <= target) - 1 == off[1]
+
+
+def test_closed_form_sphere():
+    pts, K, H = datasets.sphere_fibonacci(20000)
+    rows = np.arange(0, 20000, 40)
+    res = oracle.knn_curvature(pts, 20, rows=rows)
+    rep = oracle.compare.closed_form_report(res["K"], res["H"], K[rows], H[rows])
+    assert rep["K_abs_p99"] < 2e-2 and rep["H_abs_p99"] < 1e-2, rep
+
+
+def test_knn_errors():
+    pts = np.random.default_rng(0).normal(size=(10, 3)).astype(np.float32)
+    with pytest.raises(IndexError):
+        oracle.knn_canonical(pts, 10)
+    with pytest.raises(ValueError):
+        oracle.best_fit_plane_and_rotate(np.array([[0, 0, np.nan], [1, 0, 0], [0, 1, 0]], np.float32))
