@@ -107,11 +107,12 @@ int pct_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
 /* epsilon-ball (advertised README.md:8, absent in the reference; semantics of
  * scipy `query_ball_point`: d2 <= radius*radius in fp64, self excluded).
  * count: rows x int32.  fill: CSR rows given exclusive `offsets` (rows + 1, int64),
- * each row ordered by (d2, index). */
+ * each row ordered by (d2, index); nnz = offsets[rows] = length of idx / dist. */
 int pct_ball_count(const pct_index* index, int64_t q_begin, int64_t q_end, double radius,
                    int32_t* counts, int layout, void* stream);
 int pct_ball_fill(const pct_index* index, int64_t q_begin, int64_t q_end, double radius,
-                  const int64_t* offsets, int32_t* idx, float* dist, int layout, void* stream);
+                  const int64_t* offsets, int64_t nnz, int32_t* idx, float* dist, int layout,
+                  void* stream);
 
 /* Fit from given neighbour lists: replaces fit_explicit_quadratic_surfaces_to_neighborhoods
  * (ref :635-647) + calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points

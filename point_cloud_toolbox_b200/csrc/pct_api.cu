@@ -1,0 +1,181 @@
+// extern "C" surface of libpct_b200.so (include/pct_b200.h): argument checks,
+// error strings, launches.  No C++ exception crosses this file.
+#include <cstdio>
+#include <string>
+
+#include "pct_internal.h"
+
+namespace pct {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return PCT_ERR_NO_DEVICE;
+    return PCT_ERR_CUDA;
+}
+
+__global__ void permutation_kernel(const Pt* __restrict__ pts, long long n, int32_t* __restrict__ perm) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = (int32_t)pts[i].idx;
+}
+
+static int check_range(const pct_index* ix, int64_t q_begin, int64_t q_end, int layout, const char* who) {
+    if (!ix) { set_error(std::string(who) + ": index is NULL"); return PCT_ERR_INVALID_ARGUMENT; }
+    if (q_begin < 0 || q_end < q_begin || q_end > ix->view.n) { set_error(std::string(who) + ": bad query range"); return PCT_ERR_INVALID_ARGUMENT; }
+    if (layout != PCT_LAYOUT_ORIGINAL && layout != PCT_LAYOUT_SLICE) { set_error(std::string(who) + ": bad layout"); return PCT_ERR_INVALID_ARGUMENT; }
+    return PCT_OK;
+}
+
+static int check_k(const pct_index* ix, int k, const char* who) {
+    if (k < 1 || k > PCT_MAX_K) { set_error(std::string(who) + ": k must be in [1, 128]"); return PCT_ERR_INVALID_ARGUMENT; }
+    if ((long long)k + 1 > ix->view.n) { set_error(std::string(who) + ": k + 1 exceeds the number of points"); return PCT_ERR_K_TOO_LARGE; }
+    return PCT_OK;
+}
+
+}  // namespace pct
+
+using namespace pct;
+
+extern "C" {
+
+int pct_version(void) { return PCT_VERSION; }
+
+const char* pct_last_error(void) { return g_last_error.c_str(); }
+
+int pct_index_permutation(const pct_index* ix, int32_t* perm, void* stream) {
+    PCT_REQUIRE(ix && perm, "pct_index_permutation: NULL argument");
+    const long long n = ix->view.n;
+    permutation_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->pts, n, perm);
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* stats) {
+    PCT_REQUIRE(ix && stats, "pct_index_last_stats: NULL argument");
+    unsigned int h[4];
+    PCT_CUDA(cudaMemcpyAsync(h, ix->stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PCT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    stats->level1_retries = h[0];
+    stats->exact_path = h[1];
+    stats->kernel_launches = h[2];
+    stats->queries = h[3];
+    return PCT_OK;
+}
+
+int pct_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, int32_t* idx, float* dist, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_knn");
+    if (rc) return rc;
+    rc = check_k(ix, k, "pct_knn");
+    if (rc) return rc;
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    return launch_knn(ix, q_begin, q_end, k, false, idx, dist, none, layout, (cudaStream_t)stream);
+}
+
+int pct_curvature_fused_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, float* normals, float* coeffs,
+                            float* curv, uint8_t* status, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_knn");
+    if (rc) return rc;
+    rc = check_k(ix, k, "pct_curvature_fused_knn");
+    if (rc) return rc;
+    FitOutputs out{normals, coeffs, curv, status};
+    return launch_knn(ix, q_begin, q_end, k, true, nullptr, nullptr, out, layout, (cudaStream_t)stream);
+}
+
+int pct_ball_count(const pct_index* ix, int64_t q_begin, int64_t q_end, double radius, int32_t* counts, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_ball_count");
+    if (rc) return rc;
+    PCT_REQUIRE(radius >= 0.0 && counts, "pct_ball_count: radius must be >= 0 and counts non-NULL");
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    return launch_ball(ix, q_begin, q_end, radius, 0, counts, nullptr, 0, nullptr, nullptr, none, layout, (cudaStream_t)stream);
+}
+
+int pct_ball_fill(const pct_index* ix, int64_t q_begin, int64_t q_end, double radius, const int64_t* offsets, int64_t nnz,
+                  int32_t* idx, float* dist, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_ball_fill");
+    if (rc) return rc;
+    PCT_REQUIRE(radius >= 0.0 && offsets && idx && nnz >= 0, "pct_ball_fill: bad argument");
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    return launch_ball(ix, q_begin, q_end, radius, 1, nullptr, (const long long*)offsets, nnz, idx, dist, none, layout,
+                       (cudaStream_t)stream);
+}
+
+int pct_curvature_fused_ball(const pct_index* ix, int64_t q_begin, int64_t q_end, double radius, int32_t* counts,
+                             float* normals, float* coeffs, float* curv, uint8_t* status, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_ball");
+    if (rc) return rc;
+    PCT_REQUIRE(radius >= 0.0, "pct_curvature_fused_ball: radius must be >= 0");
+    FitOutputs out{normals, coeffs, curv, status};
+    return launch_ball(ix, q_begin, q_end, radius, 2, counts, nullptr, 0, nullptr, nullptr, out, layout, (cudaStream_t)stream);
+}
+
+int pct_fit_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, const int32_t* query_ids,
+                           float* normals, float* coeffs, float* curv, uint8_t* status, void* stream) {
+    PCT_REQUIRE(xyz && idx && n >= 1 && nq >= 0 && k >= 1, "pct_fit_from_neighbors: bad argument");
+    FitOutputs out{normals, coeffs, curv, status};
+    return launch_fit_rows(xyz, n, idx, nq, k, query_ids, out, (cudaStream_t)stream);
+}
+
+int pct_fit_from_csr(const float* xyz, int64_t n, const int64_t* offsets, const int32_t* idx, int64_t nq,
+                     const int32_t* query_ids, float* normals, float* coeffs, float* curv, uint8_t* status, void* stream) {
+    PCT_REQUIRE(xyz && offsets && n >= 1 && nq >= 0, "pct_fit_from_csr: bad argument");
+    FitOutputs out{normals, coeffs, curv, status};
+    return launch_fit_csr(xyz, n, (const long long*)offsets, idx, nq, query_ids, out, (cudaStream_t)stream);
+}
+
+int pct_plane_rotate(const float* centered, int64_t nq, int k, double* rotated, double* normals, uint8_t* status, void* stream) {
+    PCT_REQUIRE(centered && rotated && nq >= 0 && k >= 1, "pct_plane_rotate: bad argument");
+    return launch_plane_rotate(centered, nq, k, rotated, normals, status, (cudaStream_t)stream);
+}
+
+int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uint8_t* status, void* stream) {
+    PCT_REQUIRE(rotated && coeffs && nq >= 0 && k >= 1, "pct_quadric_fit: bad argument");
+    return launch_quadric_fit(rotated, nq, k, coeffs, status, (cudaStream_t)stream);
+}
+
+int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream) {
+    PCT_REQUIRE(coeffs && curv && nq >= 0, "pct_quadric_curvature: bad argument");
+    return launch_quadric_curvature(coeffs, nq, curv, (cudaStream_t)stream);
+}
+
+int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_host, float* H_host) {
+    PCT_REQUIRE(xyz_host && K_host && H_host && n >= 1, "pct_curvature_knn_host: bad argument");
+    cudaStream_t s;
+    PCT_CUDA(cudaStreamCreate(&s));
+    float* d_xyz = nullptr;
+    float* d_curv = nullptr;
+    float* h_curv = nullptr;
+    pct_index* ix = nullptr;
+    int rc = PCT_OK;
+    auto cleanup = [&]() {
+        if (ix) pct_index_destroy(ix);
+        if (d_xyz) cudaFree(d_xyz);
+        if (d_curv) cudaFree(d_curv);
+        if (h_curv) cudaFreeHost(h_curv);
+        cudaStreamDestroy(s);
+    };
+#define PCT_TRY(call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } \
+    } while (0)
+    PCT_TRY(cudaMalloc(&d_xyz, sizeof(float) * 3 * (size_t)n));
+    PCT_TRY(cudaMalloc(&d_curv, sizeof(float) * 5 * (size_t)n));
+    PCT_TRY(cudaMallocHost(&h_curv, sizeof(float) * 5 * (size_t)n));
+    PCT_TRY(cudaMemcpyAsync(d_xyz, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+    rc = pct_index_build(d_xyz, n, 3, 0.f, k, s, &ix);
+    if (rc == PCT_OK) rc = pct_curvature_fused_knn(ix, 0, n, k, nullptr, nullptr, d_curv, nullptr, PCT_LAYOUT_ORIGINAL, s);
+    if (rc != PCT_OK) { cleanup(); return rc; }
+    PCT_TRY(cudaMemcpyAsync(h_curv, d_curv, sizeof(float) * 5 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    PCT_TRY(cudaStreamSynchronize(s));
+#undef PCT_TRY
+    for (int64_t i = 0; i < n; ++i) { K_host[i] = h_curv[5 * i]; H_host[i] = h_curv[5 * i + 1]; }
+    cleanup();
+    return PCT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// Morton-sorted uniform grid: the view a query kernel sees, and the per-query
+// search routines (one thread = one query point).
+//
+// Replaces scipy.spatial.cKDTree as used by PointCloud.plant_kdtree
+// (/root/reference/pointCloudToolbox.py:74, :83).  Layout in HBM:
+//
+//   pts[N]           16-byte records {x, y, z, original index}, sorted by the
+//                    Morton key of their level-0 cell
+//   level tables     for level L = 0 .. bits: open-addressing hash
+//                    {key >> 3L  ->  [start, end) in pts}; an aligned 2^L-cube of
+//                    level-0 cells is one contiguous run of pts (Morton property),
+//                    so coarser levels need no second copy of the cloud
+//
+// Search = 3x3x3 cells of one level around the query's cell.  Everything closer
+// than `safe` (distance to the faces of that block, minus rounding slack) is
+// guaranteed to have been seen; a query whose k-th neighbour is not inside
+// `safe` is retried one level up (cells twice as large).
+//
+// Exactness: candidates are culled with an fp32 squared distance, the survivors
+// are re-ranked with scipy's fp64 key ((dx*dx + dy*dy) + dz*dz, ties by index).
+// |d32 - d64| <= 5 * 2^-24 * d64, so every true neighbour survives a cull at
+// tau * (1 + 2.5e-6) where tau is the k-th smallest d32 (proof in DESIGN.md).
+#pragma once
+
+#include "pct_math.cuh"
+
+namespace pct {
+
+struct alignas(16) Pt {
+    float x, y, z;
+    uint32_t idx;  // original index
+};
+
+struct alignas(16) HashSlot {
+    unsigned long long key;
+    uint32_t start, end;
+};
+
+static constexpr unsigned long long kEmptyKey = ~0ull;
+static constexpr int kMaxLevels = 22;
+
+struct LevelTable {
+    const HashSlot* slots;
+    uint32_t mask;  // capacity - 1 (capacity is a power of two)
+    uint32_t pad;
+};
+
+struct IndexView {
+    const Pt* pts;
+    long long n;
+    float ox, oy, oz;  // grid origin = bounding-box minimum
+    float h, inv_h;    // level-0 cell edge
+    float slack;       // rounding slack of a cell coordinate, in level-0 cells
+    int dims[3];       // level-0 grid size
+    int bits;          // bits per axis of the Morton key
+    int num_levels;    // tables for levels 0 .. num_levels-1 (last one: a single cell)
+    LevelTable lvl[kMaxLevels];
+};
+
+PCT_HD Pt load_pt(const Pt* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    Pt r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.idx = __float_as_uint(v.w);
+    return r;
+#else
+    return *p;
+#endif
+}
+
+PCT_HD HashSlot load_slot(const HashSlot* p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    HashSlot s;
+    s.key = ((unsigned long long)v.y << 32) | v.x;
+    s.start = v.z; s.end = v.w;
+    return s;
+#else
+    return *p;
+#endif
+}
+
+PCT_HD unsigned long long spread3(uint32_t v) {
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+PCT_HD unsigned long long morton3(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+PCT_HD uint32_t hash_key(unsigned long long key) {
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32);
+}
+
+// continuous cell coordinate of one axis; monotone in x, identical in build and query
+PCT_HD float cell_coord(float x, float origin, float inv_h) { return fmul_rn(fsub_rn(x, origin), inv_h); }
+
+PCT_HD bool lookup_cell(const LevelTable& t, unsigned long long key, uint32_t& start, uint32_t& end) {
+    uint32_t slot = hash_key(key) & t.mask;
+    for (;;) {
+        const HashSlot s = load_slot(t.slots + slot);
+        if (s.key == key) { start = s.start; end = s.end; return true; }
+        if (s.key == kEmptyKey) return false;
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+// The 3x3x3 block of level-L cells around a query, and how far the query is from leaving it.
+struct Stencil {
+    int lx, ly, lz;      // the query's cell at this level
+    int dx, dy, dz;      // grid size at this level
+    float safe2;         // squared radius within which every cloud point has been visited
+    const LevelTable* table;
+};
+
+PCT_HD int imin_(int a, int b) { return a < b ? a : b; }
+
+// level-0 cell of a point (shared by the build and every query)
+PCT_HD void cell_of(const IndexView& ix, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = imin_((int)cell_coord(x, ix.ox, ix.inv_h), ix.dims[0] - 1);
+    cy = imin_((int)cell_coord(y, ix.oy, ix.inv_h), ix.dims[1] - 1);
+    cz = imin_((int)cell_coord(z, ix.oz, ix.inv_h), ix.dims[2] - 1);
+}
+
+// One axis of the block [cell-1, cell+1]: cells below it exist iff cell >= 2,
+// cells above it iff cell + 2 <= dim - 1.  `u` is the continuous coordinate.
+PCT_HD float axis_gap(float u, int cell, int dim, float gap) {
+    const float f = u - (float)cell;  // position inside the cell, [0, 1)
+    if (cell >= 2) gap = fminf(gap, f + 1.f);
+    if (cell + 2 <= dim - 1) gap = fminf(gap, (1.f - f) + 1.f);
+    return gap;
+}
+
+PCT_HD void make_stencil(const IndexView& ix, int level, float qx, float qy, float qz, Stencil& st) {
+    const float sc = ldexpf(1.f, -level);  // exact
+    const float ux = cell_coord(qx, ix.ox, ix.inv_h) * sc;
+    const float uy = cell_coord(qy, ix.oy, ix.inv_h) * sc;
+    const float uz = cell_coord(qz, ix.oz, ix.inv_h) * sc;
+    st.dx = ((ix.dims[0] - 1) >> level) + 1;
+    st.dy = ((ix.dims[1] - 1) >> level) + 1;
+    st.dz = ((ix.dims[2] - 1) >> level) + 1;
+    st.lx = imin_((int)ux, st.dx - 1);
+    st.ly = imin_((int)uy, st.dy - 1);
+    st.lz = imin_((int)uz, st.dz - 1);
+    st.table = &ix.lvl[level];
+    // distance (in cells of this level) to the nearest block face beyond which cells exist
+    float gap = 3.0e38f;
+    gap = axis_gap(ux, st.lx, st.dx, gap);
+    gap = axis_gap(uy, st.ly, st.dy, gap);
+    gap = axis_gap(uz, st.lz, st.dz, gap);
+    if (gap > 1.0e38f) {
+        st.safe2 = 3.0e38f;  // the block covers the whole grid on every axis
+    } else {
+        const float g = fmaxf(gap - ix.slack, 0.f) * (ix.h * ldexpf(1.f, level));
+        st.safe2 = g * g * 0.99999f;
+    }
+}
+
+// visit every point of the 27 cells: fn(j, pt) with j the sorted position
+template <class F>
+PCT_HD void for_each_candidate(const IndexView& ix, const Stencil& st, F& fn) {
+    for (int cz = st.lz - 1; cz <= st.lz + 1; ++cz) {
+        if (cz < 0 || cz >= st.dz) continue;
+        for (int cy = st.ly - 1; cy <= st.ly + 1; ++cy) {
+            if (cy < 0 || cy >= st.dy) continue;
+            for (int cx = st.lx - 1; cx <= st.lx + 1; ++cx) {
+                if (cx < 0 || cx >= st.dx) continue;
+                uint32_t s, e;
+                if (!lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), s, e)) continue;
+                for (uint32_t j = s; j < e; ++j) {
+                    const Pt p = load_pt(ix.pts + j);
+                    fn(j, p);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kNN selection, thread per query
+// ---------------------------------------------------------------------------
+enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
+
+template <int KT>
+struct TopKeys {
+    float key[KT];
+    // Only k of the KT slots are live: the first KT - k are pinned to -1 (below any
+    // squared distance), so the k-th smallest real key always sits in key[KT-1] and
+    // no slot is ever addressed with a runtime index (the array stays in registers).
+    PCT_HD void reset(int k) {
+#pragma unroll
+        for (int s = 0; s < KT; ++s) key[s] = (s < KT - k) ? -1.f : 3.4e38f;
+    }
+    // branch-free sorted insertion: 2 min/max per slot, no index payload
+    PCT_HD void insert(float d) {
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+            const float lo = fminf(key[s], d);
+            d = fmaxf(key[s], d);
+            key[s] = lo;
+        }
+    }
+    PCT_HD float kth() const { return key[KT - 1]; }
+};
+
+// Finds the exact k nearest neighbours (scipy order, self excluded) of sorted
+// point `i` inside the level-`level` stencil.  On SEL_OK, list[m * stride]
+// (m < k) holds their sorted positions (unordered) and `first`/`last` the
+// nearest / farthest by (d2 fp64, original index).
+//   list capacity = cap entries (cap >= k)
+template <int KT>
+PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, int k,
+                      uint32_t* list, int stride, int cap, uint32_t& first, uint32_t& last,
+                      double& d2_last) {
+    Stencil st;
+    make_stencil(ix, level, q.x, q.y, q.z, st);
+
+    // pass 1: k-th smallest fp32 squared distance
+    struct P1 {
+        TopKeys<KT> top;
+        uint32_t self;
+        float qx, qy, qz;
+        PCT_HD void operator()(uint32_t j, const Pt& p) {
+            const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
+            top.insert(j == self ? 3.4e38f : d);
+        }
+    } p1;
+    p1.top.reset(k);
+    p1.self = i; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z;
+    for_each_candidate(ix, st, p1);
+    const float tau = p1.top.kth();
+    if (!(tau < 3.0e38f)) return SEL_RETRY_COARSER;           // fewer than k candidates here
+    if (!(tau * 1.00001f < st.safe2)) return SEL_RETRY_COARSER;  // k-th neighbour may lie outside the block
+    if (!(tau > 1.0e-30f)) return SEL_EXACT;                   // duplicates / denormal range: fp64 only
+
+    // pass 2: everything that can belong to the fp64 top-k
+    struct P2 {
+        uint32_t self, cnt;
+        int cap, stride;
+        uint32_t* list;
+        float qx, qy, qz, thr;
+        PCT_HD void operator()(uint32_t j, const Pt& p) {
+            const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
+            if (d <= thr && j != self) {
+                if ((int)cnt < cap) list[(size_t)cnt * stride] = j;
+                ++cnt;
+            }
+        }
+    } p2;
+    p2.self = i; p2.cnt = 0; p2.cap = cap; p2.stride = stride; p2.list = list;
+    p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.thr = tau * 1.0000025f;
+    for_each_candidate(ix, st, p2);
+    int cnt = (int)p2.cnt;
+    if (cnt > cap) return SEL_EXACT;  // a large group of (near-)ties
+
+    // fp64 re-rank.  Almost always cnt == k and this only finds first / last.
+    for (;;) {
+        double dmin = 1.0e300, dmax = -1.0;
+        uint32_t imin = 0, imax = 0, jmin = 0, jmax = 0;
+        int mmax = 0;
+        bool zero = false;
+        for (int m = 0; m < cnt; ++m) {
+            const uint32_t j = list[(size_t)m * stride];
+            const Pt p = load_pt(ix.pts + j);
+            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+            zero = zero || (d == 0.0);
+            if (m == 0 || key_less(d, p.idx, dmin, imin)) { dmin = d; imin = p.idx; jmin = j; }
+            if (m == 0 || key_less(dmax, imax, d, p.idx)) { dmax = d; imax = p.idx; jmax = j; mmax = m; }
+        }
+        if (zero) return SEL_EXACT;  // exact duplicates of the query: the "drop the first hit" rule decides
+        if (cnt == k) {
+            first = jmin; last = jmax; d2_last = dmax;
+            return SEL_OK;
+        }
+        // drop the farthest and look again
+        list[(size_t)mmax * stride] = list[(size_t)(cnt - 1) * stride];
+        --cnt;
+    }
+}
+
+// Neighbourhood adaptor over a list of sorted positions (fused kNN path).
+struct ListNeighbourhood {
+    const IndexView* ix;
+    const uint32_t* list;
+    int stride, count;
+    Pt q;
+    uint32_t first, last;
+    template <class F>
+    PCT_HD void pass(F& fn) const {
+        for (int m = 0; m < count; ++m) {
+            const Pt p = load_pt(ix->pts + list[(size_t)m * stride]);
+            fn.add(fsub_rn(p.x, q.x), fsub_rn(p.y, q.y), fsub_rn(p.z, q.z));
+        }
+    }
+    PCT_HD void reference(float& rx, float& ry, float& rz) const {
+        const Pt a = load_pt(ix->pts + first), b = load_pt(ix->pts + last);
+        rx = fsub_rn(fsub_rn(b.x, q.x), fsub_rn(a.x, q.x));  // ref :286 on fp32 centred points
+        ry = fsub_rn(fsub_rn(b.y, q.y), fsub_rn(a.y, q.y));
+        rz = fsub_rn(fsub_rn(b.z, q.z), fsub_rn(a.z, q.z));
+    }
+};
+
+// ---------------------------------------------------------------------------
+// epsilon-ball, thread per query, streaming (no lists)
+// ---------------------------------------------------------------------------
+struct BallTest {
+    float r2_lo, r2_hi;  // fp32 brackets of r*r
+    double r2;           // fl(r*r) in fp64: scipy's inclusive bound
+    PCT_HD void set(double radius) {
+        r2 = radius * radius;
+        r2_lo = (float)(r2 * (1.0 - 2e-6));
+        r2_hi = (float)(r2 * (1.0 + 2e-6));
+        if (!(r2_lo > 1.0e-30f)) { r2_lo = -1.f; }  // tiny radii: always take the fp64 test
+    }
+    PCT_HD bool inside(const Pt& q, const Pt& p) const {
+        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (d > r2_hi) return false;
+        if (d < r2_lo) return true;
+        return dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z) <= r2;
+    }
+};
+
+// Neighbourhood adaptor that re-walks the stencil (fused ball path).  The first
+// pass also finds the nearest / farthest member by (d2, index).
+struct BallNeighbourhood {
+    const IndexView* ix;
+    Stencil st;
+    BallTest test;
+    Pt q;
+    uint32_t self;
+    // tracking
+    double dmin, dmax;
+    uint32_t imin, imax;
+    Pt pmin, pmax;
+    int count;
+    bool tracked;
+
+    template <class F>
+    struct Visit {
+        BallNeighbourhood* nb;
+        F* fn;
+        bool track;
+        PCT_HD void operator()(uint32_t j, const Pt& p) {
+            if (j == nb->self || !nb->test.inside(nb->q, p)) return;
+            fn->add(fsub_rn(p.x, nb->q.x), fsub_rn(p.y, nb->q.y), fsub_rn(p.z, nb->q.z));
+            if (track) {
+                const double d = dist2_f64(nb->q.x, nb->q.y, nb->q.z, p.x, p.y, p.z);
+                if (nb->count == 0 || key_less(d, p.idx, nb->dmin, nb->imin)) { nb->dmin = d; nb->imin = p.idx; nb->pmin = p; }
+                if (nb->count == 0 || key_less(nb->dmax, nb->imax, d, p.idx)) { nb->dmax = d; nb->imax = p.idx; nb->pmax = p; }
+                ++nb->count;
+            }
+        }
+    };
+    template <class F>
+    PCT_HD void pass(F& fn) {
+        Visit<F> v;
+        v.nb = this; v.fn = &fn; v.track = !tracked;
+        if (!tracked) count = 0;
+        for_each_candidate(*ix, st, v);
+        tracked = true;
+    }
+    PCT_HD void reference(float& rx, float& ry, float& rz) const {
+        rx = fsub_rn(fsub_rn(pmax.x, q.x), fsub_rn(pmin.x, q.x));
+        ry = fsub_rn(fsub_rn(pmax.y, q.y), fsub_rn(pmin.y, q.y));
+        rz = fsub_rn(fsub_rn(pmax.z, q.z), fsub_rn(pmin.z, q.z));
+    }
+};
+
+// Neighbourhood adaptor over caller-provided index rows on the ORIGINAL cloud
+// (packed xyz, stride 3): the fit of fit_explicit_quadratic_surfaces_to_neighborhoods
+// (ref :638-647) -- first / last are the row's first / last entries, as in the reference.
+struct RowNeighbourhood {
+    const float* xyz;
+    const int32_t* row;
+    int count;
+    float qx, qy, qz;
+    template <class F>
+    PCT_HD void pass(F& fn) const {
+        for (int m = 0; m < count; ++m) {
+            const float* p = xyz + 3 * (size_t)row[m];
+            fn.add(fsub_rn(p[0], qx), fsub_rn(p[1], qy), fsub_rn(p[2], qz));
+        }
+    }
+    PCT_HD void reference(float& rx, float& ry, float& rz) const {
+        const float* a = xyz + 3 * (size_t)row[0];
+        const float* b = xyz + 3 * (size_t)row[count - 1];
+        rx = fsub_rn(fsub_rn(b[0], qx), fsub_rn(a[0], qx));
+        ry = fsub_rn(fsub_rn(b[1], qy), fsub_rn(a[1], qy));
+        rz = fsub_rn(fsub_rn(b[2], qz), fsub_rn(a[2], qz));
+    }
+};
+
+}  // namespace pct

@@ -1,0 +1,383 @@
+// Spatial index build: bounding box -> density pilot -> Morton keys -> radix sort
+// -> sorted 16-byte records -> per-level hash tables of cell ranges.
+//
+// Replaces `sp.spatial.cKDTree(np.array(self.points, dtype=np.float32))`
+// (/root/reference/pointCloudToolbox.py:74).  All kernels here are HBM-bound
+// streaming passes; the sort uses CUB's radix sort (library code, 8-bit digits
+// over 3*bits key bits).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "pct_internal.h"
+
+namespace pct {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPilotSample = 1 << 18;
+constexpr int kPilotBits = 10;  // 1024^3 virtual grid
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// partial[block][6] = {min xyz, max xyz}; *nonfinite |= 1 when a coordinate is NaN/Inf
+__global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict__ xyz, long long n, int stride,
+                                                         float* __restrict__ partial, unsigned* __restrict__ nonfinite) {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* p = xyz + i * stride;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(p + a);
+            bad = bad || !(fabsf(v) <= 3.0e38f);
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+    __shared__ float sm[kThreads / 32][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = warp_min(lo[a]);
+        hi[a] = warp_max(hi[a]);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nonfinite, 1u);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { sm[warp][a] = lo[a]; sm[warp][3 + a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = sm[0][threadIdx.x];
+        for (int w = 1; w < kThreads / 32; ++w) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void bbox_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= 6) return;
+    float v = partial[c];
+    for (int b = 1; b < blocks; ++b) v = c < 3 ? fminf(v, partial[b * 6 + c]) : fmaxf(v, partial[b * 6 + c]);
+    out[c] = v;
+}
+
+// ---- density pilot: 30-bit Morton keys of a strided sample on a 1024^3 grid ----
+__global__ void pilot_keys_kernel(const float* __restrict__ xyz, long long n, int stride, long long step, int samples,
+                                  float ox, float oy, float oz, float inv_cell, uint32_t* __restrict__ keys) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= samples) return;
+    const long long i = min((long long)t * step, n - 1);
+    const float* p = xyz + i * stride;
+    const int lim = (1 << kPilotBits) - 1;
+    const int cx = min((int)((__ldg(p) - ox) * inv_cell), lim);
+    const int cy = min((int)((__ldg(p + 1) - oy) * inv_cell), lim);
+    const int cz = min((int)((__ldg(p + 2) - oz) * inv_cell), lim);
+    keys[t] = (uint32_t)morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+}
+
+// hist[l] += #adjacent pairs of sorted keys whose highest differing bit lies in level l
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) level_hist_kernel(const KeyT* __restrict__ keys, long long n,
+                                                              unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int sh[kMaxLevels];
+    if (threadIdx.x < kMaxLevels) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x + 1; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long x = (unsigned long long)(keys[i] ^ keys[i - 1]);
+        if (x) atomicAdd(&sh[(63 - __clzll((long long)x)) / 3], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxLevels && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kThreads) morton_keys_kernel(const float* __restrict__ xyz, long long n, int stride,
+                                                                IndexView ix, unsigned long long* __restrict__ keys,
+                                                                uint32_t* __restrict__ vals) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = xyz + i * stride;
+    int cx, cy, cz;
+    cell_of(ix, __ldg(p), __ldg(p + 1), __ldg(p + 2), cx, cy, cz);
+    keys[i] = morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kThreads) gather_kernel(const float* __restrict__ xyz, long long n, int stride,
+                                                           const uint32_t* __restrict__ vals, Pt* __restrict__ pts) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = vals[i];
+    const float* p = xyz + (long long)v * stride;
+    float4 r;
+    r.x = __ldg(p); r.y = __ldg(p + 1); r.z = __ldg(p + 2); r.w = __uint_as_float(v);
+    reinterpret_cast<float4*>(pts)[i] = r;
+}
+
+struct BuildTables {
+    HashSlot* slots[kMaxLevels];
+    uint32_t mask[kMaxLevels];
+    int num_levels;
+};
+
+__device__ __forceinline__ HashSlot* claim_slot(HashSlot* slots, uint32_t mask, unsigned long long key) {
+    uint32_t s = hash_key(key) & mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&slots[s].key, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) return slots + s;
+        s = (s + 1) & mask;
+    }
+}
+
+// position i in [0, n] is a boundary between sorted points i-1 and i: it ends the
+// cells of point i-1 and starts the cells of point i at every level where they differ
+__global__ void __launch_bounds__(kThreads) fill_tables_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                                                BuildTables t) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int top;
+    if (i == 0 || i == n) {
+        top = t.num_levels - 1;
+    } else {
+        const unsigned long long x = keys[i] ^ keys[i - 1];
+        if (!x) return;
+        top = (63 - __clzll((long long)x)) / 3;
+    }
+    for (int L = 0; L <= top; ++L) {
+        if (i > 0) claim_slot(t.slots[L], t.mask[L], keys[i - 1] >> (3 * L))->end = (uint32_t)i;
+        if (i < n) claim_slot(t.slots[L], t.mask[L], keys[i] >> (3 * L))->start = (uint32_t)i;
+    }
+}
+
+struct DeviceTemp {
+    void* p = nullptr;
+    cudaStream_t s;
+    explicit DeviceTemp(cudaStream_t st) : s(st) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
+    ~DeviceTemp() { if (p) cudaFreeAsync(p, s); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+static int choose_cell_size(const float* xyz, long long n, int stride, const float lo[3], float extent_max,
+                            int k_hint, cudaStream_t s, float* h_out, float* dim_out) {
+    *dim_out = 2.f;
+    if (!(extent_max > 0.f)) { *h_out = 1.f; return PCT_OK; }
+    const int samples = (int)std::min<long long>(n, kPilotSample);
+    const long long step = std::max<long long>(1, n / samples);
+    const float cell = extent_max * (1.0f + 1e-6f) / (float)(1 << kPilotBits);
+    DeviceTemp keys_a(s), keys_b(s), tmp(s), hist(s);
+    PCT_CUDA(keys_a.alloc(sizeof(uint32_t) * samples));
+    PCT_CUDA(keys_b.alloc(sizeof(uint32_t) * samples));
+    PCT_CUDA(hist.alloc(sizeof(unsigned long long) * kMaxLevels));
+    PCT_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * kMaxLevels, s));
+    pilot_keys_kernel<<<(samples + kThreads - 1) / kThreads, kThreads, 0, s>>>(xyz, n, stride, step, samples, lo[0], lo[1], lo[2],
+                                                                                 1.0f / cell, keys_a.as<uint32_t>());
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_a.as<uint32_t>(), keys_b.as<uint32_t>(), samples, 0,
+                                            3 * kPilotBits, s));
+    PCT_CUDA(tmp.alloc(tmp_bytes));
+    PCT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, keys_a.as<uint32_t>(), keys_b.as<uint32_t>(), samples, 0,
+                                            3 * kPilotBits, s));
+    level_hist_kernel<uint32_t><<<std::min(1024, (samples + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        keys_b.as<uint32_t>(), samples, hist.as<unsigned long long>());
+    unsigned long long h_hist[kMaxLevels];
+    PCT_CUDA(cudaMemcpyAsync(h_hist, hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+
+    // occupied cells of the sample at level L (cell edge = cell * 2^L)
+    double cells[kPilotBits + 1];
+    double acc = 1.0;
+    for (int L = kPilotBits; L >= 0; --L) {
+        if (L < kPilotBits) acc += (double)h_hist[L];
+        cells[L] = acc;
+    }
+    // finest level at which the sample still puts >= 8 points in a cell
+    int Ls = kPilotBits;
+    for (int L = 0; L <= kPilotBits; ++L)
+        if ((double)samples / cells[L] >= 8.0) { Ls = L; break; }
+    double dim = 2.0;
+    if (Ls + 1 <= kPilotBits && cells[Ls + 1] >= 8.0) dim = std::log2(cells[Ls] / cells[Ls + 1]);
+    dim = std::min(3.0, std::max(1.0, dim));
+    const double ppc_full = (double)n / cells[Ls];
+    const double target = 0.5 * (double)(k_hint > 0 ? k_hint : 20);
+    double h = (double)cell * std::ldexp(1.0, Ls) * std::pow(target / ppc_full, 1.0 / dim);
+    h = std::min(h, 2.0 * (double)extent_max);
+    *h_out = (float)h;
+    *dim_out = (float)dim;
+    return PCT_OK;
+}
+
+static int build_impl(const float* xyz, long long n, int stride, float cell_hint, int k_hint, cudaStream_t s,
+                      pct_index* ix) {
+    PCT_CUDA(cudaGetDevice(&ix->device));
+    PCT_CUDA(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, ix->device));
+
+    // 1. bounding box + finiteness
+    const int bb_blocks = std::max(1, std::min<int>(ix->sm_count * 8, (int)((n + kThreads - 1) / kThreads)));
+    DeviceTemp partial(s), bbox(s);
+    PCT_CUDA(partial.alloc(sizeof(float) * 6 * bb_blocks));
+    PCT_CUDA(bbox.alloc(sizeof(float) * 8));
+    PCT_CUDA(cudaMemsetAsync(bbox.p, 0, sizeof(float) * 8, s));
+    bbox_kernel<<<bb_blocks, kThreads, 0, s>>>(xyz, n, stride, partial.as<float>(), reinterpret_cast<unsigned*>(bbox.as<float>() + 6));
+    bbox_final_kernel<<<1, 32, 0, s>>>(partial.as<float>(), bb_blocks, bbox.as<float>());
+    float h_bbox[8];
+    PCT_CUDA(cudaMemcpyAsync(h_bbox, bbox.p, sizeof(h_bbox), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    unsigned bad;
+    std::memcpy(&bad, &h_bbox[6], sizeof(bad));
+    if (bad) {
+        set_error("Non-finite values in input points");
+        return PCT_ERR_NONFINITE;
+    }
+    const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
+    const float ext[3] = {h_bbox[3] - h_bbox[0], h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]};
+    const float extent_max = std::max(ext[0], std::max(ext[1], ext[2]));
+
+    // 2. cell size
+    float h = cell_hint, est_dim = 2.f;
+    if (!(h > 0.f)) {
+        const int rc = choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &h, &est_dim);
+        if (rc != PCT_OK) return rc;
+    }
+    if (!(h > 0.f) || !std::isfinite(h)) h = 1.f;
+    const float h_min = extent_max / (float)((1 << 20) - 2);  // at most 2^20 cells per axis
+    if (h < h_min) h = h_min;
+
+    IndexView& v = ix->view;
+    std::memset(&v, 0, sizeof(v));
+    v.n = n;
+    v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
+    v.h = h;
+    v.inv_h = 1.0f / h;
+    int maxdim = 1;
+    for (int a = 0; a < 3; ++a) {
+        v.dims[a] = (int)((h_bbox[3 + a] - lo[a]) * v.inv_h) + 1;  // same arithmetic as cell_coord()
+        maxdim = std::max(maxdim, v.dims[a]);
+    }
+    v.bits = 1;
+    while ((1 << v.bits) < maxdim) ++v.bits;
+    v.num_levels = v.bits + 1;
+    v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
+
+    // 3. keys, sort, gather
+    DeviceTemp keys_a(s), keys_b(s), vals_a(s), vals_b(s), sort_tmp(s), hist(s);
+    PCT_CUDA(keys_a.alloc(sizeof(unsigned long long) * n));
+    PCT_CUDA(keys_b.alloc(sizeof(unsigned long long) * n));
+    PCT_CUDA(vals_a.alloc(sizeof(uint32_t) * n));
+    PCT_CUDA(vals_b.alloc(sizeof(uint32_t) * n));
+    const int blocks_n = (int)((n + kThreads - 1) / kThreads);
+    morton_keys_kernel<<<blocks_n, kThreads, 0, s>>>(xyz, n, stride, v, keys_a.as<unsigned long long>(), vals_a.as<uint32_t>());
+    cub::DoubleBuffer<unsigned long long> dk(keys_a.as<unsigned long long>(), keys_b.as<unsigned long long>());
+    cub::DoubleBuffer<uint32_t> dv(vals_a.as<uint32_t>(), vals_b.as<uint32_t>());
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (long long)n, 0, 3 * v.bits, s));
+    PCT_CUDA(sort_tmp.alloc(tmp_bytes));
+    PCT_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, dk, dv, (long long)n, 0, 3 * v.bits, s));
+    const unsigned long long* keys = dk.Current();
+    PCT_CUDA(cudaMalloc(&ix->pts, sizeof(Pt) * (size_t)n));
+    gather_kernel<<<blocks_n, kThreads, 0, s>>>(xyz, n, stride, dv.Current(), ix->pts);
+    v.pts = ix->pts;
+
+    // 4. occupied cells per level
+    PCT_CUDA(hist.alloc(sizeof(unsigned long long) * kMaxLevels));
+    PCT_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * kMaxLevels, s));
+    level_hist_kernel<unsigned long long><<<std::min(ix->sm_count * 8, blocks_n), kThreads, 0, s>>>(keys, n, hist.as<unsigned long long>());
+    unsigned long long h_hist[kMaxLevels];
+    PCT_CUDA(cudaMemcpyAsync(h_hist, hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    long long cells[kMaxLevels];
+    long long acc = 1;
+    for (int L = v.num_levels - 1; L >= 0; --L) {
+        if (L < v.num_levels - 1) acc += (long long)h_hist[L];
+        cells[L] = acc;
+    }
+
+    // 5. hash tables
+    BuildTables bt;
+    size_t total_slots = 0;
+    size_t offset[kMaxLevels];
+    for (int L = 0; L < v.num_levels; ++L) {
+        size_t cap = 16;
+        while (cap < (size_t)(2 * cells[L])) cap <<= 1;
+        offset[L] = total_slots;
+        total_slots += cap;
+        bt.mask[L] = (uint32_t)(cap - 1);
+    }
+    PCT_CUDA(cudaMalloc(&ix->table_mem, sizeof(HashSlot) * total_slots));
+    PCT_CUDA(cudaMemsetAsync(ix->table_mem, 0xFF, sizeof(HashSlot) * total_slots, s));
+    bt.num_levels = v.num_levels;
+    for (int L = 0; L < v.num_levels; ++L) {
+        bt.slots[L] = ix->table_mem + offset[L];
+        v.lvl[L].slots = bt.slots[L];
+        v.lvl[L].mask = bt.mask[L];
+    }
+    fill_tables_kernel<<<(int)((n + 1 + kThreads - 1) / kThreads), kThreads, 0, s>>>(keys, n, bt);
+
+    PCT_CUDA(cudaMalloc(&ix->stats, sizeof(unsigned int) * 8));
+    PCT_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(unsigned int) * 8, s));
+    PCT_CUDA(cudaGetLastError());
+
+    pct_index_info& info = ix->info;
+    info.num_points = n;
+    info.cell_size = h;
+    for (int a = 0; a < 3; ++a) { info.origin[a] = lo[a]; info.extent[a] = ext[a]; info.dims[a] = v.dims[a]; }
+    info.bits_per_axis = v.bits;
+    info.num_levels = v.num_levels;
+    info.cells_level0 = cells[0];
+    info.device_bytes = (int64_t)(sizeof(Pt) * (size_t)n + sizeof(HashSlot) * total_slots);
+    info.est_dimension = est_dim;
+    return PCT_OK;
+}
+
+}  // namespace pct
+
+extern "C" {
+
+int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, int k_hint, void* stream, pct_index** out) {
+    PCT_REQUIRE(out != nullptr, "pct_index_build: out is NULL");
+    *out = nullptr;
+    PCT_REQUIRE(xyz != nullptr, "pct_index_build: xyz is NULL");
+    PCT_REQUIRE(n >= 1 && n < (1ll << 31), "pct_index_build: N must be in [1, 2^31)");
+    PCT_REQUIRE(stride == 3 || stride == 4, "pct_index_build: stride must be 3 or 4 floats");
+    pct_index* ix = new pct_index();
+    const int rc = pct::build_impl(xyz, n, stride, cell_hint, k_hint, (cudaStream_t)stream, ix);
+    if (rc != PCT_OK) {
+        pct_index_destroy(ix);
+        return rc;
+    }
+    *out = ix;
+    return PCT_OK;
+}
+
+int pct_index_destroy(pct_index* ix) {
+    if (!ix) return PCT_OK;
+    if (ix->pts) cudaFree(ix->pts);
+    if (ix->table_mem) cudaFree(ix->table_mem);
+    if (ix->stats) cudaFree(ix->stats);
+    delete ix;
+    return PCT_OK;
+}
+
+int pct_index_get_info(const pct_index* ix, pct_index_info* info) {
+    PCT_REQUIRE(ix && info, "pct_index_get_info: NULL argument");
+    *info = ix->info;
+    return PCT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Host-side internals shared by the translation units of libpct_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/pct_b200.h"
+#include "pct_dispatch.h"
+#include "pct_grid.cuh"
+
+struct pct_index {
+    pct::IndexView view;       // device pointers inside
+    pct::Pt* pts = nullptr;    // N sorted records
+    pct::HashSlot* table_mem = nullptr;  // all level tables, one allocation
+    unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries]
+    pct_index_info info{};
+    int device = 0;
+    int sm_count = 148;
+};
+
+namespace pct {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define PCT_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return pct::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PCT_REQUIRE(cond, msg)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            pct::set_error(msg);               \
+            return PCT_ERR_INVALID_ARGUMENT;   \
+        }                                      \
+    } while (0)
+
+// per-row output pointers of the fit (any may be null)
+struct FitOutputs {
+    float* normals;
+    float* coeffs;
+    float* curv;
+    uint8_t* status;
+};
+
+__device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, const FitResult& r) {
+    if (o.normals) {
+        float* p = o.normals + 3 * row;
+        p[0] = r.normal[0]; p[1] = r.normal[1]; p[2] = r.normal[2];
+    }
+    if (o.coeffs) {
+        float* p = o.coeffs + 6 * row;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) p[c] = r.coeffs[c];
+    }
+    if (o.curv) {
+        float* p = o.curv + 5 * row;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) p[c] = r.curv[c];
+    }
+    if (o.status) o.status[row] = (uint8_t)r.status;
+}
+
+// query-side launchers (pct_query.cu)
+int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, bool fused,
+               int32_t* idx, float* dist, FitOutputs out, int layout, cudaStream_t s);
+int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode,
+                int32_t* counts, const long long* offsets, long long nnz, int32_t* idx, float* dist,
+                FitOutputs out, int layout, cudaStream_t s);
+
+// fit-side launchers (pct_fit.cu)
+int launch_fit_rows(const float* xyz, long long n, const int32_t* idx, long long nq, int k,
+                    const int32_t* qids, FitOutputs out, cudaStream_t s);
+int launch_fit_csr(const float* xyz, long long n, const long long* offsets, const int32_t* idx, long long nq,
+                   const int32_t* qids, FitOutputs out, cudaStream_t s);
+int launch_plane_rotate(const float* centered, long long nq, int k, double* rotated, double* normals,
+                        uint8_t* status, cudaStream_t s);
+int launch_quadric_fit(const double* rotated, long long nq, int k, float* coeffs, uint8_t* status, cudaStream_t s);
+int launch_quadric_curvature(const float* coeffs, long long nq, float* curv, cudaStream_t s);
+
+}  // namespace pct

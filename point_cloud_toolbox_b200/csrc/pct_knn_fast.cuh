@@ -1,0 +1,137 @@
+// Thread-per-query kNN kernel (selection in registers, exact set in shared memory,
+// fused fp64 fit).  Each compile-time bucket KT is instantiated in its own
+// translation unit (pct_knn_ktNNN.cu) so the buckets build in parallel.
+// See pct_query.cu for the overview of the query path.
+#pragma once
+
+#include <algorithm>
+
+#include "pct_internal.h"
+
+namespace pct {
+
+constexpr int kBlock = 128;
+
+struct QueryRange {
+    long long q_begin, q_end;
+    const uint32_t* list;       // when non-null: sorted positions to process ...
+    const unsigned int* count;  // ... and how many of them
+    int layout;
+};
+
+struct Queues {
+    uint32_t* retry;   // queries to redo one level coarser (may be null: go straight to exact)
+    uint32_t* exact;   // queries for the exact kernel
+    unsigned int* counters;  // [0] = retry count, [1] = exact count
+};
+
+__device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, uint32_t orig) {
+    return qr.layout == PCT_LAYOUT_ORIGINAL ? (long long)orig : (long long)i - qr.q_begin;
+}
+
+template <int KT>
+constexpr int min_blocks() { return KT <= 32 ? 4 : (KT <= 64 ? 3 : 2); }
+
+template <int KT, bool FUSED>
+__global__ void __launch_bounds__(kBlock, min_blocks<KT>())
+knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const int k, const int cap,
+                int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
+    extern __shared__ uint32_t smem_list[];  // [cap][kBlock]
+    long long total = qr.q_end - qr.q_begin;
+    if (qr.list) total = (long long)*qr.count;
+    for (long long base = (long long)blockIdx.x * kBlock; base < total; base += (long long)gridDim.x * kBlock) {
+        const long long t = base + threadIdx.x;
+        if (t >= total) continue;
+        const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
+        const Pt q = load_pt(ix.pts + i);
+        uint32_t* list = smem_list + threadIdx.x;
+        uint32_t first = 0, last = 0;
+        double d2_last = 0.0;
+        const int rc = knn_select<KT>(ix, level, i, q, k, list, kBlock, cap, first, last, d2_last);
+        if (rc != SEL_OK) {
+            if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
+                qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
+            } else {
+                qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
+            }
+            continue;
+        }
+        const long long row = out_row(qr, i, q.idx);
+        if (FUSED) {
+            ListNeighbourhood nb;
+            nb.ix = &ix; nb.list = list; nb.stride = kBlock; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+            FitResult r;
+            r.status = 0;
+            fit_neighbourhood(nb, r);
+            store_fit(out, row, r);
+        } else {
+            // ordered rows: successive minima of (d2, index) over the k members
+            double pd = -1.0;
+            uint32_t pi = 0;
+            for (int m = 0; m < k; ++m) {
+                double bd = 1.0e300;
+                uint32_t bi = 0xffffffffu;
+                for (int c = 0; c < k; ++c) {
+                    const Pt p = load_pt(ix.pts + list[c * kBlock]);
+                    const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+                    if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
+                }
+                if (out_idx) out_idx[row * k + m] = (int32_t)bi;
+                if (out_dist) out_dist[row * k + m] = (float)sqrt(bd);
+                pd = bd; pi = bi;
+            }
+        }
+    }
+}
+
+
+struct FastLaunch {
+    const pct_index* ix;
+    QueryRange qr;
+    int k, cap;
+    bool fused;
+    int32_t* idx;
+    float* dist;
+    FitOutputs out;
+    uint32_t* retry1;
+    uint32_t* exactq;
+    unsigned int* counters;
+    cudaStream_t s;
+};
+
+// level 0 over the whole range, then level 1 over whatever level 0 queued
+template <int KT>
+int launch_fast_kt(const FastLaunch& a, unsigned int* launches);
+
+template <int KT, bool FUSED>
+static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
+    const IndexView& v = a.ix->view;
+    const long long nq = a.qr.q_end - a.qr.q_begin;
+    const size_t smem = sizeof(uint32_t) * (size_t)a.cap * kBlock;
+    const int grid_all = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 64);
+    const int grid_retry = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
+    auto kern = knn_fast_kernel<KT, FUSED>;
+    PCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.counters};
+    kern<<<grid_all, kBlock, smem, a.s>>>(v, 0, a.qr, a.k, a.cap, a.idx, a.dist, a.out, q0);
+    ++*launches;
+    if (v.num_levels > 1) {
+        QueryRange q1 = a.qr;
+        q1.list = a.retry1;
+        q1.count = a.counters;
+        Queues qq{nullptr, a.exactq, a.counters};
+        kern<<<grid_retry, kBlock, smem, a.s>>>(v, 1, q1, a.k, a.cap, a.idx, a.dist, a.out, qq);
+        ++*launches;
+    }
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+#define PCT_INSTANTIATE_FAST(KT_)                                                   \
+    template <>                                                                     \
+    int launch_fast_kt<KT_>(const FastLaunch& a, unsigned int* launches) {          \
+        return a.fused ? launch_fast_impl<KT_, true>(a, launches)                   \
+                       : launch_fast_impl<KT_, false>(a, launches);                 \
+    }
+
+}  // namespace pct

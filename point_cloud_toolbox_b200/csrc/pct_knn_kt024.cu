@@ -1,0 +1,6 @@
+// knn_fast_kernel<24, *>: see pct_knn_fast.cuh
+#include "pct_knn_fast.cuh"
+
+namespace pct {
+PCT_INSTANTIATE_FAST(24)
+}  // namespace pct

@@ -1,0 +1,272 @@
+// Neighbour search fused with the per-point fit.
+//
+// Replaces the per-point Python loops of the reference:
+//   plant_kdtree                                   /root/reference/pointCloudToolbox.py:81-85
+//   fit_explicit_quadratic_surfaces_to_neighborhoods                           :638-647
+//   calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points         :663-672
+//
+// Kernels
+//   knn_fast_kernel<KT, FUSED>   one thread per query (queries are consecutive
+//       Morton-sorted points, so the lanes of a warp walk the same few cells and
+//       their loads hit L1).  Selection list in registers (KT fp32 keys), exact
+//       neighbour set in shared memory, then either the fp64 fit (FUSED) or the
+//       ordered (index, distance) rows.  Neighbourhoods never go to HBM.
+//       Queries that cannot be finished at this grid level are queued.
+//   knn_exact_kernel<FUSED>      one warp per queued query: successive minima of
+//       the fp64 key over a stencil that grows until it provably holds the
+//       (k+1)-list.  Handles arbitrary tie groups, duplicates of the query point
+//       and isolated points.  Warp shuffles carry the (d2, index) reductions.
+//   ball_kernel<MODE>            epsilon-ball count / CSR fill / fused fit.
+#include <algorithm>
+#include <cmath>
+
+#include "pct_knn_fast.cuh"
+
+namespace pct {
+
+namespace {
+
+
+// ---- exact path: one warp per query ----------------------------------------
+struct Key {
+    double d;
+    uint32_t idx;  // original index
+    uint32_t pos;  // sorted position
+};
+
+__device__ __forceinline__ Key warp_min_key(Key k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        Key other;
+        other.d = __shfl_xor_sync(0xffffffffu, k.d, o);
+        other.idx = __shfl_xor_sync(0xffffffffu, k.idx, o);
+        other.pos = __shfl_xor_sync(0xffffffffu, k.pos, o);
+        if (key_less(other.d, other.idx, k.d, k.idx)) k = other;
+    }
+    return k;
+}
+
+constexpr int kExactWarps = 4;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kExactWarps * 32)
+knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* __restrict__ out_idx,
+                 float* __restrict__ out_dist, const FitOutputs out, const uint32_t* __restrict__ queue,
+                 const unsigned int* __restrict__ queue_count) {
+    extern __shared__ uint32_t smem_rows[];  // [kExactWarps][k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* mine = smem_rows + warp * k;
+    const unsigned int total = *queue_count;
+    for (unsigned int w = blockIdx.x * kExactWarps + warp; w < total; w += gridDim.x * kExactWarps) {
+        const uint32_t i = queue[w];
+        const Pt q = load_pt(ix.pts + i);
+        // 1. smallest level whose block provably contains the (k+1)-list (self included)
+        Stencil st;
+        uint32_t cs = 0, ce = 0;  // lane c < 27 owns cell c of the block
+        int level = 0;
+        for (;; ++level) {
+            make_stencil(ix, level, q.x, q.y, q.z, st);
+            cs = ce = 0;
+            if (lane < 27) {
+                const int cx = st.lx + lane % 3 - 1, cy = st.ly + (lane / 3) % 3 - 1, cz = st.lz + lane / 9 - 1;
+                if (cx >= 0 && cx < st.dx && cy >= 0 && cy < st.dy && cz >= 0 && cz < st.dz)
+                    if (!lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), cs, ce)) cs = ce = 0;
+            }
+            if (level + 1 >= ix.num_levels) break;  // top: the block is the whole cloud
+            const double safe2 = (double)st.safe2;
+            unsigned int inside = 0;
+            for (int c = 0; c < 27; ++c) {
+                const uint32_t s = __shfl_sync(0xffffffffu, cs, c), e = __shfl_sync(0xffffffffu, ce, c);
+                for (uint32_t j = s + lane; j < e; j += 32) {
+                    const Pt p = load_pt(ix.pts + j);
+                    inside += dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z) < safe2 ? 1u : 0u;
+                }
+            }
+            inside = __reduce_add_sync(0xffffffffu, inside);
+            if (inside >= (unsigned int)(k + 1)) break;
+        }
+        const double bound = (level + 1 >= ix.num_levels) ? 1.0e300 : (double)st.safe2;
+        // 2. k+1 successive minima of (d2, index); the first one is dropped (ref :84-85)
+        Key prev;
+        prev.d = -1.0; prev.idx = 0; prev.pos = 0;
+        for (int m = 0; m <= k; ++m) {
+            Key best;
+            best.d = 1.0e301; best.idx = 0xffffffffu; best.pos = 0;
+            for (int c = 0; c < 27; ++c) {
+                const uint32_t s = __shfl_sync(0xffffffffu, cs, c), e = __shfl_sync(0xffffffffu, ce, c);
+                for (uint32_t j = s + lane; j < e; j += 32) {
+                    const Pt p = load_pt(ix.pts + j);
+                    const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+                    if (d < bound && key_less(prev.d, prev.idx, d, p.idx) && key_less(d, p.idx, best.d, best.idx)) {
+                        best.d = d; best.idx = p.idx; best.pos = j;
+                    }
+                }
+            }
+            best = warp_min_key(best);
+            if (m >= 1 && lane == 0) {
+                mine[m - 1] = best.pos;
+                const long long row = out_row(qr, i, q.idx);
+                if (!FUSED) {
+                    if (out_idx) out_idx[row * k + (m - 1)] = (int32_t)best.idx;
+                    if (out_dist) out_dist[row * k + (m - 1)] = (float)sqrt(best.d);
+                }
+            }
+            prev = best;
+        }
+        __syncwarp();
+        if (FUSED && lane == 0) {
+            ListNeighbourhood nb;
+            nb.ix = &ix; nb.list = mine; nb.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
+            FitResult r;
+            r.status = ST_EXACT_PATH;
+            fit_neighbourhood(nb, r);
+            store_fit(out, out_row(qr, i, q.idx), r);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void publish_stats_kernel(const unsigned int* counters, unsigned int* stats, unsigned int queries, unsigned int launches) {
+    stats[0] = counters[0];
+    stats[1] = counters[1];
+    stats[2] = launches;
+    stats[3] = queries;
+}
+
+// ---- epsilon ball ----------------------------------------------------------
+enum BallMode : int { BALL_COUNT = 0, BALL_FILL = 1, BALL_FUSED = 2 };
+
+struct CountOnly {
+    int n;
+    __device__ __forceinline__ void add(float, float, float) { ++n; }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+ball_kernel(const IndexView ix, const int level, const QueryRange qr, const double radius, int32_t* __restrict__ counts,
+            const long long* __restrict__ offsets, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
+            double* __restrict__ scratch_d2, const FitOutputs out) {
+    const long long total = qr.q_end - qr.q_begin;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += (long long)gridDim.x * kBlock) {
+        const uint32_t i = (uint32_t)(qr.q_begin + t);
+        BallNeighbourhood nb;
+        nb.ix = &ix; nb.q = load_pt(ix.pts + i); nb.self = i; nb.tracked = false; nb.count = 0;
+        nb.test.set(radius);
+        make_stencil(ix, level, nb.q.x, nb.q.y, nb.q.z, nb.st);
+        const long long row = out_row(qr, i, nb.q.idx);
+        if (MODE == BALL_COUNT) {
+            CountOnly c;
+            c.n = 0;
+            nb.tracked = true;  // no first/last bookkeeping needed
+            nb.pass(c);
+            counts[row] = c.n;
+        } else if (MODE == BALL_FUSED) {
+            FitResult r;
+            r.status = 0;
+            fit_neighbourhood(nb, r);
+            if (counts) counts[row] = nb.count;
+            store_fit(out, row, r);
+        } else {
+            // CSR fill: members in walk order, then insertion sort of the row by (d2, index)
+            const long long o = offsets[row];
+            int n = 0;
+            struct Walk {
+                BallNeighbourhood* nb;
+                long long o;
+                int* n;
+                int32_t* idx;
+                double* d2;
+                __device__ __forceinline__ void operator()(uint32_t j, const Pt& p) {
+                    if (j == nb->self || !nb->test.inside(nb->q, p)) return;
+                    const double d = dist2_f64(nb->q.x, nb->q.y, nb->q.z, p.x, p.y, p.z);
+                    int m = (*n)++;
+                    // insertion from the back keeps the row ordered as it grows
+                    while (m > 0 && key_less(d, p.idx, d2[o + m - 1], (uint32_t)idx[o + m - 1])) {
+                        d2[o + m] = d2[o + m - 1];
+                        idx[o + m] = idx[o + m - 1];
+                        --m;
+                    }
+                    d2[o + m] = d;
+                    idx[o + m] = (int32_t)p.idx;
+                }
+            } wk;
+            wk.nb = &nb; wk.o = o; wk.n = &n; wk.idx = out_idx; wk.d2 = scratch_d2;
+            for_each_candidate(ix, nb.st, wk);
+            if (out_dist)
+                for (int m = 0; m < n; ++m) out_dist[o + m] = (float)sqrt(scratch_d2[o + m]);
+        }
+    }
+}
+
+int ball_level(const IndexView& v, double radius) {
+    // smallest level whose cell edge (less rounding slack) is >= radius: then the 3x3x3 block holds the ball
+    int level = 0;
+    while (level + 1 < v.num_levels) {
+        const double edge = (double)v.h * std::ldexp(1.0, level);
+        const double safe = (1.0 - (double)v.slack) * edge * 0.99999;
+        if (safe * safe * 0.99999 > radius * radius) break;
+        ++level;
+    }
+    return level;
+}
+
+}  // namespace
+
+int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, bool fused, int32_t* idx, float* dist,
+               FitOutputs out, int layout, cudaStream_t s) {
+    const IndexView& v = ix->view;
+    const long long nq = q_end - q_begin;
+    if (nq == 0) return PCT_OK;
+    const int cap = k + PCT_TIE_SLACK;
+    uint32_t* queues = nullptr;
+    unsigned int* counters = nullptr;
+    PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 2 * (size_t)nq, s));
+    PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 4, s));
+    PCT_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, s));
+    uint32_t* retry1 = queues;
+    uint32_t* exactq = queues + nq;
+    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout};
+    unsigned int launches = 0;
+    FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, counters, s};
+    int rc = PCT_OK;
+    PCT_DISPATCH_KT(k, rc = launch_fast_kt<KT>(fl, &launches));
+    if (rc != PCT_OK) return rc;
+
+    const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
+    const int grid_exact = ix->sm_count * 4;
+    if (fused)
+        knn_exact_kernel<true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1);
+    else
+        knn_exact_kernel<false><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1);
+    ++launches;
+    publish_stats_kernel<<<1, 1, 0, s>>>(counters, ix->stats, (unsigned int)nq, launches);
+    PCT_CUDA(cudaGetLastError());
+    PCT_CUDA(cudaFreeAsync(queues, s));
+    PCT_CUDA(cudaFreeAsync(counters, s));
+    return PCT_OK;
+}
+
+int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode, int32_t* counts,
+                const long long* offsets, long long nnz, int32_t* idx, float* dist, FitOutputs out, int layout,
+                cudaStream_t s) {
+    const IndexView& v = ix->view;
+    const long long nq = q_end - q_begin;
+    if (nq == 0) return PCT_OK;
+    const int level = ball_level(v, radius);
+    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout};
+    const int grid = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)ix->sm_count * 64);
+    if (mode == BALL_COUNT) {
+        ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+    } else if (mode == BALL_FUSED) {
+        ball_kernel<BALL_FUSED><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+    } else {
+        double* scratch = nullptr;
+        PCT_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));
+        ball_kernel<BALL_FILL><<<grid, kBlock, 0, s>>>(v, level, qr, radius, nullptr, offsets, idx, dist, scratch, out);
+        PCT_CUDA(cudaFreeAsync(scratch, s));
+    }
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+}  // namespace pct

@@ -1,0 +1,204 @@
+// CPU harness around the __host__ __device__ per-query code of the CUDA library.
+//
+// TEST INFRASTRUCTURE ONLY: it lets tests/test_host_logic.py run the exact
+// search / fit routines of csrc/pct_grid.cuh and csrc/pct_math.cuh against the
+// oracle in the dev container, where there is no GPU.  It is never loaded by the
+// product (point_cloud_toolbox_b200 refuses to work without its CUDA library).
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (see tests/host_harness/build.py).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pct_grid.cuh"
+#include "pct_dispatch.h"
+
+using namespace pct;
+
+struct HostIndex {
+    std::vector<Pt> pts;
+    std::vector<std::vector<HashSlot>> tables;
+    IndexView view;
+};
+
+static void table_set(std::vector<HashSlot>& t, unsigned long long key, uint32_t start, uint32_t end) {
+    const uint32_t mask = (uint32_t)t.size() - 1;
+    uint32_t slot = hash_key(key) & mask;
+    while (t[slot].key != kEmptyKey) slot = (slot + 1) & mask;
+    t[slot].key = key; t[slot].start = start; t[slot].end = end;
+}
+
+extern "C" {
+
+void* h_build(const float* xyz, long long n, float h) {
+    HostIndex* ix = new HostIndex();
+    IndexView& v = ix->view;
+    std::memset(&v, 0, sizeof(v));
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (long long i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], xyz[3 * i + a]); hi[a] = std::max(hi[a], xyz[3 * i + a]); }
+    v.n = n; v.ox = lo[0]; v.oy = lo[1]; v.oz = lo[2];
+    v.h = h; v.inv_h = 1.0f / h;
+    int maxdim = 1;
+    for (int a = 0; a < 3; ++a) {
+        v.dims[a] = (int)cell_coord(hi[a], lo[a], v.inv_h) + 1;
+        maxdim = std::max(maxdim, v.dims[a]);
+    }
+    v.bits = 1;
+    while ((1 << v.bits) < maxdim) ++v.bits;
+    v.num_levels = v.bits + 1;
+    v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
+    std::vector<std::pair<unsigned long long, uint32_t>> keyed(n);
+    for (long long i = 0; i < n; ++i) {
+        int cx, cy, cz;
+        cell_of(v, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], cx, cy, cz);
+        keyed[i] = {morton3(cx, cy, cz), (uint32_t)i};
+    }
+    std::stable_sort(keyed.begin(), keyed.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    ix->pts.resize(n);
+    for (long long i = 0; i < n; ++i) {
+        const uint32_t o = keyed[i].second;
+        ix->pts[i] = Pt{xyz[3 * o], xyz[3 * o + 1], xyz[3 * o + 2], o};
+    }
+    ix->tables.resize(v.num_levels);
+    for (int L = 0; L < v.num_levels; ++L) {
+        long long cells = 0;
+        for (long long i = 0; i < n; ++i)
+            if (i == 0 || (keyed[i].first >> (3 * L)) != (keyed[i - 1].first >> (3 * L))) ++cells;
+        size_t cap = 16;
+        while (cap < (size_t)(2 * cells)) cap <<= 1;
+        ix->tables[L].assign(cap, HashSlot{kEmptyKey, 0, 0});
+        long long start = 0;
+        for (long long i = 1; i <= n; ++i)
+            if (i == n || (keyed[i].first >> (3 * L)) != (keyed[i - 1].first >> (3 * L))) {
+                table_set(ix->tables[L], keyed[start].first >> (3 * L), (uint32_t)start, (uint32_t)i);
+                start = i;
+            }
+        v.lvl[L].slots = ix->tables[L].data();
+        v.lvl[L].mask = (uint32_t)cap - 1;
+    }
+    v.pts = ix->pts.data();
+    return ix;
+}
+
+void h_destroy(void* p) { delete (HostIndex*)p; }
+void h_perm(void* p, int32_t* perm) {
+    HostIndex* ix = (HostIndex*)p;
+    for (long long i = 0; i < ix->view.n; ++i) perm[i] = (int32_t)ix->pts[i].idx;
+}
+int h_levels(void* p) { return ((HostIndex*)p)->view.num_levels; }
+
+}  // extern "C"
+
+// Exact brute-force (k+1)-list minus first, sorted positions; stands in for the GPU's exact kernel.
+static void exact_rows(const IndexView& v, uint32_t i, int k, uint32_t* out) {
+    const Pt q = v.pts[i];
+    std::vector<std::pair<std::pair<double, uint32_t>, uint32_t>> all(v.n);
+    for (long long j = 0; j < v.n; ++j) {
+        const Pt p = v.pts[j];
+        all[j] = {{dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z), p.idx}, (uint32_t)j};
+    }
+    std::partial_sort(all.begin(), all.begin() + k + 1, all.end());
+    for (int m = 0; m < k; ++m) out[m] = all[m + 1].second;
+}
+
+// kNN lists (original indices, sorted by key) + per-query path code:
+// 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback
+template <int KT>
+static void knn_impl(HostIndex* ix, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
+                     float* normals, float* coeffs, float* curv, uint8_t* status) {
+    const IndexView& v = ix->view;
+    const int cap = k + PCT_TIE_SLACK;
+    std::vector<uint32_t> list(cap);
+    for (long long i = 0; i < v.n; ++i) {
+        const Pt q = v.pts[i];
+        uint32_t first = 0, last = 0;
+        double d2_last = 0;
+        int rc = SEL_RETRY_COARSER, level = 0;
+        for (; level <= max_fast_level && level < v.num_levels; ++level) {
+            rc = knn_select<KT>(v, level, (uint32_t)i, q, k, list.data(), 1, cap, first, last, d2_last);
+            if (rc != SEL_RETRY_COARSER) break;
+        }
+        const long long row = q.idx;
+        bool exact = (rc != SEL_OK);
+        if (exact) {
+            exact_rows(v, (uint32_t)i, k, list.data());
+            first = list[0]; last = list[k - 1];
+        } else {
+            // order by key for list output
+            std::sort(list.begin(), list.begin() + k, [&](uint32_t a, uint32_t b) {
+                const Pt pa = v.pts[a], pb = v.pts[b];
+                return key_less(dist2_f64(q.x, q.y, q.z, pa.x, pa.y, pa.z), pa.idx,
+                                dist2_f64(q.x, q.y, q.z, pb.x, pb.y, pb.z), pb.idx);
+            });
+            if (list[0] != first || list[k - 1] != last) { code[row] = -1; continue; }  // internal inconsistency
+        }
+        code[row] = exact ? 100 : level;
+        for (int m = 0; m < k; ++m) {
+            const Pt p = v.pts[list[m]];
+            if (idx) idx[row * k + m] = (int32_t)p.idx;
+            if (dist) dist[row * k + m] = (float)sqrt(dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z));
+        }
+        if (curv) {
+            ListNeighbourhood nb;
+            nb.ix = &v; nb.list = list.data(); nb.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+            FitResult r;
+            r.status = exact ? ST_EXACT_PATH : 0;
+            fit_neighbourhood(nb, r);
+            for (int c = 0; c < 3; ++c) normals[row * 3 + c] = r.normal[c];
+            for (int c = 0; c < 6; ++c) coeffs[row * 6 + c] = r.coeffs[c];
+            for (int c = 0; c < 5; ++c) curv[row * 5 + c] = r.curv[c];
+            status[row] = (uint8_t)r.status;
+        }
+    }
+}
+
+extern "C" {
+
+void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
+           float* normals, float* coeffs, float* curv, uint8_t* status) {
+    HostIndex* ix = (HostIndex*)p;
+    PCT_DISPATCH_KT(k, knn_impl<KT>(ix, k, max_fast_level, idx, dist, code, normals, coeffs, curv, status));
+}
+
+void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,
+                float* normals, float* coeffs, float* curv, uint8_t* status) {
+    for (long long r = 0; r < nq; ++r) {
+        const long long qi = qids ? qids[r] : r;
+        RowNeighbourhood nb;
+        nb.xyz = xyz; nb.row = idx + r * k; nb.count = k;
+        nb.qx = xyz[3 * qi]; nb.qy = xyz[3 * qi + 1]; nb.qz = xyz[3 * qi + 2];
+        FitResult o;
+        o.status = 0;
+        fit_neighbourhood(nb, o);
+        for (int c = 0; c < 3; ++c) normals[r * 3 + c] = o.normal[c];
+        for (int c = 0; c < 6; ++c) coeffs[r * 6 + c] = o.coeffs[c];
+        for (int c = 0; c < 5; ++c) curv[r * 5 + c] = o.curv[c];
+        status[r] = (uint8_t)o.status;
+    }
+}
+
+// epsilon ball at the coarsest sufficient level: counts + fused fit
+void h_ball(void* p, double radius, int32_t* counts, float* normals, float* coeffs, float* curv, uint8_t* status) {
+    HostIndex* ix = (HostIndex*)p;
+    const IndexView& v = ix->view;
+    int level = 0;
+    while (level + 1 < v.num_levels && (double)v.h * (double)(1 << level) * (1.0 - 1e-4) - (double)v.slack * v.h < radius) ++level;
+    for (long long i = 0; i < v.n; ++i) {
+        BallNeighbourhood nb;
+        nb.ix = &v; nb.q = v.pts[i]; nb.self = (uint32_t)i; nb.tracked = false; nb.count = 0;
+        nb.test.set(radius);
+        make_stencil(v, level, nb.q.x, nb.q.y, nb.q.z, nb.st);
+        FitResult o;
+        o.status = 0;
+        fit_neighbourhood(nb, o);
+        const long long row = nb.q.idx;
+        counts[row] = nb.count;
+        for (int c = 0; c < 3; ++c) normals[row * 3 + c] = o.normal[c];
+        for (int c = 0; c < 6; ++c) coeffs[row * 6 + c] = o.coeffs[c];
+        for (int c = 0; c < 5; ++c) curv[row * 5 + c] = o.curv[c];
+        status[row] = (uint8_t)o.status;
+    }
+}
+
+}  // extern "C"
