@@ -1,0 +1,389 @@
+"""Headline benchmark: points/s for kNN + PCA + quadric curvature on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--k 20]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path on the host cores
+
+A step is one pass of the hot path over one synthetic cloud:
+    value  index build + fused kNN/fit kernel, raw xyz already in HBM        (device timed)
+    e2e    PointCloud(points=host) -> plant_kdtree(k) -> compute_pointwise_explicit_quadratic_curvature()
+           with pinned host input and host K, H output inside the timed region
+Multi-GPU is strong scaling on one fixed cloud: the cloud is replicated (NCCL broadcast),
+every rank builds the index and answers its slice of the Morton-sorted queries.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "points/sec for kNN+SVD+quadric curvature"
+ALG_BYTES_QUERY = 44   # per point: 16 B own record read + 28 B result written
+ALG_BYTES_E2E = 76     # + 12 B raw read + 16 B sorted record + 4 B permutation
+OUR_KERNELS_PER_STEP = 12  # bbox x2, pilot x2, keys, gather, level hist, table fill, fast L0, fast L1, exact, stats
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=100_000_000)
+    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, k):
+    return f"synthetic torus surface (R=1, r=1/3, uniform u,v, seed 3), N={n}, k={k} kNN"
+
+
+def host_sample(n_sample, seed=3):
+    """Host copy of the workload's distribution for the CPU legs (same surface, same sampling law)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(0, 2 * np.pi, n_sample)
+    v = rng.uniform(0, 2 * np.pi, n_sample)
+    R, r = 1.0, 1.0 / 3.0
+    return np.stack(((R + r * np.cos(v)) * np.cos(u), (R + r * np.cos(v)) * np.sin(u), r * np.sin(v)), 1).astype(np.float32)
+
+
+def cpu_sample_cloud(n_total, rows_needed):
+    """A cloud whose point spacing equals the full workload's would need all N points; the CPU path's
+    cost per point does not depend on spacing, so the legs run on a self-contained sample cloud."""
+    return host_sample(int(min(n_total, max(20_000, rows_needed))))
+
+
+# --------------------------------------------------------------------------
+# reference arm / cpu baseline
+# --------------------------------------------------------------------------
+def run_cpu_leg(n_total, k, seconds):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    from oracle import baseline
+
+    cores = baseline.host_cores()
+    pts = cpu_sample_cloud(n_total, 400_000)
+    res = baseline.timed_reference(pts, k, seconds=seconds, procs=cores)
+    return res, len(pts)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    k = args.k
+    step_seconds = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    info = None
+    for s in range(args.warmup + args.steps):
+        res, cloud_n = run_cpu_leg(args.points, k, step_seconds)
+        if s >= args.warmup:
+            vals.append(res)
+        info = (res, cloud_n)
+    total_rows = sum(r["rows"] for r in vals)
+    total_s = sum(r["seconds"] for r in vals)
+    value = total_rows / total_s
+    res, cloud_n = info
+    sample = (f"{res['rows']} query points per step of a {cloud_n}-point cloud drawn from the workload's surface; the "
+              f"reference's per-point loop (cKDTree.query + np.cov + svd + lstsq per point) fanned out over {res['cores']} processes")
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, len(vals)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 inputs, f64 LAPACK", "data": "synthetic",
+        "config": {"workload": workload_name(args.points, k), "k": k, "points": args.points},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": res["cores"], "kind": "port", "sample": sample,
+                         "per_point_us_single_core": res["per_point_us_single_core"]},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic(points_per_launch, k):
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if int(t.get("k", -1)) != k:
+            return None
+        return float(t["dram_bytes_per_point"]) * points_per_launch
+    except Exception:
+        return None
+
+
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n, k = args.points, args.k
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised in this process: the leg forks worker processes
+        res, cloud_n = run_cpu_leg(n, k, args.cpu_seconds)
+        cpu = {"value": res["points_per_s"], "unit": "points/s", "cores": res["cores"], "kind": "port",
+               "sample": (f"{res['rows']} query points of a {cloud_n}-point cloud from the workload's surface, the reference's "
+                          f"per-point loop on {res['cores']} processes, {res['seconds']:.1f} s"),
+               "per_point_us_single_core": res["per_point_us_single_core"]}
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from point_cloud_toolbox_b200 import GridIndex, PointCloud
+    from point_cloud_toolbox_b200 import distributed as pdist
+    from point_cloud_toolbox_b200._lib import LAYOUT_SLICE
+
+    # ---- the cloud: generated on the device (rank 0), replicated before any timing ----
+    if rank == 0:
+        gen = torch.Generator(device=dev).manual_seed(3)
+        pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        chunk = 1 << 24
+        R, r = 1.0, 1.0 / 3.0
+        for s in range(0, n, chunk):
+            m = min(chunk, n - s)
+            u = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
+            v = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
+            w = R + r * torch.cos(v)
+            pts[s:s + m, 0] = (w * torch.cos(u)).float()
+            pts[s:s + m, 1] = (w * torch.sin(u)).float()
+            pts[s:s + m, 2] = (r * torch.sin(v)).float()
+            del u, v, w
+    else:
+        pts = None
+    if world > 1:
+        pts = pdist.broadcast_cloud(pts, n, None, 0, dev)
+    host_pts = None
+    if rank == 0:
+        host = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+        host.copy_(pts)
+        torch.cuda.synchronize()
+        host_pts = host.numpy()
+    begin, end = pdist.shard_bounds(n, world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(record=None):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e2 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        index = GridIndex(pts, k_hint=k)
+        e1.record()
+        if world == 1:
+            fit = index.curvature_knn(k, want_coeffs=False)
+        else:
+            fit = index.curvature_knn(k, begin, end, layout=LAYOUT_SLICE, want_coeffs=False)
+        e2.record()
+        if record is not None:
+            record.append((e0, e1, e2))
+        return index, fit
+
+    def e2e_step():
+        if world == 1:
+            pc = PointCloud(points=host_pts, normals=np.zeros((n, 0), np.float32), k_neighbors=k)
+            pc.plant_kdtree(k)
+            K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+            return K, H
+        out = pdist.curvature_knn_sharded(host_pts, n, k, device=dev)
+        if rank == 0:
+            from point_cloud_toolbox_b200.engine import to_host
+
+            kh = to_host(out.t())
+            return kh[0], kh[1]
+        return None, None
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident metric ----
+    for _ in range(args.warmup):
+        index, fit = device_step()
+        index.close()
+        del fit
+    barrier()
+    if rank == 0:
+        sampler.start()
+    events = []
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    last = None
+    for _ in range(args.steps):
+        index, fit = device_step(events)
+        if last is not None:
+            last[0].close()
+        last = (index, fit)
+    t_end.record()
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    build_ms = sum(a.elapsed_time(b) for a, b, _ in events) / len(events)
+    query_ms = sum(b.elapsed_time(c) for _, b, c in events) / len(events)
+    stats = last[0].last_stats()
+    info = last[0].info()
+    status_bad = int((last[1].status != 0).sum().item())
+    nan_rows = int(torch.isnan(last[1].curv[:, 0]).sum().item())
+    last[0].close()
+    del last, index, fit
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the public API ----
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    s0 = torch.cuda.Event(enable_timing=True)
+    s1 = torch.cuda.Event(enable_timing=True)
+    s0.record()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        K, H = e2e_step()
+    s1.record()
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - wall0)
+    e2e_ms = s0.elapsed_time(s1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms, query_ms, build_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, query_ms, build_ms, e2e_wall_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+    e2e_value = n / (max(e2e_ms, e2e_wall_ms) / args.steps * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    pts_per_launch = end - begin
+    achieved = pts_per_launch * ALG_BYTES_QUERY / (query_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 search keys, f64 re-rank and fit, f32 outputs", "data": "synthetic",
+        "config": {
+            "workload": workload_name(n, k), "k": k, "points": n, "parallelism": f"query-sharded x{world}, cloud replicated",
+            "l2": "inputs (1.2 GB raw + 1.6 GB sorted at 100M) exceed the 126 MB L2; no flush needed",
+            "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
+            "level1_retries": stats.level1_retries, "exact_path": stats.exact_path,
+            "build_ms": build_ms, "query_ms": query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "knn_fast_kernel<KT,true> (+ level-1 retry + exact tail, timed as one call)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": profiled_traffic(pts_per_launch, k), "peak_source": peak_src,
+            "note": "algorithmic 44 B/point; the kernel is FP32/ALU-issue and latency bound, not HBM bound (DESIGN.md)",
+        },
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
+                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
+        "gpu_launches": OUR_KERNELS_PER_STEP * args.steps * 2,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,229 @@
+"""Device-side objects behind the PointCloud drop-in: torch owns memory and
+streams, libpct_b200.so (through ctypes) does all the work.
+
+``GridIndex`` stands where the reference keeps ``self.kdtree``
+(/root/reference/pointCloudToolbox.py:74).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_ORIGINAL, LAYOUT_SLICE, check, lib, ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "point_cloud_toolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback"
+        )
+
+
+def to_device_points(points, device=None):
+    """(N, 3) float32 contiguous CUDA tensor from numpy / torch input (H2D when on host)."""
+    require_cuda()
+    if isinstance(points, torch.Tensor):
+        t = points
+    else:
+        import numpy as np
+
+        t = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32))
+    if t.ndim != 2 or t.shape[1] < 3:
+        raise ValueError("points must have shape (N, 3)")
+    if t.shape[1] != 3:
+        t = t[:, :3]
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def to_host(t: torch.Tensor):
+    """Device tensor -> numpy array backed by pinned host memory (torch caches the pinned blocks)."""
+    if not t.is_cuda:
+        return t.numpy()
+    t = t.contiguous()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
+@dataclass
+class FitOutputs:
+    normals: torch.Tensor | None
+    coeffs: torch.Tensor | None
+    curv: torch.Tensor | None      # columns K, H, k1, k2, H^2
+    status: torch.Tensor | None
+    counts: torch.Tensor | None = None
+
+
+def _alloc_outputs(rows, device, want_normals=True, want_coeffs=True, want_status=True):
+    f32 = dict(dtype=torch.float32, device=device)
+    return FitOutputs(
+        normals=torch.empty((rows, 3), **f32) if want_normals else None,
+        coeffs=torch.empty((rows, 6), **f32) if want_coeffs else None,
+        curv=torch.empty((rows, 5), **f32),
+        status=torch.empty((rows,), dtype=torch.uint8, device=device) if want_status else None,
+    )
+
+
+class GridIndex:
+    """Morton-sorted uniform grid over a cloud resident in HBM."""
+
+    def __init__(self, points_dev: torch.Tensor, k_hint: int = 20, cell_hint: float = 0.0):
+        require_cuda()
+        if points_dev.dtype != torch.float32 or not points_dev.is_cuda or not points_dev.is_contiguous():
+            raise ValueError("GridIndex needs a contiguous float32 CUDA tensor of shape (N, 3|4)")
+        self.points = points_dev
+        self.n = int(points_dev.shape[0])
+        self.device = points_dev.device
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.pct_index_build(ptr(points_dev), self.n, int(points_dev.shape[1]), float(cell_hint), int(k_hint),
+                                      _stream(), ctypes.byref(self._handle)))
+        self.k_hint = k_hint
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            lib.pct_index_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection -----------------------------------------------------
+    def info(self) -> _lib.IndexInfo:
+        out = _lib.IndexInfo()
+        check(lib.pct_index_get_info(self._handle, ctypes.byref(out)))
+        return out
+
+    def last_stats(self) -> _lib.QueryStats:
+        out = _lib.QueryStats()
+        with torch.cuda.device(self.device):
+            check(lib.pct_index_last_stats(self._handle, _stream(), ctypes.byref(out)))
+        return out
+
+    def permutation(self) -> torch.Tensor:
+        perm = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_index_permutation(self._handle, ptr(perm), _stream()))
+        return perm
+
+    def _range(self, q_begin, q_end, layout):
+        q_begin = 0 if q_begin is None else int(q_begin)
+        q_end = self.n if q_end is None else int(q_end)
+        rows = self.n if layout == LAYOUT_ORIGINAL else q_end - q_begin
+        return q_begin, q_end, rows
+
+    # -- queries -----------------------------------------------------------
+    def knn(self, k, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL, want_dist=True):
+        q_begin, q_end, rows = self._range(q_begin, q_end, layout)
+        idx = torch.empty((rows, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((rows, k), dtype=torch.float32, device=self.device) if want_dist else None
+        with torch.cuda.device(self.device):
+            check(lib.pct_knn(self._handle, q_begin, q_end, int(k), ptr(idx), ptr(dist), layout, _stream()))
+        return idx, dist
+
+    def curvature_knn(self, k, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL, want_normals=True, want_coeffs=True,
+                      want_status=True) -> FitOutputs:
+        q_begin, q_end, rows = self._range(q_begin, q_end, layout)
+        out = _alloc_outputs(rows, self.device, want_normals, want_coeffs, want_status)
+        with torch.cuda.device(self.device):
+            check(lib.pct_curvature_fused_knn(self._handle, q_begin, q_end, int(k), ptr(out.normals), ptr(out.coeffs),
+                                              ptr(out.curv), ptr(out.status), layout, _stream()))
+        return out
+
+    def ball_count(self, radius, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL):
+        q_begin, q_end, rows = self._range(q_begin, q_end, layout)
+        counts = torch.empty((rows,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_ball_count(self._handle, q_begin, q_end, float(radius), ptr(counts), layout, _stream()))
+        return counts
+
+    def ball(self, radius, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL):
+        """CSR (offsets int64, idx int32, dist float32), rows ordered by (d2, index)."""
+        counts = self.ball_count(radius, q_begin, q_end, layout)
+        offsets = torch.zeros((counts.numel() + 1,), dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        nnz = int(offsets[-1].item())
+        idx = torch.empty((max(nnz, 1),), dtype=torch.int32, device=self.device)
+        dist = torch.empty((max(nnz, 1),), dtype=torch.float32, device=self.device)
+        q_begin, q_end, _ = self._range(q_begin, q_end, layout)
+        with torch.cuda.device(self.device):
+            check(lib.pct_ball_fill(self._handle, q_begin, q_end, float(radius), ptr(offsets), nnz, ptr(idx), ptr(dist),
+                                    layout, _stream()))
+        return offsets, idx[:nnz], dist[:nnz]
+
+    def curvature_ball(self, radius, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL) -> FitOutputs:
+        q_begin, q_end, rows = self._range(q_begin, q_end, layout)
+        out = _alloc_outputs(rows, self.device)
+        out.counts = torch.empty((rows,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_curvature_fused_ball(self._handle, q_begin, q_end, float(radius), ptr(out.counts), ptr(out.normals),
+                                               ptr(out.coeffs), ptr(out.curv), ptr(out.status), layout, _stream()))
+        return out
+
+
+# -- list-driven fit and the batched static methods ---------------------------
+def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:
+    """Fit rows of original-index neighbour lists (nq, k) on an (N, 3) cloud."""
+    if points_dev.shape[1] != 3 or not points_dev.is_contiguous():
+        raise ValueError("fit_from_neighbors needs packed (N, 3) points")
+    idx_dev = idx_dev.to(torch.int32).contiguous()
+    nq, k = idx_dev.shape
+    out = _alloc_outputs(nq, points_dev.device)
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_fit_from_neighbors(ptr(points_dev), int(points_dev.shape[0]), ptr(idx_dev), nq, k, ptr(query_ids),
+                                         ptr(out.normals), ptr(out.coeffs), ptr(out.curv), ptr(out.status), _stream()))
+    return out
+
+
+def fit_from_csr(points_dev, offsets_dev, idx_dev, query_ids=None) -> FitOutputs:
+    nq = int(offsets_dev.numel()) - 1
+    out = _alloc_outputs(nq, points_dev.device)
+    idx_dev = idx_dev.to(torch.int32).contiguous()
+    offsets_dev = offsets_dev.to(torch.int64).contiguous()
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_fit_from_csr(ptr(points_dev), int(points_dev.shape[0]), ptr(offsets_dev), ptr(idx_dev), nq,
+                                   ptr(query_ids), ptr(out.normals), ptr(out.coeffs), ptr(out.curv), ptr(out.status),
+                                   _stream()))
+    return out
+
+
+def plane_rotate(centered_dev):
+    """(nq, k, 3) float32 centred neighbourhoods -> rotated float64, unit normals float64, status."""
+    c = centered_dev.to(torch.float32).contiguous()
+    nq, k, _ = c.shape
+    rotated = torch.empty((nq, k, 3), dtype=torch.float64, device=c.device)
+    normals = torch.empty((nq, 3), dtype=torch.float64, device=c.device)
+    status = torch.empty((nq,), dtype=torch.uint8, device=c.device)
+    with torch.cuda.device(c.device):
+        check(lib.pct_plane_rotate(ptr(c), nq, k, ptr(rotated), ptr(normals), ptr(status), _stream()))
+    return rotated, normals, status
+
+
+def quadric_fit(rotated_dev):
+    r = rotated_dev.to(torch.float64).contiguous()
+    nq, k, _ = r.shape
+    coeffs = torch.empty((nq, 6), dtype=torch.float32, device=r.device)
+    status = torch.empty((nq,), dtype=torch.uint8, device=r.device)
+    with torch.cuda.device(r.device):
+        check(lib.pct_quadric_fit(ptr(r), nq, k, ptr(coeffs), ptr(status), _stream()))
+    return coeffs, status
+
+
+def quadric_curvature(coeffs_dev):
+    c = coeffs_dev.to(torch.float32).contiguous()
+    curv = torch.empty((c.shape[0], 5), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        check(lib.pct_quadric_curvature(ptr(c), int(c.shape[0]), ptr(curv), _stream()))
+    return curv

@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA path (through the C ABI, via the PointCloud drop-in) against the
+oracle and the reference's golden vectors.  Everything here needs a B200: -m gpu.
+
+Tolerances are the policy of oracle/compare.py (relative 1e-3 + absolute floor scaled by
+r_k, neighbour sets bit-exact); the observed agreement is asserted much tighter where the
+path is expected to reproduce the reference's fp64 steps (tight_fraction).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import compare, datasets
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def pct():
+    import point_cloud_toolbox_b200 as m
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return m
+
+
+def _cloud(name):
+    return load_golden(name + "_points")["points"]
+
+
+def _empty_normals(n):
+    return np.zeros((n, 0), np.float32)
+
+
+def _gpu_dict(pc):
+    return dict(normal=pc.normals_quadratic, K=pc.K_quadratic, H=pc.H_quadratic, k1=pc.k1_quadratic, k2=pc.k2_quadratic)
+
+
+CASES = [("bunny", 20), ("bunny", 30), ("egg_carton", 20), ("torus_c1", 20)]
+
+
+@pytest.mark.parametrize("name,k", CASES)
+def test_knn_lists_bit_exact(pct, name, k):
+    pts = _cloud(name)
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+    pc.plant_kdtree(k)
+    idx, dist = pc.neighbor_indices, pc.dists
+    assert idx.dtype == np.int32 and dist.dtype == np.float32 and idx.shape == (len(pts), k)
+    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+    assert compare.neighbor_rows_differing(idx, ref_idx) == 0
+    assert np.array_equal(dist, ref_dist)
+    # and the reference's own rows (scipy order) wherever no exact tie is involved
+    g = load_golden(f"{name}_k{k}")
+    same = (idx[g["rows"]] == g["neighbor_indices"]).all(axis=1)
+    assert np.array_equal(dist[g["rows"]], g["dists"])
+    if name == "bunny":
+        assert same.all()
+    else:
+        assert same.mean() > 0.9
+
+
+@pytest.mark.parametrize("name,k", CASES)
+def test_fused_curvature_matches_oracle(pct, name, k):
+    pts = _cloud(name)
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+    pc.plant_kdtree(k)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    assert K.dtype == np.float32 and K.shape == (len(pts),)
+    ref = oracle.knn_curvature(pts, k)
+    rep = compare.curvature_report(_gpu_dict(pc), ref, ref["dist"][:, -1])
+    assert rep["violations"] == 0, rep
+    assert rep["tight_fraction"] > 0.999, rep
+    assert not np.isnan(K).any() and not np.isnan(H).any()
+    # golden: the reference's own K / H on rows where its neighbour row equals the canonical one
+    g = load_golden(f"{name}_k{k}")
+    canon = (ref["idx"][g["rows"]] == g["neighbor_indices"]).all(axis=1)
+    Kg, Hg = g["K_quadratic"][canon], g["H_quadratic"][canon]
+    rk = g["dists"][canon, -1].astype(np.float64)
+    assert np.all(np.abs(K[g["rows"]][canon] - Kg) <= 1e-3 * np.abs(Kg) + 1e-5 / rk ** 2)
+    safe = ref["margin"][g["rows"]][canon] >= compare.MARGIN
+    dH = np.abs(H[g["rows"]][canon] - Hg)
+    assert np.all(dH[safe] <= 1e-3 * np.abs(Hg[safe]) + 1e-5 / rk[safe])
+    st = pc.kdtree.index.last_stats()
+    assert st.queries == len(pts)
+
+
+@pytest.mark.parametrize("name,k", [("bunny", 20), ("egg_carton", 20)])
+def test_fit_from_reference_rows_reproduces_reference(pct, name, k):
+    """pct_fit_from_neighbors on the reference's own neighbour rows vs the reference's coefficients."""
+    g = load_golden(f"{name}_k{k}")
+    pts = _cloud(name)
+    d_pts = torch.from_numpy(pts).cuda()
+    idx = torch.from_numpy(g["neighbor_indices"]).cuda()
+    qids = torch.from_numpy(g["rows"].astype(np.int32)).cuda()
+    out = pct.fit_from_neighbors(d_pts, idx, qids)
+    coeffs = out.coeffs.cpu().numpy()
+    ref_c = g["quadratic_coefficients"]
+    scale = np.abs(ref_c).max(axis=1, keepdims=True)
+    assert np.max(np.abs(coeffs - ref_c) / scale) < 2e-5
+    assert np.mean(coeffs == ref_c) > 0.9  # the same fp32 numbers, not merely close ones
+    curv = out.curv.cpu().numpy()
+    rk = g["dists"][:, -1].astype(np.float64)
+    assert np.all(np.abs(curv[:, 0] - g["K_quadratic"]) <= 1e-4 * np.abs(g["K_quadratic"]) + 1e-6 / rk ** 2)
+    assert np.all(np.abs(curv[:, 1] - g["H_quadratic"]) <= 1e-4 * np.abs(g["H_quadratic"]) + 1e-6 / rk)
+    assert np.allclose(curv[:, 4], g["K_H_sq_quadratic"], rtol=1e-4, atol=1e-6)
+
+
+def test_list_path_equals_fused_path(pct, bunny):
+    k = 20
+    a = pct.PointCloud(points=bunny, normals=_empty_normals(len(bunny)))
+    a.plant_kdtree(k)
+    Ka, Ha = a.compute_pointwise_explicit_quadratic_curvature()
+    b = pct.PointCloud(points=bunny, normals=_empty_normals(len(bunny)))
+    b.plant_kdtree(k)
+    _ = b.neighbor_indices  # materialise -> the fit now runs from the stored rows (ref :640)
+    b.fit_explicit_quadratic_surfaces_to_neighborhoods()
+    Kb, Hb = b.calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points()
+    assert np.allclose(Ka, Kb, rtol=1e-5, atol=1e-3) and np.allclose(Ha, Hb, rtol=1e-5, atol=1e-4)
+    assert np.allclose(b.K_H_sq_quadratic, Hb * Hb, rtol=1e-6)
+    assert b.quadratic_coefficients.shape == (len(bunny), 6)
+    assert np.allclose(a.quadratic_coefficients, b.quadratic_coefficients, rtol=1e-4, atol=1e-6)
+
+
+def test_validate_shape_call_sequence(pct, bunny):
+    """utils.py:484-501: plant(100), fit, re-plant(k), curvature -> curvature belongs to the k=100 fit."""
+    pts = bunny[:12000]
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)))
+    pc.plant_kdtree(100)
+    pc.fit_explicit_quadratic_surfaces_to_neighborhoods()
+    pc.plant_kdtree(23)
+    K, H = pc.calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points()
+    rows = np.arange(0, len(pts), 6)
+    ref = oracle.knn_curvature(pts, 100, rows=rows)
+    got = dict(normal=pc.normals_quadratic[rows], K=K[rows], H=H[rows], k1=pc.k1_quadratic[rows], k2=pc.k2_quadratic[rows])
+    rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
+    assert rep["violations"] == 0, rep
+    assert pc.k_neighbors == 23
+
+
+def test_static_methods(pct):
+    g = load_golden("bunny_k20")
+    pts = _cloud("bunny")
+    pos = {int(r): j for j, r in enumerate(g["rows"])}
+    for j, i in enumerate(g["static_rows"][:16]):
+        nb = g["neighbor_indices"][pos[int(i)]]
+        centered = pts[nb] - pts[i]
+        rot = pct.PointCloud.get_best_fit_plane_and_rotate(centered)
+        assert rot.dtype == np.float64 and rot.shape == (20, 3)
+        assert np.allclose(rot, g["static_rotated"][j], rtol=0, atol=1e-12 * np.abs(centered).max() * 1e3)
+        coeffs = pct.PointCloud.fit_quadratic_surface(g["static_rotated"][j])
+        want = oracle.fit_quadratic_surface(g["static_rotated"][j])
+        assert coeffs.dtype == np.float32
+        assert np.allclose(coeffs, want, rtol=2e-6, atol=1e-9)
+        got = pct.PointCloud.calculate_explicit_quadratic_curvatures(want)
+        ref = oracle.explicit_quadratic_curvatures(want)
+        assert np.allclose(got, ref, rtol=2e-6, atol=0)
+    with pytest.raises(ValueError):
+        pct.PointCloud.get_best_fit_plane_and_rotate(np.array([[0, 0, np.inf], [1, 0, 0], [0, 1, 0]], np.float32))
+    with pytest.raises(ValueError):
+        pct.PointCloud.fit_quadratic_surface(np.zeros((5, 2)))
+
+
+@pytest.mark.parametrize("radius", [3.8e-3, 7.6e-3])
+def test_ball_query_matches_scipy(pct, bunny, radius):
+    pc = pct.PointCloud(points=bunny, normals=_empty_normals(len(bunny)))
+    pc.plant_ball(radius)
+    off, idx, dist = pc.ball_neighbors()
+    roff, ridx, rdist = oracle.ball_canonical(bunny, radius)
+    assert compare.csr_equal(off, idx, roff, ridx)
+    assert np.array_equal(dist, rdist)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    rows = np.arange(0, len(bunny), 5)
+    sub_off = np.concatenate(([0], np.cumsum(np.diff(roff)[rows])))
+    sub_idx = np.concatenate([ridx[roff[r]:roff[r + 1]] for r in rows])
+    ref = oracle.curvature_from_csr(bunny, sub_off, sub_idx, rows=rows)
+    enough = np.diff(roff)[rows] >= 8
+    r_k = np.full(len(rows), radius)
+    got = dict(normal=pc.normals_quadratic[rows], K=K[rows], H=H[rows], k1=pc.k1_quadratic[rows], k2=pc.k2_quadratic[rows])
+    rep = compare.curvature_report(got, ref, r_k, rows_ok=enough)
+    assert rep["violations"] == 0, rep
+    assert rep["rows"] > 0.9 * len(rows)
+
+
+def test_exact_path_duplicates_lattice_outliers(pct):
+    rng = np.random.default_rng(7)
+    # 3-D integer lattice: huge exact tie groups at the k-th distance
+    g = np.arange(9, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    # duplicated points + far outliers + a dense cluster
+    base = rng.normal(size=(3000, 3)).astype(np.float32)
+    dup = np.concatenate((base, base[:200], base[:50]))
+    outliers = np.concatenate((base * 0.01, rng.normal(size=(5, 3)).astype(np.float32) * 500))
+    for name, pts, k in (("lattice", lattice, 12), ("dup", dup, 10), ("outliers", outliers, 20), ("tiny", base[:9], 8)):
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)))
+        pc.plant_kdtree(k)
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+        assert compare.neighbor_rows_differing(pc.neighbor_indices, ref_idx) == 0, name
+        assert np.array_equal(pc.dists, ref_dist), name
+    st = pc.kdtree.index.last_stats()
+    assert st.queries == 9
+
+
+def test_errors_mirror_reference(pct):
+    with pytest.raises(ValueError, match="Either file_path or points and normals"):
+        pct.PointCloud()
+    pts = np.random.default_rng(0).normal(size=(50, 3)).astype(np.float32)
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(50))
+    with pytest.raises(IndexError):
+        pc.plant_kdtree(50)
+    bad = pts.copy()
+    bad[3, 1] = np.nan
+    pc = pct.PointCloud(points=bad, normals=_empty_normals(50))
+    with pytest.raises(ValueError, match="Non-finite"):
+        pc.plant_kdtree(5)
+
+
+def test_file_loader(pct, tmp_path):
+    g = load_golden("loader_case")
+    path = tmp_path / "cloud.txt"
+    np.savetxt(path, g["table"], fmt="%.5f")
+    pc = pct.PointCloud(str(path), k_neighbors=5)
+    assert pc.points.dtype == np.float32 and np.array_equal(pc.points, g["points"])
+    assert np.array_equal(pc.normals, g["normals"])
+    assert np.allclose(pc.x_domain, g["x_domain"]) and np.allclose(pc.z_domain, g["z_domain"])
+    assert np.isclose(pc.l1_norm, g["l1_norm"], rtol=1e-5)
+    assert np.isclose(pc.l2_norm, g["l2_norm"], rtol=1e-5)
+    assert np.isclose(pc.infinity_norm, g["infinity_norm"], rtol=1e-5)
+    assert pc.num_points == 50 and pc.num_features == 3
+
+
+def test_slice_layout_and_ranges(pct, bunny):
+    from point_cloud_toolbox_b200._lib import LAYOUT_SLICE
+
+    d = torch.from_numpy(bunny).cuda()
+    ix = pct.GridIndex(d, k_hint=20)
+    full = ix.curvature_knn(20)
+    perm = ix.permutation().long()
+    n = len(bunny)
+    a, b = n // 3, n // 3 + 5001
+    part = ix.curvature_knn(20, a, b, layout=LAYOUT_SLICE)
+    assert part.curv.shape == (b - a, 5)
+    assert torch.equal(part.curv, full.curv[perm[a:b]])
+    assert torch.equal(part.normals, full.normals[perm[a:b]])
+    idx_s, dist_s = ix.knn(20, a, b, layout=LAYOUT_SLICE)
+    idx_f, dist_f = ix.knn(20)
+    assert torch.equal(idx_s, idx_f[perm[a:b]]) and torch.equal(dist_s, dist_f[perm[a:b]])
+    assert sorted(perm.cpu().tolist()) == list(range(n))
+    info = ix.info()
+    assert info.num_points == n and info.cells_level0 > 0
+
+
+@pytest.mark.parametrize("shape,k", [("sphere", 20), ("sphere", 50), ("torus", 20), ("egg", 50)])
+def test_c3_analytic_surfaces_1m(pct, shape, k):
+    n = 1_000_000
+    if shape == "sphere":
+        pts, Kt, Ht = datasets.sphere_fibonacci(n)
+        mask = np.ones(n, bool)
+    elif shape == "torus":
+        pts, Kt, Ht = datasets.torus_random(n, seed=0)
+        mask = np.ones(n, bool)
+    else:
+        pts, Kt, Ht = datasets.egg_carton_random(n, seed=1)
+        mask = datasets.interior_mask_xy(pts, 2 * np.pi, 0.2)
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+    pc.plant_kdtree(k)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    cf = compare.closed_form_report(K, H, Kt, Ht, mask)
+    # discretisation error of the estimator itself: h^2 scaling from 2e-3 at N = 2e4
+    lim = {"sphere": (2e-3, 2e-3), "torus": (0.15, 0.08), "egg": (0.05, 0.03)}[shape]
+    assert cf["K_abs_p99"] < lim[0] and cf["H_abs_p99"] < lim[1], cf
+    rows = np.sort(np.random.default_rng(3).choice(n, 40_000, replace=False))
+    ref = oracle.knn_curvature(pts, k, rows=rows)
+    idx, dist = pc.kdtree.index.knn(k)
+    sel = torch.from_numpy(rows).cuda()
+    assert compare.neighbor_rows_differing(idx[sel].cpu().numpy(), ref["idx"]) == 0
+    assert np.array_equal(dist[sel].cpu().numpy(), ref["dist"])
+    got = dict(normal=pc.normals_quadratic[rows], K=K[rows], H=H[rows], k1=pc.k1_quadratic[rows], k2=pc.k2_quadratic[rows])
+    rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
+    assert rep["violations"] == 0, rep
+    assert rep["tight_fraction"] > 0.995, rep
+
+
+def test_c4_scanned_sheet_ball(pct):
+    pts, _, _ = datasets.scanned_sheet()
+    n = len(pts)
+    tree_idx, tree_dist, _ = oracle.knn_canonical(pts, 1, rows=np.arange(0, n, 50))
+    radius = float(2.5 * np.median(tree_dist[:, 0]))
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(n))
+    pc.plant_ball(radius)
+    counts = pc.kdtree.index.ball_count(radius).cpu().numpy()
+    rows = np.sort(np.random.default_rng(4).choice(n, 20_000, replace=False))
+    roff, ridx, rdist = oracle.ball_canonical(pts, radius, rows=rows)
+    assert np.array_equal(counts[rows], np.diff(roff))
+    assert counts.max() > 10 * max(1, np.median(counts))  # the density really varies
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    ref = oracle.curvature_from_csr(pts, roff, ridx, rows=rows)
+    got = dict(normal=pc.normals_quadratic[rows], K=K[rows], H=H[rows], k1=pc.k1_quadratic[rows], k2=pc.k2_quadratic[rows])
+    rep = compare.curvature_report(got, ref, np.full(len(rows), radius), rows_ok=np.diff(roff) >= 10)
+    assert rep["violations"] == 0, rep
+    # also k = 100, the profiled configuration of the reference (profile_stats)
+    pc.plant_kdtree(100)
+    K100, H100 = pc.compute_pointwise_explicit_quadratic_curvature()
+    ref100 = oracle.knn_curvature(pts, 100, rows=rows[:5000])
+    got = dict(normal=pc.normals_quadratic[rows[:5000]], K=K100[rows[:5000]], H=H100[rows[:5000]],
+               k1=pc.k1_quadratic[rows[:5000]], k2=pc.k2_quadratic[rows[:5000]])
+    rep = compare.curvature_report(got, ref100, ref100["dist"][:, -1])
+    assert rep["violations"] == 0, rep
+
+
+def test_large_cloud_properties(pct):
+    """C5-shaped input at a size the oracle cannot sweep: size-independent properties."""
+    n = 8_000_000
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * (2 * np.pi)
+    v = torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * (2 * np.pi)
+    R, r = 1.0, 1.0 / 3.0
+    pts = torch.stack(((R + r * torch.cos(v)) * torch.cos(u), (R + r * torch.cos(v)) * torch.sin(u), r * torch.sin(v)), 1).float().contiguous()
+    ix = pct.GridIndex(pts, k_hint=32)
+    out1 = ix.curvature_knn(32)
+    out2 = ix.curvature_knn(32)
+    assert torch.equal(out1.curv, out2.curv)  # deterministic / idempotent
+    K = out1.curv[:, 0].double()
+    Kt = torch.cos(v) / (r * (R + r * torch.cos(v)))
+    err = (K - Kt).abs()
+    assert float(err.median()) < 5e-3 and float(err.quantile(0.99)) < 0.05
+    assert int((out1.status != 0).sum()) <= n // 1000
+    k1, k2, H = out1.curv[:, 2], out1.curv[:, 3], out1.curv[:, 1]
+    assert bool((k1 >= k2).all()) and torch.allclose(0.5 * (k1 + k2), H, rtol=1e-4, atol=1e-4)
+    # neighbour rows of a slice: sorted distances, no self, symmetric closest pair
+    idx, dist = ix.knn(32, 1000, 201000, layout=1)
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all())
+    perm = ix.permutation().long()
+    assert not bool((idx == perm[1000:201000, None]).any())
+    # a sample against the oracle on a spatial crop (everything within the crop + margin)
+    host = pts.cpu().numpy()
+    crop = np.nonzero((np.abs(host[:, 0] - 1.2) < 0.05) & (np.abs(host[:, 1]) < 0.05))[0]
+    inner = np.nonzero((np.abs(host[crop, 0] - 1.2) < 0.03) & (np.abs(host[crop, 1]) < 0.03))[0]
+    ref_idx, ref_dist, _ = oracle.knn_canonical(host[crop], 32, rows=inner)
+    gi, gd = ix.knn(32)
+    sel = torch.from_numpy(crop[inner]).cuda()
+    assert np.array_equal(crop[ref_idx], gi[sel].cpu().numpy())
+    assert np.array_equal(ref_dist, gd[sel].cpu().numpy())

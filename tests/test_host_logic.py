@@ -1,0 +1,168 @@
+"""CPU checks of the device code's logic and of the C ABI (no GPU needed).
+
+The per-query search and fit routines of the CUDA library are __host__ __device__
+(csrc/pct_grid.cuh, csrc/pct_math.cuh); tests/host_harness compiles them for the CPU so
+their exactness logic is exercised against the oracle here, before any GPU time is spent.
+This harness is test infrastructure -- the product never loads it.
+"""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import compare
+from conftest import ROOT, load_golden
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "host_harness"))
+
+
+@pytest.fixture(scope="module")
+def harness():
+    import build as hb
+
+    lib = ctypes.CDLL(hb.build())
+    lib.h_build.restype = ctypes.c_void_p
+    lib.h_build.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float]
+    lib.h_destroy.argtypes = [ctypes.c_void_p]
+    lib.h_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+    lib.h_fit_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5
+    lib.h_ball.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
+    return lib
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_knn(lib, pts, k, h, max_fast_level=1):
+    n = len(pts)
+    pts = np.ascontiguousarray(pts, np.float32)
+    ix = lib.h_build(P(pts), n, float(h))
+    out = dict(idx=np.zeros((n, k), np.int32), dist=np.zeros((n, k), np.float32), code=np.full(n, -9, np.int32),
+               normal=np.zeros((n, 3), np.float32), coeffs=np.zeros((n, 6), np.float32), curv=np.zeros((n, 5), np.float32),
+               status=np.zeros(n, np.uint8))
+    lib.h_knn(ix, k, max_fast_level, P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]),
+              P(out["curv"]), P(out["status"]))
+    lib.h_destroy(ix)
+    out.update(K=out["curv"][:, 0], H=out["curv"][:, 1], k1=out["curv"][:, 2], k2=out["curv"][:, 3])
+    return out
+
+
+@pytest.mark.parametrize("name,k,stride", [("bunny", 20, 3), ("bunny", 30, 5), ("egg_carton", 20, 9), ("torus_c1", 20, 9)])
+def test_search_and_fit_logic_against_oracle(harness, name, k, stride):
+    pts = load_golden(name + "_points")["points"][::stride]
+    ref = oracle.knn_curvature(pts, k)
+    h = 1.25 * float(np.median(ref["dist"][:, -1]))
+    got = run_knn(harness, pts, k, h)
+    assert (got["code"] >= 0).all()
+    assert compare.neighbor_rows_differing(got["idx"], ref["idx"]) == 0
+    assert np.array_equal(got["dist"], ref["dist"])
+    rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
+    assert rep["violations"] == 0, rep
+    assert rep["tight_fraction"] > 0.999, rep
+    # the frame is the reference's Rodrigues frame, so even the coefficients agree
+    scale = np.abs(ref["coeffs"]).max(axis=1, keepdims=True)
+    assert np.quantile(np.abs(got["coeffs"] - ref["coeffs"]) / scale, 0.999) < 1e-5
+
+
+def test_cell_size_never_changes_the_answer(harness, bunny):
+    pts = bunny[::7]
+    ref = oracle.knn_canonical(pts, 12)
+    for h in (5e-4, 2e-3, 8e-3, 5e-2, 1.0):
+        got = run_knn(harness, pts, 12, h, max_fast_level=2)
+        assert compare.neighbor_rows_differing(got["idx"], ref[0]) == 0, h
+        assert np.array_equal(got["dist"], ref[1]), h
+
+
+def test_ties_duplicates_and_outliers(harness):
+    rng = np.random.default_rng(11)
+    g = np.arange(7, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    base = rng.normal(size=(1500, 3)).astype(np.float32)
+    dup = np.concatenate((base, base[:100], base[:20]))
+    far = np.concatenate((base * 0.01, rng.normal(size=(4, 3)).astype(np.float32) * 300))
+    for name, pts, k, h in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.25), ("far", far, 16, 0.004)):
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+        got = run_knn(harness, pts, k, h)
+        assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, name
+        assert np.array_equal(got["dist"], ref_dist), name
+
+
+def test_fit_rows_on_reference_rows(harness):
+    g = load_golden("bunny_k20")
+    pts = load_golden("bunny_points")["points"]
+    nq, k = g["neighbor_indices"].shape
+    normal = np.zeros((nq, 3), np.float32); coeffs = np.zeros((nq, 6), np.float32)
+    curv = np.zeros((nq, 5), np.float32); status = np.zeros(nq, np.uint8)
+    idx = np.ascontiguousarray(g["neighbor_indices"], np.int32)
+    qids = np.ascontiguousarray(g["rows"], np.int32)
+    harness.h_fit_rows(P(pts), P(idx), nq, k, P(qids), P(normal), P(coeffs), P(curv), P(status))
+    assert not status.any()
+    assert np.mean(coeffs == g["quadratic_coefficients"]) > 0.9
+    assert np.allclose(curv[:, 0], g["K_quadratic"], rtol=1e-4, atol=1e-2)
+    assert np.allclose(curv[:, 1], g["H_quadratic"], rtol=1e-4, atol=1e-3)
+
+
+def test_ball_logic(harness, bunny):
+    pts = np.ascontiguousarray(bunny[::4])
+    n = len(pts)
+    radius = 6e-3
+    roff, ridx, _ = oracle.ball_canonical(pts, radius)
+    for h in (radius * 1.001, radius / 3):  # index built for the radius, or reused from a finer grid
+        ix = harness.h_build(P(pts), n, float(h))
+        counts = np.zeros(n, np.int32); normal = np.zeros((n, 3), np.float32); coeffs = np.zeros((n, 6), np.float32)
+        curv = np.zeros((n, 5), np.float32); status = np.zeros(n, np.uint8)
+        harness.h_ball(ix, radius, P(counts), P(normal), P(coeffs), P(curv), P(status))
+        harness.h_destroy(ix)
+        assert np.array_equal(counts, np.diff(roff))
+    rows = np.arange(0, n, 9)
+    sub_off = np.concatenate(([0], np.cumsum(np.diff(roff)[rows])))
+    sub_idx = np.concatenate([ridx[roff[r]:roff[r + 1]] for r in rows])
+    ref = oracle.curvature_from_csr(pts, sub_off, sub_idx, rows=rows)
+    got = dict(normal=normal[rows], K=curv[rows, 0], H=curv[rows, 1], k1=curv[rows, 2], k2=curv[rows, 3])
+    rep = compare.curvature_report(got, ref, np.full(len(rows), radius), rows_ok=np.diff(roff)[rows] >= 8)
+    assert rep["violations"] == 0, rep
+
+
+# ---------------------------------------------------------------------------
+# C ABI: the shipped library loads here (no GPU) and exports what the header declares
+# ---------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from point_cloud_toolbox_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "pct_b200.h")).read()
+    declared = set(re.findall(r"\b(pct_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pct_index", "pct_index_info", "pct_query_stats"}
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pct_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib.pct_version() == 100
+
+
+def test_no_cpu_fallback_without_a_device():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    import point_cloud_toolbox_b200 as m
+
+    pts = np.random.default_rng(0).normal(size=(100, 3)).astype(np.float32)
+    pc = m.PointCloud(points=pts, normals=np.zeros((100, 0), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pc.plant_kdtree(5)
+    with pytest.raises(ValueError, match="Either file_path or points and normals"):
+        m.PointCloud()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "point_cloud_toolbox_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
