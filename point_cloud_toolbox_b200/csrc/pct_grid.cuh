@@ -160,25 +160,74 @@ PCT_HD void make_stencil(const IndexView& ix, int level, float qx, float qy, flo
     }
 }
 
-// visit every point of the 27 cells: fn(j, pt) with j the sorted position
+// cell c (0..26) of the block; false when it lies outside the grid or holds no point
+PCT_HD bool stencil_cell(const Stencil& st, int c, uint32_t& s, uint32_t& e) {
+    const int cz = st.lz + c / 9 - 1, cy = st.ly + (c / 3) % 3 - 1, cx = st.lx + c % 3 - 1;
+    if (cx < 0 || cx >= st.dx || cy < 0 || cy >= st.dy || cz < 0 || cz >= st.dz) return false;
+    return lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), s, e);
+}
+
+// visit every point of the 27 cells: fn(j, pt) with j the sorted position.
+// Deliberately NOT unrolled: 27 inlined copies of a selection body blow the
+// instruction cache (ncu r01: stall_no_instruction dominated the fused kernel).
 template <class F>
 PCT_HD void for_each_candidate(const IndexView& ix, const Stencil& st, F& fn) {
-    for (int cz = st.lz - 1; cz <= st.lz + 1; ++cz) {
-        if (cz < 0 || cz >= st.dz) continue;
-        for (int cy = st.ly - 1; cy <= st.ly + 1; ++cy) {
-            if (cy < 0 || cy >= st.dy) continue;
-            for (int cx = st.lx - 1; cx <= st.lx + 1; ++cx) {
-                if (cx < 0 || cx >= st.dx) continue;
-                uint32_t s, e;
-                if (!lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), s, e)) continue;
-                for (uint32_t j = s; j < e; ++j) {
-                    const Pt p = load_pt(ix.pts + j);
-                    fn(j, p);
-                }
-            }
+#pragma unroll 1
+    for (int c = 0; c < 27; ++c) {
+        uint32_t s, e;
+        if (!stencil_cell(st, c, s, e)) continue;
+#pragma unroll 1
+        for (uint32_t j = s; j < e; ++j) {
+            const Pt p = load_pt(ix.pts + j);
+            fn(j, p);
         }
     }
 }
+
+// The non-empty cell runs of a block, kept by the thread that owns the query
+// (shared memory on the GPU: word w of run r lives at buf[(2r + w) * stride]).
+// Adjacent runs are merged; both selection passes and nothing else read them.
+struct CellRuns {
+    uint32_t* buf;
+    int stride;
+    int n;
+    PCT_HD void collect(const Stencil& st) {
+        n = 0;
+        uint32_t prev_end = 0xffffffffu;
+#pragma unroll 1
+        for (int c = 0; c < 27; ++c) {
+            uint32_t s, e;
+            if (!stencil_cell(st, c, s, e)) continue;
+            if (s == prev_end) {
+                buf[(size_t)(2 * n - 1) * stride] = e;  // extends the previous run
+            } else {
+                buf[(size_t)(2 * n) * stride] = s;
+                buf[(size_t)(2 * n + 1) * stride] = e;
+                ++n;
+            }
+            prev_end = e;
+        }
+    }
+    // one flat loop over all candidates: lanes of a warp stay in the same loop body
+    // even though their runs have different lengths
+    template <class F>
+    PCT_HD void scan(const Pt* pts, F& fn) const {
+        int r = 0;
+        uint32_t j = 0, e = 0;
+#pragma unroll 1
+        for (;;) {
+            if (j == e) {
+                if (r == n) break;
+                j = buf[(size_t)(2 * r) * stride];
+                e = buf[(size_t)(2 * r + 1) * stride];
+                ++r;
+            }
+            const Pt p = load_pt(pts + j);
+            fn(j, p);
+            ++j;
+        }
+    }
+};
 
 // ---------------------------------------------------------------------------
 // kNN selection, thread per query
@@ -211,13 +260,17 @@ struct TopKeys {
 // point `i` inside the level-`level` stencil.  On SEL_OK, list[m * stride]
 // (m < k) holds their sorted positions (unordered) and `first`/`last` the
 // nearest / farthest by (d2 fp64, original index).
-//   list capacity = cap entries (cap >= k)
+//   list capacity = cap entries (cap >= k); runs_buf holds 54 words (27 runs), same stride
 template <int KT>
 PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, int k,
-                      uint32_t* list, int stride, int cap, uint32_t& first, uint32_t& last,
+                      uint32_t* runs_buf, uint32_t* list, int stride, int cap, uint32_t& first, uint32_t& last,
                       double& d2_last) {
     Stencil st;
     make_stencil(ix, level, q.x, q.y, q.z, st);
+    CellRuns runs;
+    runs.buf = runs_buf;
+    runs.stride = stride;
+    runs.collect(st);
 
     // pass 1: k-th smallest fp32 squared distance
     struct P1 {
@@ -231,7 +284,7 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
     } p1;
     p1.top.reset(k);
     p1.self = i; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z;
-    for_each_candidate(ix, st, p1);
+    runs.scan(ix.pts, p1);
     const float tau = p1.top.kth();
     if (!(tau < 3.0e38f)) return SEL_RETRY_COARSER;           // fewer than k candidates here
     if (!(tau * 1.00001f < st.safe2)) return SEL_RETRY_COARSER;  // k-th neighbour may lie outside the block
@@ -253,7 +306,7 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
     } p2;
     p2.self = i; p2.cnt = 0; p2.cap = cap; p2.stride = stride; p2.list = list;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.thr = tau * 1.0000025f;
-    for_each_candidate(ix, st, p2);
+    runs.scan(ix.pts, p2);
     int cnt = (int)p2.cnt;
     if (cnt > cap) return SEL_EXACT;  // a large group of (near-)ties
 

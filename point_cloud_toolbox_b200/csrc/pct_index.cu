@@ -33,9 +33,26 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// partial[block][6] = {min xyz, max xyz}; *nonfinite |= 1 when a coordinate is NaN/Inf
+// order-preserving float <-> uint map so that atomicMin / atomicMax work on floats
+__host__ __device__ __forceinline__ unsigned int ordered_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    const unsigned int u = __float_as_uint(f);
+#else
+    unsigned int u;
+    std::memcpy(&u, &f, sizeof(u));
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float from_ordered_bits(unsigned int o) {
+    const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    float f;
+    std::memcpy(&f, &u, sizeof(f));
+    return f;
+}
+
+// box[0..2] = min xyz, box[3..5] = max xyz (ordered bits); box[6] |= 1 when a coordinate is NaN/Inf
 __global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict__ xyz, long long n, int stride,
-                                                         float* __restrict__ partial, unsigned* __restrict__ nonfinite) {
+                                                         unsigned int* __restrict__ box) {
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -55,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict_
         lo[a] = warp_min(lo[a]);
         hi[a] = warp_max(hi[a]);
     }
-    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nonfinite, 1u);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(box + 6, 1u);
     if (lane == 0) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { sm[warp][a] = lo[a]; sm[warp][3 + a] = hi[a]; }
@@ -64,16 +81,9 @@ __global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict_
     if (threadIdx.x < 6) {
         float v = sm[0][threadIdx.x];
         for (int w = 1; w < kThreads / 32; ++w) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
-        partial[blockIdx.x * 6 + threadIdx.x] = v;
+        if (threadIdx.x < 3) atomicMin(box + threadIdx.x, ordered_bits(v));
+        else atomicMax(box + threadIdx.x, ordered_bits(v));
     }
-}
-
-__global__ void bbox_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out) {
-    const int c = threadIdx.x;
-    if (c >= 6) return;
-    float v = partial[c];
-    for (int b = 1; b < blocks; ++b) v = c < 3 ? fminf(v, partial[b * 6 + c]) : fmaxf(v, partial[b * 6 + c]);
-    out[c] = v;
 }
 
 // ---- density pilot: 30-bit Morton keys of a strided sample on a 1024^3 grid ----
@@ -228,23 +238,30 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     PCT_CUDA(cudaGetDevice(&ix->device));
     PCT_CUDA(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, ix->device));
 
+    // temporaries come from the stream-ordered pool; keep freed blocks cached across builds
+    {
+        cudaMemPool_t pool;
+        PCT_CUDA(cudaDeviceGetDefaultMemPool(&pool, ix->device));
+        unsigned long long keep = ~0ull;
+        PCT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+
     // 1. bounding box + finiteness
     const int bb_blocks = std::max(1, std::min<int>(ix->sm_count * 8, (int)((n + kThreads - 1) / kThreads)));
-    DeviceTemp partial(s), bbox(s);
-    PCT_CUDA(partial.alloc(sizeof(float) * 6 * bb_blocks));
-    PCT_CUDA(bbox.alloc(sizeof(float) * 8));
-    PCT_CUDA(cudaMemsetAsync(bbox.p, 0, sizeof(float) * 8, s));
-    bbox_kernel<<<bb_blocks, kThreads, 0, s>>>(xyz, n, stride, partial.as<float>(), reinterpret_cast<unsigned*>(bbox.as<float>() + 6));
-    bbox_final_kernel<<<1, 32, 0, s>>>(partial.as<float>(), bb_blocks, bbox.as<float>());
-    float h_bbox[8];
-    PCT_CUDA(cudaMemcpyAsync(h_bbox, bbox.p, sizeof(h_bbox), cudaMemcpyDeviceToHost, s));
+    DeviceTemp bbox(s);
+    PCT_CUDA(bbox.alloc(sizeof(unsigned int) * 8));
+    PCT_CUDA(cudaMemsetAsync(bbox.p, 0xFF, sizeof(unsigned int) * 3, s));
+    PCT_CUDA(cudaMemsetAsync(bbox.as<unsigned int>() + 3, 0, sizeof(unsigned int) * 5, s));
+    bbox_kernel<<<bb_blocks, kThreads, 0, s>>>(xyz, n, stride, bbox.as<unsigned int>());
+    unsigned int h_box[8];
+    PCT_CUDA(cudaMemcpyAsync(h_box, bbox.p, sizeof(h_box), cudaMemcpyDeviceToHost, s));
     PCT_CUDA(cudaStreamSynchronize(s));
-    unsigned bad;
-    std::memcpy(&bad, &h_bbox[6], sizeof(bad));
-    if (bad) {
+    if (h_box[6]) {
         set_error("Non-finite values in input points");
         return PCT_ERR_NONFINITE;
     }
+    float h_bbox[6];
+    for (int a = 0; a < 6; ++a) h_bbox[a] = from_ordered_bits(h_box[a]);
     const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
     const float ext[3] = {h_bbox[3] - h_bbox[0], h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]};
     const float extent_max = std::max(ext[0], std::max(ext[1], ext[2]));
@@ -290,7 +307,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     PCT_CUDA(sort_tmp.alloc(tmp_bytes));
     PCT_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, dk, dv, (long long)n, 0, 3 * v.bits, s));
     const unsigned long long* keys = dk.Current();
-    PCT_CUDA(cudaMalloc(&ix->pts, sizeof(Pt) * (size_t)n));
+    PCT_CUDA(cudaMallocAsync(&ix->pts, sizeof(Pt) * (size_t)n, s));
     gather_kernel<<<blocks_n, kThreads, 0, s>>>(xyz, n, stride, dv.Current(), ix->pts);
     v.pts = ix->pts;
 
@@ -319,7 +336,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
         total_slots += cap;
         bt.mask[L] = (uint32_t)(cap - 1);
     }
-    PCT_CUDA(cudaMalloc(&ix->table_mem, sizeof(HashSlot) * total_slots));
+    PCT_CUDA(cudaMallocAsync(&ix->table_mem, sizeof(HashSlot) * total_slots, s));
     PCT_CUDA(cudaMemsetAsync(ix->table_mem, 0xFF, sizeof(HashSlot) * total_slots, s));
     bt.num_levels = v.num_levels;
     for (int L = 0; L < v.num_levels; ++L) {
@@ -329,7 +346,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     }
     fill_tables_kernel<<<(int)((n + 1 + kThreads - 1) / kThreads), kThreads, 0, s>>>(keys, n, bt);
 
-    PCT_CUDA(cudaMalloc(&ix->stats, sizeof(unsigned int) * 8));
+    PCT_CUDA(cudaMallocAsync(&ix->stats, sizeof(unsigned int) * 8, s));
     PCT_CUDA(cudaMemsetAsync(ix->stats, 0, sizeof(unsigned int) * 8, s));
     PCT_CUDA(cudaGetLastError());
 
@@ -367,6 +384,7 @@ int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, in
 
 int pct_index_destroy(pct_index* ix) {
     if (!ix) return PCT_OK;
+    // pool memory: cudaFree synchronises the device, then hands the blocks back to the pool
     if (ix->pts) cudaFree(ix->pts);
     if (ix->table_mem) cudaFree(ix->table_mem);
     if (ix->stats) cudaFree(ix->stats);

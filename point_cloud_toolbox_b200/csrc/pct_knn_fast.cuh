@@ -36,7 +36,7 @@ template <int KT, bool FUSED>
 __global__ void __launch_bounds__(kBlock, min_blocks<KT>())
 knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const int k, const int cap,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
-    extern __shared__ uint32_t smem_list[];  // [cap][kBlock]
+    extern __shared__ uint32_t smem_list[];  // [54 + cap][kBlock]: cell runs, then the neighbour list
     long long total = qr.q_end - qr.q_begin;
     if (qr.list) total = (long long)*qr.count;
     for (long long base = (long long)blockIdx.x * kBlock; base < total; base += (long long)gridDim.x * kBlock) {
@@ -44,10 +44,11 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         if (t >= total) continue;
         const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
         const Pt q = load_pt(ix.pts + i);
-        uint32_t* list = smem_list + threadIdx.x;
+        uint32_t* runs_buf = smem_list + threadIdx.x;
+        uint32_t* list = smem_list + 54 * kBlock + threadIdx.x;
         uint32_t first = 0, last = 0;
         double d2_last = 0.0;
-        const int rc = knn_select<KT>(ix, level, i, q, k, list, kBlock, cap, first, last, d2_last);
+        const int rc = knn_select<KT>(ix, level, i, q, k, runs_buf, list, kBlock, cap, first, last, d2_last);
         if (rc != SEL_OK) {
             if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
                 qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -107,7 +108,7 @@ template <int KT, bool FUSED>
 static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const IndexView& v = a.ix->view;
     const long long nq = a.qr.q_end - a.qr.q_begin;
-    const size_t smem = sizeof(uint32_t) * (size_t)a.cap * kBlock;
+    const size_t smem = sizeof(uint32_t) * (size_t)(54 + a.cap) * kBlock;
     const int grid_all = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 64);
     const int grid_retry = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
     auto kern = knn_fast_kernel<KT, FUSED>;

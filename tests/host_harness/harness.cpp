@@ -109,14 +109,14 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int32_t* idx, flo
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK;
-    std::vector<uint32_t> list(cap);
+    std::vector<uint32_t> list(cap), runs(54);
     for (long long i = 0; i < v.n; ++i) {
         const Pt q = v.pts[i];
         uint32_t first = 0, last = 0;
         double d2_last = 0;
         int rc = SEL_RETRY_COARSER, level = 0;
         for (; level <= max_fast_level && level < v.num_levels; ++level) {
-            rc = knn_select<KT>(v, level, (uint32_t)i, q, k, list.data(), 1, cap, first, last, d2_last);
+            rc = knn_select<KT>(v, level, (uint32_t)i, q, k, runs.data(), list.data(), 1, cap, first, last, d2_last);
             if (rc != SEL_RETRY_COARSER) break;
         }
         const long long row = q.idx;
