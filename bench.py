@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--clock-interval-ms", type=int, default=200)
     return ap.parse_args()
 
 
@@ -77,7 +79,10 @@ def run_cpu_leg(n_total, k, seconds):
     from oracle import baseline
 
     cores = baseline.host_cores()
-    pts = cpu_sample_cloud(n_total, 400_000)
+    # size the sample cloud so that the leg really spends `seconds` on all cores
+    cost = baseline.per_point_seconds(host_sample(20_000), k, probe=1000)
+    rows = int(min(n_total, 4_000_000, max(50_000, cores * seconds / cost)))
+    pts = cpu_sample_cloud(n_total, rows)
     res = baseline.timed_reference(pts, k, seconds=seconds, procs=cores)
     return res, len(pts)
 
@@ -119,54 +124,73 @@ def reference_arm(args):
 # clocks
 # --------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region.
 
-    def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+    In-process NVML (nvidia_ml_py) from a thread: an `nvidia-smi -lms` child process was
+    measured to slow the synchronisation-heavy index build by 2-4x on this pool (r01 notes
+    in profiles/README.md); the NVML calls below do not.
+    """
+
+    def __init__(self, gpu_index, interval_ms=200, enabled=True):
+        self.interval = interval_ms / 1e3
+        self.enabled = enabled
         self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.error = None
+
+    def _run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.gpu
+            if visible:
+                try:
+                    index = int(visible.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    index = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                try:
+                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    power = None
+                self.samples.append((sm, mx, int(reasons), power))
+                self.stop_flag.wait(self.interval)
+            pynvml.nvmlShutdown()
+        except Exception as exc:  # pragma: no cover
+            self.error = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        if not self.enabled:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling disabled"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"NVML unavailable: {self.error}"]}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = set()
+        for _, _, r, _ in self.samples:
+            for bit, name in bits.items():
+                if r & bit:
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(x[0] for x in self.samples)
+        power = [x[3] for x in self.samples if x[3] is not None]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": "NVML in-process"}
 
 
 # --------------------------------------------------------------------------
@@ -285,12 +309,34 @@ def ours(args):
             return kh[0], kh[1]
         return None, None
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval_ms, not args.no_clocks)
+
+    # Warm-up and timed steps run the SAME loop (same object lifetimes: the previous step's
+    # results stay alive until the next step has produced its own, as they would in a caller
+    # that keeps its latest result), so pools and caches are in steady state when timing starts.
+    def device_loop(steps, events=None):
+        last = None
+        for _ in range(steps):
+            index, fit = device_step(events)
+            if last is not None:
+                last[0].close()
+            last = (index, fit)
+        return last
+
+    def e2e_loop(steps, walls=None):
+        K = H = None
+        for _ in range(steps):
+            tw = time.perf_counter()
+            K, H = e2e_step()
+            if walls is not None:
+                walls.append(round(1e3 * (time.perf_counter() - tw), 1))
+        return K, H
+
     # ---- device-resident metric ----
-    for _ in range(args.warmup):
-        index, fit = device_step()
-        index.close()
-        del fit
+    last = device_loop(args.warmup)
+    if last is not None:
+        last[0].close()
+    del last
     barrier()
     if rank == 0:
         sampler.start()
@@ -298,35 +344,30 @@ def ours(args):
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
-    last = None
-    for _ in range(args.steps):
-        index, fit = device_step(events)
-        if last is not None:
-            last[0].close()
-        last = (index, fit)
+    last = device_loop(args.steps, events)
     t_end.record()
     barrier()
     total_ms = t_start.elapsed_time(t_end)
-    build_ms = sum(a.elapsed_time(b) for a, b, _ in events) / len(events)
+    build_steps = [round(a.elapsed_time(b), 2) for a, b, _ in events]
+    build_ms = sum(build_steps) / len(events)
     query_ms = sum(b.elapsed_time(c) for _, b, c in events) / len(events)
     stats = last[0].last_stats()
     info = last[0].info()
     status_bad = int((last[1].status != 0).sum().item())
     nan_rows = int(torch.isnan(last[1].curv[:, 0]).sum().item())
     last[0].close()
-    del last, index, fit
+    del last
     torch.cuda.empty_cache()
 
     # ---- end to end through the public API ----
-    for _ in range(args.warmup):
-        e2e_step()
+    e2e_loop(args.warmup)
     barrier()
     s0 = torch.cuda.Event(enable_timing=True)
     s1 = torch.cuda.Event(enable_timing=True)
     s0.record()
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        K, H = e2e_step()
+    step_walls = []
+    K, H = e2e_loop(args.steps, step_walls)
     s1.record()
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - wall0)
@@ -341,6 +382,10 @@ def ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if os.environ.get("PCT_B200_TRACE"):
+        from point_cloud_toolbox_b200 import trace
+
+        print("trace (ms, summed over all e2e steps incl. warm-up):", trace.timings, file=sys.stderr)
 
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3)
@@ -357,7 +402,7 @@ def ours(args):
             "l2": "inputs (1.2 GB raw + 1.6 GB sorted at 100M) exceed the 126 MB L2; no flush needed",
             "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
             "level1_retries": stats.level1_retries, "exact_path": stats.exact_path,
-            "build_ms": build_ms, "query_ms": query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
+            "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
         },
         "roofline": {
             "bound": "hbm", "kernel": "knn_fast_kernel<KT,true> (+ level-1 retry + exact tail, timed as one call)",
@@ -366,7 +411,7 @@ def ours(args):
             "note": "algorithmic 44 B/point; the kernel is FP32/ALU-issue and latency bound, not HBM bound (DESIGN.md)",
         },
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
-                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps},
+                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "step_wall_ms": step_walls},
         "gpu_launches": OUR_KERNELS_PER_STEP * args.steps * 2,
         "clocks": clocks,
     }

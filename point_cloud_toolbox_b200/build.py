@@ -39,6 +39,8 @@ def _digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
+            if not name.endswith((".cu", ".cuh", ".h")):
+                continue
             with open(os.path.join(root, name), "rb") as f:
                 h.update(name.encode() + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())

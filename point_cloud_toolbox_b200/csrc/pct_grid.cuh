@@ -191,40 +191,91 @@ struct CellRuns {
     uint32_t* buf;
     int stride;
     int n;
+
+    PCT_HD void push(uint32_t s, uint32_t e, uint32_t& prev_end) {
+        if (s == prev_end) {
+            buf[(size_t)(2 * n - 1) * stride] = e;  // extends the previous run
+        } else {
+            buf[(size_t)(2 * n) * stride] = s;
+            buf[(size_t)(2 * n + 1) * stride] = e;
+            ++n;
+        }
+        prev_end = e;
+    }
+
+    // The 27 hash probes are issued nine at a time (one z-layer) before any of them
+    // is consumed, so their latencies overlap; the Morton bits of the three cell
+    // coordinates per axis are spread once and OR-ed together per cell.
     PCT_HD void collect(const Stencil& st) {
         n = 0;
         uint32_t prev_end = 0xffffffffu;
-#pragma unroll 1
-        for (int c = 0; c < 27; ++c) {
-            uint32_t s, e;
-            if (!stencil_cell(st, c, s, e)) continue;
-            if (s == prev_end) {
-                buf[(size_t)(2 * n - 1) * stride] = e;  // extends the previous run
-            } else {
-                buf[(size_t)(2 * n) * stride] = s;
-                buf[(size_t)(2 * n + 1) * stride] = e;
-                ++n;
+        unsigned long long bx[3], by[3], bz[3];
+        bool vx[3], vy[3], vz[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int cx = st.lx + t - 1, cy = st.ly + t - 1, cz = st.lz + t - 1;
+            vx[t] = cx >= 0 && cx < st.dx;
+            vy[t] = cy >= 0 && cy < st.dy;
+            vz[t] = cz >= 0 && cz < st.dz;
+            bx[t] = spread3((uint32_t)cx);
+            by[t] = spread3((uint32_t)cy) << 1;
+            bz[t] = spread3((uint32_t)cz) << 2;
+        }
+        const LevelTable tab = *st.table;
+#pragma unroll
+        for (int zi = 0; zi < 3; ++zi) {
+            if (!vz[zi]) continue;
+            HashSlot probe[9];
+            uint32_t slot[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const unsigned long long key = bx[t % 3] | by[t / 3] | bz[zi];
+                slot[t] = hash_key(key) & tab.mask;
+                probe[t].key = kEmptyKey;
+                if (vx[t % 3] && vy[t / 3]) probe[t] = load_slot(tab.slots + slot[t]);
             }
-            prev_end = e;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const unsigned long long key = bx[t % 3] | by[t / 3] | bz[zi];
+                HashSlot hs = probe[t];
+                uint32_t sl = slot[t];
+                while (hs.key != key && hs.key != kEmptyKey) {  // linear probing, rarely more than one step
+                    sl = (sl + 1) & tab.mask;
+                    hs = load_slot(tab.slots + sl);
+                }
+                if (hs.key == key) push(hs.start, hs.end, prev_end);
+            }
         }
     }
-    // one flat loop over all candidates: lanes of a warp stay in the same loop body
-    // even though their runs have different lengths
+
+    // One flat loop over all candidates (the lanes of a warp stay in the same loop
+    // body although their runs differ), software-pipelined by one element: the
+    // next record is in flight while the current one is processed.
     template <class F>
     PCT_HD void scan(const Pt* pts, F& fn) const {
-        int r = 0;
-        uint32_t j = 0, e = 0;
+        if (n == 0) return;
+        int r = 1;
+        uint32_t j = buf[0], e = buf[stride];
+        Pt cur = load_pt(pts + j);
 #pragma unroll 1
         for (;;) {
-            if (j == e) {
-                if (r == n) break;
-                j = buf[(size_t)(2 * r) * stride];
-                e = buf[(size_t)(2 * r + 1) * stride];
-                ++r;
+            uint32_t jn = j + 1;
+            bool more = true;
+            if (jn == e) {
+                if (r == n) {
+                    more = false;
+                    jn = j;
+                } else {
+                    jn = buf[(size_t)(2 * r) * stride];
+                    e = buf[(size_t)(2 * r + 1) * stride];
+                    ++r;
+                }
             }
-            const Pt p = load_pt(pts + j);
-            fn(j, p);
-            ++j;
+            const Pt nxt = load_pt(pts + jn);
+            fn(j, cur);
+            if (!more) break;
+            cur = nxt;
+            j = jn;
         }
     }
 };
@@ -344,9 +395,14 @@ struct ListNeighbourhood {
     uint32_t first, last;
     template <class F>
     PCT_HD void pass(F& fn) const {
+        if (count <= 0) return;
+        Pt p = load_pt(ix->pts + list[0]);
+#pragma unroll 1
         for (int m = 0; m < count; ++m) {
-            const Pt p = load_pt(ix->pts + list[(size_t)m * stride]);
+            const int mn = m + 1 < count ? m + 1 : m;
+            const Pt nxt = load_pt(ix->pts + list[(size_t)mn * stride]);  // in flight during the fp64 work below
             fn.add(fsub_rn(p.x, q.x), fsub_rn(p.y, q.y), fsub_rn(p.z, q.z));
+            p = nxt;
         }
     }
     PCT_HD void reference(float& rx, float& ry, float& rz) const {

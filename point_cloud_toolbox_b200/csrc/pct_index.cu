@@ -225,7 +225,7 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
     if (Ls + 1 <= kPilotBits && cells[Ls + 1] >= 8.0) dim = std::log2(cells[Ls] / cells[Ls + 1]);
     dim = std::min(3.0, std::max(1.0, dim));
     const double ppc_full = (double)n / cells[Ls];
-    const double target = 0.5 * (double)(k_hint > 0 ? k_hint : 20);
+    const double target = 0.4 * (double)(k_hint > 0 ? k_hint : 20);  // tuned on B200 (scripts/tune.py)
     double h = (double)cell * std::ldexp(1.0, Ls) * std::pow(target / ppc_full, 1.0 / dim);
     h = std::min(h, 2.0 * (double)extent_max);
     *h_out = (float)h;
@@ -236,6 +236,7 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
 static int build_impl(const float* xyz, long long n, int stride, float cell_hint, int k_hint, cudaStream_t s,
                       pct_index* ix) {
     PCT_CUDA(cudaGetDevice(&ix->device));
+    ix->stream = s;
     PCT_CUDA(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, ix->device));
 
     // temporaries come from the stream-ordered pool; keep freed blocks cached across builds
@@ -384,10 +385,15 @@ int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, in
 
 int pct_index_destroy(pct_index* ix) {
     if (!ix) return PCT_OK;
-    // pool memory: cudaFree synchronises the device, then hands the blocks back to the pool
-    if (ix->pts) cudaFree(ix->pts);
-    if (ix->table_mem) cudaFree(ix->table_mem);
-    if (ix->stats) cudaFree(ix->stats);
+    // stream-ordered free: safe against work already queued on the build stream, returns the
+    // blocks to the pool for the next build without a device synchronisation
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != ix->device) cudaSetDevice(ix->device);
+    if (ix->pts) cudaFreeAsync(ix->pts, ix->stream);
+    if (ix->table_mem) cudaFreeAsync(ix->table_mem, ix->stream);
+    if (ix->stats) cudaFreeAsync(ix->stats, ix->stream);
+    if (cur != ix->device) cudaSetDevice(cur);
     delete ix;
     return PCT_OK;
 }

@@ -18,6 +18,7 @@ struct pct_index {
     pct_index_info info{};
     int device = 0;
     int sm_count = 148;
+    cudaStream_t stream = nullptr;  // stream the index was built on; its memory is freed in that stream's order
 };
 
 namespace pct {

@@ -43,12 +43,54 @@ def to_device_points(points, device=None):
     return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 
+def _storage_refs(buf):
+    return torch._C._storage_Use_Count(buf.untyped_storage()._cdata)
+
+
+class _PinnedPool:
+    """Recycles pinned host buffers behind the numpy arrays handed to the caller.
+
+    ``cudaHostAlloc`` costs about as much as copying the data it will hold, so result
+    buffers are reused -- but only once every numpy array (and view of it) that was made
+    from a buffer is gone: those arrays keep the buffer's storage alive, so the storage's
+    reference count is back at its idle value exactly when nobody can see the old data.
+    """
+
+    def __init__(self, max_bytes=16 << 30):
+        self.entries = []  # [pinned uint8 tensor, idle reference count of its storage]
+        self.max_bytes = max_bytes
+        self.allocations = 0
+
+    def take(self, shape, dtype):
+        nbytes = 1
+        for d in shape:
+            nbytes *= int(d)
+        nbytes *= torch.empty((), dtype=dtype).element_size()
+        for buf, idle in self.entries:
+            if nbytes <= buf.numel() <= 2 * nbytes + 4096 and _storage_refs(buf) == idle:
+                return buf[:nbytes].view(dtype).view(shape)
+        held = sum(b.numel() for b, _ in self.entries)
+        for ent in list(self.entries):
+            if held + nbytes <= self.max_bytes:
+                break
+            if _storage_refs(ent[0]) == ent[1]:
+                self.entries.remove(ent)
+                held -= ent[0].numel()
+        self.allocations += 1
+        buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
+        self.entries.append([buf, _storage_refs(buf)])
+        return buf[:nbytes].view(dtype).view(shape)
+
+
+_PINNED = _PinnedPool()
+
+
 def to_host(t: torch.Tensor):
-    """Device tensor -> numpy array backed by pinned host memory (torch caches the pinned blocks)."""
+    """Device tensor -> numpy array backed by (recycled) pinned host memory; synchronises the stream."""
     if not t.is_cuda:
         return t.numpy()
     t = t.contiguous()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h = _PINNED.take(tuple(t.shape), t.dtype)
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return h.numpy()

@@ -27,10 +27,12 @@ observe, all additive or representational:
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
-from . import engine
+from . import engine, trace
 from ._lib import STATUS_NONFINITE, MAX_K
 
 
@@ -38,7 +40,7 @@ class _Tree:
     """What ``self.kdtree`` holds: the device grid index plus a scipy-like ``query``."""
 
     def __init__(self, cloud, index):
-        self._cloud = cloud
+        self._cloud_ref = weakref.ref(cloud)  # no reference cycle: the cloud frees its device memory on refcount
         self.index = index
         self.n = index.n
         self.m = 3
@@ -52,7 +54,7 @@ class _Tree:
         """
         x = np.asarray(x, dtype=np.float32)
         single = x.ndim == 1
-        rows = self._cloud._locate(np.atleast_2d(x))
+        rows = self._cloud_ref()._locate(np.atleast_2d(x))
         if k < 2:
             d = np.zeros((len(rows), 1))
             i = rows[:, None].astype(np.int64)
@@ -184,8 +186,10 @@ class PointCloud:
             # scipy pads with index N, which the reference trips over at ref :640
             raise IndexError(f"index {n} is out of bounds for axis 0 with size {n}")
         self.k_neighbors = k_neighbors
-        d_points = self._upload()
-        index = engine.GridIndex(d_points, k_hint=k_neighbors)
+        with trace.stage("h2d"):
+            d_points = self._upload()
+        with trace.stage("index_build"):
+            index = engine.GridIndex(d_points, k_hint=k_neighbors)
         self.kdtree = _Tree(self, index)
         self._lists = None
         self._lists_dev = None
@@ -299,8 +303,10 @@ class PointCloud:
         """Compute explicit quadratic curvature and return pointwise values (ref :505-509)."""
         if (self._lists is None or self._lists[0] is None) and self.kdtree is not None:
             # throughput path: one fused kernel, and only K and H have to come back to the host
-            fit = self._fused_fit(want_coeffs=False)
-            kh = engine.to_host(fit.curv[:, :2].t())
+            with trace.stage("fused_kernel"):
+                fit = self._fused_fit(want_coeffs=False)
+            with trace.stage("d2h"):
+                kh = engine.to_host(fit.curv[:, :2].t())
             for name in ("quadratic_coefficients", "normals_quadratic", "fit_status", "K_H_sq_quadratic",
                          "k1_quadratic", "k2_quadratic"):
                 self.__dict__.pop(name, None)
