@@ -28,7 +28,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "points/sec for kNN+SVD+quadric curvature"
-ALG_BYTES_QUERY = 44   # per point: 16 B own record read + 28 B result written
+ALG_BYTES_QUERY = 44   # per point: 16 B own record read + 28 B result written; 32 B are actually written
 ALG_BYTES_E2E = 76     # + 12 B raw read + 16 B sorted record + 4 B permutation
 OUR_KERNELS_PER_STEP = 12  # bbox x2, pilot x2, keys, gather, level hist, table fill, fast L0, fast L1, exact, stats
 
@@ -354,7 +354,7 @@ def ours(args):
     stats = last[0].last_stats()
     info = last[0].info()
     status_bad = int((last[1].status != 0).sum().item())
-    nan_rows = int(torch.isnan(last[1].curv[:, 0]).sum().item())
+    nan_rows = int(torch.isnan(last[1].column("K")).sum().item())
     last[0].close()
     del last
     torch.cuda.empty_cache()

@@ -140,6 +140,15 @@ int pct_curvature_fused_ball(const pct_index* index, int64_t q_begin, int64_t q_
                              int32_t* counts, float* normals, float* coeffs, float* curv,
                              uint8_t* status, int layout, void* stream);
 
+/* Same kernels, packed output: `records` = rows x 8 fp32 {nx, ny, nz, K, H, k1, k2, status bits},
+ * 32-byte aligned.  One full DRAM sector per point even when rows are scattered to original
+ * order (the separate arrays above cost three partial sectors); H^2 = H*H is left to the caller. */
+int pct_curvature_fused_knn_records(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
+                                    float* records, int layout, void* stream);
+int pct_curvature_fused_ball_records(const pct_index* index, int64_t q_begin, int64_t q_end,
+                                     double radius, int32_t* counts, float* records, int layout,
+                                     void* stream);
+
 /* Batched forms of the three static methods.
  * pct_plane_rotate: get_best_fit_plane_and_rotate (ref :270-321) on nq neighbourhoods of
  *   k centred points (fp32, nq x k x 3) -> rotated fp64 (nq x k x 3), unit normals fp64 (nq x 3).

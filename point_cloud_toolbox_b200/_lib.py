@@ -70,6 +70,8 @@ SIGNATURES = {
     "pct_fit_from_csr": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pct_curvature_fused_knn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_curvature_fused_ball": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pct_curvature_fused_knn_records": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "pct_curvature_fused_ball_records": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_plane_rotate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pct_quadric_fit": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pct_quadric_curvature": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
@@ -78,11 +80,15 @@ SIGNATURES = {
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        # a source checkout without the built library: build it (needs nvcc), never fall back
-        from . import build as _build
+    # (re)build when the library is missing or older than its sources (digest check, needs nvcc);
+    # never fall back to anything else
+    from . import build as _build
 
+    try:
         _build.build()
+    except Exception:
+        if not os.path.exists(LIB_PATH):
+            raise
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = the library is stale or broken

@@ -1,5 +1,6 @@
 // extern "C" surface of libpct_b200.so (include/pct_b200.h): argument checks,
 // error strings, launches.  No C++ exception crosses this file.
+#include <cstdint>
 #include <cstdio>
 #include <string>
 
@@ -72,7 +73,7 @@ int pct_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, int32_t*
     if (rc) return rc;
     rc = check_k(ix, k, "pct_knn");
     if (rc) return rc;
-    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr, nullptr};
     return launch_knn(ix, q_begin, q_end, k, false, idx, dist, none, layout, (cudaStream_t)stream);
 }
 
@@ -82,15 +83,37 @@ int pct_curvature_fused_knn(const pct_index* ix, int64_t q_begin, int64_t q_end,
     if (rc) return rc;
     rc = check_k(ix, k, "pct_curvature_fused_knn");
     if (rc) return rc;
-    FitOutputs out{normals, coeffs, curv, status};
+    FitOutputs out{normals, coeffs, curv, status, nullptr};
     return launch_knn(ix, q_begin, q_end, k, true, nullptr, nullptr, out, layout, (cudaStream_t)stream);
+}
+
+int pct_curvature_fused_knn_records(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, float* records, int layout,
+                                    void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_knn_records");
+    if (rc) return rc;
+    rc = check_k(ix, k, "pct_curvature_fused_knn_records");
+    if (rc) return rc;
+    PCT_REQUIRE(records != nullptr && (reinterpret_cast<uintptr_t>(records) & 31) == 0,
+                "pct_curvature_fused_knn_records: records must be non-NULL and 32-byte aligned");
+    FitOutputs out{nullptr, nullptr, nullptr, nullptr, records};
+    return launch_knn(ix, q_begin, q_end, k, true, nullptr, nullptr, out, layout, (cudaStream_t)stream);
+}
+
+int pct_curvature_fused_ball_records(const pct_index* ix, int64_t q_begin, int64_t q_end, double radius, int32_t* counts,
+                                     float* records, int layout, void* stream) {
+    int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_ball_records");
+    if (rc) return rc;
+    PCT_REQUIRE(radius >= 0.0 && records != nullptr && (reinterpret_cast<uintptr_t>(records) & 31) == 0,
+                "pct_curvature_fused_ball_records: bad radius or records not 32-byte aligned");
+    FitOutputs out{nullptr, nullptr, nullptr, nullptr, records};
+    return launch_ball(ix, q_begin, q_end, radius, 2, counts, nullptr, 0, nullptr, nullptr, out, layout, (cudaStream_t)stream);
 }
 
 int pct_ball_count(const pct_index* ix, int64_t q_begin, int64_t q_end, double radius, int32_t* counts, int layout, void* stream) {
     int rc = check_range(ix, q_begin, q_end, layout, "pct_ball_count");
     if (rc) return rc;
     PCT_REQUIRE(radius >= 0.0 && counts, "pct_ball_count: radius must be >= 0 and counts non-NULL");
-    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr, nullptr};
     return launch_ball(ix, q_begin, q_end, radius, 0, counts, nullptr, 0, nullptr, nullptr, none, layout, (cudaStream_t)stream);
 }
 
@@ -99,7 +122,7 @@ int pct_ball_fill(const pct_index* ix, int64_t q_begin, int64_t q_end, double ra
     int rc = check_range(ix, q_begin, q_end, layout, "pct_ball_fill");
     if (rc) return rc;
     PCT_REQUIRE(radius >= 0.0 && offsets && idx && nnz >= 0, "pct_ball_fill: bad argument");
-    FitOutputs none{nullptr, nullptr, nullptr, nullptr};
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr, nullptr};
     return launch_ball(ix, q_begin, q_end, radius, 1, nullptr, (const long long*)offsets, nnz, idx, dist, none, layout,
                        (cudaStream_t)stream);
 }
@@ -109,21 +132,21 @@ int pct_curvature_fused_ball(const pct_index* ix, int64_t q_begin, int64_t q_end
     int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_ball");
     if (rc) return rc;
     PCT_REQUIRE(radius >= 0.0, "pct_curvature_fused_ball: radius must be >= 0");
-    FitOutputs out{normals, coeffs, curv, status};
+    FitOutputs out{normals, coeffs, curv, status, nullptr};
     return launch_ball(ix, q_begin, q_end, radius, 2, counts, nullptr, 0, nullptr, nullptr, out, layout, (cudaStream_t)stream);
 }
 
 int pct_fit_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, const int32_t* query_ids,
                            float* normals, float* coeffs, float* curv, uint8_t* status, void* stream) {
     PCT_REQUIRE(xyz && idx && n >= 1 && nq >= 0 && k >= 1, "pct_fit_from_neighbors: bad argument");
-    FitOutputs out{normals, coeffs, curv, status};
+    FitOutputs out{normals, coeffs, curv, status, nullptr};
     return launch_fit_rows(xyz, n, idx, nq, k, query_ids, out, (cudaStream_t)stream);
 }
 
 int pct_fit_from_csr(const float* xyz, int64_t n, const int64_t* offsets, const int32_t* idx, int64_t nq,
                      const int32_t* query_ids, float* normals, float* coeffs, float* curv, uint8_t* status, void* stream) {
     PCT_REQUIRE(xyz && offsets && n >= 1 && nq >= 0, "pct_fit_from_csr: bad argument");
-    FitOutputs out{normals, coeffs, curv, status};
+    FitOutputs out{normals, coeffs, curv, status, nullptr};
     return launch_fit_csr(xyz, n, (const long long*)offsets, idx, nq, query_ids, out, (cudaStream_t)stream);
 }
 

@@ -248,34 +248,40 @@ struct CellRuns {
         }
     }
 
-    // One flat loop over all candidates (the lanes of a warp stay in the same loop
-    // body although their runs differ), software-pipelined by one element: the
-    // next record is in flight while the current one is processed.
+    // One flat loop over all candidates (the lanes of a warp stay in the same loop body
+    // although their runs differ), in batches of kDepth: the positions of the next kDepth
+    // candidates are generated first, their records are loaded together (kDepth
+    // independent 16-byte loads in flight per thread) and only then processed.  With the
+    // shared-memory carve-out this kernel leaves little L1, so most loads are L2 hits
+    // (~300 cycles); one-ahead prefetching left the warps stalled on the scoreboard.
+    static constexpr int kDepth = 4;
     template <class F>
     PCT_HD void scan(const Pt* pts, F& fn) const {
-        if (n == 0) return;
-        int r = 1;
-        uint32_t j = buf[0], e = buf[stride];
-        Pt cur = load_pt(pts + j);
+        int r = 0;
+        uint32_t j = 0, e = 0, safe = 0;
+        if (n > 0) safe = buf[0];
 #pragma unroll 1
         for (;;) {
-            uint32_t jn = j + 1;
-            bool more = true;
-            if (jn == e) {
-                if (r == n) {
-                    more = false;
-                    jn = j;
-                } else {
-                    jn = buf[(size_t)(2 * r) * stride];
+            uint32_t pos[kDepth];
+            bool valid[kDepth];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+                if (j == e && r < n) {
+                    j = buf[(size_t)(2 * r) * stride];
                     e = buf[(size_t)(2 * r + 1) * stride];
                     ++r;
                 }
+                valid[u] = j != e;
+                pos[u] = valid[u] ? j : safe;
+                j += valid[u] ? 1u : 0u;
             }
-            const Pt nxt = load_pt(pts + jn);
-            fn(j, cur);
-            if (!more) break;
-            cur = nxt;
-            j = jn;
+            if (!valid[0]) break;
+            Pt rec[kDepth];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) rec[u] = load_pt(pts + pos[u]);
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u)
+                if (valid[u]) fn(pos[u], rec[u]);
         }
     }
 };
@@ -285,105 +291,168 @@ struct CellRuns {
 // ---------------------------------------------------------------------------
 enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 
-template <int KT>
-struct TopKeys {
-    float key[KT];
-    // Only k of the KT slots are live: the first KT - k are pinned to -1 (below any
-    // squared distance), so the k-th smallest real key always sits in key[KT-1] and
-    // no slot is ever addressed with a runtime index (the array stays in registers).
-    PCT_HD void reset(int k) {
-#pragma unroll
-        for (int s = 0; s < KT; ++s) key[s] = (s < KT - k) ? -1.f : 3.4e38f;
-    }
-    // branch-free sorted insertion: 2 min/max per slot, no index payload
-    PCT_HD void insert(float d) {
-#pragma unroll
-        for (int s = 0; s < KT; ++s) {
-            const float lo = fminf(key[s], d);
-            d = fmaxf(key[s], d);
-            key[s] = lo;
-        }
-    }
-    PCT_HD float kth() const { return key[KT - 1]; }
+// Selection scratch of one query.  On the GPU all three areas live in shared memory:
+//   runs  54 words, word w at runs[w * stride]           (27 cell runs)
+//   list  cap words, slot m at list[m * stride]          (neighbour positions)
+//   hist  kHistBins bytes, contiguous per query          (distance histogram)
+static constexpr int kHistBins = 64;
+static constexpr int kHistRowBytes = 68;  // 17 words per thread: odd word stride, bank-conflict free
+
+struct SelectScratch {
+    uint32_t* runs;
+    uint32_t* list;
+    uint8_t* hist;
+    int stride;
+    int cap;
 };
 
 // Finds the exact k nearest neighbours (scipy order, self excluded) of sorted
-// point `i` inside the level-`level` stencil.  On SEL_OK, list[m * stride]
-// (m < k) holds their sorted positions (unordered) and `first`/`last` the
-// nearest / farthest by (d2 fp64, original index).
-//   list capacity = cap entries (cap >= k); runs_buf holds 54 words (27 runs), same stride
-template <int KT>
-PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, int k,
-                      uint32_t* runs_buf, uint32_t* list, int stride, int cap, uint32_t& first, uint32_t& last,
-                      double& d2_last) {
+// point `i` inside the level-`level` stencil, in O(candidates) work:
+//
+//   pass 1  histogram of the fp32 squared distances over kHistBins equal bins of
+//           [0, range2) (squared distance is uniform in area on a surface, so the
+//           bins are evenly filled); the bin b that holds the k-th neighbour follows
+//           from a prefix sum.  No sorted list, no dependence on k.
+//   pass 2  candidates clearly below bin b (d32 < lo) are neighbours and go to the
+//           front of the list; candidates in the boundary zone [lo, hi] -- bin b widened
+//           by 1e-5 relative on both sides, far more than the 3e-7 fp32 error -- go
+//           to the back; everything above hi is out.
+//   exact   the k - |front| nearest of the boundary zone are chosen with scipy's fp64
+//           key (d2, index).  The zone holds one or two points on average.  If the
+//           farthest front point and the nearest zone point are closer than 2e-6
+//           relative the cut itself is ambiguous and the query goes to the exact kernel.
+//
+// On SEL_OK, list[m * stride] (m < k) holds the neighbours' sorted positions
+// (unordered), `first` / `last` the nearest / farthest by (d2 fp64, original index).
+PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, int k, const SelectScratch& sc,
+                      uint32_t& first, uint32_t& last, double& d2_last) {
     Stencil st;
     make_stencil(ix, level, q.x, q.y, q.z, st);
     CellRuns runs;
-    runs.buf = runs_buf;
-    runs.stride = stride;
+    runs.buf = sc.runs;
+    runs.stride = sc.stride;
     runs.collect(st);
 
-    // pass 1: k-th smallest fp32 squared distance
+    // everything closer than sqrt(range2) is certain to be among the candidates
+    const float cell = ix.h * ldexpf(1.f, level);
+    const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
+    const float bin_w = range2 * (1.f / kHistBins);
+    const float inv_w = (float)kHistBins / range2;
+    if (!(range2 > 1.0e-30f) || !(inv_w < 3.0e38f)) return SEL_EXACT;
+
+    uint32_t* hist32 = reinterpret_cast<uint32_t*>(sc.hist);
+#pragma unroll
+    for (int w = 0; w < kHistBins / 4; ++w) hist32[w] = 0u;
+
     struct P1 {
-        TopKeys<KT> top;
+        uint8_t* hist;
         uint32_t self;
-        float qx, qy, qz;
+        float qx, qy, qz, range2, inv_w;
         PCT_HD void operator()(uint32_t j, const Pt& p) {
             const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-            top.insert(j == self ? 3.4e38f : d);
+            if (d < range2 && j != self) {
+                int b = (int)(d * inv_w);
+                b = b < kHistBins - 1 ? b : kHistBins - 1;
+                const uint8_t v = hist[b];
+                hist[b] = (uint8_t)(v + (v < 255 ? 1 : 0));
+            }
         }
     } p1;
-    p1.top.reset(k);
-    p1.self = i; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z;
+    p1.hist = sc.hist; p1.self = i; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w;
     runs.scan(ix.pts, p1);
-    const float tau = p1.top.kth();
-    if (!(tau < 3.0e38f)) return SEL_RETRY_COARSER;           // fewer than k candidates here
-    if (!(tau * 1.00001f < st.safe2)) return SEL_RETRY_COARSER;  // k-th neighbour may lie outside the block
-    if (!(tau > 1.0e-30f)) return SEL_EXACT;                   // duplicates / denormal range: fp64 only
 
-    // pass 2: everything that can belong to the fp64 top-k
+    // bin of the k-th neighbour
+    int b = -1;
+    uint32_t cum = 0;
+#pragma unroll 4
+    for (int w = 0; w < kHistBins / 4; ++w) {
+        const uint32_t word = hist32[w];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            cum += (word >> (8 * t)) & 255u;
+            if (b < 0 && cum >= (uint32_t)k) b = 4 * w + t;
+        }
+    }
+    if (b < 0) return SEL_RETRY_COARSER;  // fewer than k points within the certain radius
+
+    const float hi = (float)(b + 1) * bin_w * 1.00001f;
+    const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
+
     struct P2 {
-        uint32_t self, cnt;
-        int cap, stride;
         uint32_t* list;
-        float qx, qy, qz, thr;
+        int stride, cap;
+        uint32_t self, n_front, n_zone, j_min;
+        float qx, qy, qz, lo, hi, d_min, d_min2, front_max, zone_min;
         PCT_HD void operator()(uint32_t j, const Pt& p) {
             const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= thr && j != self) {
-                if ((int)cnt < cap) list[(size_t)cnt * stride] = j;
-                ++cnt;
+            if (d <= hi && j != self) {
+                if (d < lo) {
+                    if ((int)(n_front + n_zone) < cap) list[(size_t)n_front * stride] = j;
+                    ++n_front;
+                    front_max = fmaxf(front_max, d);
+                } else {
+                    if ((int)(n_front + n_zone) < cap) list[(size_t)(cap - 1 - (int)n_zone) * stride] = j;
+                    ++n_zone;
+                    zone_min = fminf(zone_min, d);
+                }
+                // nearest and runner-up by fp32 distance
+                const bool closer = d < d_min;
+                d_min2 = closer ? d_min : fminf(d_min2, d);
+                j_min = closer ? j : j_min;
+                d_min = closer ? d : d_min;
             }
         }
     } p2;
-    p2.self = i; p2.cnt = 0; p2.cap = cap; p2.stride = stride; p2.list = list;
-    p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.thr = tau * 1.0000025f;
+    p2.list = sc.list; p2.stride = sc.stride; p2.cap = sc.cap; p2.self = i; p2.n_front = 0; p2.n_zone = 0; p2.j_min = 0;
+    p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi; p2.d_min = 3.4e38f; p2.d_min2 = 3.4e38f;
+    p2.front_max = 0.f; p2.zone_min = 3.4e38f;
     runs.scan(ix.pts, p2);
-    int cnt = (int)p2.cnt;
-    if (cnt > cap) return SEL_EXACT;  // a large group of (near-)ties
 
-    // fp64 re-rank.  Almost always cnt == k and this only finds first / last.
-    for (;;) {
-        double dmin = 1.0e300, dmax = -1.0;
-        uint32_t imin = 0, imax = 0, jmin = 0, jmax = 0;
-        int mmax = 0;
-        bool zero = false;
-        for (int m = 0; m < cnt; ++m) {
-            const uint32_t j = list[(size_t)m * stride];
+    const int n_front = (int)p2.n_front;
+    int n_zone = (int)p2.n_zone;
+    if (n_front + n_zone > sc.cap) return SEL_EXACT;   // a large group of (near-)ties in the boundary bin
+    if (!(p2.d_min > 1.0e-30f)) return SEL_EXACT;      // duplicates of the query / denormal range: fp64 only
+    // `lo` is an arbitrary cut: front and zone must be separated by more than the fp32 error,
+    // otherwise a front member could rank behind a zone member in fp64
+    if (n_front > 0 && !(p2.zone_min > p2.front_max * 1.000002f)) return SEL_EXACT;
+    const int need = k - n_front;                      // 1 <= need <= n_zone by construction
+    if (need < 1 || need > n_zone) return SEL_EXACT;   // (a saturated histogram bin can break the invariant)
+
+    // exact choice inside the boundary zone: `need` successive minima of (d2, index)
+    uint32_t* zone = sc.list + (size_t)(sc.cap - n_zone) * sc.stride;
+    for (int t = 0; t < need; ++t) {
+        double bd = 0.0;
+        uint32_t bi = 0, bj = 0;
+        int bm = 0;
+        for (int m = 0; m < n_zone; ++m) {
+            const uint32_t j = zone[(size_t)m * sc.stride];
             const Pt p = load_pt(ix.pts + j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
-            zero = zero || (d == 0.0);
-            if (m == 0 || key_less(d, p.idx, dmin, imin)) { dmin = d; imin = p.idx; jmin = j; }
-            if (m == 0 || key_less(dmax, imax, d, p.idx)) { dmax = d; imax = p.idx; jmax = j; mmax = m; }
+            if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
         }
-        if (zero) return SEL_EXACT;  // exact duplicates of the query: the "drop the first hit" rule decides
-        if (cnt == k) {
-            first = jmin; last = jmax; d2_last = dmax;
-            return SEL_OK;
-        }
-        // drop the farthest and look again
-        list[(size_t)mmax * stride] = list[(size_t)(cnt - 1) * stride];
-        --cnt;
+        // zone entries sit at the back in reverse order of arrival: remove bm by moving entry 0 into it
+        zone[(size_t)bm * sc.stride] = zone[0];
+        zone += sc.stride;
+        --n_zone;
+        sc.list[(size_t)(n_front + t) * sc.stride] = bj;
+        last = bj;
+        d2_last = bd;
     }
+
+    // nearest neighbour: decided in fp32 when the runner-up is clearly farther
+    if (p2.d_min2 > p2.d_min * 1.00001f) {
+        first = p2.j_min;
+    } else {
+        double bd = 0.0;
+        uint32_t bi = 0;
+        for (int m = 0; m < k; ++m) {
+            const uint32_t j = sc.list[(size_t)m * sc.stride];
+            const Pt p = load_pt(ix.pts + j);
+            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
+        }
+    }
+    return SEL_OK;
 }
 
 // Neighbourhood adaptor over a list of sorted positions (fused kNN path).

@@ -46,6 +46,7 @@ struct FitOutputs {
     float* coeffs;
     float* curv;
     uint8_t* status;
+    float* records;  // rows x 8 floats {nx, ny, nz, K, H, k1, k2, status bits}: one aligned 32-byte sector per point
 };
 
 __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, const FitResult& r) {
@@ -64,6 +65,13 @@ __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, co
         for (int c = 0; c < 5; ++c) p[c] = r.curv[c];
     }
     if (o.status) o.status[row] = (uint8_t)r.status;
+    if (o.records) {
+        // two 16-byte stores that together fill exactly one 32-byte sector: a scattered
+        // (original-order) row costs 32 B of DRAM traffic instead of three partial sectors
+        float4* p = reinterpret_cast<float4*>(o.records + 8 * row);
+        p[0] = make_float4(r.normal[0], r.normal[1], r.normal[2], r.curv[0]);
+        p[1] = make_float4(r.curv[1], r.curv[2], r.curv[3], __uint_as_float(r.status));
+    }
 }
 
 // query-side launchers (pct_query.cu)

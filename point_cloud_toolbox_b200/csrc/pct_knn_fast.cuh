@@ -1,6 +1,5 @@
-// Thread-per-query kNN kernel (selection in registers, exact set in shared memory,
-// fused fp64 fit).  Each compile-time bucket KT is instantiated in its own
-// translation unit (pct_knn_ktNNN.cu) so the buckets build in parallel.
+// Thread-per-query kNN kernel: histogram selection, exact neighbour set in shared
+// memory, fused fp64 fit.  One kernel for every k (the selection is O(candidates)).
 // See pct_query.cu for the overview of the query path.
 #pragma once
 
@@ -29,14 +28,22 @@ __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, u
     return qr.layout == PCT_LAYOUT_ORIGINAL ? (long long)orig : (long long)i - qr.q_begin;
 }
 
-template <int KT>
-constexpr int min_blocks() { return KT <= 32 ? 4 : (KT <= 64 ? 3 : 2); }
+// shared memory of one block: [54][kBlock] cell runs, [cap][kBlock] neighbour list, [kBlock][68 B] histograms
+__host__ __device__ inline size_t fast_smem_bytes(int cap) {
+    return sizeof(uint32_t) * (size_t)(54 + cap) * kBlock + (size_t)kHistRowBytes * kBlock;
+}
 
-template <int KT, bool FUSED>
-__global__ void __launch_bounds__(kBlock, min_blocks<KT>())
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock, 4)
 knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const int k, const int cap,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
-    extern __shared__ uint32_t smem_list[];  // [54 + cap][kBlock]: cell runs, then the neighbour list
+    extern __shared__ uint32_t smem_words[];
+    SelectScratch sc;
+    sc.runs = smem_words + threadIdx.x;
+    sc.list = smem_words + 54 * kBlock + threadIdx.x;
+    sc.hist = reinterpret_cast<uint8_t*>(smem_words + (54 + cap) * kBlock) + kHistRowBytes * threadIdx.x;
+    sc.stride = kBlock;
+    sc.cap = cap;
     long long total = qr.q_end - qr.q_begin;
     if (qr.list) total = (long long)*qr.count;
     for (long long base = (long long)blockIdx.x * kBlock; base < total; base += (long long)gridDim.x * kBlock) {
@@ -44,11 +51,10 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         if (t >= total) continue;
         const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
         const Pt q = load_pt(ix.pts + i);
-        uint32_t* runs_buf = smem_list + threadIdx.x;
-        uint32_t* list = smem_list + 54 * kBlock + threadIdx.x;
+        uint32_t* list = sc.list;
         uint32_t first = 0, last = 0;
         double d2_last = 0.0;
-        const int rc = knn_select<KT>(ix, level, i, q, k, runs_buf, list, kBlock, cap, first, last, d2_last);
+        const int rc = knn_select(ix, level, i, q, k, sc, first, last, d2_last);
         if (rc != SEL_OK) {
             if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
                 qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -85,7 +91,6 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
     }
 }
 
-
 struct FastLaunch {
     const pct_index* ix;
     QueryRange qr;
@@ -101,17 +106,14 @@ struct FastLaunch {
 };
 
 // level 0 over the whole range, then level 1 over whatever level 0 queued
-template <int KT>
-int launch_fast_kt(const FastLaunch& a, unsigned int* launches);
-
-template <int KT, bool FUSED>
+template <bool FUSED>
 static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const IndexView& v = a.ix->view;
     const long long nq = a.qr.q_end - a.qr.q_begin;
-    const size_t smem = sizeof(uint32_t) * (size_t)(54 + a.cap) * kBlock;
+    const size_t smem = fast_smem_bytes(a.cap);
     const int grid_all = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 64);
     const int grid_retry = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
-    auto kern = knn_fast_kernel<KT, FUSED>;
+    auto kern = knn_fast_kernel<FUSED>;
     PCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.counters};
     kern<<<grid_all, kBlock, smem, a.s>>>(v, 0, a.qr, a.k, a.cap, a.idx, a.dist, a.out, q0);
@@ -128,11 +130,8 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     return PCT_OK;
 }
 
-#define PCT_INSTANTIATE_FAST(KT_)                                                   \
-    template <>                                                                     \
-    int launch_fast_kt<KT_>(const FastLaunch& a, unsigned int* launches) {          \
-        return a.fused ? launch_fast_impl<KT_, true>(a, launches)                   \
-                       : launch_fast_impl<KT_, false>(a, launches);                 \
-    }
+static int launch_fast(const FastLaunch& a, unsigned int* launches) {
+    return a.fused ? launch_fast_impl<true>(a, launches) : launch_fast_impl<false>(a, launches);
+}
 
 }  // namespace pct

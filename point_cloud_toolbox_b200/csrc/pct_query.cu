@@ -6,9 +6,9 @@
 //   calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points         :663-672
 //
 // Kernels
-//   knn_fast_kernel<KT, FUSED>   one thread per query (queries are consecutive
+//   knn_fast_kernel<FUSED>       one thread per query (queries are consecutive
 //       Morton-sorted points, so the lanes of a warp walk the same few cells and
-//       their loads hit L1).  Selection list in registers (KT fp32 keys), exact
+//       their loads hit L1).  Histogram selection of the k-th distance, exact
 //       neighbour set in shared memory, then either the fp64 fit (FUSED) or the
 //       ordered (index, distance) rows.  Neighbourhoods never go to HBM.
 //       Queries that cannot be finished at this grid level are queued.
@@ -229,7 +229,7 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     unsigned int launches = 0;
     FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, counters, s};
     int rc = PCT_OK;
-    PCT_DISPATCH_KT(k, rc = launch_fast_kt<KT>(fl, &launches));
+    rc = launch_fast(fl, &launches);
     if (rc != PCT_OK) return rc;
 
     const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;

@@ -84,8 +84,9 @@ def curvature_knn_sharded(points, n: int, k: int, group=None, device=None, colum
     cloud = broadcast_cloud(d_points, n, group, 0, device)
     index = engine.GridIndex(cloud, k_hint=k)
     begin, end = shard_bounds(n, world, rank)
-    fit = index.curvature_knn(k, begin, end, layout=LAYOUT_SLICE, want_normals=False, want_coeffs=False, want_status=False)
-    local = fit.curv[:, list(columns)].contiguous()
+    fit = index.curvature_knn(k, begin, end, layout=LAYOUT_SLICE, want_coeffs=False)
+    names = ("K", "H", "k1", "k2", "H2")
+    local = torch.stack([fit.column(names[c]) for c in columns], 1)
     gathered = gather_rows(local, n, group, 0)
     if rank != 0:
         return None

@@ -7,8 +7,6 @@ streams, libpct_b200.so (through ctypes) does all the work.
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass
-
 import torch
 
 from . import _lib
@@ -96,13 +94,50 @@ def to_host(t: torch.Tensor):
     return h.numpy()
 
 
-@dataclass
 class FitOutputs:
-    normals: torch.Tensor | None
-    coeffs: torch.Tensor | None
-    curv: torch.Tensor | None      # columns K, H, k1, k2, H^2
-    status: torch.Tensor | None
-    counts: torch.Tensor | None = None
+    """Per-point results of a fit, resident on the device.
+
+    Two storage forms: separate arrays (``normals (n,3)``, ``coeffs (n,6)``, ``curv (n,5)``
+    = K, H, k1, k2, H^2, ``status (n,) uint8``) or packed 32-byte ``records (n,8)`` =
+    nx, ny, nz, K, H, k1, k2, status bits.  The accessors work on either.
+    """
+
+    _COL = {"K": 0, "H": 1, "k1": 2, "k2": 3, "H2": 4}
+
+    def __init__(self, normals=None, coeffs=None, curv=None, status=None, counts=None, records=None):
+        self._normals, self.coeffs, self._curv, self._status = normals, coeffs, curv, status
+        self.counts = counts
+        self.records = records
+
+    def column(self, name):
+        c = self._COL[name]
+        if self.records is None:
+            return self._curv[:, c]
+        if name == "H2":
+            h = self.records[:, 4]
+            return h * h  # fp32 product, the same rounding as the kernel's / the reference's K_h**2
+        return self.records[:, 3 + c]
+
+    def kh(self):
+        """(2, n) contiguous tensor [K; H]."""
+        src = self.records[:, 3:5] if self.records is not None else self._curv[:, :2]
+        return src.t().contiguous()
+
+    @property
+    def normals(self):
+        return self.records[:, :3] if self.records is not None else self._normals
+
+    @property
+    def status(self):
+        if self.records is not None:
+            return self.records[:, 7].contiguous().view(torch.int32).to(torch.uint8)
+        return self._status
+
+    @property
+    def curv(self):
+        if self.records is not None:
+            return torch.stack([self.column(n) for n in ("K", "H", "k1", "k2", "H2")], 1)
+        return self._curv
 
 
 def _alloc_outputs(rows, device, want_normals=True, want_coeffs=True, want_status=True):
@@ -177,11 +212,16 @@ class GridIndex:
 
     def curvature_knn(self, k, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL, want_normals=True, want_coeffs=True,
                       want_status=True) -> FitOutputs:
+        """Fused search + fit.  Without coefficients the result is written as packed 32-byte records."""
         q_begin, q_end, rows = self._range(q_begin, q_end, layout)
-        out = _alloc_outputs(rows, self.device, want_normals, want_coeffs, want_status)
         with torch.cuda.device(self.device):
-            check(lib.pct_curvature_fused_knn(self._handle, q_begin, q_end, int(k), ptr(out.normals), ptr(out.coeffs),
-                                              ptr(out.curv), ptr(out.status), layout, _stream()))
+            if not want_coeffs:
+                rec = torch.empty((rows, 8), dtype=torch.float32, device=self.device)
+                check(lib.pct_curvature_fused_knn_records(self._handle, q_begin, q_end, int(k), ptr(rec), layout, _stream()))
+                return FitOutputs(records=rec)
+            out = _alloc_outputs(rows, self.device, want_normals, want_coeffs, want_status)
+            check(lib.pct_curvature_fused_knn(self._handle, q_begin, q_end, int(k), ptr(out._normals), ptr(out.coeffs),
+                                              ptr(out._curv), ptr(out._status), layout, _stream()))
         return out
 
     def ball_count(self, radius, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL):
@@ -210,8 +250,8 @@ class GridIndex:
         out = _alloc_outputs(rows, self.device)
         out.counts = torch.empty((rows,), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib.pct_curvature_fused_ball(self._handle, q_begin, q_end, float(radius), ptr(out.counts), ptr(out.normals),
-                                               ptr(out.coeffs), ptr(out.curv), ptr(out.status), layout, _stream()))
+            check(lib.pct_curvature_fused_ball(self._handle, q_begin, q_end, float(radius), ptr(out.counts), ptr(out._normals),
+                                               ptr(out.coeffs), ptr(out._curv), ptr(out._status), layout, _stream()))
         return out
 
 
@@ -225,7 +265,7 @@ def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:
     out = _alloc_outputs(nq, points_dev.device)
     with torch.cuda.device(points_dev.device):
         check(lib.pct_fit_from_neighbors(ptr(points_dev), int(points_dev.shape[0]), ptr(idx_dev), nq, k, ptr(query_ids),
-                                         ptr(out.normals), ptr(out.coeffs), ptr(out.curv), ptr(out.status), _stream()))
+                                         ptr(out._normals), ptr(out.coeffs), ptr(out._curv), ptr(out._status), _stream()))
     return out
 
 
@@ -236,7 +276,7 @@ def fit_from_csr(points_dev, offsets_dev, idx_dev, query_ids=None) -> FitOutputs
     offsets_dev = offsets_dev.to(torch.int64).contiguous()
     with torch.cuda.device(points_dev.device):
         check(lib.pct_fit_from_csr(ptr(points_dev), int(points_dev.shape[0]), ptr(offsets_dev), ptr(idx_dev), nq,
-                                   ptr(query_ids), ptr(out.normals), ptr(out.coeffs), ptr(out.curv), ptr(out.status),
+                                   ptr(query_ids), ptr(out._normals), ptr(out.coeffs), ptr(out._curv), ptr(out._status),
                                    _stream()))
     return out
 

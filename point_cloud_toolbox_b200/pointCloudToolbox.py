@@ -276,7 +276,8 @@ class PointCloud:
 
     @staticmethod
     def _raise_on_nonfinite(fit):
-        if fit.status is not None and bool((fit.status & STATUS_NONFINITE).any()):
+        status = fit.status
+        if status is not None and bool((status & STATUS_NONFINITE).any()):
             raise ValueError("Non-finite values after rotation")  # ref :318-319 / :356-357
 
     # ------------------------------------------------------------------
@@ -306,7 +307,7 @@ class PointCloud:
             with trace.stage("fused_kernel"):
                 fit = self._fused_fit(want_coeffs=False)
             with trace.stage("d2h"):
-                kh = engine.to_host(fit.curv[:, :2].t())
+                kh = engine.to_host(fit.kh())
             for name in ("quadratic_coefficients", "normals_quadratic", "fit_status", "K_H_sq_quadratic",
                          "k1_quadratic", "k2_quadratic"):
                 self.__dict__.pop(name, None)
@@ -342,8 +343,8 @@ class PointCloud:
             elif name == "fit_status":
                 val = engine.to_host(fit.status)
             else:
-                col = {"k1_quadratic": 2, "k2_quadratic": 3, "K_H_sq_quadratic": 4}[name]
-                val = engine.to_host(fit.curv[:, col])
+                col = {"k1_quadratic": "k1", "k2_quadratic": "k2", "K_H_sq_quadratic": "H2"}[name]
+                val = engine.to_host(fit.column(col))
             self.__dict__[name] = val
             return val
         raise AttributeError(f"'PointCloud' object has no attribute '{name}'")

@@ -104,19 +104,20 @@ static void exact_rows(const IndexView& v, uint32_t i, int k, uint32_t* out) {
 
 // kNN lists (original indices, sorted by key) + per-query path code:
 // 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback
-template <int KT>
 static void knn_impl(HostIndex* ix, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK;
     std::vector<uint32_t> list(cap), runs(54);
+    std::vector<uint32_t> hist(kHistRowBytes / 4);
+    SelectScratch sc{runs.data(), list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
     for (long long i = 0; i < v.n; ++i) {
         const Pt q = v.pts[i];
         uint32_t first = 0, last = 0;
         double d2_last = 0;
         int rc = SEL_RETRY_COARSER, level = 0;
         for (; level <= max_fast_level && level < v.num_levels; ++level) {
-            rc = knn_select<KT>(v, level, (uint32_t)i, q, k, runs.data(), list.data(), 1, cap, first, last, d2_last);
+            rc = knn_select(v, level, (uint32_t)i, q, k, sc, first, last, d2_last);
             if (rc != SEL_RETRY_COARSER) break;
         }
         const long long row = q.idx;
@@ -158,7 +159,7 @@ extern "C" {
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    PCT_DISPATCH_KT(k, knn_impl<KT>(ix, k, max_fast_level, idx, dist, code, normals, coeffs, curv, status));
+    knn_impl(ix, k, max_fast_level, idx, dist, code, normals, coeffs, curv, status);
 }
 
 void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,
