@@ -77,6 +77,7 @@ typedef struct pct_query_stats {
     int64_t level1_retries; /* queries whose k-th neighbour left the level-0 stencil */
     int64_t exact_path;     /* queries resolved by the exact (tie / expansion) kernel */
     int64_t kernel_launches;
+    int64_t unstaged;       /* queries whose chunk did not fit the shared-memory staging buffer */
 } pct_query_stats;
 
 int pct_version(void);

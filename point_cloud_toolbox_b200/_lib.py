@@ -51,6 +51,7 @@ class QueryStats(ctypes.Structure):
         ("level1_retries", c_int64),
         ("exact_path", c_int64),
         ("kernel_launches", c_int64),
+        ("unstaged", c_int64),
     ]
 
 

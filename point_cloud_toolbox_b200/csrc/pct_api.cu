@@ -58,13 +58,14 @@ int pct_index_permutation(const pct_index* ix, int32_t* perm, void* stream) {
 
 int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* stats) {
     PCT_REQUIRE(ix && stats, "pct_index_last_stats: NULL argument");
-    unsigned int h[4];
+    unsigned int h[5];
     PCT_CUDA(cudaMemcpyAsync(h, ix->stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PCT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     stats->level1_retries = h[0];
     stats->exact_path = h[1];
     stats->kernel_launches = h[2];
     stats->queries = h[3];
+    stats->unstaged = h[4];
     return PCT_OK;
 }
 

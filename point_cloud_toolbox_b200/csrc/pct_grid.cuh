@@ -291,17 +291,87 @@ struct CellRuns {
 // ---------------------------------------------------------------------------
 enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 
-// Selection scratch of one query.  On the GPU all three areas live in shared memory:
-//   runs  54 words, word w at runs[w * stride]           (27 cell runs)
-//   list  cap words, slot m at list[m * stride]          (neighbour positions)
+// Selection scratch of one query.  On the GPU all of it lives in shared memory:
+//   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
+//   list  cap entries, slot m at list[m * stride]        (neighbour positions)
 //   hist  kHistBins bytes, contiguous per query          (distance histogram)
 static constexpr int kHistBins = 64;
 static constexpr int kHistRowBytes = 68;  // 17 words per thread: odd word stride, bank-conflict free
 
+// Where the candidates of a query come from.  knn_select() and the fit only need
+//   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
+//   src.load(pos)  the record at a position handed out by scan
+// GlobalSource reads the Morton-sorted cloud through L1/L2 (positions = sorted positions);
+// StagedSource reads a region a warp has copied to shared memory (positions = slots of
+// that copy, 16 bit).
+struct GlobalSource {
+    typedef uint32_t Pos;
+    const Pt* pts;
+    CellRuns runs;
+    template <class F>
+    PCT_HD void scan(F& fn) const { runs.scan(pts, fn); }
+    PCT_HD Pt load(uint32_t pos) const { return load_pt(pts + pos); }
+};
+
+// Staged candidates.  A CTA copies, for every aligned cube of (1 << U)^3 level-0 cells
+// ("parent") its queries fall into, that cube plus a one-cell halo into shared memory:
+// a REGION of kSide^3 cells.  The points of a region are laid out cell by cell in raster
+// order (x fastest), so the three x-neighbours of a stencil row are one contiguous run
+// and the 27 cells of a query are 9 runs, found by direct indexing of a prefix table:
+//   off[c]  first staged slot of raster cell c; the tables of the CTA's regions are
+//           concatenated and cumulative, off[last + 1] = number of staged points
+template <int U>
+struct RegionShape {
+    static constexpr int kSide = (1 << U) + 2;
+    static constexpr int kCells = kSide * kSide * kSide;
+};
+
+struct StagedSource {
+    typedef uint16_t Pos;
+    const Pt* pts;        // staged records (shared memory)
+    const uint16_t* off;  // prefix table, already advanced to the query's region
+    int corner;           // raster index of the lowest cell of the query's 3x3x3 block
+    int side;             // kSide
+
+    static constexpr int kDepth = 2;
+    // One flat loop over the 9 runs, kDepth candidates per trip (see CellRuns::scan).
+    template <class F>
+    PCT_HD void scan(F& fn) const {
+        int r = 0;
+        uint32_t j = 0, e = 0;
+#pragma unroll 1
+        for (;;) {
+            uint32_t pos[kDepth];
+            bool valid[kDepth];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) {
+                while (j == e && r < 9) {
+                    const int z = (r * 11) >> 5;  // r / 3 for r < 9
+                    const int c0 = corner + side * (r - 3 * z) + side * side * z;
+                    j = off[c0];
+                    e = off[c0 + 3];
+                    ++r;
+                }
+                valid[u] = j != e;
+                pos[u] = valid[u] ? j : 0u;
+                j += valid[u] ? 1u : 0u;
+            }
+            if (!valid[0]) break;
+            Pt rec[kDepth];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u) rec[u] = pts[pos[u]];
+#pragma unroll
+            for (int u = 0; u < kDepth; ++u)
+                if (valid[u]) fn((uint16_t)pos[u], rec[u]);
+        }
+    }
+    PCT_HD Pt load(uint16_t pos) const { return pts[pos]; }
+};
+
+template <class PosT>
 struct SelectScratch {
-    uint32_t* runs;
-    uint32_t* list;
-    uint8_t* hist;
+    PosT* list;     // slot m at list[m * stride]
+    uint8_t* hist;  // kHistBins bytes, contiguous
     int stride;
     int cap;
 };
@@ -324,14 +394,12 @@ struct SelectScratch {
 //
 // On SEL_OK, list[m * stride] (m < k) holds the neighbours' sorted positions
 // (unordered), `first` / `last` the nearest / farthest by (d2 fp64, original index).
-PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, int k, const SelectScratch& sc,
-                      uint32_t& first, uint32_t& last, double& d2_last) {
-    Stencil st;
-    make_stencil(ix, level, q.x, q.y, q.z, st);
-    CellRuns runs;
-    runs.buf = sc.runs;
-    runs.stride = sc.stride;
-    runs.collect(st);
+template <class Source>
+PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
+                      const SelectScratch<typename Source::Pos>& sc, typename Source::Pos& first,
+                      typename Source::Pos& last, double& d2_last) {
+    typedef typename Source::Pos Pos;
+    const uint32_t self = q.idx;  // original indices are unique: identifies the query among the candidates
 
     // everything closer than sqrt(range2) is certain to be among the candidates
     const float cell = ix.h * ldexpf(1.f, level);
@@ -348,9 +416,9 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
         uint8_t* hist;
         uint32_t self;
         float qx, qy, qz, range2, inv_w;
-        PCT_HD void operator()(uint32_t j, const Pt& p) {
+        PCT_HD void operator()(Pos, const Pt& p) {
             const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-            if (d < range2 && j != self) {
+            if (d < range2 && p.idx != self) {
                 int b = (int)(d * inv_w);
                 b = b < kHistBins - 1 ? b : kHistBins - 1;
                 const uint8_t v = hist[b];
@@ -358,8 +426,8 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
             }
         }
     } p1;
-    p1.hist = sc.hist; p1.self = i; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w;
-    runs.scan(ix.pts, p1);
+    p1.hist = sc.hist; p1.self = self; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w;
+    src.scan(p1);
 
     // bin of the k-th neighbour
     int b = -1;
@@ -379,13 +447,14 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
     const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
 
     struct P2 {
-        uint32_t* list;
+        Pos* list;
         int stride, cap;
-        uint32_t self, n_front, n_zone, j_min;
+        uint32_t self, n_front, n_zone;
+        Pos j_min;
         float qx, qy, qz, lo, hi, d_min, d_min2, front_max, zone_min;
-        PCT_HD void operator()(uint32_t j, const Pt& p) {
+        PCT_HD void operator()(Pos j, const Pt& p) {
             const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-            if (d <= hi && j != self) {
+            if (d <= hi && p.idx != self) {
                 if (d < lo) {
                     if ((int)(n_front + n_zone) < cap) list[(size_t)n_front * stride] = j;
                     ++n_front;
@@ -403,10 +472,10 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
             }
         }
     } p2;
-    p2.list = sc.list; p2.stride = sc.stride; p2.cap = sc.cap; p2.self = i; p2.n_front = 0; p2.n_zone = 0; p2.j_min = 0;
+    p2.list = sc.list; p2.stride = sc.stride; p2.cap = sc.cap; p2.self = self; p2.n_front = 0; p2.n_zone = 0; p2.j_min = 0;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi; p2.d_min = 3.4e38f; p2.d_min2 = 3.4e38f;
     p2.front_max = 0.f; p2.zone_min = 3.4e38f;
-    runs.scan(ix.pts, p2);
+    src.scan(p2);
 
     const int n_front = (int)p2.n_front;
     int n_zone = (int)p2.n_zone;
@@ -419,14 +488,15 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
     if (need < 1 || need > n_zone) return SEL_EXACT;   // (a saturated histogram bin can break the invariant)
 
     // exact choice inside the boundary zone: `need` successive minima of (d2, index)
-    uint32_t* zone = sc.list + (size_t)(sc.cap - n_zone) * sc.stride;
+    Pos* zone = sc.list + (size_t)(sc.cap - n_zone) * sc.stride;
     for (int t = 0; t < need; ++t) {
         double bd = 0.0;
-        uint32_t bi = 0, bj = 0;
+        uint32_t bi = 0;
+        Pos bj = 0;
         int bm = 0;
         for (int m = 0; m < n_zone; ++m) {
-            const uint32_t j = zone[(size_t)m * sc.stride];
-            const Pt p = load_pt(ix.pts + j);
+            const Pos j = zone[(size_t)m * sc.stride];
+            const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
         }
@@ -446,8 +516,8 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
         double bd = 0.0;
         uint32_t bi = 0;
         for (int m = 0; m < k; ++m) {
-            const uint32_t j = sc.list[(size_t)m * sc.stride];
-            const Pt p = load_pt(ix.pts + j);
+            const Pos j = sc.list[(size_t)m * sc.stride];
+            const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
         }
@@ -455,27 +525,29 @@ PCT_HD int knn_select(const IndexView& ix, int level, uint32_t i, const Pt& q, i
     return SEL_OK;
 }
 
-// Neighbourhood adaptor over a list of sorted positions (fused kNN path).
+// Neighbourhood adaptor over a list of candidate positions (fused kNN path).
+template <class Source>
 struct ListNeighbourhood {
-    const IndexView* ix;
-    const uint32_t* list;
+    typedef typename Source::Pos Pos;
+    const Source* src;
+    const Pos* list;
     int stride, count;
     Pt q;
-    uint32_t first, last;
+    Pos first, last;
     template <class F>
     PCT_HD void pass(F& fn) const {
         if (count <= 0) return;
-        Pt p = load_pt(ix->pts + list[0]);
+        Pt p = src->load(list[0]);
 #pragma unroll 1
         for (int m = 0; m < count; ++m) {
             const int mn = m + 1 < count ? m + 1 : m;
-            const Pt nxt = load_pt(ix->pts + list[(size_t)mn * stride]);  // in flight during the fp64 work below
+            const Pt nxt = src->load(list[(size_t)mn * stride]);  // in flight during the fp64 work below
             fn.add(fsub_rn(p.x, q.x), fsub_rn(p.y, q.y), fsub_rn(p.z, q.z));
             p = nxt;
         }
     }
     PCT_HD void reference(float& rx, float& ry, float& rz) const {
-        const Pt a = load_pt(ix->pts + first), b = load_pt(ix->pts + last);
+        const Pt a = src->load(first), b = src->load(last);
         rx = fsub_rn(fsub_rn(b.x, q.x), fsub_rn(a.x, q.x));  // ref :286 on fp32 centred points
         ry = fsub_rn(fsub_rn(b.y, q.y), fsub_rn(a.y, q.y));
         rz = fsub_rn(fsub_rn(b.z, q.z), fsub_rn(a.z, q.z));

@@ -238,6 +238,8 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     PCT_CUDA(cudaGetDevice(&ix->device));
     ix->stream = s;
     PCT_CUDA(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, ix->device));
+    PCT_CUDA(cudaDeviceGetAttribute(&ix->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ix->device));
+    PCT_CUDA(cudaDeviceGetAttribute(&ix->smem_per_block_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device));
 
     // temporaries come from the stream-ordered pool; keep freed blocks cached across builds
     {

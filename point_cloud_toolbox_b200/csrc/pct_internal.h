@@ -14,10 +14,12 @@ struct pct_index {
     pct::IndexView view;       // device pointers inside
     pct::Pt* pts = nullptr;    // N sorted records
     pct::HashSlot* table_mem = nullptr;  // all level tables, one allocation
-    unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries]
+    unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries, unstaged, -, -, -]
     pct_index_info info{};
     int device = 0;
     int sm_count = 148;
+    int smem_per_sm = 233472;           // shared memory of one SM
+    int smem_per_block_optin = 232448;  // largest dynamic allocation of one block
     cudaStream_t stream = nullptr;  // stream the index was built on; its memory is freed in that stream's order
 };
 

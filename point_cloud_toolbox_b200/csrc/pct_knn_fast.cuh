@@ -1,5 +1,17 @@
-// Thread-per-query kNN kernel: histogram selection, exact neighbour set in shared
+// Thread-per-query kNN kernels: histogram selection, exact neighbour set in shared
 // memory, fused fp64 fit.  One kernel for every k (the selection is O(candidates)).
+//
+//   knn_staged_kernel<U, FUSED>  the throughput path.  A CTA owns 128 consecutive
+//       Morton-sorted queries, copies the cells they can reach (their parent cubes plus
+//       a one-cell halo) into shared memory with coalesced 16-byte loads, and every
+//       thread then selects and fits its own query out of that copy.  The cloud is read
+//       from L2/HBM a handful of times per query instead of once per candidate per pass,
+//       and no thread probes the hash table for its own 27 cells.
+//   knn_fast_kernel<FUSED>       the same selection reading candidates through L1/L2.
+//       Runs over queued queries only: chunks whose regions do not fit the staging
+//       buffer (level 0) and queries whose k-th neighbour left the level-0 block
+//       (level 1).
+//
 // See pct_query.cu for the overview of the query path.
 #pragma once
 
@@ -19,15 +31,52 @@ struct QueryRange {
 };
 
 struct Queues {
-    uint32_t* retry;   // queries to redo one level coarser (may be null: go straight to exact)
-    uint32_t* exact;   // queries for the exact kernel
-    unsigned int* counters;  // [0] = retry count, [1] = exact count
+    uint32_t* retry;     // queries to redo one level coarser (may be null: go straight to exact)
+    uint32_t* exact;     // queries for the exact kernel
+    uint32_t* fallback;  // staged kernel only: queries of chunks that could not be staged
+    unsigned int* counters;  // [0] = retry count, [1] = exact count, [2] = fallback count
 };
 
 __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, uint32_t orig) {
     return qr.layout == PCT_LAYOUT_ORIGINAL ? (long long)orig : (long long)i - qr.q_begin;
 }
 
+// What a query does once its k neighbours sit in list[m * stride]: the fused fit, or the
+// ordered (index, distance) rows of plant_kdtree (ref :78-85).
+template <bool FUSED, class Source>
+__device__ __forceinline__ void emit_query(const Source& src, const typename Source::Pos* list, int stride, int k,
+                                           const Pt& q, typename Source::Pos first, typename Source::Pos last,
+                                           long long row, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
+                                           const FitOutputs& out) {
+    if (FUSED) {
+        ListNeighbourhood<Source> nb;
+        nb.src = &src; nb.list = list; nb.stride = stride; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+        FitResult r;
+        r.status = 0;
+        fit_neighbourhood(nb, r);
+        store_fit(out, row, r);
+    } else {
+        // ordered rows: successive minima of (d2, index) over the k members
+        double pd = -1.0;
+        uint32_t pi = 0;
+        for (int m = 0; m < k; ++m) {
+            double bd = 1.0e300;
+            uint32_t bi = 0xffffffffu;
+            for (int c = 0; c < k; ++c) {
+                const Pt p = src.load(list[(size_t)c * stride]);
+                const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
+            }
+            if (out_idx) out_idx[row * k + m] = (int32_t)bi;
+            if (out_dist) out_dist[row * k + m] = (float)sqrt(bd);
+            pd = bd; pi = bi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// candidates through L1/L2
+// ---------------------------------------------------------------------------
 // shared memory of one block: [54][kBlock] cell runs, [cap][kBlock] neighbour list, [kBlock][68 B] histograms
 __host__ __device__ inline size_t fast_smem_bytes(int cap) {
     return sizeof(uint32_t) * (size_t)(54 + cap) * kBlock + (size_t)kHistRowBytes * kBlock;
@@ -38,8 +87,11 @@ __global__ void __launch_bounds__(kBlock, 4)
 knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const int k, const int cap,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
     extern __shared__ uint32_t smem_words[];
-    SelectScratch sc;
-    sc.runs = smem_words + threadIdx.x;
+    GlobalSource src;
+    src.pts = ix.pts;
+    src.runs.buf = smem_words + threadIdx.x;
+    src.runs.stride = kBlock;
+    SelectScratch<uint32_t> sc;
     sc.list = smem_words + 54 * kBlock + threadIdx.x;
     sc.hist = reinterpret_cast<uint8_t*>(smem_words + (54 + cap) * kBlock) + kHistRowBytes * threadIdx.x;
     sc.stride = kBlock;
@@ -51,10 +103,12 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         if (t >= total) continue;
         const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
         const Pt q = load_pt(ix.pts + i);
-        uint32_t* list = sc.list;
+        Stencil st;
+        make_stencil(ix, level, q.x, q.y, q.z, st);
+        src.runs.collect(st);
         uint32_t first = 0, last = 0;
         double d2_last = 0.0;
-        const int rc = knn_select(ix, level, i, q, k, sc, first, last, d2_last);
+        const int rc = knn_select(ix, st, level, src, q, k, sc, first, last, d2_last);
         if (rc != SEL_OK) {
             if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
                 qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -63,33 +117,201 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
             }
             continue;
         }
-        const long long row = out_row(qr, i, q.idx);
-        if (FUSED) {
-            ListNeighbourhood nb;
-            nb.ix = &ix; nb.list = list; nb.stride = kBlock; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
-            FitResult r;
-            r.status = 0;
-            fit_neighbourhood(nb, r);
-            store_fit(out, row, r);
-        } else {
-            // ordered rows: successive minima of (d2, index) over the k members
-            double pd = -1.0;
-            uint32_t pi = 0;
-            for (int m = 0; m < k; ++m) {
-                double bd = 1.0e300;
-                uint32_t bi = 0xffffffffu;
-                for (int c = 0; c < k; ++c) {
-                    const Pt p = load_pt(ix.pts + list[c * kBlock]);
-                    const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
-                    if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
-                }
-                if (out_idx) out_idx[row * k + m] = (int32_t)bi;
-                if (out_dist) out_dist[row * k + m] = (float)sqrt(bd);
-                pd = bd; pi = bi;
-            }
-        }
+        emit_query<FUSED>(src, sc.list, kBlock, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
     }
 }
+
+// ---------------------------------------------------------------------------
+// candidates staged in shared memory
+// ---------------------------------------------------------------------------
+template <int U>
+struct StageShape : RegionShape<U> {
+    // a chunk of 128 Morton-consecutive queries touches this many parent cubes at most
+    static constexpr int kMaxRegions = U >= 2 ? 4 : 8;
+    static constexpr int kTable = kMaxRegions * RegionShape<U>::kCells;
+    static constexpr int kItemsPerThread = (kTable + kBlock - 1) / kBlock;
+};
+
+struct StagedCell {
+    uint32_t first;  // position in the sorted cloud
+    uint16_t slot;   // first staged slot
+    uint16_t count;
+};
+
+// dynamic shared memory of the staged kernel, in this order (every part 16-byte aligned):
+//   Pt       pts[cap_pts]
+//   uint16   off[kTable + 8]
+//   int      hdr[32]                 region origins, block-scan partials, flags
+//   scratch  max(per-query scratch, staging temporaries)
+//       per query  : uint16 list[cap][kBlock], uint8 hist[kBlock][68]
+//       temporaries: uint32 first[kTable], uint16 count[kTable], StagedCell cells[kTable]
+template <int U>
+__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
+    const size_t per_query = ((size_t)cap * sizeof(uint16_t) + kHistRowBytes) * kBlock;
+    const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
+    const size_t scratch = per_query > temps ? per_query : temps;
+    const size_t off = ((size_t)(StageShape<U>::kTable + 8) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    return sizeof(Pt) * (size_t)cap_pts + off + 32 * sizeof(int) + ((scratch + 15) & ~(size_t)15);
+}
+
+#if defined(__CUDACC__)
+template <int U, bool FUSED>
+__global__ void __launch_bounds__(kBlock, 4)
+knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
+    typedef StageShape<U> Shape;
+    constexpr int S = Shape::kSide, C = Shape::kCells;
+    extern __shared__ uint4 smem_u4[];
+    Pt* const pts_s = reinterpret_cast<Pt*>(smem_u4);
+    uint16_t* const off = reinterpret_cast<uint16_t*>(pts_s + cap_pts);
+    int* const hdr = reinterpret_cast<int*>(reinterpret_cast<char*>(off) + (((Shape::kTable + 8) * sizeof(uint16_t) + 15) & ~(size_t)15));
+    char* const scratch = reinterpret_cast<char*>(hdr + 32);
+    // hdr: [0..3] warp partials (points), [4..7] warp partials (cells / heads), [8] regions, [9] flags,
+    //      [10] queue base, [12 + 3 r ..] origin of region r
+    int* const org = hdr + 12;
+    // staging temporaries (dead before the per-query scratch is first written)
+    uint32_t* const t_first = reinterpret_cast<uint32_t*>(scratch);
+    StagedCell* const t_cells = reinterpret_cast<StagedCell*>(t_first + Shape::kTable);
+    uint16_t* const t_count = reinterpret_cast<uint16_t*>(t_cells + Shape::kTable);
+    unsigned long long* const t_parent = reinterpret_cast<unsigned long long*>(t_cells);  // [kBlock], before the cells exist
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long total = qr.q_end - qr.q_begin;
+    const long long tq = (long long)blockIdx.x * kBlock + t;
+    const bool active = tq < total;
+    const uint32_t i = (uint32_t)(qr.q_begin + (active ? tq : total - 1));
+    const Pt q = load_pt(ix.pts + i);
+
+    // ---- A. the parent cubes of the chunk (Morton order keeps equal parents adjacent)
+    int cx, cy, cz;
+    cell_of(ix, q.x, q.y, q.z, cx, cy, cz);
+    const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
+                                      ((unsigned long long)(cz >> U) << 42);
+    t_parent[t] = parent;
+    if (t == 0) hdr[9] = 0;
+    __syncthreads();
+    const bool head = t == 0 || t_parent[t - 1] != parent;
+    const unsigned int heads = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) hdr[4 + warp] = __popc(heads);
+    __syncthreads();
+    int region = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+    for (int w = 0; w < warp; ++w) region += hdr[4 + w];
+    const int regions = hdr[4] + hdr[5] + hdr[6] + hdr[7];
+    if (regions > Shape::kMaxRegions) {
+        if (t == 0) hdr[9] = 1;
+    } else if (head) {
+        org[3 * region] = ((cx >> U) << U) - 1;
+        org[3 * region + 1] = ((cy >> U) << U) - 1;
+        org[3 * region + 2] = ((cz >> U) << U) - 1;
+    }
+    __syncthreads();  // t_parent is dead from here on
+
+    // ---- B. one hash probe per region cell
+    const int n_table = regions > Shape::kMaxRegions ? 0 : regions * C;
+    for (int item = t; item < n_table; item += kBlock) {
+        const int r = item / C, c = item - r * C;
+        const int lz = c / (S * S), ly = (c - lz * S * S) / S, lx = c - lz * S * S - ly * S;
+        const int gx = org[3 * r] + lx, gy = org[3 * r + 1] + ly, gz = org[3 * r + 2] + lz;
+        uint32_t s = 0, e = 0;
+        if (gx >= 0 && gx < ix.dims[0] && gy >= 0 && gy < ix.dims[1] && gz >= 0 && gz < ix.dims[2])
+            if (!lookup_cell(ix.lvl[0], morton3((uint32_t)gx, (uint32_t)gy, (uint32_t)gz), s, e)) s = e = 0;
+        uint32_t n = e - s;
+        if (n > 0xffffu) { n = 0xffffu; hdr[9] = 1; }
+        t_first[item] = s;
+        t_count[item] = (uint16_t)n;
+    }
+    __syncthreads();
+
+    // ---- C. prefix sums over the table: staged slot of every cell, list of non-empty cells
+    uint32_t my_pts = 0, my_cells = 0;
+#pragma unroll
+    for (int u = 0; u < Shape::kItemsPerThread; ++u) {
+        const int item = t * Shape::kItemsPerThread + u;
+        const uint32_t n = item < n_table ? t_count[item] : 0u;
+        my_pts += n;
+        my_cells += n ? 1u : 0u;
+    }
+    uint32_t inc_pts = my_pts, inc_cells = my_cells;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc_pts, o), b = __shfl_up_sync(0xffffffffu, inc_cells, o);
+        if (lane >= o) { inc_pts += a; inc_cells += b; }
+    }
+    if (lane == 31) { hdr[warp] = (int)inc_pts; hdr[4 + warp] = (int)inc_cells; }
+    __syncthreads();
+    uint32_t run = inc_pts - my_pts, cell = inc_cells - my_cells;
+    for (int w = 0; w < warp; ++w) { run += (uint32_t)hdr[w]; cell += (uint32_t)hdr[4 + w]; }
+    const uint32_t staged = (uint32_t)(hdr[0] + hdr[1] + hdr[2] + hdr[3]);
+    const int n_cells = hdr[4] + hdr[5] + hdr[6] + hdr[7];
+    const bool unstaged = hdr[9] != 0 || staged > (uint32_t)cap_pts;
+    if (unstaged) {
+        // the chunk goes to the L1/L2 kernel as a whole
+        unsigned int n_active = __popc(__ballot_sync(0xffffffffu, active));
+        __syncthreads();
+        if (lane == 0) hdr[warp] = (int)n_active;
+        __syncthreads();
+        if (t == 0) hdr[10] = (int)atomicAdd(&qu.counters[2], (unsigned int)(hdr[0] + hdr[1] + hdr[2] + hdr[3]));
+        __syncthreads();
+        if (active) qu.fallback[(unsigned int)hdr[10] + (unsigned int)t] = i;  // active threads are a prefix of the block
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < Shape::kItemsPerThread; ++u) {
+        const int item = t * Shape::kItemsPerThread + u;
+        if (item < n_table) {
+            const uint32_t n = t_count[item];
+            off[item] = (uint16_t)run;
+            if (n) {
+                StagedCell sc;
+                sc.first = t_first[item]; sc.slot = (uint16_t)run; sc.count = (uint16_t)n;
+                t_cells[cell++] = sc;
+            }
+            run += n;
+        }
+    }
+    if (t == 0) off[n_table] = (uint16_t)staged;
+    __syncthreads();
+
+    // ---- D. copy the non-empty cells, eight lanes per cell
+    for (int e = t >> 3; e < n_cells; e += kBlock / 8) {
+        const StagedCell sc = t_cells[e];
+        for (uint32_t m = t & 7; m < sc.count; m += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(ix.pts + sc.first + m));
+            reinterpret_cast<float4*>(pts_s)[sc.slot + m] = v;
+        }
+    }
+    __syncthreads();  // temporaries are dead, the per-query scratch may be written
+    if (!active) return;
+
+    // ---- E. select out of the staged copy
+    const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
+    StagedSource src;
+    src.pts = pts_s;
+    src.off = off + region * C;
+    src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
+    src.side = S;
+    SelectScratch<uint16_t> sel;
+    sel.list = reinterpret_cast<uint16_t*>(scratch) + t;
+    sel.hist = reinterpret_cast<uint8_t*>(scratch) + sizeof(uint16_t) * (size_t)cap * kBlock + kHistRowBytes * t;
+    sel.stride = kBlock;
+    sel.cap = cap;
+    Stencil st;
+    make_stencil(ix, 0, q.x, q.y, q.z, st);
+    uint16_t first = 0, last = 0;
+    double d2_last = 0.0;
+    const int rc = knn_select(ix, st, 0, src, q, k, sel, first, last, d2_last);
+    if (rc != SEL_OK) {
+        if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
+            qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
+        } else {
+            qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
+        }
+        return;
+    }
+    // ---- F. fit (or ordered rows) out of the staged copy
+    emit_query<FUSED>(src, sel.list, kBlock, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
+}
+#endif
 
 struct FastLaunch {
     const pct_index* ix;
@@ -101,29 +323,52 @@ struct FastLaunch {
     FitOutputs out;
     uint32_t* retry1;
     uint32_t* exactq;
+    uint32_t* fallback0;
     unsigned int* counters;
     cudaStream_t s;
 };
 
-// level 0 over the whole range, then level 1 over whatever level 0 queued
+// staged level 0 over the whole range; L1/L2 kernel at level 0 over the chunks that could
+// not be staged, then at level 1 over whatever level 0 queued
 template <bool FUSED>
 static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const IndexView& v = a.ix->view;
     const long long nq = a.qr.q_end - a.qr.q_begin;
     const size_t smem = fast_smem_bytes(a.cap);
-    const int grid_all = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 64);
-    const int grid_retry = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
+    const int grid_list = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
     auto kern = knn_fast_kernel<FUSED>;
     PCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.counters};
-    kern<<<grid_all, kBlock, smem, a.s>>>(v, 0, a.qr, a.k, a.cap, a.idx, a.dist, a.out, q0);
-    ++*launches;
+    Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.fallback0, a.counters};
+
+    // staging buffer: what is left of a quarter SM's shared memory after the fixed parts
+    constexpr int U = 2;
+    auto staged = knn_staged_kernel<U, FUSED>;
+    const size_t fixed = staged_smem_bytes<U>(a.cap, 0);
+    const size_t budget = (size_t)a.ix->smem_per_sm / 4 - 1024;  // __launch_bounds__(kBlock, 4)
+    int cap_pts = fixed + 16 * 512 <= budget ? (int)((budget - fixed) / sizeof(Pt)) : 512;
+    if (cap_pts > 0xffff) cap_pts = 0xffff;
+    const size_t smem_staged = staged_smem_bytes<U>(a.cap, cap_pts);
+    if (smem_staged <= (size_t)a.ix->smem_per_block_optin) {
+        PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
+        const long long chunks = (nq + kBlock - 1) / kBlock;
+        staged<<<(unsigned int)chunks, kBlock, smem_staged, a.s>>>(v, a.qr, a.k, a.cap, cap_pts, a.idx, a.dist, a.out, q0);
+        ++*launches;
+        QueryRange qf = a.qr;
+        qf.list = a.fallback0;
+        qf.count = a.counters + 2;
+        kern<<<grid_list, kBlock, smem, a.s>>>(v, 0, qf, a.k, a.cap, a.idx, a.dist, a.out, q0);
+        ++*launches;
+    } else {
+        const int grid_all = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 64);
+        kern<<<grid_all, kBlock, smem, a.s>>>(v, 0, a.qr, a.k, a.cap, a.idx, a.dist, a.out, q0);
+        ++*launches;
+    }
     if (v.num_levels > 1) {
         QueryRange q1 = a.qr;
         q1.list = a.retry1;
         q1.count = a.counters;
-        Queues qq{nullptr, a.exactq, a.counters};
-        kern<<<grid_retry, kBlock, smem, a.s>>>(v, 1, q1, a.k, a.cap, a.idx, a.dist, a.out, qq);
+        Queues qq{nullptr, a.exactq, nullptr, a.counters};
+        kern<<<grid_list, kBlock, smem, a.s>>>(v, 1, q1, a.k, a.cap, a.idx, a.dist, a.out, qq);
         ++*launches;
     }
     PCT_CUDA(cudaGetLastError());

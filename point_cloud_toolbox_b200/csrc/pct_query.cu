@@ -115,8 +115,10 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
         }
         __syncwarp();
         if (FUSED && lane == 0) {
-            ListNeighbourhood nb;
-            nb.ix = &ix; nb.list = mine; nb.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
+            GlobalSource src;
+            src.pts = ix.pts;
+            ListNeighbourhood<GlobalSource> nb;
+            nb.src = &src; nb.list = mine; nb.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
             FitResult r;
             r.status = ST_EXACT_PATH;
             fit_neighbourhood(nb, r);
@@ -131,6 +133,7 @@ __global__ void publish_stats_kernel(const unsigned int* counters, unsigned int*
     stats[1] = counters[1];
     stats[2] = launches;
     stats[3] = queries;
+    stats[4] = counters[2];
 }
 
 // ---- epsilon ball ----------------------------------------------------------
@@ -220,14 +223,15 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     const int cap = k + PCT_TIE_SLACK;
     uint32_t* queues = nullptr;
     unsigned int* counters = nullptr;
-    PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 2 * (size_t)nq, s));
+    PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 3 * (size_t)nq, s));
     PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 4, s));
     PCT_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, s));
     uint32_t* retry1 = queues;
     uint32_t* exactq = queues + nq;
+    uint32_t* fallback0 = queues + 2 * nq;
     QueryRange qr{q_begin, q_end, nullptr, nullptr, layout};
     unsigned int launches = 0;
-    FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, counters, s};
+    FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, fallback0, counters, s};
     int rc = PCT_OK;
     rc = launch_fast(fl, &launches);
     if (rc != PCT_OK) return rc;

@@ -43,7 +43,7 @@ def main():
             ix.curvature_knn(k, want_coeffs=False)
             st = ix.last_stats()
             print(f"N={n} k={k} k_hint={hint} ppc={n / info.cells_level0:.2f} build={t_build:.2f}ms fused={t_q:.2f}ms "
-                  f"({n / t_q / 1e3:.1f} Mq/s) lists={t_l:.2f}ms retries={st.level1_retries} exact={st.exact_path}", flush=True)
+                  f"({n / t_q / 1e3:.1f} Mq/s) lists={t_l:.2f}ms retries={st.level1_retries} exact={st.exact_path} unstaged={st.unstaged}", flush=True)
             ix.close()
 
 

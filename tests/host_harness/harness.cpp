@@ -18,6 +18,7 @@ using namespace pct;
 struct HostIndex {
     std::vector<Pt> pts;
     std::vector<std::vector<HashSlot>> tables;
+    std::vector<uint32_t> pos_of;  // original index -> sorted position
     IndexView view;
 };
 
@@ -60,6 +61,8 @@ void* h_build(const float* xyz, long long n, float h) {
         const uint32_t o = keyed[i].second;
         ix->pts[i] = Pt{xyz[3 * o], xyz[3 * o + 1], xyz[3 * o + 2], o};
     }
+    ix->pos_of.resize(n);
+    for (long long i = 0; i < n; ++i) ix->pos_of[ix->pts[i].idx] = (uint32_t)i;
     ix->tables.resize(v.num_levels);
     for (int L = 0; L < v.num_levels; ++L) {
         long long cells = 0;
@@ -102,22 +105,103 @@ static void exact_rows(const IndexView& v, uint32_t i, int k, uint32_t* out) {
     for (int m = 0; m < k; ++m) out[m] = all[m + 1].second;
 }
 
+// Host emulation of the staged kernel's region tables (csrc/pct_knn_fast.cuh, steps A-D) for one
+// chunk of 128 consecutive sorted queries: same geometry, same table layout, serial code.
+template <int U>
+struct HostStage {
+    static constexpr int S = RegionShape<U>::kSide, C = RegionShape<U>::kCells;
+    std::vector<Pt> pts;
+    std::vector<uint16_t> off;
+    std::vector<int> org;       // 3 per region
+    std::vector<int> region_of; // per query of the chunk
+    bool ok = true;
+    void build(const IndexView& v, long long begin, long long end, int max_regions, size_t cap_pts) {
+        pts.clear(); off.clear(); org.clear(); region_of.clear();
+        unsigned long long prev = ~0ull;
+        for (long long i = begin; i < end; ++i) {
+            int cx, cy, cz;
+            cell_of(v, v.pts[i].x, v.pts[i].y, v.pts[i].z, cx, cy, cz);
+            const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
+                                              ((unsigned long long)(cz >> U) << 42);
+            if (i == begin || parent != prev) {
+                org.push_back(((cx >> U) << U) - 1);
+                org.push_back(((cy >> U) << U) - 1);
+                org.push_back(((cz >> U) << U) - 1);
+            }
+            prev = parent;
+            region_of.push_back((int)org.size() / 3 - 1);
+        }
+        const int regions = (int)org.size() / 3;
+        ok = regions <= max_regions;
+        if (!ok) return;
+        for (int r = 0; r < regions; ++r)
+            for (int c = 0; c < C; ++c) {
+                const int lz = c / (S * S), ly = (c - lz * S * S) / S, lx = c - lz * S * S - ly * S;
+                const int gx = org[3 * r] + lx, gy = org[3 * r + 1] + ly, gz = org[3 * r + 2] + lz;
+                uint32_t s = 0, e = 0;
+                if (gx >= 0 && gx < v.dims[0] && gy >= 0 && gy < v.dims[1] && gz >= 0 && gz < v.dims[2])
+                    if (!lookup_cell(v.lvl[0], morton3((uint32_t)gx, (uint32_t)gy, (uint32_t)gz), s, e)) s = e = 0;
+                off.push_back((uint16_t)pts.size());
+                if (e - s > 0xffffu || pts.size() + (e - s) > cap_pts) { ok = false; return; }
+                for (uint32_t j = s; j < e; ++j) pts.push_back(v.pts[j]);
+            }
+        off.push_back((uint16_t)pts.size());
+    }
+};
+
 // kNN lists (original indices, sorted by key) + per-query path code:
-// 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback
-static void knn_impl(HostIndex* ix, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
+// 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback, +50 = staged source.
+// staged_u: 0 = candidates straight from the sorted cloud, 1 / 2 = staged regions of (1 << U)^3 cells
+template <int U>
+static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int32_t* idx, float* dist, int32_t* code,
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK;
     std::vector<uint32_t> list(cap), runs(54);
+    std::vector<uint16_t> list16(cap);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
-    SelectScratch sc{runs.data(), list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
+    SelectScratch<uint32_t> sc{list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
+    SelectScratch<uint16_t> sc16{list16.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
+    GlobalSource gsrc;
+    gsrc.pts = v.pts;
+    gsrc.runs.buf = runs.data();
+    gsrc.runs.stride = 1;
+    HostStage<(U > 0 ? U : 1)> stage;
     for (long long i = 0; i < v.n; ++i) {
         const Pt q = v.pts[i];
+        if (U > 0 && i % 128 == 0)
+            stage.build(v, i, std::min<long long>(i + 128, v.n), U >= 2 ? 4 : 8, (size_t)cap_pts);
         uint32_t first = 0, last = 0;
         double d2_last = 0;
         int rc = SEL_RETRY_COARSER, level = 0;
+        bool staged = false;
         for (; level <= max_fast_level && level < v.num_levels; ++level) {
-            rc = knn_select(v, level, (uint32_t)i, q, k, sc, first, last, d2_last);
+            Stencil st;
+            make_stencil(v, level, q.x, q.y, q.z, st);
+            if (U > 0 && level == 0 && stage.ok) {
+                constexpr int S = RegionShape<(U > 0 ? U : 1)>::kSide, C = RegionShape<(U > 0 ? U : 1)>::kCells;
+                const int r = stage.region_of[i % 128];
+                int cx, cy, cz;
+                cell_of(v, q.x, q.y, q.z, cx, cy, cz);
+                const int lx = cx - stage.org[3 * r], ly = cy - stage.org[3 * r + 1], lz = cz - stage.org[3 * r + 2];
+                StagedSource ssrc;
+                ssrc.pts = stage.pts.data();
+                ssrc.off = stage.off.data() + r * C;
+                ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
+                ssrc.side = S;
+                uint16_t f16 = 0, l16 = 0;
+                rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                if (rc == SEL_OK) {
+                    // staged slots -> sorted positions, so that the rest of this routine is shared
+                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[list16[m]].idx];
+                    first = ix->pos_of[stage.pts[f16].idx];
+                    last = ix->pos_of[stage.pts[l16].idx];
+                    staged = true;
+                }
+            } else {
+                gsrc.runs.collect(st);
+                rc = knn_select(v, st, level, gsrc, q, k, sc, first, last, d2_last);
+            }
             if (rc != SEL_RETRY_COARSER) break;
         }
         const long long row = q.idx;
@@ -134,15 +218,15 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int32_t* idx, flo
             });
             if (list[0] != first || list[k - 1] != last) { code[row] = -1; continue; }  // internal inconsistency
         }
-        code[row] = exact ? 100 : level;
+        code[row] = exact ? 100 : level + (staged ? 50 : 0);
         for (int m = 0; m < k; ++m) {
             const Pt p = v.pts[list[m]];
             if (idx) idx[row * k + m] = (int32_t)p.idx;
             if (dist) dist[row * k + m] = (float)sqrt(dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z));
         }
         if (curv) {
-            ListNeighbourhood nb;
-            nb.ix = &v; nb.list = list.data(); nb.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+            ListNeighbourhood<GlobalSource> nb;
+            nb.src = &gsrc; nb.list = list.data(); nb.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
             FitResult r;
             r.status = exact ? ST_EXACT_PATH : 0;
             fit_neighbourhood(nb, r);
@@ -159,7 +243,15 @@ extern "C" {
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    knn_impl(ix, k, max_fast_level, idx, dist, code, normals, coeffs, curv, status);
+    knn_impl<0>(ix, k, max_fast_level, 0, idx, dist, code, normals, coeffs, curv, status);
+}
+
+// same through the staged source (level 0), staging buffer of cap_pts points
+void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int32_t* idx, float* dist, int32_t* code,
+                  float* normals, float* coeffs, float* curv, uint8_t* status) {
+    HostIndex* ix = (HostIndex*)p;
+    if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
+    else knn_impl<2>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
 }
 
 void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,

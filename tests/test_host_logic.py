@@ -29,6 +29,7 @@ def harness():
     lib.h_build.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float]
     lib.h_destroy.argtypes = [ctypes.c_void_p]
     lib.h_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+    lib.h_knn_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
     lib.h_fit_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5
     lib.h_ball.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
     return lib
@@ -38,15 +39,18 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=2048):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
     out = dict(idx=np.zeros((n, k), np.int32), dist=np.zeros((n, k), np.float32), code=np.full(n, -9, np.int32),
                normal=np.zeros((n, 3), np.float32), coeffs=np.zeros((n, 6), np.float32), curv=np.zeros((n, 5), np.float32),
                status=np.zeros(n, np.uint8))
-    lib.h_knn(ix, k, max_fast_level, P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]),
-              P(out["curv"]), P(out["status"]))
+    args = (P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]), P(out["curv"]), P(out["status"]))
+    if staged_u:
+        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, *args)
+    else:
+        lib.h_knn(ix, k, max_fast_level, *args)
     lib.h_destroy(ix)
     out.update(K=out["curv"][:, 0], H=out["curv"][:, 1], k1=out["curv"][:, 2], k2=out["curv"][:, 3])
     return out
@@ -67,6 +71,39 @@ def test_search_and_fit_logic_against_oracle(harness, name, k, stride):
     # the frame is the reference's Rodrigues frame, so even the coefficients agree
     scale = np.abs(ref["coeffs"]).max(axis=1, keepdims=True)
     assert np.quantile(np.abs(got["coeffs"] - ref["coeffs"]) / scale, 0.999) < 1e-5
+
+
+@pytest.mark.parametrize("staged_u", [1, 2])
+def test_staged_source_gives_the_same_rows(harness, bunny, staged_u):
+    """The staged kernel's region tables (host emulation of its steps A-D) feed the same selection."""
+    pts = bunny[::3]
+    k = 20
+    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+    h = 1.25 * float(np.median(ref_dist[:, -1]))
+    got = run_knn(harness, pts, k, h, staged_u=staged_u)
+    assert (got["code"] >= 0).all()
+    assert np.mean(got["code"] == 50) > 0.8, np.bincount(got["code"])  # most queries are answered out of the staged copy
+    assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0
+    assert np.array_equal(got["dist"], ref_dist)
+    # a staging buffer that is too small sends chunks to the L1/L2 path; nothing else changes
+    small = run_knn(harness, pts, k, h, staged_u=staged_u, cap_pts=600)
+    assert 0.0 < np.mean(small["code"] == 50) < np.mean(got["code"] == 50)
+    assert np.array_equal(small["idx"], got["idx"])
+
+
+def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
+    rng = np.random.default_rng(5)
+    g = np.arange(9, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    base = rng.normal(size=(1200, 3)).astype(np.float32)
+    dup = np.concatenate((base, base[:150]))
+    tiny = rng.normal(size=(23, 3)).astype(np.float32)
+    for name, pts, k, h in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+        for u in (1, 2):
+            got = run_knn(harness, pts, k, h, staged_u=u)
+            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u)
+            assert np.array_equal(got["dist"], ref_dist), (name, u)
 
 
 def test_cell_size_never_changes_the_answer(harness, bunny):
