@@ -22,7 +22,13 @@
 // tau * (1 + 2.5e-6) where tau is the k-th smallest d32 (proof in DESIGN.md).
 #pragma once
 
+#include "pct_dispatch.h"
 #include "pct_math.cuh"
+
+// host test harness only: lets a CPU build count which way pass 2 went
+#ifndef PCT_SELECT_TRACE
+#define PCT_SELECT_TRACE(used_list)
+#endif
 
 namespace pct {
 
@@ -54,6 +60,8 @@ struct IndexView {
     int dims[3];       // level-0 grid size
     int bits;          // bits per axis of the Morton key
     int num_levels;    // tables for levels 0 .. num_levels-1 (last one: a single cell)
+    int volumetric;    // density pilot saw a space-filling cloud (intrinsic dimension > 2.5), not a surface
+    float cut_gain;    // head-room of the k-th-distance estimate used to pre-collect candidates
     LevelTable lvl[kMaxLevels];
 };
 
@@ -281,7 +289,7 @@ struct CellRuns {
             for (int u = 0; u < kDepth; ++u) rec[u] = load_pt(pts + pos[u]);
 #pragma unroll
             for (int u = 0; u < kDepth; ++u)
-                if (valid[u]) fn(pos[u], rec[u]);
+                if (valid[u]) fn(pos[u], rec[u], true);
         }
     }
 };
@@ -301,9 +309,9 @@ static constexpr int kHistRowBytes = 68;  // 17 words per thread: odd word strid
 // Where the candidates of a query come from.  knn_select() and the fit only need
 //   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
 //   src.load(pos)  the record at a position handed out by scan
+//   src.count()    number of points in the 27 cells
 // GlobalSource reads the Morton-sorted cloud through L1/L2 (positions = sorted positions);
-// StagedSource reads a region a warp has copied to shared memory (positions = slots of
-// that copy, 16 bit).
+// StagedSource reads the copy a CTA has made in shared memory (positions = 16-bit).
 struct GlobalSource {
     typedef uint32_t Pos;
     const Pt* pts;
@@ -311,15 +319,25 @@ struct GlobalSource {
     template <class F>
     PCT_HD void scan(F& fn) const { runs.scan(pts, fn); }
     PCT_HD Pt load(uint32_t pos) const { return load_pt(pts + pos); }
+    PCT_HD uint32_t count() const {
+        uint32_t c = 0;
+        for (int r = 0; r < runs.n; ++r)
+            c += runs.buf[(size_t)(2 * r + 1) * runs.stride] - runs.buf[(size_t)(2 * r) * runs.stride];
+        return c;
+    }
 };
 
 // Staged candidates.  A CTA copies, for every aligned cube of (1 << U)^3 level-0 cells
 // ("parent") its queries fall into, that cube plus a one-cell halo into shared memory:
 // a REGION of kSide^3 cells.  The points of a region are laid out cell by cell in raster
 // order (x fastest), so the three x-neighbours of a stencil row are one contiguous run
-// and the 27 cells of a query are 9 runs, found by direct indexing of a prefix table:
-//   off[c]  first staged slot of raster cell c; the tables of the CTA's regions are
-//           concatenated and cumulative, off[last + 1] = number of staged points
+// and the 27 cells of a query are 9 runs, found by direct indexing of a table:
+//   tab[c]  byte address of the first record of raster cell c; the tables of the CTA's
+//           regions are concatenated, one extra entry closes the last cell
+// On the GPU the addresses are shared-window addresses and every access is an explicit
+// ld.shared (the compiler otherwise rebuilds the window base inside the candidate loop);
+// a position is the record's address / 16, which fits 16 bits.  On the host (test harness)
+// addresses are byte offsets into `arena`.
 template <int U>
 struct RegionShape {
     static constexpr int kSide = (1 << U) + 2;
@@ -328,44 +346,71 @@ struct RegionShape {
 
 struct StagedSource {
     typedef uint16_t Pos;
-    const Pt* pts;        // staged records (shared memory)
-    const uint16_t* off;  // prefix table, already advanced to the query's region
-    int corner;           // raster index of the lowest cell of the query's 3x3x3 block
-    int side;             // kSide
+#if defined(__CUDACC__)
+    uint32_t tab;  // shared address of the table of the query's region
+    PCT_HD uint32_t cell_begin(int c) const {
+        uint32_t v = 0;
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tab + 4u * (uint32_t)c));
+#endif
+        return v;
+    }
+    PCT_HD Pt load_at(uint32_t addr) const {
+        Pt p = {};
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=r"(p.idx)
+                     : "r"(addr));
+#endif
+        return p;
+    }
+#else
+    const char* arena;
+    const uint32_t* tab;
+    uint32_t cell_begin(int c) const { return tab[c]; }
+    Pt load_at(uint32_t addr) const { return *reinterpret_cast<const Pt*>(arena + addr); }
+#endif
+    int corner;  // raster index of the lowest cell of the query's 3x3x3 block
+    int side;    // kSide
 
-    static constexpr int kDepth = 2;
-    // One flat loop over the 9 runs, kDepth candidates per trip (see CellRuns::scan).
+    // One flat loop over the 9 runs: the lanes of a warp sit in different cells, so their
+    // runs end at different trips; a flat loop makes the warp pay max-of-sums, not sum-of-maxes.
+    // Two candidates per trip: both records are loaded before either is used (the second
+    // load may run one record past the run; it stays inside the staging buffer and is
+    // discarded through `valid`), which overlaps their latencies and halves the loop control.
     template <class F>
     PCT_HD void scan(F& fn) const {
-        int r = 0;
-        uint32_t j = 0, e = 0;
+        int r = 0, c0 = corner;
+        uint32_t a = 0, e = 0;
 #pragma unroll 1
         for (;;) {
-            uint32_t pos[kDepth];
-            bool valid[kDepth];
-#pragma unroll
-            for (int u = 0; u < kDepth; ++u) {
-                while (j == e && r < 9) {
-                    const int z = (r * 11) >> 5;  // r / 3 for r < 9
-                    const int c0 = corner + side * (r - 3 * z) + side * side * z;
-                    j = off[c0];
-                    e = off[c0 + 3];
+            if (a == e) {
+                do {
+                    if (r == 9) return;
+                    a = cell_begin(c0);
+                    e = cell_begin(c0 + 3);
                     ++r;
-                }
-                valid[u] = j != e;
-                pos[u] = valid[u] ? j : 0u;
-                j += valid[u] ? 1u : 0u;
+                    c0 += (r == 3 || r == 6) ? side * side - 2 * side : side;
+                } while (a == e);
             }
-            if (!valid[0]) break;
-            Pt rec[kDepth];
-#pragma unroll
-            for (int u = 0; u < kDepth; ++u) rec[u] = pts[pos[u]];
-#pragma unroll
-            for (int u = 0; u < kDepth; ++u)
-                if (valid[u]) fn((uint16_t)pos[u], rec[u]);
+            const Pt p0 = load_at(a), p1 = load_at(a + 16);
+            const bool two = a + 16 != e;
+            fn((uint16_t)(a >> 4), p0, true);
+            fn((uint16_t)((a >> 4) + 1), p1, two);
+            a += two ? 32u : 16u;
         }
     }
-    PCT_HD Pt load(uint16_t pos) const { return pts[pos]; }
+    PCT_HD Pt load(uint16_t pos) const { return load_at((uint32_t)pos << 4); }
+    PCT_HD uint32_t count() const {
+        uint32_t c = 0;
+        int c0 = corner;
+#pragma unroll
+        for (int r = 1; r <= 9; ++r) {
+            c += cell_begin(c0 + 3) - cell_begin(c0);
+            c0 += (r == 3 || r == 6) ? side * side - 2 * side : side;
+        }
+        return c >> 4;
+    }
 };
 
 template <class PosT>
@@ -373,27 +418,33 @@ struct SelectScratch {
     PosT* list;     // slot m at list[m * stride]
     uint8_t* hist;  // kHistBins bytes, contiguous
     int stride;
-    int cap;
+    int cap;        // list slots; the last PCT_TIE_SLACK of them hold the boundary zone
+    bool collect;   // pre-collect candidates during pass 1 (needs cap well above k + PCT_TIE_SLACK)
 };
 
-// Finds the exact k nearest neighbours (scipy order, self excluded) of sorted
-// point `i` inside the level-`level` stencil, in O(candidates) work:
+// Finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
+// level-`level` stencil, in O(candidates) work:
 //
 //   pass 1  histogram of the fp32 squared distances over kHistBins equal bins of
 //           [0, range2) (squared distance is uniform in area on a surface, so the
 //           bins are evenly filled); the bin b that holds the k-th neighbour follows
-//           from a prefix sum.  No sorted list, no dependence on k.
+//           from a prefix sum.  No sorted list, no dependence on k.  The same pass
+//           copies every candidate closer than an ESTIMATE of the k-th distance
+//           (local density from the population of the 27 cells) into the list.
 //   pass 2  candidates clearly below bin b (d32 < lo) are neighbours and go to the
 //           front of the list; candidates in the boundary zone [lo, hi] -- bin b widened
 //           by 1e-5 relative on both sides, far more than the 3e-7 fp32 error -- go
-//           to the back; everything above hi is out.
+//           to the last PCT_TIE_SLACK slots; everything above hi is out.  When the estimate
+//           covered bin b this pass reads the pre-collected list (about 2 k entries, in
+//           place); otherwise it walks all candidates again.  The estimate only ever
+//           decides how much work is done, never the result.
 //   exact   the k - |front| nearest of the boundary zone are chosen with scipy's fp64
 //           key (d2, index).  The zone holds one or two points on average.  If the
 //           farthest front point and the nearest zone point are closer than 2e-6
 //           relative the cut itself is ambiguous and the query goes to the exact kernel.
 //
-// On SEL_OK, list[m * stride] (m < k) holds the neighbours' sorted positions
-// (unordered), `first` / `last` the nearest / farthest by (d2 fp64, original index).
+// On SEL_OK, list[m * stride] (m < k) holds the neighbours' positions (unordered),
+// `first` / `last` the nearest / farthest by (d2 fp64, original index).
 template <class Source>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
                       const SelectScratch<typename Source::Pos>& sc, typename Source::Pos& first,
@@ -404,29 +455,50 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     // everything closer than sqrt(range2) is certain to be among the candidates
     const float cell = ix.h * ldexpf(1.f, level);
     const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
-    const float bin_w = range2 * (1.f / kHistBins);
-    const float inv_w = (float)kHistBins / range2;
+    const float inv_w = (float)kHistBins / range2 * 0.99999f;  // rounded down: bin < kHistBins for d < range2
     if (!(range2 > 1.0e-30f) || !(inv_w < 3.0e38f)) return SEL_EXACT;
+
+    // estimated squared distance of the k-th neighbour, with head-room (cut_gain): on a surface the
+    // population C of the 3x3 block of cells is density * 9 cell^2 * tilt, in a volume density * 27 cell^3
+    const int zone_slots = PCT_TIE_SLACK;
+    const int coll_slots = sc.cap - zone_slots;
+    float cut2 = 0.f;
+    if (sc.collect) {
+        const float frac = (float)k / (float)(src.count() + 1u);
+        const float f = ix.volumetric ? cbrtf(frac * frac) : frac;
+        cut2 = fminf(ix.cut_gain * f * cell * cell, range2);
+    }
 
     uint32_t* hist32 = reinterpret_cast<uint32_t*>(sc.hist);
 #pragma unroll
     for (int w = 0; w < kHistBins / 4; ++w) hist32[w] = 0u;
 
+    // The bodies of both passes are executed by the whole warp whenever one lane needs them,
+    // so they are kept short; everything that can wait is done on the list afterwards.
+    // Pass 1 counts the query itself (bin 0): the k-th neighbour is entry k + 1.  Counters are
+    // bytes that may wrap; `seen` detects that afterwards.
     struct P1 {
         uint8_t* hist;
-        uint32_t self;
-        float qx, qy, qz, range2, inv_w;
-        PCT_HD void operator()(Pos, const Pt& p) {
-            const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-            if (d < range2 && p.idx != self) {
-                int b = (int)(d * inv_w);
-                b = b < kHistBins - 1 ? b : kHistBins - 1;
-                const uint8_t v = hist[b];
-                hist[b] = (uint8_t)(v + (v < 255 ? 1 : 0));
+        Pos* list;
+        int stride;
+        uint32_t seen, n_coll, coll_slots;
+        float qx, qy, qz, range2, inv_w, cut2;
+        PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
+            const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
+            if (d < range2) {
+                const int b = (int)(d * inv_w);
+                hist[b] = (uint8_t)(hist[b] + 1);
+                ++seen;
+                if (d < cut2) {
+                    if (n_coll < coll_slots) list[(size_t)n_coll * stride] = j;
+                    ++n_coll;
+                }
             }
         }
     } p1;
-    p1.hist = sc.hist; p1.self = self; p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w;
+    p1.hist = sc.hist; p1.list = sc.list; p1.stride = sc.stride; p1.seen = 0; p1.n_coll = 0;
+    p1.coll_slots = (uint32_t)coll_slots;
+    p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
     src.scan(p1);
 
     // bin of the k-th neighbour
@@ -438,52 +510,80 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             cum += (word >> (8 * t)) & 255u;
-            if (b < 0 && cum >= (uint32_t)k) b = 4 * w + t;
+            if (b < 0 && cum > (uint32_t)k) b = 4 * w + t;
         }
     }
-    if (b < 0) return SEL_RETRY_COARSER;  // fewer than k points within the certain radius
+    if (cum != p1.seen) return SEL_EXACT;  // a counter wrapped (> 255 candidates in one bin)
+    if (b < 0) return SEL_RETRY_COARSER;   // fewer than k points within the certain radius
 
+    // bin b is [b, b + 1) / inv_w; widened by 1e-5 relative on both sides
+    const float bin_w = 1.f / inv_w;
     const float hi = (float)(b + 1) * bin_w * 1.00001f;
     const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
 
     struct P2 {
         Pos* list;
-        int stride, cap;
+        int stride, zone_top, zone_slots;
         uint32_t self, n_front, n_zone;
-        Pos j_min;
-        float qx, qy, qz, lo, hi, d_min, d_min2, front_max, zone_min;
-        PCT_HD void operator()(Pos j, const Pt& p) {
-            const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
+        float qx, qy, qz, lo, hi;
+        PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
+            const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
             if (d <= hi && p.idx != self) {
                 if (d < lo) {
-                    if ((int)(n_front + n_zone) < cap) list[(size_t)n_front * stride] = j;
+                    list[(size_t)n_front * stride] = j;  // n_front < k: always room
                     ++n_front;
-                    front_max = fmaxf(front_max, d);
                 } else {
-                    if ((int)(n_front + n_zone) < cap) list[(size_t)(cap - 1 - (int)n_zone) * stride] = j;
+                    if ((int)n_zone < zone_slots) list[(size_t)(zone_top - (int)n_zone) * stride] = j;
                     ++n_zone;
-                    zone_min = fminf(zone_min, d);
                 }
-                // nearest and runner-up by fp32 distance
-                const bool closer = d < d_min;
-                d_min2 = closer ? d_min : fminf(d_min2, d);
-                j_min = closer ? j : j_min;
-                d_min = closer ? d : d_min;
             }
         }
     } p2;
-    p2.list = sc.list; p2.stride = sc.stride; p2.cap = sc.cap; p2.self = self; p2.n_front = 0; p2.n_zone = 0; p2.j_min = 0;
-    p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi; p2.d_min = 3.4e38f; p2.d_min2 = 3.4e38f;
-    p2.front_max = 0.f; p2.zone_min = 3.4e38f;
-    src.scan(p2);
+    p2.list = sc.list; p2.stride = sc.stride; p2.zone_top = sc.cap - 1; p2.zone_slots = zone_slots;
+    p2.self = self; p2.n_front = 0; p2.n_zone = 0;
+    p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi;
+    PCT_SELECT_TRACE(hi < cut2 && p1.n_coll <= (uint32_t)coll_slots);
+    if (hi < cut2 && p1.n_coll <= (uint32_t)coll_slots) {
+        // every candidate up to hi was collected: partition the list in place (the write
+        // position of the front never passes the read position)
+#pragma unroll 1
+        for (uint32_t m = 0; m < p1.n_coll; ++m) {
+            const Pos j = sc.list[(size_t)m * sc.stride];
+            p2(j, src.load(j), true);
+        }
+    } else {
+        src.scan(p2);
+    }
 
     const int n_front = (int)p2.n_front;
     int n_zone = (int)p2.n_zone;
-    if (n_front + n_zone > sc.cap) return SEL_EXACT;   // a large group of (near-)ties in the boundary bin
-    if (!(p2.d_min > 1.0e-30f)) return SEL_EXACT;      // duplicates of the query / denormal range: fp64 only
+    if (n_zone > zone_slots) return SEL_EXACT;   // a large group of (near-)ties in the boundary bin
+
+    // one walk over the k + few listed candidates: the nearest and its runner-up (fp32), the
+    // farthest front member and the nearest zone member
+    float d_min = 3.4e38f, d_min2 = 3.4e38f, front_max = 0.f, zone_min = 3.4e38f;
+    Pos j_min = 0;
+    {
+        const int n_list = n_front + n_zone;
+        const int skip = sc.cap - n_list;  // the unused slots between the front and the zone
+#pragma unroll 1
+        for (int m = 0; m < n_list; ++m) {
+            const bool is_front = m < n_front;
+            const Pos j = sc.list[(size_t)(is_front ? m : m + skip) * sc.stride];
+            const Pt p = src.load(j);
+            const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+            front_max = is_front ? fmaxf(front_max, d) : front_max;
+            zone_min = is_front ? zone_min : fminf(zone_min, d);
+            const bool closer = d < d_min;
+            d_min2 = closer ? d_min : fminf(d_min2, d);
+            j_min = closer ? j : j_min;
+            d_min = closer ? d : d_min;
+        }
+    }
+    if (!(d_min > 1.0e-30f)) return SEL_EXACT;         // duplicates of the query / denormal range: fp64 only
     // `lo` is an arbitrary cut: front and zone must be separated by more than the fp32 error,
     // otherwise a front member could rank behind a zone member in fp64
-    if (n_front > 0 && !(p2.zone_min > p2.front_max * 1.000002f)) return SEL_EXACT;
+    if (n_front > 0 && !(zone_min > front_max * 1.000002f)) return SEL_EXACT;
     const int need = k - n_front;                      // 1 <= need <= n_zone by construction
     if (need < 1 || need > n_zone) return SEL_EXACT;   // (a saturated histogram bin can break the invariant)
 
@@ -510,8 +610,8 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     }
 
     // nearest neighbour: decided in fp32 when the runner-up is clearly farther
-    if (p2.d_min2 > p2.d_min * 1.00001f) {
-        first = p2.j_min;
+    if (d_min2 > d_min * 1.00001f) {
+        first = j_min;
     } else {
         double bd = 0.0;
         uint32_t bi = 0;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -294,6 +295,14 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     while ((1 << v.bits) < maxdim) ++v.bits;
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
+    // k-th-distance estimate of knn_select(): cut^2 = gain * (k / C) cell^2 on a surface (C = population of the
+    // 3x3x3 block = density * 9 cell^2 * tilt), gain * (k / C)^(2/3) cell^2 in a volume.  Performance only.
+    v.volumetric = est_dim > 2.5f ? 1 : 0;
+    v.cut_gain = v.volumetric ? 5.1f : 6.5f;
+    if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
+        const float gv = (float)std::atof(g);
+        if (gv >= 0.f) v.cut_gain = gv;
+    }
 
     // 3. keys, sort, gather
     DeviceTemp keys_a(s), keys_b(s), vals_a(s), vals_b(s), sort_tmp(s), hist(s);

@@ -16,6 +16,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cmath>
 
 #include "pct_internal.h"
 
@@ -96,6 +97,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
     sc.hist = reinterpret_cast<uint8_t*>(smem_words + (54 + cap) * kBlock) + kHistRowBytes * threadIdx.x;
     sc.stride = kBlock;
     sc.cap = cap;
+    sc.collect = false;  // this kernel sees the hard cases; its list is k + PCT_TIE_SLACK wide
     long long total = qr.q_end - qr.q_begin;
     if (qr.list) total = (long long)*qr.count;
     for (long long base = (long long)blockIdx.x * kBlock; base < total; base += (long long)gridDim.x * kBlock) {
@@ -140,7 +142,7 @@ struct StagedCell {
 
 // dynamic shared memory of the staged kernel, in this order (every part 16-byte aligned):
 //   Pt       pts[cap_pts]
-//   uint16   off[kTable + 8]
+//   uint32   tab[kTable + 4]         shared address of the first record of every region cell
 //   int      hdr[32]                 region origins, block-scan partials, flags
 //   scratch  max(per-query scratch, staging temporaries)
 //       per query  : uint16 list[cap][kBlock], uint8 hist[kBlock][68]
@@ -150,8 +152,8 @@ __host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
     const size_t per_query = ((size_t)cap * sizeof(uint16_t) + kHistRowBytes) * kBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
-    const size_t off = ((size_t)(StageShape<U>::kTable + 8) * sizeof(uint16_t) + 15) & ~(size_t)15;
-    return sizeof(Pt) * (size_t)cap_pts + off + 32 * sizeof(int) + ((scratch + 15) & ~(size_t)15);
+    const size_t tab = (size_t)(StageShape<U>::kTable + 4) * sizeof(uint32_t);
+    return sizeof(Pt) * (size_t)cap_pts + tab + 32 * sizeof(int) + ((scratch + 15) & ~(size_t)15);
 }
 
 #if defined(__CUDACC__)
@@ -163,8 +165,9 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     constexpr int S = Shape::kSide, C = Shape::kCells;
     extern __shared__ uint4 smem_u4[];
     Pt* const pts_s = reinterpret_cast<Pt*>(smem_u4);
-    uint16_t* const off = reinterpret_cast<uint16_t*>(pts_s + cap_pts);
-    int* const hdr = reinterpret_cast<int*>(reinterpret_cast<char*>(off) + (((Shape::kTable + 8) * sizeof(uint16_t) + 15) & ~(size_t)15));
+    uint32_t* const tab = reinterpret_cast<uint32_t*>(pts_s + cap_pts);
+    int* const hdr = reinterpret_cast<int*>(tab + Shape::kTable + 4);
+    const uint32_t pts_addr = (uint32_t)__cvta_generic_to_shared(pts_s);
     char* const scratch = reinterpret_cast<char*>(hdr + 32);
     // hdr: [0..3] warp partials (points), [4..7] warp partials (cells / heads), [8] regions, [9] flags,
     //      [10] queue base, [12 + 3 r ..] origin of region r
@@ -260,7 +263,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         const int item = t * Shape::kItemsPerThread + u;
         if (item < n_table) {
             const uint32_t n = t_count[item];
-            off[item] = (uint16_t)run;
+            tab[item] = pts_addr + 16u * run;
             if (n) {
                 StagedCell sc;
                 sc.first = t_first[item]; sc.slot = (uint16_t)run; sc.count = (uint16_t)n;
@@ -269,7 +272,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
             run += n;
         }
     }
-    if (t == 0) off[n_table] = (uint16_t)staged;
+    if (t == 0) tab[n_table] = pts_addr + 16u * staged;
     __syncthreads();
 
     // ---- D. copy the non-empty cells, eight lanes per cell
@@ -286,8 +289,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     // ---- E. select out of the staged copy
     const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
     StagedSource src;
-    src.pts = pts_s;
-    src.off = off + region * C;
+    src.tab = (uint32_t)__cvta_generic_to_shared(tab + region * C);
     src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
     src.side = S;
     SelectScratch<uint16_t> sel;
@@ -295,6 +297,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     sel.hist = reinterpret_cast<uint8_t*>(scratch) + sizeof(uint16_t) * (size_t)cap * kBlock + kHistRowBytes * t;
     sel.stride = kBlock;
     sel.cap = cap;
+    sel.collect = cap >= 2 * k + PCT_TIE_SLACK;
     Stencil st;
     make_stencil(ix, 0, q.x, q.y, q.z, st);
     uint16_t first = 0, last = 0;
@@ -316,7 +319,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
 struct FastLaunch {
     const pct_index* ix;
     QueryRange qr;
-    int k, cap;
+    int k, cap;  // cap: list slots of the L1/L2 kernel (k + PCT_TIE_SLACK)
     bool fused;
     int32_t* idx;
     float* dist;
@@ -327,6 +330,12 @@ struct FastLaunch {
     unsigned int* counters;
     cudaStream_t s;
 };
+
+// candidates the pre-collection of knn_select() expects below its cut (see IndexView::cut_gain)
+static double expected_collected(const IndexView& v, int k) {
+    if (v.volumetric) return (double)k * std::pow((double)v.cut_gain / 3.46, 1.5);
+    return 0.349 * (double)v.cut_gain * (double)k;  // pi / 9, tilt 1
+}
 
 // staged level 0 over the whole range; L1/L2 kernel at level 0 over the chunks that could
 // not be staged, then at level 1 over whatever level 0 queued
@@ -340,18 +349,22 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     PCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.fallback0, a.counters};
 
+    // list of the staged kernel: room for the candidates pre-collected below the estimated k-th distance
+    // (expected number + 3 sigma) and the boundary zone
+    const double lambda = expected_collected(v, a.k);
+    const int cap_staged = std::max(a.cap, (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK);
     // staging buffer: what is left of a quarter SM's shared memory after the fixed parts
     constexpr int U = 2;
     auto staged = knn_staged_kernel<U, FUSED>;
-    const size_t fixed = staged_smem_bytes<U>(a.cap, 0);
+    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0);
     const size_t budget = (size_t)a.ix->smem_per_sm / 4 - 1024;  // __launch_bounds__(kBlock, 4)
     int cap_pts = fixed + 16 * 512 <= budget ? (int)((budget - fixed) / sizeof(Pt)) : 512;
     if (cap_pts > 0xffff) cap_pts = 0xffff;
-    const size_t smem_staged = staged_smem_bytes<U>(a.cap, cap_pts);
+    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts);
     if (smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         const long long chunks = (nq + kBlock - 1) / kBlock;
-        staged<<<(unsigned int)chunks, kBlock, smem_staged, a.s>>>(v, a.qr, a.k, a.cap, cap_pts, a.idx, a.dist, a.out, q0);
+        staged<<<(unsigned int)chunks, kBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);
         ++*launches;
         QueryRange qf = a.qr;
         qf.list = a.fallback0;

@@ -26,7 +26,7 @@
 
 #if defined(__CUDACC__)
 #define PCT_HD __host__ __device__ __forceinline__
-#define PCT_HD_NOINLINE __host__ __device__ __noinline__
+#define PCT_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define PCT_HD inline
 #define PCT_HD_NOINLINE inline
@@ -143,7 +143,7 @@ PCT_HD void jacobi_rotate(double& app, double& aqq, double& apq, double& arp, do
     a = v2p; b = v2q; v2p = a - s * (b + tau * a); v2q = b + s * (a - tau * b);
 }
 
-PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double a11, double a12, double a22,
+PCT_HD_NOINLINE void smallest_eigenvector_sym3_jacobi(double a00, double a01, double a02, double a11, double a12, double a22,
                                       double n[3]) {
     // scale by the trace: eigenvectors are unchanged, fp range issues vanish
     const double tr = a00 + a11 + a22;
@@ -165,6 +165,77 @@ PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double
     if (a00 <= a11 && a00 <= a22) { n[0] = v00; n[1] = v10; n[2] = v20; }
     else if (a11 <= a22)          { n[0] = v01; n[1] = v11; n[2] = v21; }
     else                          { n[0] = v02; n[1] = v12; n[2] = v22; }
+}
+
+// fp32 rotation of the same cyclic Jacobi (used to get a starting vector cheaply)
+PCT_HD void jacobi_rotate_f32(float& app, float& aqq, float& apq, float& arp, float& arq,
+                              float& v0p, float& v0q, float& v1p, float& v1q, float& v2p, float& v2q) {
+    if (apq == 0.f) return;
+    const float theta = (aqq - app) / (2.f * apq);
+    const float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+    const float c = 1.f / sqrtf(t * t + 1.f);
+    const float s = t * c;
+    const float tau = s / (1.f + c);
+    app -= t * apq;
+    aqq += t * apq;
+    apq = 0.f;
+    const float rp = arp, rq = arq;
+    arp = rp - s * (rq + tau * rp);
+    arq = rq + s * (rp - tau * rq);
+    float a, b;
+    a = v0p; b = v0q; v0p = a - s * (b + tau * a); v0q = b + s * (a - tau * b);
+    a = v1p; b = v1q; v1p = a - s * (b + tau * a); v1q = b + s * (a - tau * b);
+    a = v2p; b = v2q; v2p = a - s * (b + tau * a); v2q = b + s * (a - tau * b);
+}
+
+// Smallest eigenvector in fp64 accuracy for a fraction of the fp64 Jacobi's cost (its
+// rotations are serial chains of fp64 divisions and square roots): an fp32 Jacobi gives
+// the eigenvector to ~1e-7 / gap, two Rayleigh-quotient iterations in fp64 -- each a
+// multiplication by the adjugate of (A - lambda I), no division -- converge cubically
+// from there.  When the two smallest eigenvalues are closer than 1e-4 of the trace the
+// start may be poor and the fp64 Jacobi is used instead.
+PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double a11, double a12, double a22,
+                                      double n[3]) {
+    const double tr = a00 + a11 + a22;
+    if (!(tr > 0.0)) {  // all neighbours coincide with their mean (or NaN): any unit vector
+        n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
+        return;
+    }
+    const double inv = 1.0 / tr;
+    a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+    float b00 = (float)a00, b01 = (float)a01, b02 = (float)a02, b11 = (float)a11, b12 = (float)a12, b22 = (float)a22;
+    float v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; ++sweep) {
+        const float off = b01 * b01 + b02 * b02 + b12 * b12;
+        if (off < 1e-15f) break;  // relative to trace^2 == 1
+        jacobi_rotate_f32(b00, b11, b01, b02, b12, v00, v01, v10, v11, v20, v21);
+        jacobi_rotate_f32(b00, b22, b02, b01, b12, v00, v02, v10, v12, v20, v22);
+        jacobi_rotate_f32(b11, b22, b12, b01, b02, v01, v02, v11, v12, v21, v22);
+    }
+    float lmin, lmid;
+    double x, y, z;
+    if (b00 <= b11 && b00 <= b22) { lmin = b00; lmid = fminf(b11, b22); x = v00; y = v10; z = v20; }
+    else if (b11 <= b22)          { lmin = b11; lmid = fminf(b00, b22); x = v01; y = v11; z = v21; }
+    else                          { lmin = b22; lmid = fminf(b00, b11); x = v02; y = v12; z = v22; }
+    if (!(lmid - lmin > 1e-4f)) {
+        smallest_eigenvector_sym3_jacobi(a00, a01, a02, a11, a12, a22, n);
+        return;
+    }
+#pragma unroll
+    for (int step = 0; step < 2; ++step) {
+        const double ax = a00 * x + a01 * y + a02 * z, ay = a01 * x + a11 * y + a12 * z, az = a02 * x + a12 * y + a22 * z;
+        const double lam = (x * ax + y * ay + z * az) / (x * x + y * y + z * z);
+        const double m00 = a00 - lam, m11 = a11 - lam, m22 = a22 - lam;
+        const double c00 = m11 * m22 - a12 * a12, c01 = a02 * a12 - a01 * m22, c02 = a01 * a12 - a02 * m11;
+        const double c11 = m00 * m22 - a02 * a02, c12 = a01 * a02 - m00 * a12, c22 = m00 * m11 - a01 * a01;
+        const double nx = c00 * x + c01 * y + c02 * z, ny = c01 * x + c11 * y + c12 * z, nz = c02 * x + c12 * y + c22 * z;
+        const double nn = nx * nx + ny * ny + nz * nz;
+        if (!(nn > 1e-280)) break;
+        const double s = 1.0 / sqrt(nn);
+        x = nx * s; y = ny * s; z = nz * s;
+    }
+    n[0] = x; n[1] = y; n[2] = z;
 }
 
 // ---- tangent frame ---------------------------------------------------------

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <vector>
 
+static long long g_pass2[2];  // [0] = pass 2 walked all candidates, [1] = pass 2 read the pre-collected list
+#define PCT_SELECT_TRACE(used_list) (++g_pass2[(used_list) ? 1 : 0])
 #include "pct_grid.cuh"
 #include "pct_dispatch.h"
 
@@ -49,6 +51,8 @@ void* h_build(const float* xyz, long long n, float h) {
     while ((1 << v.bits) < maxdim) ++v.bits;
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
+    v.volumetric = 0;
+    v.cut_gain = 6.5f;
     std::vector<std::pair<unsigned long long, uint32_t>> keyed(n);
     for (long long i = 0; i < n; ++i) {
         int cx, cy, cz;
@@ -85,6 +89,10 @@ void* h_build(const float* xyz, long long n, float h) {
 }
 
 void h_destroy(void* p) { delete (HostIndex*)p; }
+void h_pass2_counts(long long* out, int reset) {
+    out[0] = g_pass2[0]; out[1] = g_pass2[1];
+    if (reset) g_pass2[0] = g_pass2[1] = 0;
+}
 void h_perm(void* p, int32_t* perm) {
     HostIndex* ix = (HostIndex*)p;
     for (long long i = 0; i < ix->view.n; ++i) perm[i] = (int32_t)ix->pts[i].idx;
@@ -111,7 +119,7 @@ template <int U>
 struct HostStage {
     static constexpr int S = RegionShape<U>::kSide, C = RegionShape<U>::kCells;
     std::vector<Pt> pts;
-    std::vector<uint16_t> off;
+    std::vector<uint32_t> off;  // byte offsets into pts (the device keeps shared-window addresses)
     std::vector<int> org;       // 3 per region
     std::vector<int> region_of; // per query of the chunk
     bool ok = true;
@@ -141,11 +149,11 @@ struct HostStage {
                 uint32_t s = 0, e = 0;
                 if (gx >= 0 && gx < v.dims[0] && gy >= 0 && gy < v.dims[1] && gz >= 0 && gz < v.dims[2])
                     if (!lookup_cell(v.lvl[0], morton3((uint32_t)gx, (uint32_t)gy, (uint32_t)gz), s, e)) s = e = 0;
-                off.push_back((uint16_t)pts.size());
+                off.push_back((uint32_t)(pts.size() * sizeof(Pt)));
                 if (e - s > 0xffffu || pts.size() + (e - s) > cap_pts) { ok = false; return; }
                 for (uint32_t j = s; j < e; ++j) pts.push_back(v.pts[j]);
             }
-        off.push_back((uint16_t)pts.size());
+        off.push_back((uint32_t)(pts.size() * sizeof(Pt)));
     }
 };
 
@@ -153,15 +161,15 @@ struct HostStage {
 // 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback, +50 = staged source.
 // staged_u: 0 = candidates straight from the sorted cloud, 1 / 2 = staged regions of (1 << U)^3 cells
 template <int U>
-static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int32_t* idx, float* dist, int32_t* code,
+static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int coll_extra, int32_t* idx, float* dist, int32_t* code,
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
-    const int cap = k + PCT_TIE_SLACK;
+    const int cap = k + PCT_TIE_SLACK + coll_extra;  // coll_extra > 0 switches the pre-collection of pass 1 on
     std::vector<uint32_t> list(cap), runs(54);
     std::vector<uint16_t> list16(cap);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
-    SelectScratch<uint32_t> sc{list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
-    SelectScratch<uint16_t> sc16{list16.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap};
+    SelectScratch<uint32_t> sc{list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap, coll_extra > 0};
+    SelectScratch<uint16_t> sc16{list16.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap, coll_extra > 0};
     GlobalSource gsrc;
     gsrc.pts = v.pts;
     gsrc.runs.buf = runs.data();
@@ -185,8 +193,8 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int3
                 cell_of(v, q.x, q.y, q.z, cx, cy, cz);
                 const int lx = cx - stage.org[3 * r], ly = cy - stage.org[3 * r + 1], lz = cz - stage.org[3 * r + 2];
                 StagedSource ssrc;
-                ssrc.pts = stage.pts.data();
-                ssrc.off = stage.off.data() + r * C;
+                ssrc.arena = reinterpret_cast<const char*>(stage.pts.data());
+                ssrc.tab = stage.off.data() + r * C;
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
@@ -243,15 +251,17 @@ extern "C" {
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    knn_impl<0>(ix, k, max_fast_level, 0, idx, dist, code, normals, coeffs, curv, status);
+    knn_impl<0>(ix, k, max_fast_level, 0, 0, idx, dist, code, normals, coeffs, curv, status);
 }
 
 // same through the staged source (level 0), staging buffer of cap_pts points
-void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int32_t* idx, float* dist, int32_t* code,
+void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int coll_extra, float cut_gain, int32_t* idx, float* dist, int32_t* code,
                   float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
-    else knn_impl<2>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
+    ix->view.cut_gain = cut_gain;
+    if (staged_u == 0) knn_impl<0>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
+    else if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
+    else knn_impl<2>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
 }
 
 void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,

@@ -29,7 +29,7 @@ def harness():
     lib.h_build.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float]
     lib.h_destroy.argtypes = [ctypes.c_void_p]
     lib.h_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
-    lib.h_knn_staged.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+    lib.h_knn_staged.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_float] + [ctypes.c_void_p] * 7
     lib.h_fit_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5
     lib.h_ball.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
     return lib
@@ -39,7 +39,7 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=2048):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=2048, coll_extra=0, cut_gain=6.5):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
@@ -47,8 +47,8 @@ def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=2048):
                normal=np.zeros((n, 3), np.float32), coeffs=np.zeros((n, 6), np.float32), curv=np.zeros((n, 5), np.float32),
                status=np.zeros(n, np.uint8))
     args = (P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]), P(out["curv"]), P(out["status"]))
-    if staged_u:
-        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, *args)
+    if staged_u or coll_extra:
+        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, coll_extra, cut_gain, *args)
     else:
         lib.h_knn(ix, k, max_fast_level, *args)
     lib.h_destroy(ix)
@@ -89,6 +89,18 @@ def test_staged_source_gives_the_same_rows(harness, bunny, staged_u):
     small = run_knn(harness, pts, k, h, staged_u=staged_u, cap_pts=600)
     assert 0.0 < np.mean(small["code"] == 50) < np.mean(got["code"] == 50)
     assert np.array_equal(small["idx"], got["idx"])
+    # pre-collection during pass 1: the estimate of the k-th distance (any gain, any list size) only
+    # changes how much work is done
+    counts = (ctypes.c_longlong * 2)()
+    for gain, extra in ((6.5, 2 * k), (1.0, 2 * k), (40.0, 2 * k), (6.5, 5), (40.0, 200)):
+        harness.h_pass2_counts(counts, 1)
+        coll = run_knn(harness, pts, k, h, staged_u=staged_u, coll_extra=extra, cut_gain=gain)
+        harness.h_pass2_counts(counts, 0)
+        if (gain, extra) == (6.5, 2 * k):  # the shipped setting: most queries never walk the candidates twice
+            assert counts[1] > 0.8 * (counts[0] + counts[1]), list(counts)
+        assert np.array_equal(coll["idx"], got["idx"]), (gain, extra)
+        assert np.array_equal(coll["dist"], got["dist"]), (gain, extra)
+        assert np.array_equal(coll["code"], got["code"]), (gain, extra)
 
 
 def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
@@ -100,10 +112,10 @@ def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
     tiny = rng.normal(size=(23, 3)).astype(np.float32)
     for name, pts, k, h in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
         ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
-        for u in (1, 2):
-            got = run_knn(harness, pts, k, h, staged_u=u)
-            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u)
-            assert np.array_equal(got["dist"], ref_dist), (name, u)
+        for u, extra in ((1, 0), (2, 0), (2, 3 * k), (0, 3 * k)):
+            got = run_knn(harness, pts, k, h, staged_u=u, coll_extra=extra)
+            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u, extra)
+            assert np.array_equal(got["dist"], ref_dist), (name, u, extra)
 
 
 def test_cell_size_never_changes_the_answer(harness, bunny):
