@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "--fmad=true",          # contraction is pinned per operation with __f*_rn intrinsics where it matters
     "-Xptxas", "-v",
     "-diag-suppress", "550,177",
-]
+] + os.environ.get("PCT_NVCC_EXTRA", "").split()  # experiments only (e.g. -DPCT_STAGED_CTAS=5)
 
 
 def _nvcc():

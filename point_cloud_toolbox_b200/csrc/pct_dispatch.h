@@ -5,3 +5,12 @@
 
 // extra neighbour-list slots for the boundary bin of the distance histogram (ties with the k-th neighbour)
 #define PCT_TIE_SLACK 16
+
+// staged kNN kernel: queries (threads) per CTA, and the resident CTAs per SM it is compiled for
+// (register cap) and sized for (shared memory)
+#ifndef PCT_STAGED_BLOCK
+#define PCT_STAGED_BLOCK 256
+#endif
+#ifndef PCT_STAGED_CTAS
+#define PCT_STAGED_CTAS 3
+#endif

@@ -62,8 +62,8 @@ plane_rotate_kernel(const float* __restrict__ centered, long long nq, int k, dou
         row.pass(mom);
         uint32_t st = 0;
         double* o = rotated + r * k * 3;
-        if (mom.n < 2 || !mom.finite) {
-            st = mom.finite ? ST_FEW : ST_NONFINITE;  // ref :273-274 raises on non-finite input
+        if (mom.n < 2 || !mom.finite()) {
+            st = mom.finite() ? ST_FEW : ST_NONFINITE;  // ref :273-274 raises on non-finite input
             const double nanv = nan("");
             for (int m = 0; m < 3 * k; ++m) o[m] = nanv;
             if (normals) { normals[3 * r] = nanv; normals[3 * r + 1] = nanv; normals[3 * r + 2] = nanv; }
@@ -100,7 +100,7 @@ quadric_fit_kernel(const double* __restrict__ rotated, long long nq, int k, floa
         uint32_t st = 0;
         float c[6];
         double w[6];
-        if (!q.finite || !(max_abs <= 3.0e38f)) st = ST_NONFINITE;  // ref :356-357
+        if (!q.finite() || !(max_abs <= 3.0e38f)) st = ST_NONFINITE;  // ref :356-357
         else if (!solve_normal_equations(q, w)) st = ST_RANK;
         if (st) {
             for (int j = 0; j < 6; ++j) c[j] = nanf("");

@@ -100,6 +100,14 @@ PCT_HD unsigned long long spread3(uint32_t v) {
 PCT_HD unsigned long long morton3(uint32_t x, uint32_t y, uint32_t z) {
     return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
 }
+// sum of the four bytes of a word
+PCT_HD uint32_t byte_sum4(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(w, 0x01010101u, 0u);
+#else
+    return (w & 255u) + ((w >> 8) & 255u) + ((w >> 16) & 255u) + (w >> 24);
+#endif
+}
 PCT_HD uint32_t hash_key(unsigned long long key) {
     return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32);
 }
@@ -302,9 +310,10 @@ enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 // Selection scratch of one query.  On the GPU all of it lives in shared memory:
 //   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
 //   list  cap entries, slot m at list[m * stride]        (neighbour positions)
-//   hist  kHistBins bytes, contiguous per query          (distance histogram)
+//   hist  kHistBins byte counters = 16 words, word w at hist[w * hist_stride]   (distance histogram);
+//         with hist_stride = threads of the block every thread stays in its own bank
 static constexpr int kHistBins = 64;
-static constexpr int kHistRowBytes = 68;  // 17 words per thread: odd word stride, bank-conflict free
+static constexpr int kHistRowBytes = kHistBins;
 
 // Where the candidates of a query come from.  knn_select() and the fit only need
 //   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
@@ -416,10 +425,10 @@ struct StagedSource {
 template <class PosT>
 struct SelectScratch {
     PosT* list;     // slot m at list[m * stride]
-    uint8_t* hist;  // kHistBins bytes, contiguous
+    uint32_t* hist; // word w of the byte histogram at hist[w * hist_stride]
+    int hist_stride;
     int stride;
-    int cap;        // list slots; the last PCT_TIE_SLACK of them hold the boundary zone
-    bool collect;   // pre-collect candidates during pass 1 (needs cap well above k + PCT_TIE_SLACK)
+    int cap;        // list slots; the last PCT_TIE_SLACK of them hold the boundary zone (COLLECT needs cap well above k + that)
 };
 
 // Finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
@@ -445,7 +454,7 @@ struct SelectScratch {
 //
 // On SEL_OK, list[m * stride] (m < k) holds the neighbours' positions (unordered),
 // `first` / `last` the nearest / farthest by (d2 fp64, original index).
-template <class Source>
+template <bool COLLECT, class Source>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
                       const SelectScratch<typename Source::Pos>& sc, typename Source::Pos& first,
                       typename Source::Pos& last, double& d2_last) {
@@ -463,15 +472,14 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     const int zone_slots = PCT_TIE_SLACK;
     const int coll_slots = sc.cap - zone_slots;
     float cut2 = 0.f;
-    if (sc.collect) {
+    if (COLLECT) {
         const float frac = (float)k / (float)(src.count() + 1u);
         const float f = ix.volumetric ? cbrtf(frac * frac) : frac;
         cut2 = fminf(ix.cut_gain * f * cell * cell, range2);
     }
 
-    uint32_t* hist32 = reinterpret_cast<uint32_t*>(sc.hist);
 #pragma unroll
-    for (int w = 0; w < kHistBins / 4; ++w) hist32[w] = 0u;
+    for (int w = 0; w < kHistBins / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
 
     // The bodies of both passes are executed by the whole warp whenever one lane needs them,
     // so they are kept short; everything that can wait is done on the list afterwards.
@@ -479,6 +487,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     // bytes that may wrap; `seen` detects that afterwards.
     struct P1 {
         uint8_t* hist;
+        int hist_stride4;  // bytes between consecutive words
         Pos* list;
         int stride;
         uint32_t seen, n_coll, coll_slots;
@@ -487,30 +496,44 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
             if (d < range2) {
                 const int b = (int)(d * inv_w);
-                hist[b] = (uint8_t)(hist[b] + 1);
+                uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
+                *c = (uint8_t)(*c + 1);
                 ++seen;
-                if (d < cut2) {
+                if (COLLECT && d < cut2) {
                     if (n_coll < coll_slots) list[(size_t)n_coll * stride] = j;
                     ++n_coll;
                 }
             }
         }
     } p1;
-    p1.hist = sc.hist; p1.list = sc.list; p1.stride = sc.stride; p1.seen = 0; p1.n_coll = 0;
+    p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.stride = sc.stride; p1.seen = 0; p1.n_coll = 0;
     p1.coll_slots = (uint32_t)coll_slots;
     p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
     src.scan(p1);
 
-    // bin of the k-th neighbour
+    // bin of the k-th neighbour: word-wise byte sums first (one dp4a per four bins), then the
+    // four bins of the word in which the running count passes k
     int b = -1;
     uint32_t cum = 0;
-#pragma unroll 4
-    for (int w = 0; w < kHistBins / 4; ++w) {
-        const uint32_t word = hist32[w];
+    {
+        int w_hit = -1;
+        uint32_t cum_hit = 0;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            cum += (word >> (8 * t)) & 255u;
-            if (b < 0 && cum > (uint32_t)k) b = 4 * w + t;
+        for (int w = 0; w < kHistBins / 4; ++w) {
+            const uint32_t s4 = byte_sum4(sc.hist[(size_t)w * sc.hist_stride]);
+            const bool hit = w_hit < 0 && cum + s4 > (uint32_t)k;
+            w_hit = hit ? w : w_hit;
+            cum_hit = hit ? cum : cum_hit;
+            cum += s4;
+        }
+        if (w_hit >= 0) {
+            const uint32_t word = sc.hist[(size_t)w_hit * sc.hist_stride];
+            uint32_t c = cum_hit;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                c += (word >> (8 * t)) & 255u;
+                if (b < 0 && c > (uint32_t)k) b = 4 * w_hit + t;
+            }
         }
     }
     if (cum != p1.seen) return SEL_EXACT;  // a counter wrapped (> 255 candidates in one bin)
@@ -543,7 +566,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     p2.self = self; p2.n_front = 0; p2.n_zone = 0;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi;
     PCT_SELECT_TRACE(hi < cut2 && p1.n_coll <= (uint32_t)coll_slots);
-    if (hi < cut2 && p1.n_coll <= (uint32_t)coll_slots) {
+    if (COLLECT && hi < cut2 && p1.n_coll <= (uint32_t)coll_slots) {
         // every candidate up to hi was collected: partition the list in place (the write
         // position of the front never passes the read position)
 #pragma unroll 1

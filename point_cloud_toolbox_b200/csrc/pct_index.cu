@@ -298,7 +298,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     // k-th-distance estimate of knn_select(): cut^2 = gain * (k / C) cell^2 on a surface (C = population of the
     // 3x3x3 block = density * 9 cell^2 * tilt), gain * (k / C)^(2/3) cell^2 in a volume.  Performance only.
     v.volumetric = est_dim > 2.5f ? 1 : 0;
-    v.cut_gain = v.volumetric ? 5.1f : 6.5f;
+    v.cut_gain = 0.f;  // off: at 24 warps/SM the list space is worth more as staging buffer (profiles/README.md)
     if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
         const float gv = (float)std::atof(g);
         if (gv >= 0.f) v.cut_gain = gv;

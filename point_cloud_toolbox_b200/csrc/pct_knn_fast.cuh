@@ -78,7 +78,7 @@ __device__ __forceinline__ void emit_query(const Source& src, const typename Sou
 // ---------------------------------------------------------------------------
 // candidates through L1/L2
 // ---------------------------------------------------------------------------
-// shared memory of one block: [54][kBlock] cell runs, [cap][kBlock] neighbour list, [kBlock][68 B] histograms
+// shared memory of one block: [54][kBlock] cell runs, [cap][kBlock] neighbour list, [16][kBlock] histogram words
 __host__ __device__ inline size_t fast_smem_bytes(int cap) {
     return sizeof(uint32_t) * (size_t)(54 + cap) * kBlock + (size_t)kHistRowBytes * kBlock;
 }
@@ -94,10 +94,10 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
     src.runs.stride = kBlock;
     SelectScratch<uint32_t> sc;
     sc.list = smem_words + 54 * kBlock + threadIdx.x;
-    sc.hist = reinterpret_cast<uint8_t*>(smem_words + (54 + cap) * kBlock) + kHistRowBytes * threadIdx.x;
+    sc.hist = smem_words + (54 + cap) * kBlock + threadIdx.x;
+    sc.hist_stride = kBlock;
     sc.stride = kBlock;
     sc.cap = cap;
-    sc.collect = false;  // this kernel sees the hard cases; its list is k + PCT_TIE_SLACK wide
     long long total = qr.q_end - qr.q_begin;
     if (qr.list) total = (long long)*qr.count;
     for (long long base = (long long)blockIdx.x * kBlock; base < total; base += (long long)gridDim.x * kBlock) {
@@ -110,7 +110,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         src.runs.collect(st);
         uint32_t first = 0, last = 0;
         double d2_last = 0.0;
-        const int rc = knn_select(ix, st, level, src, q, k, sc, first, last, d2_last);
+        const int rc = knn_select<false>(ix, st, level, src, q, k, sc, first, last, d2_last);  // no pre-collection: the list is k + PCT_TIE_SLACK wide
         if (rc != SEL_OK) {
             if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
                 qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -126,12 +126,18 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
 // ---------------------------------------------------------------------------
 // candidates staged in shared memory
 // ---------------------------------------------------------------------------
+constexpr int kStagedBlock = PCT_STAGED_BLOCK;  // queries (= threads) of one CTA
+constexpr int kStagedWarps = kStagedBlock / 32;
+
 template <int U>
 struct StageShape : RegionShape<U> {
-    // a chunk of 128 Morton-consecutive queries touches this many parent cubes at most
-    static constexpr int kMaxRegions = U >= 2 ? 4 : 8;
+    // a chunk of kStagedBlock Morton-consecutive queries touches this many parent cubes at most
+    static constexpr int kMaxRegions = U >= 2 ? 2 + kStagedBlock / 64 : 4 + kStagedBlock / 16;
     static constexpr int kTable = kMaxRegions * RegionShape<U>::kCells;
-    static constexpr int kItemsPerThread = (kTable + kBlock - 1) / kBlock;
+    static constexpr int kItemsPerThread = (kTable + kStagedBlock - 1) / kStagedBlock;
+    // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, then the region origins
+    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrOrg = kHdrFlag + 2;
+    static constexpr int kHdrWords = (kHdrOrg + 3 * kMaxRegions + 3) & ~3;
 };
 
 struct StagedCell {
@@ -143,44 +149,42 @@ struct StagedCell {
 // dynamic shared memory of the staged kernel, in this order (every part 16-byte aligned):
 //   Pt       pts[cap_pts]
 //   uint32   tab[kTable + 4]         shared address of the first record of every region cell
-//   int      hdr[32]                 region origins, block-scan partials, flags
+//   int      hdr[kHdrWords]          block-scan partials, flags, region origins
 //   scratch  max(per-query scratch, staging temporaries)
-//       per query  : uint16 list[cap][kBlock], uint8 hist[kBlock][68]
-//       temporaries: uint32 first[kTable], uint16 count[kTable], StagedCell cells[kTable]
+//       per query  : uint16 list[cap][kStagedBlock], uint32 hist[16][kStagedBlock]
+//       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
 __host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
-    const size_t per_query = ((size_t)cap * sizeof(uint16_t) + kHistRowBytes) * kBlock;
+    const size_t per_query = ((size_t)cap * sizeof(uint16_t) + kHistRowBytes) * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
     const size_t tab = (size_t)(StageShape<U>::kTable + 4) * sizeof(uint32_t);
-    return sizeof(Pt) * (size_t)cap_pts + tab + 32 * sizeof(int) + ((scratch + 15) & ~(size_t)15);
+    return sizeof(Pt) * (size_t)cap_pts + tab + StageShape<U>::kHdrWords * sizeof(int) + ((scratch + 15) & ~(size_t)15);
 }
 
 #if defined(__CUDACC__)
-template <int U, bool FUSED>
-__global__ void __launch_bounds__(kBlock, 4)
+template <int U, bool FUSED, bool COLLECT>
+__global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
 knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
     typedef StageShape<U> Shape;
-    constexpr int S = Shape::kSide, C = Shape::kCells;
+    constexpr int S = Shape::kSide, C = Shape::kCells, B = kStagedBlock, W = kStagedWarps;
     extern __shared__ uint4 smem_u4[];
     Pt* const pts_s = reinterpret_cast<Pt*>(smem_u4);
     uint32_t* const tab = reinterpret_cast<uint32_t*>(pts_s + cap_pts);
     int* const hdr = reinterpret_cast<int*>(tab + Shape::kTable + 4);
     const uint32_t pts_addr = (uint32_t)__cvta_generic_to_shared(pts_s);
-    char* const scratch = reinterpret_cast<char*>(hdr + 32);
-    // hdr: [0..3] warp partials (points), [4..7] warp partials (cells / heads), [8] regions, [9] flags,
-    //      [10] queue base, [12 + 3 r ..] origin of region r
-    int* const org = hdr + 12;
+    char* const scratch = reinterpret_cast<char*>(hdr + Shape::kHdrWords);
+    int* const org = hdr + Shape::kHdrOrg;
     // staging temporaries (dead before the per-query scratch is first written)
     uint32_t* const t_first = reinterpret_cast<uint32_t*>(scratch);
     StagedCell* const t_cells = reinterpret_cast<StagedCell*>(t_first + Shape::kTable);
     uint16_t* const t_count = reinterpret_cast<uint16_t*>(t_cells + Shape::kTable);
-    unsigned long long* const t_parent = reinterpret_cast<unsigned long long*>(t_cells);  // [kBlock], before the cells exist
+    unsigned long long* const t_parent = reinterpret_cast<unsigned long long*>(t_cells);  // [B], before the cells exist
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long total = qr.q_end - qr.q_begin;
-    const long long tq = (long long)blockIdx.x * kBlock + t;
+    const long long tq = (long long)blockIdx.x * B + t;
     const bool active = tq < total;
     const uint32_t i = (uint32_t)(qr.q_begin + (active ? tq : total - 1));
     const Pt q = load_pt(ix.pts + i);
@@ -191,17 +195,22 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
                                       ((unsigned long long)(cz >> U) << 42);
     t_parent[t] = parent;
-    if (t == 0) hdr[9] = 0;
+    if (t == 0) hdr[Shape::kHdrFlag] = 0;
     __syncthreads();
     const bool head = t == 0 || t_parent[t - 1] != parent;
     const unsigned int heads = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) hdr[4 + warp] = __popc(heads);
+    if (lane == 0) hdr[W + warp] = __popc(heads);
     __syncthreads();
     int region = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
-    for (int w = 0; w < warp; ++w) region += hdr[4 + w];
-    const int regions = hdr[4] + hdr[5] + hdr[6] + hdr[7];
+    int regions = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const int c = hdr[W + w];
+        region += w < warp ? c : 0;
+        regions += c;
+    }
     if (regions > Shape::kMaxRegions) {
-        if (t == 0) hdr[9] = 1;
+        if (t == 0) hdr[Shape::kHdrFlag] = 1;
     } else if (head) {
         org[3 * region] = ((cx >> U) << U) - 1;
         org[3 * region + 1] = ((cy >> U) << U) - 1;
@@ -211,7 +220,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
 
     // ---- B. one hash probe per region cell
     const int n_table = regions > Shape::kMaxRegions ? 0 : regions * C;
-    for (int item = t; item < n_table; item += kBlock) {
+    for (int item = t; item < n_table; item += B) {
         const int r = item / C, c = item - r * C;
         const int lz = c / (S * S), ly = (c - lz * S * S) / S, lx = c - lz * S * S - ly * S;
         const int gx = org[3 * r] + lx, gy = org[3 * r + 1] + ly, gz = org[3 * r + 2] + lz;
@@ -219,7 +228,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         if (gx >= 0 && gx < ix.dims[0] && gy >= 0 && gy < ix.dims[1] && gz >= 0 && gz < ix.dims[2])
             if (!lookup_cell(ix.lvl[0], morton3((uint32_t)gx, (uint32_t)gy, (uint32_t)gz), s, e)) s = e = 0;
         uint32_t n = e - s;
-        if (n > 0xffffu) { n = 0xffffu; hdr[9] = 1; }
+        if (n > 0xffffu) { n = 0xffffu; hdr[Shape::kHdrFlag] = 1; }
         t_first[item] = s;
         t_count[item] = (uint16_t)n;
     }
@@ -240,22 +249,27 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         const uint32_t a = __shfl_up_sync(0xffffffffu, inc_pts, o), b = __shfl_up_sync(0xffffffffu, inc_cells, o);
         if (lane >= o) { inc_pts += a; inc_cells += b; }
     }
-    if (lane == 31) { hdr[warp] = (int)inc_pts; hdr[4 + warp] = (int)inc_cells; }
+    if (lane == 31) { hdr[warp] = (int)inc_pts; hdr[W + warp] = (int)inc_cells; }
     __syncthreads();
     uint32_t run = inc_pts - my_pts, cell = inc_cells - my_cells;
-    for (int w = 0; w < warp; ++w) { run += (uint32_t)hdr[w]; cell += (uint32_t)hdr[4 + w]; }
-    const uint32_t staged = (uint32_t)(hdr[0] + hdr[1] + hdr[2] + hdr[3]);
-    const int n_cells = hdr[4] + hdr[5] + hdr[6] + hdr[7];
-    const bool unstaged = hdr[9] != 0 || staged > (uint32_t)cap_pts;
+    uint32_t staged = 0;
+    int n_cells = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint32_t a = (uint32_t)hdr[w], b = (uint32_t)hdr[W + w];
+        run += w < warp ? a : 0u;
+        cell += w < warp ? b : 0u;
+        staged += a;
+        n_cells += (int)b;
+    }
+    const bool unstaged = hdr[Shape::kHdrFlag] != 0 || staged > (uint32_t)cap_pts;
     if (unstaged) {
-        // the chunk goes to the L1/L2 kernel as a whole
-        unsigned int n_active = __popc(__ballot_sync(0xffffffffu, active));
+        // the chunk goes to the L1/L2 kernel as a whole; active threads are a prefix of the block
+        const long long left = total - (long long)blockIdx.x * B;
+        const unsigned int n_active = left < B ? (unsigned int)left : (unsigned int)B;
+        if (t == 0) hdr[Shape::kHdrQueue] = (int)atomicAdd(&qu.counters[2], n_active);
         __syncthreads();
-        if (lane == 0) hdr[warp] = (int)n_active;
-        __syncthreads();
-        if (t == 0) hdr[10] = (int)atomicAdd(&qu.counters[2], (unsigned int)(hdr[0] + hdr[1] + hdr[2] + hdr[3]));
-        __syncthreads();
-        if (active) qu.fallback[(unsigned int)hdr[10] + (unsigned int)t] = i;  // active threads are a prefix of the block
+        if (active) qu.fallback[(unsigned int)hdr[Shape::kHdrQueue] + (unsigned int)t] = i;
         return;
     }
 #pragma unroll
@@ -276,7 +290,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     __syncthreads();
 
     // ---- D. copy the non-empty cells, eight lanes per cell
-    for (int e = t >> 3; e < n_cells; e += kBlock / 8) {
+    for (int e = t >> 3; e < n_cells; e += B / 8) {
         const StagedCell sc = t_cells[e];
         for (uint32_t m = t & 7; m < sc.count; m += 8) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(ix.pts + sc.first + m));
@@ -294,15 +308,15 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     src.side = S;
     SelectScratch<uint16_t> sel;
     sel.list = reinterpret_cast<uint16_t*>(scratch) + t;
-    sel.hist = reinterpret_cast<uint8_t*>(scratch) + sizeof(uint16_t) * (size_t)cap * kBlock + kHistRowBytes * t;
-    sel.stride = kBlock;
+    sel.hist = reinterpret_cast<uint32_t*>(scratch + sizeof(uint16_t) * (size_t)cap * B) + t;
+    sel.hist_stride = B;
+    sel.stride = B;
     sel.cap = cap;
-    sel.collect = cap >= 2 * k + PCT_TIE_SLACK;
     Stencil st;
     make_stencil(ix, 0, q.x, q.y, q.z, st);
     uint16_t first = 0, last = 0;
     double d2_last = 0.0;
-    const int rc = knn_select(ix, st, 0, src, q, k, sel, first, last, d2_last);
+    const int rc = knn_select<COLLECT>(ix, st, 0, src, q, k, sel, first, last, d2_last);
     if (rc != SEL_OK) {
         if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
             qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -312,7 +326,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         return;
     }
     // ---- F. fit (or ordered rows) out of the staged copy
-    emit_query<FUSED>(src, sel.list, kBlock, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
+    emit_query<FUSED>(src, sel.list, B, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
 }
 #endif
 
@@ -352,19 +366,21 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     // list of the staged kernel: room for the candidates pre-collected below the estimated k-th distance
     // (expected number + 3 sigma) and the boundary zone
     const double lambda = expected_collected(v, a.k);
-    const int cap_staged = std::max(a.cap, (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK);
-    // staging buffer: what is left of a quarter SM's shared memory after the fixed parts
+    const int cap_collect = (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK;
+    const bool collect = cap_collect >= 2 * a.k + PCT_TIE_SLACK;  // cut_gain == 0 switches it off
+    const int cap_staged = collect ? cap_collect : a.cap;
+    // staging buffer: what is left of this CTA's share of the SM's shared memory after the fixed parts
     constexpr int U = 2;
-    auto staged = knn_staged_kernel<U, FUSED>;
+    auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
     const size_t fixed = staged_smem_bytes<U>(cap_staged, 0);
-    const size_t budget = (size_t)a.ix->smem_per_sm / 4 - 1024;  // __launch_bounds__(kBlock, 4)
+    const size_t budget = (size_t)a.ix->smem_per_sm / PCT_STAGED_CTAS - 1024;
     int cap_pts = fixed + 16 * 512 <= budget ? (int)((budget - fixed) / sizeof(Pt)) : 512;
     if (cap_pts > 0xffff) cap_pts = 0xffff;
     const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts);
     if (smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
-        const long long chunks = (nq + kBlock - 1) / kBlock;
-        staged<<<(unsigned int)chunks, kBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);
+        const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
+        staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);
         ++*launches;
         QueryRange qf = a.qr;
         qf.list = a.fallback0;

@@ -100,13 +100,14 @@ struct Moments {
     double sx, sy, sz, sxx, sxy, sxz, syy, syz, szz;
     float max_abs;
     int n;
-    bool finite;
     PCT_HD void reset() {
         sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0.0;
         max_abs = 0.f;
         n = 0;
-        finite = true;
     }
+    // ref :273-274: a NaN / Inf among the centred points shows in the sums of squares (which
+    // cannot overflow on their own: fp32 squares, fp64 sums)
+    PCT_HD bool finite() const { return fabs(sxx + syy + szz) <= 1.7e308; }
     // (cx, cy, cz) = neighbour - query, already rounded to fp32 (ref :641)
     PCT_HD void add(float cx, float cy, float cz) {
         const double x = cx, y = cy, z = cz;
@@ -114,7 +115,6 @@ struct Moments {
         sxx = fma(x, x, sxx); sxy = fma(x, y, sxy); sxz = fma(x, z, sxz);
         syy = fma(y, y, syy); syz = fma(y, z, syz); szz = fma(z, z, szz);
         max_abs = fmaxf(max_abs, fmaxf(fabsf(cx), fmaxf(fabsf(cy), fabsf(cz))));
-        finite = finite && (fabsf(cx) <= 3.0e38f) && (fabsf(cy) <= 3.0e38f) && (fabsf(cz) <= 3.0e38f);
         ++n;
     }
 };
@@ -286,18 +286,17 @@ PCT_HD void rotate_point(const Frame& f, float cx, float cy, float cz, double& x
 struct Quadric {
     double g[21];  // upper triangle of X^T X, row major: (0,0) (0,1) .. (0,5) (1,1) ..
     double r[6];   // X^T z
-    bool finite;
     PCT_HD void reset() {
 #pragma unroll
         for (int i = 0; i < 21; ++i) g[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) r[i] = 0.0;
-        finite = true;
     }
+    // ref :318-319, :356-357: non-finite rotated coordinates show in sum a^2, sum b^2, sum z
+    PCT_HD bool finite() const { return fabs(g[15]) <= 1.7e308 && fabs(g[18]) <= 1.7e308 && fabs(r[5]) <= 1.7e308; }
     // rotated coordinates in fp64, quantised here to fp32 like ref :350
     PCT_HD void add(double xr, double yr, double zr, float scale) {
         const float a = (float)xr * scale, b = (float)yr * scale, z = (float)zr * scale;
-        finite = finite && (fabsf(a) <= 3.0e38f) && (fabsf(b) <= 3.0e38f) && (fabsf(z) <= 3.0e38f);
         double x[6];
         x[0] = (double)fmul_rn(a, a);  // ref :358, fp32 products
         x[1] = (double)fmul_rn(b, b);
@@ -436,7 +435,7 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     mom.reset();
     nb.pass(mom);
     if (mom.n < 2) { fit_fail(out, ST_FEW); return; }
-    if (!mom.finite) { fit_fail(out, ST_NONFINITE); return; }
+    if (!mom.finite()) { fit_fail(out, ST_NONFINITE); return; }
     float rx, ry, rz;
     nb.reference(rx, ry, rz);
     Frame fr;
@@ -456,7 +455,7 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     sec.scale = pow2_scale(mom.max_abs);
     nb.pass(sec);
     out.normal[0] = (float)fr.nx; out.normal[1] = (float)fr.ny; out.normal[2] = (float)fr.nz;
-    if (!sec.q.finite) { fit_fail(out, ST_NONFINITE); return; }
+    if (!sec.q.finite()) { fit_fail(out, ST_NONFINITE); return; }
     double w[6];
     const bool ok = solve_normal_equations(sec.q, w);
     if (!ok) {

@@ -114,7 +114,7 @@ static void exact_rows(const IndexView& v, uint32_t i, int k, uint32_t* out) {
 }
 
 // Host emulation of the staged kernel's region tables (csrc/pct_knn_fast.cuh, steps A-D) for one
-// chunk of 128 consecutive sorted queries: same geometry, same table layout, serial code.
+// chunk of PCT_STAGED_BLOCK consecutive sorted queries: same geometry, same table layout, serial code.
 template <int U>
 struct HostStage {
     static constexpr int S = RegionShape<U>::kSide, C = RegionShape<U>::kCells;
@@ -168,8 +168,9 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
     std::vector<uint32_t> list(cap), runs(54);
     std::vector<uint16_t> list16(cap);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
-    SelectScratch<uint32_t> sc{list.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap, coll_extra > 0};
-    SelectScratch<uint16_t> sc16{list16.data(), reinterpret_cast<uint8_t*>(hist.data()), 1, cap, coll_extra > 0};
+    SelectScratch<uint32_t> sc{list.data(), hist.data(), 1, 1, cap};
+    SelectScratch<uint16_t> sc16{list16.data(), hist.data(), 1, 1, cap};
+    const bool collect = coll_extra > 0;
     GlobalSource gsrc;
     gsrc.pts = v.pts;
     gsrc.runs.buf = runs.data();
@@ -177,8 +178,8 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
     HostStage<(U > 0 ? U : 1)> stage;
     for (long long i = 0; i < v.n; ++i) {
         const Pt q = v.pts[i];
-        if (U > 0 && i % 128 == 0)
-            stage.build(v, i, std::min<long long>(i + 128, v.n), U >= 2 ? 4 : 8, (size_t)cap_pts);
+        if (U > 0 && i % PCT_STAGED_BLOCK == 0)
+            stage.build(v, i, std::min<long long>(i + PCT_STAGED_BLOCK, v.n), U >= 2 ? 2 + PCT_STAGED_BLOCK / 64 : 4 + PCT_STAGED_BLOCK / 16, (size_t)cap_pts);
         uint32_t first = 0, last = 0;
         double d2_last = 0;
         int rc = SEL_RETRY_COARSER, level = 0;
@@ -188,7 +189,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
             make_stencil(v, level, q.x, q.y, q.z, st);
             if (U > 0 && level == 0 && stage.ok) {
                 constexpr int S = RegionShape<(U > 0 ? U : 1)>::kSide, C = RegionShape<(U > 0 ? U : 1)>::kCells;
-                const int r = stage.region_of[i % 128];
+                const int r = stage.region_of[i % PCT_STAGED_BLOCK];
                 int cx, cy, cz;
                 cell_of(v, q.x, q.y, q.z, cx, cy, cz);
                 const int lx = cx - stage.org[3 * r], ly = cy - stage.org[3 * r + 1], lz = cz - stage.org[3 * r + 2];
@@ -198,7 +199,8 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
-                rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                rc = collect ? knn_select<true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last)
+                             : knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
                     for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[list16[m]].idx];
@@ -208,7 +210,8 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 }
             } else {
                 gsrc.runs.collect(st);
-                rc = knn_select(v, st, level, gsrc, q, k, sc, first, last, d2_last);
+                rc = collect ? knn_select<true>(v, st, level, gsrc, q, k, sc, first, last, d2_last)
+                             : knn_select<false>(v, st, level, gsrc, q, k, sc, first, last, d2_last);
             }
             if (rc != SEL_RETRY_COARSER) break;
         }

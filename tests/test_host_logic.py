@@ -39,7 +39,7 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=2048, coll_extra=0, cut_gain=6.5):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, coll_extra=0, cut_gain=6.5):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
@@ -86,7 +86,7 @@ def test_staged_source_gives_the_same_rows(harness, bunny, staged_u):
     assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0
     assert np.array_equal(got["dist"], ref_dist)
     # a staging buffer that is too small sends chunks to the L1/L2 path; nothing else changes
-    small = run_knn(harness, pts, k, h, staged_u=staged_u, cap_pts=600)
+    small = run_knn(harness, pts, k, h, staged_u=staged_u, cap_pts=1200)
     assert 0.0 < np.mean(small["code"] == 50) < np.mean(got["code"] == 50)
     assert np.array_equal(small["idx"], got["idx"])
     # pre-collection during pass 1: the estimate of the k-th distance (any gain, any list size) only
