@@ -309,7 +309,7 @@ enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 
 // Selection scratch of one query.  On the GPU all of it lives in shared memory:
 //   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
-//   list  cap entries, slot m at list[m * stride]        (neighbour positions)
+//   list  cap entries, addressed through ListRef           (neighbour positions)
 //   hist  kHistBins byte counters = 16 words, word w at hist[w * hist_stride]   (distance histogram);
 //         with hist_stride = threads of the block every thread stays in its own bank
 static constexpr int kHistBins = 64;
@@ -422,12 +422,24 @@ struct StagedSource {
     }
 };
 
+// A per-query list of positions inside an array shared by the threads of a block.  Every thread owns
+// one 32-bit word of each row of `threads` words, so rows never make two threads share a bank and a
+// thread's words can be reused for another per-thread structure (the histogram) without any
+// synchronisation: 32-bit positions take one row per slot, 16-bit positions one row per slot PAIR.
+template <class PosT>
+struct ListRef {
+    PosT* base;  // the thread's first element
+    int stride;  // elements of PosT between consecutive rows
+    PCT_HD PosT& at(int m) const {
+        return sizeof(PosT) == 2 ? base[(size_t)(m >> 1) * stride + (m & 1)] : base[(size_t)m * stride];
+    }
+};
+
 template <class PosT>
 struct SelectScratch {
-    PosT* list;     // slot m at list[m * stride]
+    ListRef<PosT> list;
     uint32_t* hist; // word w of the byte histogram at hist[w * hist_stride]
     int hist_stride;
-    int stride;
     int cap;        // list slots; the last PCT_TIE_SLACK of them hold the boundary zone (COLLECT needs cap well above k + that)
 };
 
@@ -452,7 +464,7 @@ struct SelectScratch {
 //           farthest front point and the nearest zone point are closer than 2e-6
 //           relative the cut itself is ambiguous and the query goes to the exact kernel.
 //
-// On SEL_OK, list[m * stride] (m < k) holds the neighbours' positions (unordered),
+// On SEL_OK, list.at(m) (m < k) holds the neighbours' positions (unordered),
 // `first` / `last` the nearest / farthest by (d2 fp64, original index).
 template <bool COLLECT, class Source>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
@@ -488,8 +500,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     struct P1 {
         uint8_t* hist;
         int hist_stride4;  // bytes between consecutive words
-        Pos* list;
-        int stride;
+        ListRef<Pos> list;
         uint32_t seen, n_coll, coll_slots;
         float qx, qy, qz, range2, inv_w, cut2;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
@@ -500,13 +511,13 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
                 *c = (uint8_t)(*c + 1);
                 ++seen;
                 if (COLLECT && d < cut2) {
-                    if (n_coll < coll_slots) list[(size_t)n_coll * stride] = j;
+                    if (n_coll < coll_slots) list.at((int)n_coll) = j;
                     ++n_coll;
                 }
             }
         }
     } p1;
-    p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.stride = sc.stride; p1.seen = 0; p1.n_coll = 0;
+    p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.seen = 0; p1.n_coll = 0;
     p1.coll_slots = (uint32_t)coll_slots;
     p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
     src.scan(p1);
@@ -545,24 +556,24 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
 
     struct P2 {
-        Pos* list;
-        int stride, zone_top, zone_slots;
+        ListRef<Pos> list;
+        int zone_top, zone_slots;
         uint32_t self, n_front, n_zone;
         float qx, qy, qz, lo, hi;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
             if (d <= hi && p.idx != self) {
                 if (d < lo) {
-                    list[(size_t)n_front * stride] = j;  // n_front < k: always room
+                    list.at((int)n_front) = j;  // n_front < k: always room
                     ++n_front;
                 } else {
-                    if ((int)n_zone < zone_slots) list[(size_t)(zone_top - (int)n_zone) * stride] = j;
+                    if ((int)n_zone < zone_slots) list.at(zone_top - (int)n_zone) = j;
                     ++n_zone;
                 }
             }
         }
     } p2;
-    p2.list = sc.list; p2.stride = sc.stride; p2.zone_top = sc.cap - 1; p2.zone_slots = zone_slots;
+    p2.list = sc.list; p2.zone_top = sc.cap - 1; p2.zone_slots = zone_slots;
     p2.self = self; p2.n_front = 0; p2.n_zone = 0;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi;
     PCT_SELECT_TRACE(hi < cut2 && p1.n_coll <= (uint32_t)coll_slots);
@@ -571,7 +582,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         // position of the front never passes the read position)
 #pragma unroll 1
         for (uint32_t m = 0; m < p1.n_coll; ++m) {
-            const Pos j = sc.list[(size_t)m * sc.stride];
+            const Pos j = sc.list.at((int)m);
             p2(j, src.load(j), true);
         }
     } else {
@@ -592,7 +603,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 #pragma unroll 1
         for (int m = 0; m < n_list; ++m) {
             const bool is_front = m < n_front;
-            const Pos j = sc.list[(size_t)(is_front ? m : m + skip) * sc.stride];
+            const Pos j = sc.list.at(is_front ? m : m + skip);
             const Pt p = src.load(j);
             const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
             front_max = is_front ? fmaxf(front_max, d) : front_max;
@@ -611,23 +622,23 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     if (need < 1 || need > n_zone) return SEL_EXACT;   // (a saturated histogram bin can break the invariant)
 
     // exact choice inside the boundary zone: `need` successive minima of (d2, index)
-    Pos* zone = sc.list + (size_t)(sc.cap - n_zone) * sc.stride;
+    int zone0 = sc.cap - n_zone;  // first occupied zone slot
     for (int t = 0; t < need; ++t) {
         double bd = 0.0;
         uint32_t bi = 0;
         Pos bj = 0;
         int bm = 0;
         for (int m = 0; m < n_zone; ++m) {
-            const Pos j = zone[(size_t)m * sc.stride];
+            const Pos j = sc.list.at(zone0 + m);
             const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
         }
         // zone entries sit at the back in reverse order of arrival: remove bm by moving entry 0 into it
-        zone[(size_t)bm * sc.stride] = zone[0];
-        zone += sc.stride;
+        sc.list.at(zone0 + bm) = sc.list.at(zone0);
+        ++zone0;
         --n_zone;
-        sc.list[(size_t)(n_front + t) * sc.stride] = bj;
+        sc.list.at(n_front + t) = bj;
         last = bj;
         d2_last = bd;
     }
@@ -639,7 +650,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         double bd = 0.0;
         uint32_t bi = 0;
         for (int m = 0; m < k; ++m) {
-            const Pos j = sc.list[(size_t)m * sc.stride];
+            const Pos j = sc.list.at(m);
             const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
@@ -653,18 +664,18 @@ template <class Source>
 struct ListNeighbourhood {
     typedef typename Source::Pos Pos;
     const Source* src;
-    const Pos* list;
-    int stride, count;
+    ListRef<Pos> list;
+    int count;
     Pt q;
     Pos first, last;
     template <class F>
     PCT_HD void pass(F& fn) const {
         if (count <= 0) return;
-        Pt p = src->load(list[0]);
+        Pt p = src->load(list.at(0));
 #pragma unroll 1
         for (int m = 0; m < count; ++m) {
             const int mn = m + 1 < count ? m + 1 : m;
-            const Pt nxt = src->load(list[(size_t)mn * stride]);  // in flight during the fp64 work below
+            const Pt nxt = src->load(list.at(mn));  // in flight during the fp64 work below
             fn.add(fsub_rn(p.x, q.x), fsub_rn(p.y, q.y), fsub_rn(p.z, q.z));
             p = nxt;
         }

@@ -369,6 +369,8 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     info.bits_per_axis = v.bits;
     info.num_levels = v.num_levels;
     info.cells_level0 = cells[0];
+    for (int L = 0; L < kMaxLevels; ++L) ix->cells_level[L] = L < v.num_levels ? cells[L] : 1;
+    ix->est_dimension = est_dim;
     info.device_bytes = (int64_t)(sizeof(Pt) * (size_t)n + sizeof(HashSlot) * total_slots);
     info.est_dimension = est_dim;
     return PCT_OK;

@@ -17,6 +17,8 @@ struct pct_index {
     unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries, unstaged, -, -, -]
     pct_index_info info{};
     int device = 0;
+    long long cells_level[pct::kMaxLevels] = {};  // occupied cells per level
+    float est_dimension = 2.f;                    // intrinsic dimension seen by the density pilot
     int sm_count = 148;
     int smem_per_sm = 233472;           // shared memory of one SM
     int smem_per_block_optin = 232448;  // largest dynamic allocation of one block

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "pct_internal.h"
 
@@ -45,13 +46,13 @@ __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, u
 // What a query does once its k neighbours sit in list[m * stride]: the fused fit, or the
 // ordered (index, distance) rows of plant_kdtree (ref :78-85).
 template <bool FUSED, class Source>
-__device__ __forceinline__ void emit_query(const Source& src, const typename Source::Pos* list, int stride, int k,
+__device__ __forceinline__ void emit_query(const Source& src, const ListRef<typename Source::Pos>& list, int k,
                                            const Pt& q, typename Source::Pos first, typename Source::Pos last,
                                            long long row, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
                                            const FitOutputs& out) {
     if (FUSED) {
         ListNeighbourhood<Source> nb;
-        nb.src = &src; nb.list = list; nb.stride = stride; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+        nb.src = &src; nb.list = list; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
         FitResult r;
         r.status = 0;
         fit_neighbourhood(nb, r);
@@ -64,7 +65,7 @@ __device__ __forceinline__ void emit_query(const Source& src, const typename Sou
             double bd = 1.0e300;
             uint32_t bi = 0xffffffffu;
             for (int c = 0; c < k; ++c) {
-                const Pt p = src.load(list[(size_t)c * stride]);
+                const Pt p = src.load(list.at(c));
                 const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
                 if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
             }
@@ -93,10 +94,10 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
     src.runs.buf = smem_words + threadIdx.x;
     src.runs.stride = kBlock;
     SelectScratch<uint32_t> sc;
-    sc.list = smem_words + 54 * kBlock + threadIdx.x;
+    sc.list.base = smem_words + 54 * kBlock + threadIdx.x;
+    sc.list.stride = kBlock;
     sc.hist = smem_words + (54 + cap) * kBlock + threadIdx.x;
     sc.hist_stride = kBlock;
-    sc.stride = kBlock;
     sc.cap = cap;
     long long total = qr.q_end - qr.q_begin;
     if (qr.list) total = (long long)*qr.count;
@@ -119,7 +120,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
             }
             continue;
         }
-        emit_query<FUSED>(src, sc.list, kBlock, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
+        emit_query<FUSED>(src, sc.list, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
     }
 }
 
@@ -151,11 +152,13 @@ struct StagedCell {
 //   uint32   tab[kTable + 4]         shared address of the first record of every region cell
 //   int      hdr[kHdrWords]          block-scan partials, flags, region origins
 //   scratch  max(per-query scratch, staging temporaries)
-//       per query  : uint16 list[cap][kStagedBlock], uint32 hist[16][kStagedBlock]
+//       per query  : uint16 list[cap][kStagedBlock], uint32 hist[16][kStagedBlock]; without pre-collection the
+//                    list is first written after the histogram has been read, so the two share their memory
 //       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
-__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
-    const size_t per_query = ((size_t)cap * sizeof(uint16_t) + kHistRowBytes) * kStagedBlock;
+__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool collect) {
+    const size_t list = (size_t)((cap + 1) & ~1) * sizeof(uint16_t), hist = kHistRowBytes;
+    const size_t per_query = (collect ? list + hist : (list > hist ? list : hist)) * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
     const size_t tab = (size_t)(StageShape<U>::kTable + 4) * sizeof(uint32_t);
@@ -307,10 +310,10 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
     src.side = S;
     SelectScratch<uint16_t> sel;
-    sel.list = reinterpret_cast<uint16_t*>(scratch) + t;
-    sel.hist = reinterpret_cast<uint32_t*>(scratch + sizeof(uint16_t) * (size_t)cap * B) + t;
+    sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
+    sel.list.stride = 2 * B;
+    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? sizeof(uint16_t) * (size_t)((cap + 1) & ~1) * B : 0)) + t;
     sel.hist_stride = B;
-    sel.stride = B;
     sel.cap = cap;
     Stencil st;
     make_stencil(ix, 0, q.x, q.y, q.z, st);
@@ -326,7 +329,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         return;
     }
     // ---- F. fit (or ordered rows) out of the staged copy
-    emit_query<FUSED>(src, sel.list, B, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
+    emit_query<FUSED>(src, sel.list, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
 }
 #endif
 
@@ -369,15 +372,27 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const int cap_collect = (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK;
     const bool collect = cap_collect >= 2 * a.k + PCT_TIE_SLACK;  // cut_gain == 0 switches it off
     const int cap_staged = collect ? cap_collect : a.cap;
-    // staging buffer: what is left of this CTA's share of the SM's shared memory after the fixed parts
+    // staging buffer: what is left of this CTA's share of the SM's shared memory after the fixed parts.
+    // The kernel is compiled for PCT_STAGED_CTAS resident CTAs; when the regions of a chunk are expected
+    // to be larger than that share (large k: cells hold 0.4 k points), fewer, larger CTAs are resident.
     constexpr int U = 2;
     auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
-    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0);
-    const size_t budget = (size_t)a.ix->smem_per_sm / PCT_STAGED_CTAS - 1024;
-    int cap_pts = fixed + 16 * 512 <= budget ? (int)((budget - fixed) / sizeof(Pt)) : 512;
+    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect);
+    // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide,
+    // but a few percent of unstaged chunks cost less than a third of the resident warps (scripts/gain_sweep.py)
+    const double per_parent = (double)v.n / (double)std::max<long long>(1, a.ix->cells_level[std::min(U, v.num_levels - 1)]);
+    const double wanted = 1.3 * (per_parent + kStagedBlock) * std::pow(1.5, (double)std::min(3.f, std::max(1.f, a.ix->est_dimension)));
+    int cap_pts = 0;
+    int ctas_max = PCT_STAGED_CTAS;
+    if (const char* e = std::getenv("PCT_STAGED_RESIDENT")) ctas_max = std::max(1, std::min(PCT_STAGED_CTAS, std::atoi(e)));  // experiments
+    for (int ctas = ctas_max; ctas >= 1; --ctas) {
+        const size_t budget = std::min((size_t)a.ix->smem_per_sm / ctas - 1024, (size_t)a.ix->smem_per_block_optin);
+        cap_pts = budget > fixed ? (int)((budget - fixed) / sizeof(Pt)) : 0;
+        if ((double)cap_pts >= wanted) break;
+    }
     if (cap_pts > 0xffff) cap_pts = 0xffff;
-    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts);
-    if (smem_staged <= (size_t)a.ix->smem_per_block_optin) {
+    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts, collect);
+    if (cap_pts >= 512 && smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
         staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);

@@ -118,7 +118,7 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             GlobalSource src;
             src.pts = ix.pts;
             ListNeighbourhood<GlobalSource> nb;
-            nb.src = &src; nb.list = mine; nb.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
+            nb.src = &src; nb.list.base = mine; nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
             FitResult r;
             r.status = ST_EXACT_PATH;
             fit_neighbourhood(nb, r);

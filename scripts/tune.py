@@ -17,9 +17,14 @@ def torus(n, seed=3, dev="cuda"):
     return torch.stack((w * torch.cos(u), w * torch.sin(u), torch.sin(v) / 3.0), 1).float().contiguous()
 
 
-def timed(fn, reps=3):
-    fn()
-    torch.cuda.synchronize()
+def timed(fn, reps=3, warm_s=0.4):
+    # the idle GPU sits at 120 MHz: spin until the clocks are up before timing anything
+    t0 = time.perf_counter()
+    while True:
+        fn()
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 > warm_s:
+            break
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):

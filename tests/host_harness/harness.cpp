@@ -166,10 +166,10 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK + coll_extra;  // coll_extra > 0 switches the pre-collection of pass 1 on
     std::vector<uint32_t> list(cap), runs(54);
-    std::vector<uint16_t> list16(cap);
+    std::vector<uint16_t> list16(cap + 1);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
-    SelectScratch<uint32_t> sc{list.data(), hist.data(), 1, 1, cap};
-    SelectScratch<uint16_t> sc16{list16.data(), hist.data(), 1, 1, cap};
+    SelectScratch<uint32_t> sc{{list.data(), 1}, hist.data(), 1, cap};
+    SelectScratch<uint16_t> sc16{{list16.data(), 2}, hist.data(), 1, cap};  // 16-bit slots come in pairs: row stride 2
     const bool collect = coll_extra > 0;
     GlobalSource gsrc;
     gsrc.pts = v.pts;
@@ -237,7 +237,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
         }
         if (curv) {
             ListNeighbourhood<GlobalSource> nb;
-            nb.src = &gsrc; nb.list = list.data(); nb.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+            nb.src = &gsrc; nb.list.base = list.data(); nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
             FitResult r;
             r.status = exact ? ST_EXACT_PATH : 0;
             fit_neighbourhood(nb, r);
