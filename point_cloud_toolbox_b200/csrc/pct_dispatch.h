@@ -14,3 +14,8 @@
 #ifndef PCT_STAGED_CTAS
 #define PCT_STAGED_CTAS 3
 #endif
+
+// candidates per trip of the staged candidate loop
+#ifndef PCT_SCAN_WIDTH
+#define PCT_SCAN_WIDTH 2
+#endif

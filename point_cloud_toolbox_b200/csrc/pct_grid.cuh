@@ -384,9 +384,10 @@ struct StagedSource {
 
     // One flat loop over the 9 runs: the lanes of a warp sit in different cells, so their
     // runs end at different trips; a flat loop makes the warp pay max-of-sums, not sum-of-maxes.
-    // Two candidates per trip: both records are loaded before either is used (the second
-    // load may run one record past the run; it stays inside the staging buffer and is
-    // discarded through `valid`), which overlaps their latencies and halves the loop control.
+    // kScanWidth candidates per trip: all records are loaded before any is used (loads may run
+    // past the run; they stay inside the block's shared memory and are discarded through
+    // `valid`), which overlaps their latencies and divides the loop control.
+    static constexpr int kScanWidth = PCT_SCAN_WIDTH;
     template <class F>
     PCT_HD void scan(F& fn) const {
         int r = 0, c0 = corner;
@@ -402,11 +403,14 @@ struct StagedSource {
                     c0 += (r == 3 || r == 6) ? side * side - 2 * side : side;
                 } while (a == e);
             }
-            const Pt p0 = load_at(a), p1 = load_at(a + 16);
-            const bool two = a + 16 != e;
-            fn((uint16_t)(a >> 4), p0, true);
-            fn((uint16_t)((a >> 4) + 1), p1, two);
-            a += two ? 32u : 16u;
+            // kScanWidth records per trip, all loaded before any is used
+            Pt p[kScanWidth];
+#pragma unroll
+            for (int u = 0; u < kScanWidth; ++u) p[u] = load_at(a + 16u * u);
+            const uint32_t left = (e - a) >> 4;
+#pragma unroll
+            for (int u = 0; u < kScanWidth; ++u) fn((uint16_t)((a >> 4) + u), p[u], u == 0 || (uint32_t)u < left);
+            a += left < (uint32_t)kScanWidth ? (e - a) : 16u * kScanWidth;
         }
     }
     PCT_HD Pt load(uint16_t pos) const { return load_at((uint32_t)pos << 4); }
