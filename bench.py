@@ -426,10 +426,16 @@ def ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         reference_arm(args)
     else:
         ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

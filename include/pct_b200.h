@@ -107,6 +107,14 @@ int pct_index_last_stats(const pct_index* index, void* stream, pct_query_stats* 
 int pct_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
             int32_t* idx, float* dist, int layout, void* stream);
 
+/* kNN lists of selected cloud points: replaces `self.kdtree.query(point, n + 1)` of the neighbour study
+ * (ref :759), which probes a few hundred sampled points with up to 100 neighbours.  query_ids: nq original
+ * indices; xyz: the cloud the index was built from (the points are located through their own cell).
+ * Row r = the k nearest OTHER points of point query_ids[r], ordered like pct_knn; idx nq x k, dist nq x k.
+ * Synchronises `stream`; PCT_ERR_INVALID_ARGUMENT if an id is not a point of the indexed cloud. */
+int pct_knn_points(const pct_index* index, const float* xyz, int stride, const int32_t* query_ids,
+                   int64_t nq, int k, int32_t* idx, float* dist, void* stream);
+
 /* epsilon-ball (advertised README.md:8, absent in the reference; semantics of
  * scipy `query_ball_point`: d2 <= radius*radius in fp64, self excluded).
  * count: rows x int32.  fill: CSR rows given exclusive `offsets` (rows + 1, int64),

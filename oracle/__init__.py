@@ -13,6 +13,9 @@ Parity status
   ``egg_carton.txt`` and the torus stand-in; the vectors and the script that
   made them live in ``tests/golden/`` (``oracle/make_golden.py``).
   The reference has no tests or golden vectors of its own.
+* neighbour study (ref :732-800): **pinned** -- return values of the unmodified reference's
+  ``explicit_quadratic_neighbor_study`` on ``bunny.txt`` for seeded samples and several tolerances
+  (``tests/golden/neighbor_study.npz``).
 * epsilon-ball query: **parity unpinned** -- the reference never implemented it
   (README.md:8 advertises it, pointCloudToolbox.py:101-102 only lists scipy's
   API).  The oracle composes ``scipy.spatial.cKDTree.query_ball_point`` with the
@@ -37,5 +40,6 @@ from .reference_path import (  # noqa: F401
     curvature_from_neighbors_batched,
     curvature_from_csr,
     knn_curvature,
+    neighbor_study,
 )
 from . import datasets, compare  # noqa: F401

@@ -115,7 +115,26 @@ def main():
         x_domain=np.asarray(pc.x_domain), y_domain=np.asarray(pc.y_domain), z_domain=np.asarray(pc.z_domain),
         l1_norm=pc.l1_norm, l2_norm=pc.l2_norm, infinity_norm=pc.infinity_norm,
     )
+    neighbor_study_case(ref, bunny)
     print("done")
+
+
+def neighbor_study_case(ref, bunny_path):
+    """Return values of the reference's own explicit_quadratic_neighbor_study (ref :732-800) for seeded samples."""
+    pc = ref.PointCloud(bunny_path, k_neighbors=20)
+    pc.plant_kdtree(20)
+    seeds, tols, sample_size = [0, 1], [1e-7, 5.0, 50.0, 500.0, 5000.0], 48
+    results = np.zeros((len(seeds), len(tols)), np.int64)
+    samples = np.zeros((len(seeds), sample_size), np.int64)
+    for a, seed in enumerate(seeds):
+        for b, tol in enumerate(tols):
+            np.random.seed(seed)
+            results[a, b] = pc.explicit_quadratic_neighbor_study(tol=tol, sample_size=sample_size)
+        np.random.seed(seed)
+        samples[a] = np.random.randint(0, len(pc.points), sample_size)  # the sample ref :751 drew
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "neighbor_study.npz"), seeds=np.asarray(seeds), tols=np.asarray(tols),
+                        sample_size=np.int64(sample_size), results=results, samples=samples)
+    print("neighbor study:", results.tolist())
 
 
 if __name__ == "__main__":

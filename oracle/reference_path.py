@@ -407,3 +407,43 @@ def knn_curvature(points, k, rows=None, batched=True):
     res = fn(points, idx, rows)
     res["idx"], res["dist"], res["d2"] = idx, dist, d2
     return res
+
+
+def neighbor_study(points, random_indexes, tol=1e-7, lower_bound=3, upper_bound=99, tree=None, return_counts=False):
+    """explicit_quadratic_neighbor_study (ref :732-800) for a GIVEN sample of point indices.
+
+    The reference draws the sample with ``np.random.randint(0, N, sample_size)`` (ref :751); everything
+    after that is restated here line by line: ``kdtree.query(point, n + 1)`` INCLUDING the point itself
+    (ref :759), centring (ref :761), plane + rotation (ref :763), fit with failures mapped to zero
+    coefficients (ref :764-767), Gaussian curvature (ref :769), the binary search on
+    ``abs(K(n + 1) - K(n)) < tol`` (ref :773-792) and ``int(mean) + 1`` (ref :800).
+    """
+    pts = np.asarray(points, dtype=np.float32)
+    if tree is None:
+        tree = cKDTree(pts)
+
+    def k_gauss(i, n):
+        nb = tree.query(pts[i], n + 1)[1]
+        centered = pts[nb] - pts[i]
+        rotated = best_fit_plane_and_rotate(centered)
+        try:
+            coeffs = fit_quadratic_surface(rotated)
+        except Exception:
+            coeffs = np.zeros(6, np.float32)
+        return explicit_quadratic_curvatures(coeffs)[0]
+
+    counts = []
+    for i in np.asarray(random_indexes):
+        lower, upper, best = int(lower_bound), int(upper_bound), None
+        while lower <= upper:
+            mid = (lower + upper) // 2
+            if abs(k_gauss(i, mid + 1) - k_gauss(i, mid)) < tol:
+                best = mid
+                upper = mid - 1
+            else:
+                lower = mid + 1
+        counts.append(upper if best is None else best)
+    if not counts:
+        return (0, np.zeros(0, np.int64)) if return_counts else 0
+    result = int(np.mean(counts)) + 1
+    return (result, np.asarray(counts, np.int64)) if return_counts else result

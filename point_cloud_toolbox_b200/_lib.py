@@ -65,6 +65,7 @@ SIGNATURES = {
     "pct_index_permutation": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pct_index_last_stats": (c_int, [c_void_p, c_void_p, POINTER(QueryStats)]),
     "pct_knn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "pct_knn_points": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pct_ball_count": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int, c_void_p]),
     "pct_ball_fill": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_fit_from_neighbors": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

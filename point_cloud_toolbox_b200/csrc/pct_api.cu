@@ -78,6 +78,14 @@ int pct_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, int32_t*
     return launch_knn(ix, q_begin, q_end, k, false, idx, dist, none, layout, (cudaStream_t)stream);
 }
 
+int pct_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* query_ids, int64_t nq, int k,
+                   int32_t* idx, float* dist, void* stream) {
+    PCT_REQUIRE(ix && xyz && (stride == 3 || stride == 4) && nq >= 0 && (query_ids || nq == 0), "pct_knn_points: bad argument");
+    const int rc = check_k(ix, k, "pct_knn_points");
+    if (rc) return rc;
+    return launch_knn_points(ix, xyz, stride, query_ids, nq, k, idx, dist, (cudaStream_t)stream);
+}
+
 int pct_curvature_fused_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, float* normals, float* coeffs,
                             float* curv, uint8_t* status, int layout, void* stream) {
     int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_knn");

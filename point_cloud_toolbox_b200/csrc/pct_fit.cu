@@ -100,13 +100,24 @@ quadric_fit_kernel(const double* __restrict__ rotated, long long nq, int k, floa
         uint32_t st = 0;
         float c[6];
         double w[6];
-        if (!q.finite() || !(max_abs <= 3.0e38f)) st = ST_NONFINITE;  // ref :356-357
-        else if (!solve_normal_equations(q, w)) st = ST_RANK;
-        if (st) {
-            for (int j = 0; j < 6; ++j) c[j] = nanf("");
-        } else {
+        if (!q.finite() || !(max_abs <= 3.0e38f)) {
+            st = ST_NONFINITE;  // ref :356-357
+        } else if (k < 6) {     // underdetermined: lstsq's minimum-norm solution
+            FewRows rows;
+            rows.reset();
+            for (int m = 0; m < k; ++m) rows.add(p[3 * m], p[3 * m + 1], p[3 * m + 2]);
+            if (solve_min_norm(rows, w)) {
+                for (int j = 0; j < 6; ++j) c[j] = (float)w[j];
+            } else {
+                st = ST_RANK;
+            }
+        } else if (solve_normal_equations(q, w)) {
             unscale_coefficients(w, scale, c);
+        } else {
+            st = ST_RANK;
         }
+        if (st)
+            for (int j = 0; j < 6; ++j) c[j] = nanf("");
         for (int j = 0; j < 6; ++j) coeffs[6 * r + j] = c[j];
         if (status) status[r] = (uint8_t)st;
     }

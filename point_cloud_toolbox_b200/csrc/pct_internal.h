@@ -81,6 +81,8 @@ __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, co
 // query-side launchers (pct_query.cu)
 int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, bool fused,
                int32_t* idx, float* dist, FitOutputs out, int layout, cudaStream_t s);
+int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* ids, long long nq, int k,
+                      int32_t* idx, float* dist, cudaStream_t s);
 int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode,
                 int32_t* counts, const long long* offsets, long long nnz, int32_t* idx, float* dist,
                 FitOutputs out, int layout, cudaStream_t s);

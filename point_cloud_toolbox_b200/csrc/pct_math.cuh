@@ -372,6 +372,70 @@ PCT_HD bool solve_normal_equations(Quadric& q, double w[6]) {
     return ok;
 }
 
+// Fewer than 6 rows: `lstsq` (ref :359) returns the MINIMUM-NORM solution of the underdetermined
+// system, which the neighbour study relies on for its smallest probes (ref :756-770 with n = 3, 4).
+// The norm that is minimised is that of the unscaled coefficients, so this path works on the
+// unscaled fp32 features.  Rows of X are orthonormalised (modified Gram-Schmidt, twice): X = R^T Q^T,
+// w = Q R^-T z -- conditioning of X, not of X X^T.  Rank-deficient rows -> false.
+struct FewRows {
+    double x[5][6];
+    double z[5];
+    int m;
+    PCT_HD void reset() { m = 0; }
+    PCT_HD void add(double xr, double yr, double zr) {
+        if (m >= 5) { ++m; return; }
+        const float a = (float)xr, b = (float)yr, c = (float)zr;  // ref :350
+        x[m][0] = (double)fmul_rn(a, a);
+        x[m][1] = (double)fmul_rn(b, b);
+        x[m][2] = (double)fmul_rn(a, b);
+        x[m][3] = (double)a;
+        x[m][4] = (double)b;
+        x[m][5] = 1.0;
+        z[m] = (double)c;
+        ++m;
+    }
+    PCT_HD bool finite() const {
+        for (int i = 0; i < m && i < 5; ++i)
+            if (!(fabs(x[i][3]) <= 1.7e308) || !(fabs(x[i][4]) <= 1.7e308) || !(fabs(z[i]) <= 1.7e308)) return false;
+        return true;
+    }
+};
+
+PCT_HD_NOINLINE bool solve_min_norm(FewRows& f, double w[6]) {
+    const int m = f.m;
+    double q[5][6], r[5][5], y[5];
+    for (int i = 0; i < m; ++i) {
+        double v[6], norm0 = 0.0;
+        for (int c = 0; c < 6; ++c) { v[c] = f.x[i][c]; norm0 += v[c] * v[c]; }
+        for (int j = 0; j < 5; ++j) r[j][i] = 0.0;
+        for (int rep = 0; rep < 2; ++rep)
+            for (int j = 0; j < i; ++j) {
+                double dot = 0.0;
+                for (int c = 0; c < 6; ++c) dot += q[j][c] * v[c];
+                for (int c = 0; c < 6; ++c) v[c] -= dot * q[j][c];
+                r[j][i] += dot;
+            }
+        double norm = 0.0;
+        for (int c = 0; c < 6; ++c) norm += v[c] * v[c];
+        if (!(norm > 1e-26 * norm0) || !(norm0 > 0.0)) return false;  // this row depends on the previous ones
+        norm = sqrt(norm);
+        r[i][i] = norm;
+        for (int c = 0; c < 6; ++c) q[i][c] = v[c] / norm;
+    }
+    // X = R^T Q^T  =>  R^T y = z (forward substitution), w = Q y
+    for (int i = 0; i < m; ++i) {
+        double s = f.z[i];
+        for (int j = 0; j < i; ++j) s -= r[j][i] * y[j];
+        y[i] = s / r[i][i];
+    }
+    for (int c = 0; c < 6; ++c) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s += q[i][c] * y[i];
+        w[c] = s;
+    }
+    return true;
+}
+
 // scaled solution -> reference coefficients [A,B,C,D,E,F] in fp32 (ref :359 result dtype)
 PCT_HD void unscale_coefficients(const double w[6], float scale, float c[6]) {
     const double s = (double)scale;
@@ -426,6 +490,35 @@ PCT_HD void fit_fail(FitResult& o, uint32_t status) {
 // status bits (mirrors include/pct_b200.h)
 enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u };
 
+// fewer rows than coefficients: minimum-norm solution (kept out of line, it is rare and register hungry)
+template <class Nbr>
+PCT_HD_NOINLINE void fit_few_rows(Nbr& nb, const Frame& fr, FitResult& out) {
+    struct Collect {
+        const Frame* f;
+        FewRows rows;
+        PCT_HD void add(float cx, float cy, float cz) {
+            double x, y, z;
+            rotate_point(*f, cx, cy, cz, x, y, z);
+            rows.add(x, y, z);
+        }
+    } col;
+    col.f = &fr;
+    col.rows.reset();
+    nb.pass(col);
+    out.normal[0] = (float)fr.nx; out.normal[1] = (float)fr.ny; out.normal[2] = (float)fr.nz;
+    if (!col.rows.finite()) { fit_fail(out, ST_NONFINITE); return; }
+    double w[6];
+    if (col.rows.m > 5 || !solve_min_norm(col.rows, w)) {
+        const float nx = out.normal[0], ny = out.normal[1], nz = out.normal[2];
+        fit_fail(out, ST_RANK);
+        out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out.coeffs[c] = (float)w[c];
+    monge_curvature(out.coeffs, out.curv);
+}
+
 // Whole per-point pipeline over an abstract neighbourhood.
 //   nb.pass(fn)  calls fn(cx, cy, cz) for every neighbour (fp32, centred)
 //   nb.reference(rx, ry, rz) gives c_last - c_first in fp32, valid after the first pass
@@ -440,6 +533,10 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     nb.reference(rx, ry, rz);
     Frame fr;
     plane_frame(mom, rx, ry, rz, fr);
+    if (mom.n < 6) {
+        fit_few_rows(nb, fr, out);
+        return;
+    }
     struct Second {
         const Frame* f;
         Quadric q;

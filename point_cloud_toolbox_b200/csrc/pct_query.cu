@@ -19,6 +19,7 @@
 //   ball_kernel<MODE>            epsilon-ball count / CSR fill / fused fit.
 #include <algorithm>
 #include <cmath>
+#include <string>
 
 #include "pct_knn_fast.cuh"
 
@@ -47,6 +48,25 @@ __device__ __forceinline__ Key warp_min_key(Key k) {
 }
 
 constexpr int kExactWarps = 4;
+constexpr int kLayoutList = 2;  // internal: output row = position in the queue (pct_knn_points)
+
+// sorted position of cloud points given by original index: the point's own cell holds it
+__global__ void locate_kernel(const IndexView ix, const float* __restrict__ xyz, const int stride,
+                              const int32_t* __restrict__ ids, const long long nq, uint32_t* __restrict__ positions,
+                              unsigned int* __restrict__ missing) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= nq) return;
+    const long long id = ids[r];
+    const float* p = xyz + id * stride;
+    int cx, cy, cz;
+    cell_of(ix, p[0], p[1], p[2], cx, cy, cz);
+    uint32_t s = 0, e = 0, found = 0xffffffffu;
+    if (lookup_cell(ix.lvl[0], morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), s, e))
+        for (uint32_t j = s; j < e; ++j)
+            if (load_pt(ix.pts + j).idx == (uint32_t)id) { found = j; break; }
+    if (found == 0xffffffffu) { atomicAdd(missing, 1u); found = 0; }
+    positions[r] = found;
+}
 
 template <bool FUSED>
 __global__ void __launch_bounds__(kExactWarps * 32)
@@ -105,7 +125,7 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             best = warp_min_key(best);
             if (m >= 1 && lane == 0) {
                 mine[m - 1] = best.pos;
-                const long long row = out_row(qr, i, q.idx);
+                const long long row = qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx);
                 if (!FUSED) {
                     if (out_idx) out_idx[row * k + (m - 1)] = (int32_t)best.idx;
                     if (out_dist) out_dist[row * k + (m - 1)] = (float)sqrt(best.d);
@@ -122,7 +142,7 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             FitResult r;
             r.status = ST_EXACT_PATH;
             fit_neighbourhood(nb, r);
-            store_fit(out, out_row(qr, i, q.idx), r);
+            store_fit(out, qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx), r);
         }
         __syncwarp();
     }
@@ -247,6 +267,35 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     PCT_CUDA(cudaGetLastError());
     PCT_CUDA(cudaFreeAsync(queues, s));
     PCT_CUDA(cudaFreeAsync(counters, s));
+    return PCT_OK;
+}
+
+int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* ids, long long nq, int k,
+                      int32_t* idx, float* dist, cudaStream_t s) {
+    const IndexView& v = ix->view;
+    if (nq == 0) return PCT_OK;
+    uint32_t* positions = nullptr;
+    unsigned int* counters = nullptr;  // [0] = queue length, [1] = ids that are not cloud points
+    PCT_CUDA(cudaMallocAsync(&positions, sizeof(uint32_t) * (size_t)nq, s));
+    PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 2, s));
+    const unsigned int h_init[2] = {(unsigned int)nq, 0u};
+    PCT_CUDA(cudaMemcpyAsync(counters, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
+    locate_kernel<<<(int)((nq + 127) / 128), 128, 0, s>>>(v, xyz, stride, ids, nq, positions, counters + 1);
+    QueryRange qr{0, v.n, nullptr, nullptr, kLayoutList};
+    FitOutputs none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
+    const int grid = (int)std::min<long long>((nq + kExactWarps - 1) / kExactWarps, (long long)ix->sm_count * 8);
+    knn_exact_kernel<false><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, none, positions, counters);
+    PCT_CUDA(cudaGetLastError());
+    unsigned int h_missing = 0;
+    PCT_CUDA(cudaMemcpyAsync(&h_missing, counters + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    PCT_CUDA(cudaFreeAsync(positions, s));
+    PCT_CUDA(cudaFreeAsync(counters, s));
+    if (h_missing) {
+        set_error("pct_knn_points: " + std::to_string(h_missing) + " query ids do not name points of the indexed cloud");
+        return PCT_ERR_INVALID_ARGUMENT;
+    }
     return PCT_OK;
 }
 

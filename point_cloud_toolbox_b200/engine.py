@@ -210,6 +210,19 @@ class GridIndex:
             check(lib.pct_knn(self._handle, q_begin, q_end, int(k), ptr(idx), ptr(dist), layout, _stream()))
         return idx, dist
 
+    def knn_points(self, query_ids, k):
+        """Ordered kNN rows (original indices, distances) of the cloud points named by original index."""
+        ids = torch.as_tensor(query_ids, device=self.device).to(torch.int32).contiguous()
+        nq = int(ids.numel())
+        if nq and (int(ids.min()) < 0 or int(ids.max()) >= self.n):
+            raise IndexError("query ids out of range")
+        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_knn_points(self._handle, ptr(self.points), int(self.points.shape[1]), ptr(ids), nq, int(k),
+                                     ptr(idx), ptr(dist), _stream()))
+        return idx, dist
+
     def curvature_knn(self, k, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL, want_normals=True, want_coeffs=True,
                       want_status=True) -> FitOutputs:
         """Fused search + fit.  Without coefficients the result is written as packed 32-byte records."""

@@ -328,6 +328,71 @@ class PointCloud:
         self._fit = fit
         return fit
 
+    # ------------------------------------------------------------------
+    # neighbour study                                           ref :732-800
+    # ------------------------------------------------------------------
+    def explicit_quadratic_neighbor_study(self, tol=1e-7, sample_size=500, lower_bound=3, upper_bound=99):
+        """Average neighbour count at which the quadric Gaussian curvature of sampled points converges.
+
+        Same sampling (``np.random.randint`` on the global generator), same probes and the same binary
+        search as the reference (ref :732-800).  Every probe the searches can ask for -- K of the
+        neighbourhood {point, its n nearest}, n = lower_bound .. upper_bound + 1 -- is computed in two
+        device calls (ordered kNN rows of the sampled points, then one fit per (point, n) prefix row);
+        the searches then only read that table.
+        """
+        if self.kdtree is None:
+            raise AttributeError("'PointCloud' object has no attribute 'kdtree'")
+        num_total = len(self.points)
+        sample_size = min(sample_size, num_total)
+        random_indexes = np.random.randint(0, num_total, sample_size)          # ref :751
+        if len(random_indexes) == 0:
+            return 0                                                             # ref :796-797
+        lower, upper = int(lower_bound), int(upper_bound)
+        n_max = upper + 1                                                        # the search probes mid and mid + 1
+        if lower > upper:
+            return int(np.mean(np.full(len(random_indexes), upper))) + 1         # no probe at all: best = upper (ref :791-792)
+        if n_max + 1 > num_total:
+            raise IndexError(f"index {num_total} is out of bounds for axis 0 with size {num_total}")  # scipy pads with N
+        if n_max > MAX_K:
+            raise ValueError(f"upper_bound + 1 must not exceed {MAX_K}")
+        index = self.kdtree.index
+        d_points = index.points
+        dev = d_points.device
+        uniq, inverse = np.unique(random_indexes, return_inverse=True)
+        ids = torch.from_numpy(uniq.astype(np.int32)).to(dev)
+        nbr, _ = index.knn_points(ids, n_max)                                    # (S, n_max) nearest OTHER points, ordered
+        # one CSR row per (point, n): [point, nbr_1 .. nbr_n]  -- kdtree.query(point, n + 1) of ref :759
+        counts = torch.arange(lower, n_max + 1, device=dev)                      # n values
+        S, P = len(uniq), int(counts.numel())
+        row_len = (counts + 1).repeat(S)
+        offsets = torch.zeros(S * P + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(row_len, 0)
+        full = torch.cat((ids[:, None], nbr), 1)                                 # (S, n_max + 1)
+        col = torch.arange(n_max + 1, device=dev)
+        mask = col[None, :] <= counts[:, None]                                   # (P, n_max + 1): first n + 1 entries
+        rows = full[:, None, :].expand(S, P, n_max + 1)[mask[None].expand(S, P, n_max + 1)]
+        qids = ids.repeat_interleave(P)
+        fit = engine.fit_from_csr(d_points if d_points.shape[1] == 3 else d_points[:, :3].contiguous(), offsets, rows, qids)
+        K = engine.to_host(fit.curv[:, 0]).reshape(S, P)
+        st = engine.to_host(fit.status).reshape(S, P)
+        # ref :768-769: a failed fit becomes coefficients (0,...,0), i.e. K = 0
+        K = np.where((st & ~np.uint8(1)) != 0, np.float32(0), K)
+        converged = []
+        for s_row in inverse:                                                    # ref :794-795, one search per sampled point
+            lo, hi, best = lower, upper, None
+            k_of = K[s_row]
+            while lo <= hi:                                                      # ref :778-788
+                mid = (lo + hi) // 2
+                if abs(k_of[mid + 1 - lower] - k_of[mid - lower]) < tol:
+                    best = mid
+                    hi = mid - 1
+                else:
+                    lo = mid + 1
+            if best is None:
+                best = hi
+            converged.append(best)
+        return int(np.mean(converged)) + 1                                       # ref :800
+
     def __getattr__(self, name):
         # outputs of the fused call are copied to the host only when somebody asks for them
         lazy = ("quadratic_coefficients", "normals_quadratic", "fit_status", "K_H_sq_quadratic", "k1_quadratic", "k2_quadratic")

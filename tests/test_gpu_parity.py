@@ -201,6 +201,46 @@ def test_exact_path_duplicates_lattice_outliers(pct):
     assert st.queries == 9
 
 
+def test_neighbor_study_matches_reference_and_oracle(pct, bunny):
+    """explicit_quadratic_neighbor_study (ref :732-800): same sample, same probes, same return value."""
+    g = load_golden("neighbor_study")
+    pc = pct.PointCloud(points=bunny, normals=np.zeros((len(bunny), 0), np.float32), k_neighbors=20)
+    pc.plant_kdtree(20)
+    size = int(g["sample_size"])
+    for a, seed in enumerate(g["seeds"]):
+        for b, tol in enumerate(g["tols"]):
+            np.random.seed(int(seed))
+            got = pc.explicit_quadratic_neighbor_study(tol=float(tol), sample_size=size)
+            assert got == int(g["results"][a, b]), (seed, tol, got, int(g["results"][a, b]))
+    # per-point converged counts against the oracle on another sample and bounds
+    rng = np.random.default_rng(3)
+    sample = rng.integers(0, len(bunny), 40)
+    want, counts = oracle.neighbor_study(bunny, sample, tol=80.0, lower_bound=4, upper_bound=60, return_counts=True)
+    state = np.random.get_state()
+    np.random.seed(123)
+    draw = np.random.randint(0, len(bunny), 40)
+    np.random.seed(123)
+    got = pc.explicit_quadratic_neighbor_study(tol=80.0, sample_size=40, lower_bound=4, upper_bound=60)
+    np.random.set_state(state)
+    assert got == oracle.neighbor_study(bunny, draw, tol=80.0, lower_bound=4, upper_bound=60)
+    assert 4 <= want - 1 <= 60 and len(counts) == 40
+
+
+def test_knn_points_rows_equal_full_lists(pct, bunny):
+    pts = bunny[::2]
+    d = torch.from_numpy(np.ascontiguousarray(pts)).cuda()
+    ix = pct.GridIndex(d, k_hint=20)
+    ids = np.random.default_rng(0).integers(0, len(pts), 300).astype(np.int32)
+    for k in (7, 40, 100):
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k, rows=ids)
+        idx, dist = ix.knn_points(ids, k)
+        assert np.array_equal(idx.cpu().numpy(), ref_idx)
+        assert np.array_equal(dist.cpu().numpy(), ref_dist)
+    with pytest.raises(IndexError):
+        ix.knn_points(np.array([len(pts)], np.int32), 5)
+    ix.close()
+
+
 def test_errors_mirror_reference(pct):
     with pytest.raises(ValueError, match="Either file_path or points and normals"):
         pct.PointCloud()

@@ -156,6 +156,26 @@ def test_fit_rows_on_reference_rows(harness):
     assert np.allclose(curv[:, 1], g["H_quadratic"], rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("k", [4, 5])  # k = 2: the normal is arbitrary; k = 3: three points are coplanar, z is rounding noise
+def test_fewer_rows_than_coefficients_give_lstsq_minimum_norm(harness, bunny, k):
+    """ref :359 on k < 6 rows is underdetermined; lstsq's minimum-norm solution is what the neighbour study sees."""
+    pts = np.ascontiguousarray(bunny[::5])
+    idx, _, _ = oracle.knn_canonical(pts, k)
+    rows = np.arange(0, len(pts), 3)
+    sub = np.ascontiguousarray(idx[rows], np.int32)
+    ref = oracle.curvature_from_neighbors(pts, sub, rows=rows)
+    nq = len(rows)
+    normal = np.zeros((nq, 3), np.float32); coeffs = np.zeros((nq, 6), np.float32)
+    curv = np.zeros((nq, 5), np.float32); status = np.zeros(nq, np.uint8)
+    qids = np.ascontiguousarray(rows, np.int32)
+    harness.h_fit_rows(P(pts), P(sub), nq, k, P(qids), P(normal), P(coeffs), P(curv), P(status))
+    ok = status == 0
+    assert ok.mean() > 0.99
+    scale = np.abs(ref["coeffs"]).max(axis=1, keepdims=True)
+    err = np.abs(coeffs - ref["coeffs"]) / scale
+    assert np.quantile(err[ok], 0.99) < 1e-4, np.quantile(err[ok], [0.5, 0.9, 0.99, 1.0])
+
+
 def test_ball_logic(harness, bunny):
     pts = np.ascontiguousarray(bunny[::4])
     n = len(pts)

@@ -145,3 +145,15 @@ def test_knn_errors():
         oracle.knn_canonical(pts, 10)
     with pytest.raises(ValueError):
         oracle.best_fit_plane_and_rotate(np.array([[0, 0, np.nan], [1, 0, 0], [0, 1, 0]], np.float32))
+
+
+def test_neighbor_study_reproduces_reference_returns(bunny):
+    """oracle.neighbor_study on the samples the reference drew gives the reference's own return values."""
+    g = load_golden("neighbor_study")
+    from scipy.spatial import cKDTree
+
+    tree = cKDTree(bunny)
+    for a in range(len(g["seeds"])):
+        for b, tol in enumerate(g["tols"]):
+            if tol in (1e-7, 500.0):  # the two ends: nothing converges / most converge early (keeps the CPU suite short)
+                assert oracle.neighbor_study(bunny, g["samples"][a], tol=float(tol), tree=tree) == int(g["results"][a, b])
