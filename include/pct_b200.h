@@ -56,6 +56,7 @@ extern "C" {
 #define PCT_STATUS_FEW_NEIGHBORS 2u  /* < 2 neighbours (no covariance) -> NaN */
 #define PCT_STATUS_RANK_DEFICIENT 4u /* 6x6 normal equations not positive definite -> NaN */
 #define PCT_STATUS_NONFINITE 8u      /* non-finite intermediate: ref :318-319 / :356-357 ValueError */
+#define PCT_STATUS_UNRESOLVED 16u    /* slab index only (pct_index_set_slab): the k-th neighbour may lie outside the slab */
 
 typedef struct pct_index pct_index;
 
@@ -78,6 +79,7 @@ typedef struct pct_query_stats {
     int64_t exact_path;     /* queries resolved by the exact (tie / expansion) kernel */
     int64_t kernel_launches;
     int64_t unstaged;       /* queries whose chunk did not fit the shared-memory staging buffer */
+    int64_t unresolved;     /* slab index only: queries returned with PCT_STATUS_UNRESOLVED */
 } pct_query_stats;
 
 int pct_version(void);
@@ -91,6 +93,22 @@ const char* pct_last_error(void);
  * PCT_ERR_NONFINITE if any coordinate is NaN/Inf. */
 int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, int k_hint,
                     void* stream, pct_index** out);
+/* The cell edge pct_index_build would choose for this cloud (density pilot only, no index), and the
+ * bounding box {min xyz, max xyz} if bbox_min_max != NULL.  Lets the ranks of a spatially partitioned
+ * job agree on one cell size before each builds the index of its own slab.  Synchronises `stream`. */
+int pct_estimate_cell_size(const float* xyz, int64_t n, int stride, int k_hint, void* stream,
+                           float* cell_size, float* bbox_min_max);
+/* Declares the index to be one slab of a spatially partitioned cloud (multi-GPU, new; the reference is
+ * single process): it was built from ALL cloud points with complete_lo <= coordinate[axis] <= complete_hi,
+ * and answers only queries with own_lo <= coordinate[axis] < own_hi (other query rows are left untouched).
+ * No search radius reaches beyond the complete range; a query whose k-th neighbour cannot be proven to
+ * lie inside it gets PCT_STATUS_UNRESOLVED (NaN outputs; idx -1) and must be answered from a larger index.
+ * row_map (device, N int32, may be NULL; the caller keeps it alive while the index is used): with
+ * PCT_LAYOUT_ORIGINAL the row of an owned point is row_map[original index] instead of the original index,
+ * so the outputs can be sized for the owned points only.
+ * axis = -1 removes the restriction.  kNN entry points only. */
+int pct_index_set_slab(pct_index* index, int axis, float complete_lo, float complete_hi,
+                       float own_lo, float own_hi, const int32_t* row_map);
 /* frees the index in the order of the stream it was built on (no device synchronisation);
  * queries issued on OTHER streams must have completed */
 int pct_index_destroy(pct_index* index);
@@ -114,6 +132,10 @@ int pct_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
  * Synchronises `stream`; PCT_ERR_INVALID_ARGUMENT if an id is not a point of the indexed cloud. */
 int pct_knn_points(const pct_index* index, const float* xyz, int stride, const int32_t* query_ids,
                    int64_t nq, int k, int32_t* idx, float* dist, void* stream);
+
+/* fused search + fit for selected cloud points (same addressing as pct_knn_points), packed records nq x 8 */
+int pct_curvature_points_records(const pct_index* index, const float* xyz, int stride,
+                                 const int32_t* query_ids, int64_t nq, int k, float* records, void* stream);
 
 /* epsilon-ball (advertised README.md:8, absent in the reference; semantics of
  * scipy `query_ball_point`: d2 <= radius*radius in fp64, self excluded).

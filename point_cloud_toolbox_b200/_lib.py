@@ -26,6 +26,7 @@ STATUS_EXACT_PATH = 1
 STATUS_FEW_NEIGHBORS = 2
 STATUS_RANK_DEFICIENT = 4
 STATUS_NONFINITE = 8
+STATUS_UNRESOLVED = 16
 
 MAX_K = 128
 
@@ -52,6 +53,7 @@ class QueryStats(ctypes.Structure):
         ("exact_path", c_int64),
         ("kernel_launches", c_int64),
         ("unstaged", c_int64),
+        ("unresolved", c_int64),
     ]
 
 
@@ -66,6 +68,9 @@ SIGNATURES = {
     "pct_index_last_stats": (c_int, [c_void_p, c_void_p, POINTER(QueryStats)]),
     "pct_knn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_knn_points": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "pct_curvature_points_records": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "pct_estimate_cell_size": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "pct_index_set_slab": (c_int, [c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
     "pct_ball_count": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int, c_void_p]),
     "pct_ball_fill": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_fit_from_neighbors": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -58,7 +58,7 @@ int pct_index_permutation(const pct_index* ix, int32_t* perm, void* stream) {
 
 int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* stats) {
     PCT_REQUIRE(ix && stats, "pct_index_last_stats: NULL argument");
-    unsigned int h[5];
+    unsigned int h[6];
     PCT_CUDA(cudaMemcpyAsync(h, ix->stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PCT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     stats->level1_retries = h[0];
@@ -66,6 +66,7 @@ int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* sta
     stats->kernel_launches = h[2];
     stats->queries = h[3];
     stats->unstaged = h[4];
+    stats->unresolved = h[5];
     return PCT_OK;
 }
 
@@ -83,7 +84,29 @@ int pct_knn_points(const pct_index* ix, const float* xyz, int stride, const int3
     PCT_REQUIRE(ix && xyz && (stride == 3 || stride == 4) && nq >= 0 && (query_ids || nq == 0), "pct_knn_points: bad argument");
     const int rc = check_k(ix, k, "pct_knn_points");
     if (rc) return rc;
-    return launch_knn_points(ix, xyz, stride, query_ids, nq, k, idx, dist, (cudaStream_t)stream);
+    return launch_knn_points(ix, xyz, stride, query_ids, nq, k, idx, dist, nullptr, (cudaStream_t)stream);
+}
+
+int pct_curvature_points_records(const pct_index* ix, const float* xyz, int stride, const int32_t* query_ids, int64_t nq,
+                                 int k, float* records, void* stream) {
+    PCT_REQUIRE(ix && xyz && (stride == 3 || stride == 4) && nq >= 0 && (query_ids || nq == 0) &&
+                    (records || nq == 0) && (reinterpret_cast<uintptr_t>(records) & 31) == 0,
+                "pct_curvature_points_records: bad argument (records must be 32-byte aligned)");
+    const int rc = check_k(ix, k, "pct_curvature_points_records");
+    if (rc) return rc;
+    return launch_knn_points(ix, xyz, stride, query_ids, nq, k, nullptr, nullptr, records, (cudaStream_t)stream);
+}
+
+int pct_index_set_slab(pct_index* ix, int axis, float complete_lo, float complete_hi, float own_lo, float own_hi,
+                       const int32_t* row_map) {
+    PCT_REQUIRE(ix && axis >= -1 && axis <= 2, "pct_index_set_slab: bad argument");
+    PCT_REQUIRE(axis < 0 || (complete_lo <= own_lo && own_lo <= own_hi && own_hi <= complete_hi),
+                "pct_index_set_slab: need complete_lo <= own_lo <= own_hi <= complete_hi");
+    ix->view.slab_axis = axis;
+    ix->view.complete_lo = complete_lo; ix->view.complete_hi = complete_hi;
+    ix->view.own_lo = own_lo; ix->view.own_hi = own_hi;
+    ix->row_map = axis >= 0 ? row_map : nullptr;
+    return PCT_OK;
 }
 
 int pct_curvature_fused_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, float* normals, float* coeffs,

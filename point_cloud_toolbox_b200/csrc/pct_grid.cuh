@@ -62,6 +62,11 @@ struct IndexView {
     int num_levels;    // tables for levels 0 .. num_levels-1 (last one: a single cell)
     int volumetric;    // density pilot saw a space-filling cloud (intrinsic dimension > 2.5), not a surface
     float cut_gain;    // head-room of the k-th-distance estimate used to pre-collect candidates
+    // Slab of a spatially partitioned cloud (multi-GPU): the index holds every cloud point whose
+    // coordinate on `slab_axis` lies in [complete_lo, complete_hi] and nothing is known about the rest,
+    // so no search radius may reach beyond those planes; only queries in [own_lo, own_hi) are answered.
+    int slab_axis;     // -1: the index holds the whole cloud
+    float complete_lo, complete_hi, own_lo, own_hi;
     LevelTable lvl[kMaxLevels];
 };
 
@@ -168,12 +173,21 @@ PCT_HD void make_stencil(const IndexView& ix, int level, float qx, float qy, flo
     gap = axis_gap(ux, st.lx, st.dx, gap);
     gap = axis_gap(uy, st.ly, st.dy, gap);
     gap = axis_gap(uz, st.lz, st.dz, gap);
-    if (gap > 1.0e38f) {
-        st.safe2 = 3.0e38f;  // the block covers the whole grid on every axis
-    } else {
-        const float g = fmaxf(gap - ix.slack, 0.f) * (ix.h * ldexpf(1.f, level));
-        st.safe2 = g * g * 0.99999f;
+    float g = 3.0e38f;  // the block covers the whole grid on every axis
+    if (gap <= 1.0e38f) g = fmaxf(gap - ix.slack, 0.f) * (ix.h * ldexpf(1.f, level));
+    if (ix.slab_axis >= 0) {
+        // a point closer than d to the query is at most d away on the slab axis, hence inside the slab
+        const float qa = ix.slab_axis == 0 ? qx : (ix.slab_axis == 1 ? qy : qz);
+        g = fminf(g, fmaxf(fminf(qa - ix.complete_lo, ix.complete_hi - qa), 0.f));
     }
+    st.safe2 = g < 1.0e18f ? g * g * 0.99999f : 3.0e38f;
+}
+
+// does this index answer the query (always, unless it is one slab of a partitioned cloud)
+PCT_HD bool query_owned(const IndexView& ix, float qx, float qy, float qz) {
+    if (ix.slab_axis < 0) return true;
+    const float qa = ix.slab_axis == 0 ? qx : (ix.slab_axis == 1 ? qy : qz);
+    return qa >= ix.own_lo && qa < ix.own_hi;
 }
 
 // cell c (0..26) of the block; false when it lies outside the grid or holds no point

@@ -234,6 +234,25 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
     return PCT_OK;
 }
 
+// min xyz, max xyz of the cloud; PCT_ERR_NONFINITE if any coordinate is NaN / Inf.  Synchronises `s`.
+static int bounding_box(const float* xyz, long long n, int stride, int sm_count, cudaStream_t s, float h_bbox[6]) {
+    const int bb_blocks = std::max(1, std::min<int>(sm_count * 8, (int)((n + kThreads - 1) / kThreads)));
+    DeviceTemp bbox(s);
+    PCT_CUDA(bbox.alloc(sizeof(unsigned int) * 8));
+    PCT_CUDA(cudaMemsetAsync(bbox.p, 0xFF, sizeof(unsigned int) * 3, s));
+    PCT_CUDA(cudaMemsetAsync(bbox.as<unsigned int>() + 3, 0, sizeof(unsigned int) * 5, s));
+    bbox_kernel<<<bb_blocks, kThreads, 0, s>>>(xyz, n, stride, bbox.as<unsigned int>());
+    unsigned int h_box[8];
+    PCT_CUDA(cudaMemcpyAsync(h_box, bbox.p, sizeof(h_box), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    if (h_box[6]) {
+        set_error("Non-finite values in input points");
+        return PCT_ERR_NONFINITE;
+    }
+    for (int a = 0; a < 6; ++a) h_bbox[a] = from_ordered_bits(h_box[a]);
+    return PCT_OK;
+}
+
 static int build_impl(const float* xyz, long long n, int stride, float cell_hint, int k_hint, cudaStream_t s,
                       pct_index* ix) {
     PCT_CUDA(cudaGetDevice(&ix->device));
@@ -251,21 +270,11 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     }
 
     // 1. bounding box + finiteness
-    const int bb_blocks = std::max(1, std::min<int>(ix->sm_count * 8, (int)((n + kThreads - 1) / kThreads)));
-    DeviceTemp bbox(s);
-    PCT_CUDA(bbox.alloc(sizeof(unsigned int) * 8));
-    PCT_CUDA(cudaMemsetAsync(bbox.p, 0xFF, sizeof(unsigned int) * 3, s));
-    PCT_CUDA(cudaMemsetAsync(bbox.as<unsigned int>() + 3, 0, sizeof(unsigned int) * 5, s));
-    bbox_kernel<<<bb_blocks, kThreads, 0, s>>>(xyz, n, stride, bbox.as<unsigned int>());
-    unsigned int h_box[8];
-    PCT_CUDA(cudaMemcpyAsync(h_box, bbox.p, sizeof(h_box), cudaMemcpyDeviceToHost, s));
-    PCT_CUDA(cudaStreamSynchronize(s));
-    if (h_box[6]) {
-        set_error("Non-finite values in input points");
-        return PCT_ERR_NONFINITE;
-    }
     float h_bbox[6];
-    for (int a = 0; a < 6; ++a) h_bbox[a] = from_ordered_bits(h_box[a]);
+    {
+        const int rc = bounding_box(xyz, n, stride, ix->sm_count, s, h_bbox);
+        if (rc != PCT_OK) return rc;
+    }
     const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
     const float ext[3] = {h_bbox[3] - h_bbox[0], h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]};
     const float extent_max = std::max(ext[0], std::max(ext[1], ext[2]));
@@ -297,6 +306,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
     // k-th-distance estimate of knn_select(): cut^2 = gain * (k / C) cell^2 on a surface (C = population of the
     // 3x3x3 block = density * 9 cell^2 * tilt), gain * (k / C)^(2/3) cell^2 in a volume.  Performance only.
+    v.slab_axis = -1;
     v.volumetric = est_dim > 2.5f ? 1 : 0;
     v.cut_gain = 0.f;  // off: at 24 warps/SM the list space is worth more as staging buffer (profiles/README.md)
     if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
@@ -393,6 +403,27 @@ int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, in
         return rc;
     }
     *out = ix;
+    return PCT_OK;
+}
+
+int pct_estimate_cell_size(const float* xyz, int64_t n, int stride, int k_hint, void* stream, float* cell_size,
+                           float* bbox_min_max) {
+    PCT_REQUIRE(xyz && cell_size && n >= 1 && (stride == 3 || stride == 4), "pct_estimate_cell_size: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int device = 0, sm_count = 148;
+    PCT_CUDA(cudaGetDevice(&device));
+    PCT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    float h_bbox[6];
+    int rc = pct::bounding_box(xyz, n, stride, sm_count, s, h_bbox);
+    if (rc != PCT_OK) return rc;
+    const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
+    const float extent_max = std::max(h_bbox[3] - h_bbox[0], std::max(h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]));
+    float h = 1.f, dim = 2.f;
+    rc = pct::choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &h, &dim);
+    if (rc != PCT_OK) return rc;
+    *cell_size = h;
+    if (bbox_min_max)
+        for (int a = 0; a < 6; ++a) bbox_min_max[a] = h_bbox[a];
     return PCT_OK;
 }
 

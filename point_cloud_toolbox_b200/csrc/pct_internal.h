@@ -14,6 +14,7 @@ struct pct_index {
     pct::IndexView view;       // device pointers inside
     pct::Pt* pts = nullptr;    // N sorted records
     pct::HashSlot* table_mem = nullptr;  // all level tables, one allocation
+    const int32_t* row_map = nullptr;    // caller-owned (pct_index_set_slab): output row per original index
     unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries, unstaged, -, -, -]
     pct_index_info info{};
     int device = 0;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, co
 int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, bool fused,
                int32_t* idx, float* dist, FitOutputs out, int layout, cudaStream_t s);
 int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* ids, long long nq, int k,
-                      int32_t* idx, float* dist, cudaStream_t s);
+                      int32_t* idx, float* dist, float* records, cudaStream_t s);
 int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode,
                 int32_t* counts, const long long* offsets, long long nnz, int32_t* idx, float* dist,
                 FitOutputs out, int layout, cudaStream_t s);

@@ -30,6 +30,7 @@ struct QueryRange {
     const uint32_t* list;       // when non-null: sorted positions to process ...
     const unsigned int* count;  // ... and how many of them
     int layout;
+    const int32_t* row_map;     // slab index, PCT_LAYOUT_ORIGINAL: output row of an original index (owned points only)
 };
 
 struct Queues {
@@ -40,7 +41,8 @@ struct Queues {
 };
 
 __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, uint32_t orig) {
-    return qr.layout == PCT_LAYOUT_ORIGINAL ? (long long)orig : (long long)i - qr.q_begin;
+    if (qr.layout != PCT_LAYOUT_ORIGINAL) return (long long)i - qr.q_begin;
+    return qr.row_map ? (long long)qr.row_map[orig] : (long long)orig;
 }
 
 // What a query does once its k neighbours sit in list[m * stride]: the fused fit, or the
@@ -106,6 +108,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         if (t >= total) continue;
         const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
         const Pt q = load_pt(ix.pts + i);
+        if (!query_owned(ix, q.x, q.y, q.z)) continue;
         Stencil st;
         make_stencil(ix, level, q.x, q.y, q.z, st);
         src.runs.collect(st);
@@ -301,7 +304,7 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         }
     }
     __syncthreads();  // temporaries are dead, the per-query scratch may be written
-    if (!active) return;
+    if (!active || !query_owned(ix, q.x, q.y, q.z)) return;
 
     // ---- E. select out of the staged copy
     const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];

@@ -488,7 +488,7 @@ PCT_HD void fit_fail(FitResult& o, uint32_t status) {
 }
 
 // status bits (mirrors include/pct_b200.h)
-enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u };
+enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u, ST_UNRESOLVED = 16u };
 
 // fewer rows than coefficients: minimum-norm solution (kept out of line, it is rare and register hungry)
 template <class Nbr>

@@ -72,7 +72,7 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kExactWarps * 32)
 knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* __restrict__ out_idx,
                  float* __restrict__ out_dist, const FitOutputs out, const uint32_t* __restrict__ queue,
-                 const unsigned int* __restrict__ queue_count) {
+                 const unsigned int* __restrict__ queue_count, unsigned int* __restrict__ unresolved_count) {
     extern __shared__ uint32_t smem_rows[];  // [kExactWarps][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* mine = smem_rows + warp * k;
@@ -92,7 +92,8 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
                 if (cx >= 0 && cx < st.dx && cy >= 0 && cy < st.dy && cz >= 0 && cz < st.dz)
                     if (!lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), cs, ce)) cs = ce = 0;
             }
-            if (level + 1 >= ix.num_levels) break;  // top: the block is the whole cloud
+            const bool top = level + 1 >= ix.num_levels;  // the block is the whole grid
+            if (top && ix.slab_axis < 0) break;           // ... and the grid the whole cloud
             const double safe2 = (double)st.safe2;
             unsigned int inside = 0;
             for (int c = 0; c < 27; ++c) {
@@ -104,8 +105,27 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             }
             inside = __reduce_add_sync(0xffffffffu, inside);
             if (inside >= (unsigned int)(k + 1)) break;
+            if (top) { level = -1; break; }  // slab: the k-th neighbour may lie outside what this index holds
         }
-        const double bound = (level + 1 >= ix.num_levels) ? 1.0e300 : (double)st.safe2;
+        if (level < 0) {
+            if (lane == 0) {
+                if (unresolved_count) atomicAdd(unresolved_count, 1u);
+                const long long row = qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx);
+                if (FUSED) {
+                    FitResult r;
+                    r.status = 0;
+                    fit_fail(r, ST_UNRESOLVED);
+                    store_fit(out, row, r);
+                } else {
+                    for (int m = 0; m < k; ++m) {
+                        if (out_idx) out_idx[row * k + m] = -1;
+                        if (out_dist) out_dist[row * k + m] = nanf("");
+                    }
+                }
+            }
+            continue;
+        }
+        const double bound = (level + 1 >= ix.num_levels && ix.slab_axis < 0) ? 1.0e300 : (double)st.safe2;
         // 2. k+1 successive minima of (d2, index); the first one is dropped (ref :84-85)
         Key prev;
         prev.d = -1.0; prev.idx = 0; prev.pos = 0;
@@ -154,6 +174,7 @@ __global__ void publish_stats_kernel(const unsigned int* counters, unsigned int*
     stats[2] = launches;
     stats[3] = queries;
     stats[4] = counters[2];
+    stats[5] = counters[3];
 }
 
 // ---- epsilon ball ----------------------------------------------------------
@@ -249,7 +270,7 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     uint32_t* retry1 = queues;
     uint32_t* exactq = queues + nq;
     uint32_t* fallback0 = queues + 2 * nq;
-    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout};
+    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout, ix->row_map};
     unsigned int launches = 0;
     FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, fallback0, counters, s};
     int rc = PCT_OK;
@@ -259,9 +280,9 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
     const int grid_exact = ix->sm_count * 4;
     if (fused)
-        knn_exact_kernel<true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1);
+        knn_exact_kernel<true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3);
     else
-        knn_exact_kernel<false><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1);
+        knn_exact_kernel<false><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3);
     ++launches;
     publish_stats_kernel<<<1, 1, 0, s>>>(counters, ix->stats, (unsigned int)nq, launches);
     PCT_CUDA(cudaGetLastError());
@@ -271,7 +292,7 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
 }
 
 int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* ids, long long nq, int k,
-                      int32_t* idx, float* dist, cudaStream_t s) {
+                      int32_t* idx, float* dist, float* records, cudaStream_t s) {
     const IndexView& v = ix->view;
     if (nq == 0) return PCT_OK;
     uint32_t* positions = nullptr;
@@ -281,11 +302,14 @@ int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const i
     const unsigned int h_init[2] = {(unsigned int)nq, 0u};
     PCT_CUDA(cudaMemcpyAsync(counters, h_init, sizeof(h_init), cudaMemcpyHostToDevice, s));
     locate_kernel<<<(int)((nq + 127) / 128), 128, 0, s>>>(v, xyz, stride, ids, nq, positions, counters + 1);
-    QueryRange qr{0, v.n, nullptr, nullptr, kLayoutList};
-    FitOutputs none{nullptr, nullptr, nullptr, nullptr, nullptr};
+    QueryRange qr{0, v.n, nullptr, nullptr, kLayoutList, nullptr};
+    FitOutputs outs{nullptr, nullptr, nullptr, nullptr, records};
     const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
     const int grid = (int)std::min<long long>((nq + kExactWarps - 1) / kExactWarps, (long long)ix->sm_count * 8);
-    knn_exact_kernel<false><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, none, positions, counters);
+    if (records)
+        knn_exact_kernel<true><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, nullptr, nullptr, outs, positions, counters, nullptr);
+    else
+        knn_exact_kernel<false><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, outs, positions, counters, nullptr);
     PCT_CUDA(cudaGetLastError());
     unsigned int h_missing = 0;
     PCT_CUDA(cudaMemcpyAsync(&h_missing, counters + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -306,7 +330,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
     const long long nq = q_end - q_begin;
     if (nq == 0) return PCT_OK;
     const int level = ball_level(v, radius);
-    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout};
+    QueryRange qr{q_begin, q_end, nullptr, nullptr, layout, ix->row_map};
     const int grid = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)ix->sm_count * 64);
     if (mode == BALL_COUNT) {
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);

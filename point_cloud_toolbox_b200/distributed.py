@@ -3,12 +3,20 @@
 One process per GPU (torchrun), ``torch.distributed`` for the plumbing:
 
   1. rank 0 holds the cloud; ``broadcast`` puts the raw xyz on every GPU (NVLink / NVSwitch)
-  2. every rank builds the same index (the build is deterministic)
-  3. rank g runs the fused kernel on Morton-sorted positions [g*N/G, (g+1)*N/G) -- a spatially
-     coherent slice -- writing slice-local rows (PCT_LAYOUT_SLICE)
-  4. ``gather`` to rank 0, which undoes the Morton permutation
+  2. the queries are divided
+       "slab" (default)   by position: the ranks agree on cut planes across the longest axis of the
+                          bounding box (quantiles, so the slabs hold equal numbers of points); rank g
+                          builds an index over ITS slab plus a margin of 4.5 cells only and answers the
+                          points of its slab.  The index knows where its knowledge ends
+                          (pct_index_set_slab): no search radius crosses the margin, and a query whose
+                          k-th neighbour could lie beyond it comes back PCT_STATUS_UNRESOLVED and is
+                          answered from a whole-cloud index built on demand.  The build, the serial
+                          fraction of the replicated form, shrinks with the number of ranks.
+       "replicated"       every rank builds the same whole-cloud index; rank g answers Morton-sorted
+                          positions [g*N/G, (g+1)*N/G) in slice layout (PCT_LAYOUT_SLICE)
+  3. ``gather`` to rank 0, which puts the rows in original order
 
-There is no exchange step between 2 and 4, so no other collective is involved.
+There is no exchange step between 1 and 3, so no other collective is involved.
 The reference has no distributed code at all; this is new.
 """
 from __future__ import annotations
@@ -66,7 +74,122 @@ def broadcast_cloud(points_dev, n: int, group=None, src: int = 0, device=None):
     return buf
 
 
-def curvature_knn_sharded(points, n: int, k: int, group=None, device=None, columns=(0, 1)):
+# ---------------------------------------------------------------------------
+# slabs
+# ---------------------------------------------------------------------------
+SLAB_MARGIN_CELLS = 4.5  # level-0 and level-1 searches (radius <= 3 cells) never reach the margin's end
+
+
+def slab_cuts(axis_coords: torch.Tensor, world: int, sample: int = 1 << 20):
+    """world + 1 non-decreasing cut values (first -inf, last +inf): quantiles of a strided sample.
+    A pure function of the data, so every rank computes the same cuts from its replica."""
+    n = int(axis_coords.numel())
+    step = max(1, n // sample)
+    s = axis_coords[::step].to(torch.float32).sort().values
+    m = int(s.numel())
+    inner = [float(s[min(m - 1, (m * g) // world)]) for g in range(1, world)]
+    return [float("-inf")] + inner + [float("inf")]
+
+
+def slab_bounds(cuts, rank: int, margin: float):
+    """(complete_lo, complete_hi, own_lo, own_hi) of one rank as float32 values."""
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))  # noqa: E731
+    own_lo, own_hi = f32(cuts[rank]), f32(cuts[rank + 1])
+    m = f32(margin)
+    return f32(own_lo - m), f32(own_hi + m), own_lo, own_hi
+
+
+def slab_select(axis_coords: torch.Tensor, bounds):
+    """(sel, own): ``sel`` = original indices of the points a slab index is built from, ASCENDING (the
+    index breaks distance ties by position in its input, which therefore stays the whole cloud's order);
+    ``own`` = boolean mask over ``sel`` of the points the slab owns."""
+    c_lo, c_hi, own_lo, own_hi = bounds
+    sel = ((axis_coords >= c_lo) & (axis_coords <= c_hi)).nonzero().squeeze(1)
+    xs = axis_coords.index_select(0, sel)
+    return sel, (xs >= own_lo) & (xs < own_hi)
+
+
+def gather_scattered(ids: torch.Tensor, rows: torch.Tensor, n: int, group=None, dst: int = 0):
+    """Ranks hold rows for disjoint sets of original indices; returns the (n, ...) array on ``dst``."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    count = torch.tensor([int(ids.numel())], dtype=torch.int64, device=ids.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c) for c in counts]
+    width = max(counts) if counts else 0
+    ids_p = torch.zeros((width,), dtype=torch.int64, device=ids.device)
+    ids_p[: ids.numel()] = ids.to(torch.int64)
+    rows_p = torch.zeros((width,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    rows_p[: rows.shape[0]] = rows
+    if rank == dst:
+        id_parts = [torch.empty_like(ids_p) for _ in range(world)]
+        row_parts = [torch.empty_like(rows_p) for _ in range(world)]
+        dist.gather(ids_p, id_parts, dst=dst, group=group)
+        dist.gather(rows_p, row_parts, dst=dst, group=group)
+        out = torch.empty((n,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        for r in range(world):
+            out[id_parts[r][: counts[r]]] = row_parts[r][: counts[r]]
+        return out
+    dist.gather(ids_p, None, dst=dst, group=group)
+    dist.gather(rows_p, None, dst=dst, group=group)
+    return None
+
+
+def default_mode(world: int) -> str:
+    """Slabs pay once the replicated whole-cloud build (10 ms at 100 M points) outweighs the cut / select /
+    smaller-build work of a rank (3.6 ms at 8 ranks); measured break-even is between 2 and 4 ranks."""
+    return "slab" if world >= 3 else "replicated"
+
+
+class SlabFit:
+    """Result of one rank: packed records of the points it owns (``ids`` = their original indices)."""
+
+    def __init__(self, ids, records, unresolved, index, cell_size, bounds, axis):
+        self.ids, self.records, self.unresolved = ids, records, unresolved
+        self.index, self.cell_size, self.bounds, self.axis = index, cell_size, bounds, axis
+
+
+def curvature_knn_slab(cloud: torch.Tensor, k: int, rank: int, world: int, events=()) -> SlabFit:
+    """The work of one rank on a replicated device cloud: cuts, slab index, fused kernel on its own points.
+    ``events``: optional CUDA event recorded once the slab index is built (for stage timing)."""
+    from . import engine
+    from ._lib import STATUS_UNRESOLVED
+
+    h, lo, hi = engine.estimate_cell_size(cloud, k)
+    axis = max(range(3), key=lambda a: hi[a] - lo[a])
+    x = cloud[:, axis]
+    bounds = slab_bounds(slab_cuts(x, world), rank, SLAB_MARGIN_CELLS * h)
+    sel, own = slab_select(x, bounds)
+    if int(sel.numel()) <= k + 1:
+        # degenerate slab (tiny cloud): index the whole cloud, still answer only what this rank owns
+        bounds = (float("-inf"), float("inf"), bounds[2], bounds[3])
+        sel, own = slab_select(x, bounds)
+    # compact outputs: row of an owned point = its rank among the owned points
+    row_map = torch.cumsum(own, 0, dtype=torch.int32) - 1
+    n_own = int(row_map[-1]) + 1 if row_map.numel() else 0
+    if n_own == 0:
+        empty = torch.empty((0,), dtype=torch.int64, device=cloud.device)
+        return SlabFit(empty, torch.empty((0, 8), dtype=torch.float32, device=cloud.device), 0, None, h, bounds, axis)
+    local = cloud.index_select(0, sel).contiguous()
+    index = engine.GridIndex(local, cell_hint=h, k_hint=k)
+    index.set_slab(axis, *bounds, row_map=row_map, mapped_rows=n_own)  # rows of points it does not own are never written
+    for ev in events:
+        ev.record()
+    records = index.curvature_knn(k, want_coeffs=False).records   # (n_own, 8)
+    ids = sel[own]
+    n_bad = int(index.last_stats().unresolved)
+    if n_bad:
+        bad = (records[:, 7].contiguous().view(torch.int32) & STATUS_UNRESOLVED) != 0
+        # the k-th neighbour may lie outside the margin: answer these from a whole-cloud index
+        whole = engine.GridIndex(cloud, cell_hint=h, k_hint=k)
+        redo = whole.curvature_points(ids[bad].to(torch.int32), k)
+        records[bad] = redo.records
+        whole.close()
+    return SlabFit(ids, records, n_bad, index, h, bounds, axis)
+
+
+def curvature_knn_sharded(points, n: int, k: int, group=None, device=None, columns=(0, 1), mode="auto"):
     """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() over all ranks of ``group``.
 
     ``points``: host or device (N, 3) float32 on rank 0, ignored elsewhere.
@@ -82,10 +205,20 @@ def curvature_knn_sharded(points, n: int, k: int, group=None, device=None, colum
         device = torch.device("cuda", torch.cuda.current_device())
     d_points = engine.to_device_points(points, device) if rank == 0 else None
     cloud = broadcast_cloud(d_points, n, group, 0, device)
+    names = ("K", "H", "k1", "k2", "H2")
+    if mode == "auto":
+        mode = default_mode(world)
+    if mode == "slab":
+        part = curvature_knn_slab(cloud, k, rank, world)
+        fit = engine.FitOutputs(records=part.records)
+        local = torch.stack([fit.column(names[c]) for c in columns], 1)
+        out = gather_scattered(part.ids, local, n, group, 0)
+        if part.index is not None:
+            part.index.close()
+        return out
     index = engine.GridIndex(cloud, k_hint=k)
     begin, end = shard_bounds(n, world, rank)
     fit = index.curvature_knn(k, begin, end, layout=LAYOUT_SLICE, want_coeffs=False)
-    names = ("K", "H", "k1", "k2", "H2")
     local = torch.stack([fit.column(names[c]) for c in columns], 1)
     gathered = gather_rows(local, n, group, 0)
     if rank != 0:

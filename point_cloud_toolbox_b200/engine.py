@@ -199,6 +199,8 @@ class GridIndex:
         q_begin = 0 if q_begin is None else int(q_begin)
         q_end = self.n if q_end is None else int(q_end)
         rows = self.n if layout == LAYOUT_ORIGINAL else q_end - q_begin
+        if layout == LAYOUT_ORIGINAL and getattr(self, "_mapped_rows", None) is not None:
+            rows = self._mapped_rows
         return q_begin, q_end, rows
 
     # -- queries -----------------------------------------------------------
@@ -209,6 +211,25 @@ class GridIndex:
         with torch.cuda.device(self.device):
             check(lib.pct_knn(self._handle, q_begin, q_end, int(k), ptr(idx), ptr(dist), layout, _stream()))
         return idx, dist
+
+    def set_slab(self, axis, complete_lo, complete_hi, own_lo, own_hi, row_map=None, mapped_rows=None):
+        """This index is one slab of a partitioned cloud (see pct_index_set_slab); axis=-1 undoes it.
+        ``row_map`` (N int32 on the device): output row of every owned point, outputs of original-layout
+        calls then have ``mapped_rows`` rows."""
+        self._row_map = row_map  # kept alive
+        self._mapped_rows = None if row_map is None or axis < 0 else int(mapped_rows)
+        check(lib.pct_index_set_slab(self._handle, int(axis), float(complete_lo), float(complete_hi), float(own_lo),
+                                     float(own_hi), ptr(row_map)))
+
+    def curvature_points(self, query_ids, k) -> "FitOutputs":
+        """Fused search + fit for the cloud points named by original index; packed records, row r = query r."""
+        ids = torch.as_tensor(query_ids, device=self.device).to(torch.int32).contiguous()
+        nq = int(ids.numel())
+        rec = torch.empty((nq, 8), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_curvature_points_records(self._handle, ptr(self.points), int(self.points.shape[1]), ptr(ids), nq,
+                                                   int(k), ptr(rec), _stream()))
+        return FitOutputs(records=rec)
 
     def knn_points(self, query_ids, k):
         """Ordered kNN rows (original indices, distances) of the cloud points named by original index."""
@@ -269,6 +290,16 @@ class GridIndex:
 
 
 # -- list-driven fit and the batched static methods ---------------------------
+def estimate_cell_size(points_dev, k_hint=20):
+    """(cell edge the index build would choose, bbox min (3,), bbox max (3,)) of a device cloud."""
+    h = ctypes.c_float()
+    box = (ctypes.c_float * 6)()
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_estimate_cell_size(ptr(points_dev), int(points_dev.shape[0]), int(points_dev.shape[1]), int(k_hint),
+                                         _stream(), ctypes.byref(h), box))
+    return float(h.value), [box[0], box[1], box[2]], [box[3], box[4], box[5]]
+
+
 def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:
     """Fit rows of original-index neighbour lists (nq, k) on an (N, 3) cloud."""
     if points_dev.shape[1] != 3 or not points_dev.is_contiguous():

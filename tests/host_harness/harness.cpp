@@ -53,6 +53,7 @@ void* h_build(const float* xyz, long long n, float h) {
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
     v.volumetric = 0;
     v.cut_gain = 6.5f;
+    v.slab_axis = -1;
     std::vector<std::pair<unsigned long long, uint32_t>> keyed(n);
     for (long long i = 0; i < n; ++i) {
         int cx, cy, cz;
@@ -89,6 +90,11 @@ void* h_build(const float* xyz, long long n, float h) {
 }
 
 void h_destroy(void* p) { delete (HostIndex*)p; }
+// the index is one slab of a larger cloud (pct_index_set_slab)
+void h_set_slab(void* p, int axis, float complete_lo, float complete_hi, float own_lo, float own_hi) {
+    IndexView& v = ((HostIndex*)p)->view;
+    v.slab_axis = axis; v.complete_lo = complete_lo; v.complete_hi = complete_hi; v.own_lo = own_lo; v.own_hi = own_hi;
+}
 void h_pass2_counts(long long* out, int reset) {
     out[0] = g_pass2[0]; out[1] = g_pass2[1];
     if (reset) g_pass2[0] = g_pass2[1] = 0;
@@ -180,6 +186,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
         const Pt q = v.pts[i];
         if (U > 0 && i % PCT_STAGED_BLOCK == 0)
             stage.build(v, i, std::min<long long>(i + PCT_STAGED_BLOCK, v.n), U >= 2 ? 2 + PCT_STAGED_BLOCK / 64 : 4 + PCT_STAGED_BLOCK / 16, (size_t)cap_pts);
+        if (!query_owned(v, q.x, q.y, q.z)) { code[q.idx] = -2; continue; }  // another slab answers this one
         uint32_t first = 0, last = 0;
         double d2_last = 0;
         int rc = SEL_RETRY_COARSER, level = 0;

@@ -26,6 +26,36 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) <= pdist.padded_rows(n, world)
 
 
+def test_slabs_partition_the_cloud():
+    """Cut planes, margins and ownership masks (pure tensor logic of the slab mode)."""
+    g = torch.Generator().manual_seed(1)
+    for n, world in ((5000, 3), (20000, 8), (300, 2), (50, 8)):
+        x = torch.randn(n, generator=g) * 3.0
+        x[: n // 10] = x[0]  # a pile of equal coordinates must not break the partition
+        cuts = pdist.slab_cuts(x, world)
+        assert len(cuts) == world + 1 and cuts[0] == float("-inf") and cuts[-1] == float("inf")
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        owner = torch.zeros(n, dtype=torch.int64)
+        margin = 0.25
+        for r in range(world):
+            b = pdist.slab_bounds(cuts, r, margin)
+            assert b[0] <= b[2] <= b[3] <= b[1]
+            sel, own = pdist.slab_select(x, b)
+            own_pos = own.nonzero().squeeze(1)
+            owner[sel[own_pos]] += 1
+            assert bool((sel[1:] > sel[:-1]).all())  # ascending: ties keep the whole cloud's index order
+            # the slab holds everything within the margin of what it owns
+            if len(own_pos):
+                lo, hi = x[sel[own_pos]].min() - margin, x[sel[own_pos]].max() + margin
+                inside = (x >= lo + 1e-6) & (x <= hi - 1e-6)
+                held = torch.zeros(n, dtype=torch.bool)
+                held[sel] = True
+                assert bool(held[inside].all())
+        assert bool((owner == 1).all())  # every point is answered by exactly one rank
+    sizes = [int(pdist.slab_select(x, pdist.slab_bounds(cuts, r, 0.0))[1].sum()) for r in range(world)]
+    assert sum(sizes) == n
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -55,6 +85,18 @@ def _worker(rank, world, port, n, out_path):
             np.save(out_path, np.array([float(torch.equal(full, want)), float(gathered.shape[0])]))
         else:
             assert gathered is None
+        # slab mode: ranks hold rows for disjoint, unordered sets of original indices
+        x = cloud[:, 0]
+        cuts = pdist.slab_cuts(x, world)
+        sel, own = pdist.slab_select(x, pdist.slab_bounds(cuts, rank, 4.0))
+        ids = sel[own]
+        rows = torch.stack((ids.float() * 3.0, cloud[ids, 2]), 1)
+        full = pdist.gather_scattered(ids, rows, n, None, 0)
+        if rank == 0:
+            want = torch.stack((torch.arange(n).float() * 3.0, cloud[:, 2]), 1)
+            assert torch.equal(full, want)
+        else:
+            assert full is None
     finally:
         dist.destroy_process_group()
 

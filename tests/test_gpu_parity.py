@@ -241,6 +241,73 @@ def test_knn_points_rows_equal_full_lists(pct, bunny):
     ix.close()
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_slab_mode_equals_whole_cloud_index(pct, world):
+    """Multi-GPU slab partition, its ranks run one after the other on this GPU: every point is answered by
+    exactly one slab index and the answers are those of the whole-cloud index."""
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    pts, _, _ = datasets.torus_random(200_000, seed=4)
+    k = 20
+    cloud = torch.from_numpy(pts).cuda()
+    whole = pct.GridIndex(cloud, k_hint=k)
+    ref = whole.curvature_knn(k, want_coeffs=False).records
+    got = torch.full_like(ref, float("nan"))
+    seen = torch.zeros(len(pts), dtype=torch.int32, device="cuda")
+    for rank in range(world):
+        part = pdist.curvature_knn_slab(cloud, k, rank, world)
+        assert part.index.n < 0.8 * len(pts)            # a slab index holds its slab and a margin, not the cloud
+        assert part.unresolved == 0
+        got[part.ids] = part.records
+        seen[part.ids] += 1
+        part.index.close()
+    assert bool((seen == 1).all())
+    ok = ~torch.isnan(ref[:, 3])
+    assert bool(ok.float().mean() > 0.9999)
+    rel = ((got[:, 3:7] - ref[:, 3:7]).abs() / ref[:, 3:7].abs().clamp_min(1e-3))[ok]
+    assert float(rel.max()) < 1e-4, float(rel.max())     # same neighbours, sums in another order
+    assert bool(((got[:, :3] * ref[:, :3]).sum(1)[ok] > 0.99999).all())
+    # neighbour rows of a slab index are the whole cloud's rows
+    part = pdist.curvature_knn_slab(cloud, k, 1, world)
+    idx_local, dist_local = part.index.knn(k)
+    sel, own = pdist.slab_select(cloud[:, part.axis], part.bounds)
+    idx_whole, dist_whole = whole.knn(k)
+    assert idx_local.shape[0] == int(own.sum())            # compact rows: one per owned point, in ascending original index
+    owned = sel[own]
+    assert torch.equal(sel[idx_local.long()], idx_whole[owned].long())
+    assert torch.equal(dist_local, dist_whole[owned])
+    part.index.close()
+    whole.close()
+
+
+def test_unresolved_slab_queries_fall_back_to_the_whole_cloud(pct):
+    """A cloud with far outliers: their k-th neighbour lies beyond any margin; the slab index says so
+    (PCT_STATUS_UNRESOLVED) and the rank answers them from a whole-cloud index."""
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    rng = np.random.default_rng(9)
+    base, _, _ = datasets.torus_random(60_000, seed=5)
+    # 12 < k + 1 points high above the torus, in the middle of x and y (an interior slab whichever of the
+    # two is the longest axis): their k-th neighbour is ~1.7 away, far beyond the slab's margin
+    far = (rng.normal(size=(12, 3)) * 0.02 + np.array([0.1, 0.1, 2.0])).astype(np.float32)
+    pts = np.concatenate((base, far)).astype(np.float32)
+    k = 20
+    cloud = torch.from_numpy(pts).cuda()
+    whole = pct.GridIndex(cloud, k_hint=k)
+    ref = whole.curvature_knn(k, want_coeffs=False).records
+    got = torch.full_like(ref, float("nan"))
+    unresolved = 0
+    for rank in range(4):
+        part = pdist.curvature_knn_slab(cloud, k, rank, 4)
+        unresolved += part.unresolved
+        got[part.ids] = part.records
+        part.index.close()
+    assert unresolved >= 12
+    rel = (got[:, 3:5] - ref[:, 3:5]).abs() / ref[:, 3:5].abs().clamp_min(1e-3)
+    assert float(rel.max()) < 1e-4
+    whole.close()
+
+
 def test_errors_mirror_reference(pct):
     with pytest.raises(ValueError, match="Either file_path or points and normals"):
         pct.PointCloud()

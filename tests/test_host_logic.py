@@ -30,6 +30,7 @@ def harness():
     lib.h_destroy.argtypes = [ctypes.c_void_p]
     lib.h_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
     lib.h_knn_staged.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_float] + [ctypes.c_void_p] * 7
+    lib.h_set_slab.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_float] * 4
     lib.h_fit_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5
     lib.h_ball.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
     return lib
@@ -39,10 +40,12 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, coll_extra=0, cut_gain=6.5):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, coll_extra=0, cut_gain=6.5, slab=None):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
+    if slab is not None:
+        lib.h_set_slab(ix, *slab)
     out = dict(idx=np.zeros((n, k), np.int32), dist=np.zeros((n, k), np.float32), code=np.full(n, -9, np.int32),
                normal=np.zeros((n, 3), np.float32), coeffs=np.zeros((n, 6), np.float32), curv=np.zeros((n, 5), np.float32),
                status=np.zeros(n, np.uint8))
@@ -116,6 +119,39 @@ def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
             got = run_knn(harness, pts, k, h, staged_u=u, coll_extra=extra)
             assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u, extra)
             assert np.array_equal(got["dist"], ref_dist), (name, u, extra)
+
+
+@pytest.mark.parametrize("axis", [0, 2])
+def test_slab_indices_reproduce_the_whole_cloud_answer(harness, bunny, axis):
+    """Multi-GPU partition: every slab index holds only its own points plus a margin, never lets a search
+    radius cross the margin, and still gives the rows of the WHOLE cloud for the queries it owns."""
+    pts = np.ascontiguousarray(bunny[::2])
+    k = 16
+    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+    h = 1.25 * float(np.median(ref_dist[:, -1]))
+    x = pts[:, axis]
+    cuts = np.quantile(x, [0.0, 0.3, 0.55, 1.0]).astype(np.float32)
+    cuts[0], cuts[-1] = -np.inf, np.inf
+    margin = np.float32(4.5 * h)
+    answered = np.zeros(len(pts), bool)
+    unresolved = 0
+    for g in range(3):
+        own_lo, own_hi = cuts[g], cuts[g + 1]
+        c_lo, c_hi = np.float32(own_lo - margin), np.float32(own_hi + margin)
+        sel = np.flatnonzero((x >= c_lo) & (x <= c_hi))
+        assert len(sel) < 0.75 * len(pts)  # a real subset
+        for staged_u in (0, 2):
+            got = run_knn(harness, pts[sel], k, h, max_fast_level=2, staged_u=staged_u,
+                          slab=(axis, float(c_lo), float(c_hi), float(own_lo), float(own_hi)))
+            own = (x[sel] >= own_lo) & (x[sel] < own_hi)
+            assert np.array_equal(got["code"] != -2, own)
+            fast = own & (got["code"] >= 0) & (got["code"] % 50 <= 2)   # answered by a grid level, not by the harness's brute force
+            assert fast[own].mean() > 0.995
+            assert np.array_equal(sel[got["idx"][fast]], ref_idx[sel[fast]])
+            assert np.array_equal(got["dist"][fast], ref_dist[sel[fast]])
+        answered[sel[own]] = True
+        unresolved += int((own & ~fast).sum())
+    assert answered.all() and unresolved < 0.005 * len(pts)
 
 
 def test_cell_size_never_changes_the_answer(harness, bunny):
