@@ -88,7 +88,7 @@ const char* pct_last_error(void);
 /* Spatial index: replaces `sp.spatial.cKDTree(points)` (ref :74).
  * xyz: N rows of `stride` floats (3 = packed xyz, 4 = padded), fp32.
  * cell_hint > 0 fixes the level-0 cell edge; otherwise it is chosen from a
- * density pilot so that a cell holds about 0.4 * k_hint points (k_hint <= 0: 20).
+ * density pilot so that a cell holds about 0.46 * k_hint points (k_hint <= 24; fewer per k above) (k_hint <= 0: 20).
  * Synchronises `stream` (the grid shape is needed on the host).
  * PCT_ERR_NONFINITE if any coordinate is NaN/Inf. */
 int pct_index_build(const float* xyz, int64_t n, int stride, float cell_hint, int k_hint,
