@@ -142,7 +142,11 @@ class ClockSampler:
         self.thread = None
         self.error = None
 
-    def _run(self):
+    def prepare(self):
+        """NVML initialisation in the calling thread, BEFORE any timed region: nvmlInit takes tens to
+        hundreds of milliseconds and stalls concurrent CUDA calls of the process while it runs."""
+        if not self.enabled:
+            return
         try:
             import pynvml
 
@@ -154,24 +158,36 @@ class ClockSampler:
                     index = int(visible.split(",")[self.gpu])
                 except (ValueError, IndexError):
                     index = self.gpu
-            h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+            self._sample()  # first call of every query outside the timed region too
+            self.samples.clear()
+        except Exception as exc:  # pragma: no cover
+            self.error = repr(exc)
+            self._nvml = None
+
+    def _sample(self):
+        pynvml, h = self._nvml, self._handle
+        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            power = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
+        except Exception:
+            power = None
+        self.samples.append((sm, self._max, int(reasons), power))
+
+    def _run(self):
+        try:
             while not self.stop_flag.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                try:
-                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
-                except Exception:
-                    power = None
-                self.samples.append((sm, mx, int(reasons), power))
+                self._sample()
                 self.stop_flag.wait(self.interval)
-            pynvml.nvmlShutdown()
         except Exception as exc:  # pragma: no cover
             self.error = repr(exc)
 
     def start(self):
-        if not self.enabled:
+        if not self.enabled or getattr(self, "_nvml", None) is None:
             return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -305,12 +321,38 @@ def ours(args):
             record.append((e0, e1, e2))
         return index, fit
 
+    # multi-GPU end to end: the host cloud and the host result live in shared memory mapped by every rank
+    # (a one-node job's ranks see the same input), so each rank moves its share over its own PCIe link;
+    # if the node's /dev/shm cannot hold them, rank 0 moves everything (broadcast in, gather out)
+    shared_in = shared_out = None
+    if world > 1:
+        tag = f"pct_bench_{os.environ.get('MASTER_PORT', '0')}"
+        ok = torch.ones(1, device=dev)
+        try:
+            if rank == 0:
+                shared_in = pdist.SharedHostArray(tag + "_in", (n, 3), create=True)
+                shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=True)
+                shared_in.array[:] = host_pts
+        except Exception as exc:  # pragma: no cover
+            print(f"shared host memory unavailable ({exc!r}); rank 0 moves all host data", file=sys.stderr)
+            ok.zero_()
+        dist.broadcast(ok, 0)
+        if bool(ok.item()) and rank != 0:
+            shared_in = pdist.SharedHostArray(tag + "_in", (n, 3), create=False)
+            shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=False)
+        if not bool(ok.item()):
+            shared_in = shared_out = None
+        dist.barrier()
+
     def e2e_step():
         if world == 1:
             pc = PointCloud(points=host_pts, normals=np.zeros((n, 0), np.float32), k_neighbors=k)
             pc.plant_kdtree(k)
             K, H = pc.compute_pointwise_explicit_quadratic_curvature()
             return K, H
+        if shared_in is not None:
+            pdist.curvature_knn_shared(shared_in, shared_out, k, device=dev)
+            return (shared_out.array[0], shared_out.array[1]) if rank == 0 else (None, None)
         out = pdist.curvature_knn_sharded(host_pts, n, k, device=dev)
         if rank == 0:
             from point_cloud_toolbox_b200.engine import to_host
@@ -320,6 +362,8 @@ def ours(args):
         return None, None
 
     sampler = ClockSampler(local_rank, args.clock_interval_ms, not args.no_clocks)
+    if rank == 0:
+        sampler.prepare()
 
     # Warm-up and timed steps run the SAME loop (same object lifetimes: the previous step's
     # results stay alive until the next step has produced its own, as they would in a caller
@@ -389,6 +433,12 @@ def ours(args):
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - wall0)
     e2e_ms = s0.elapsed_time(s1)
+    e2e_host_io = "one rank" if world == 1 else ("every rank its share (shared host memory)" if shared_in is not None else "rank 0")
+    if rank == 0 and world > 1 and shared_out is not None:
+        K = np.array(K[:1024])  # detach from the segment before it is unmapped
+    for sh in (shared_in, shared_out):
+        if sh is not None:
+            sh.close()
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -431,7 +481,7 @@ def ours(args):
             "note": "algorithmic 44 B/point; the kernel is instruction-issue bound (64 % of issue slots, profiles/staged_full_r01s.txt), not HBM bound (DESIGN.md 5)",
         },
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
-                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "step_wall_ms": step_walls},
+                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "step_wall_ms": step_walls, "host_io": e2e_host_io},
         "gpu_launches": OUR_KERNELS_PER_STEP * args.steps * 2,
         "clocks": clocks,
     }

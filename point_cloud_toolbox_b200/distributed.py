@@ -189,6 +189,118 @@ def curvature_knn_slab(cloud: torch.Tensor, k: int, rank: int, world: int, event
     return SlabFit(ids, records, n_bad, index, h, bounds, axis)
 
 
+# ---------------------------------------------------------------------------
+# host buffers shared by the ranks: every rank moves its own share over its own PCIe link
+# ---------------------------------------------------------------------------
+class SharedHostArray:
+    """A float32 array in POSIX shared memory that every rank of the node maps and page-locks.
+
+    The processes of a one-node job usually see the same input anyway (the same file, memory-mapped);
+    with the cloud and the result in shared host memory each rank copies only ITS share in and out,
+    over its own PCIe link, instead of rank 0 moving everything.  ``create=True`` on exactly one rank
+    (which also unlinks the segment on ``close``), ``create=False`` on the others after a barrier.
+    """
+
+    def __init__(self, name: str, shape, create: bool):
+        import numpy as np
+        from multiprocessing import shared_memory
+
+        nbytes = 4
+        for d in shape:
+            nbytes *= int(d)
+        self._shm = shared_memory.SharedMemory(name=name, create=create, size=max(nbytes, 4))
+        self._owner = create
+        if not create:
+            # Python < 3.13 registers attached segments for unlinking at exit as well; only the creator unlinks
+            try:
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.array = np.ndarray(tuple(shape), dtype=np.float32, buffer=self._shm.buf)
+        self.tensor = torch.from_numpy(self.array)
+        self._registered = False
+        if torch.cuda.is_available() and nbytes:
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+            self._registered = int(rc) == 0
+
+    def close(self):
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None
+        self.array = None
+        try:
+            self._shm.close()
+            if self._owner:
+                self._shm.unlink()
+        except (BufferError, FileNotFoundError):
+            pass
+
+
+def exchange_by_owner(ids: torch.Tensor, rows: torch.Tensor, n: int, group=None):
+    """All-to-all of per-point rows to the ranks that own their ORIGINAL index ranges.
+
+    ``ids`` ascending original indices this rank computed, ``rows`` their rows.  Rank r owns original
+    indices ``shard_bounds(n, world, r)``; returns that range filled, ``(end - begin, ...)``.
+    Ascending ids make every destination a contiguous segment, so no sort is needed."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    edges = torch.tensor([shard_bounds(n, world, r)[0] for r in range(world)] + [n], dtype=ids.dtype, device=ids.device)
+    cuts = torch.searchsorted(ids.contiguous(), edges)
+    send = (cuts[1:] - cuts[:-1]).to(torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = [int(v) for v in send.tolist()], [int(v) for v in recv.tolist()]
+    total = sum(recv_l)
+    ids_in = torch.empty((total,), dtype=ids.dtype, device=ids.device)
+    rows_in = torch.empty((total,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(ids_in, ids.contiguous(), recv_l, send_l, group=group)
+    dist.all_to_all_single(rows_in, rows.contiguous(), recv_l, send_l, group=group)
+    begin, end = shard_bounds(n, world, rank)
+    out = torch.empty((end - begin,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    out[(ids_in - begin).long()] = rows_in
+    return out
+
+
+def curvature_knn_shared(points: SharedHostArray, out: SharedHostArray, k: int, group=None, device=None):
+    """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() of a cloud in shared host memory.
+
+    ``points`` (N, 3) and ``out`` (2, N) = [K; H] are mapped by every rank.  Rank r copies rows
+    ``shard_bounds(N, world, r)`` of the cloud to its GPU, an all-gather over NVLink replicates the cloud,
+    every rank answers its slab, an all-to-all returns the rows to the ranks owning their original index
+    ranges, and each rank writes its range of ``out``.  Collective: returns after a barrier, when
+    ``out`` is complete on the host."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    n = int(points.tensor.shape[0])
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    rows = padded_rows(n, world)
+    begin, end = shard_bounds(n, world, rank)
+    padded = torch.empty((world * rows, 3), dtype=torch.float32, device=device)
+    mine = padded[rank * rows: rank * rows + (end - begin)]
+    mine.copy_(points.tensor[begin:end], non_blocking=True)                      # this rank's share, its own PCIe link
+    dist.all_gather_into_tensor(padded, padded[rank * rows:(rank + 1) * rows], group=group)
+    if n == world * rows:
+        cloud = padded
+    else:
+        cloud = torch.cat([padded[r * rows: r * rows + (shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0])]
+                           for r in range(world)], 0)
+    part = curvature_knn_slab(cloud, k, rank, world)
+    kh = part.records[:, 3:5].contiguous()
+    own = exchange_by_owner(part.ids.to(torch.int32), kh, n, group)                              # (end - begin, 2) in original order
+    khT = own.t().contiguous()
+    out.tensor[0, begin:end].copy_(khT[0], non_blocking=True)
+    out.tensor[1, begin:end].copy_(khT[1], non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    if part.index is not None:
+        part.index.close()
+    dist.barrier(group=group)
+    return part
+
+
 def curvature_knn_sharded(points, n: int, k: int, group=None, device=None, columns=(0, 1), mode="auto"):
     """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() over all ranks of ``group``.
 

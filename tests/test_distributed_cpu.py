@@ -97,6 +97,27 @@ def _worker(rank, world, port, n, out_path):
             assert torch.equal(full, want)
         else:
             assert full is None
+        # shared-host mode: rows go back to the ranks that own their original index ranges
+        mine = pdist.exchange_by_owner(ids, rows, n, None)
+        b, e = pdist.shard_bounds(n, world, rank)
+        want = torch.stack((torch.arange(b, e).float() * 3.0, cloud[b:e, 2]), 1)
+        assert torch.equal(mine, want)
+        # ... and the host arrays are one segment mapped by every rank
+        name = f"pct_test_{port}"
+        if rank == 0:
+            shared = pdist.SharedHostArray(name, (2, n), create=True)
+            shared.array[:] = 0
+        dist.barrier()
+        if rank != 0:
+            shared = pdist.SharedHostArray(name, (2, n), create=False)
+        shared.tensor[0, b:e] = mine[:, 0]
+        shared.tensor[1, b:e] = mine[:, 1]
+        dist.barrier()
+        if rank == 0:
+            assert np.array_equal(shared.array[0], np.arange(n, dtype=np.float32) * 3.0)
+            assert np.array_equal(shared.array[1], cloud[:, 2].numpy())
+        dist.barrier()
+        shared.close()
     finally:
         dist.destroy_process_group()
 

@@ -308,6 +308,38 @@ def test_unresolved_slab_queries_fall_back_to_the_whole_cloud(pct):
     whole.close()
 
 
+def test_shared_host_path_single_rank_group(pct):
+    """curvature_knn_shared (share-wise H2D, all-gather, slab, all-to-all by owner, share-wise D2H) on a
+    one-rank NCCL group: same K, H as the PointCloud call."""
+    import socket
+
+    import torch.distributed as dist
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    pts, _, _ = datasets.torus_random(150_000, seed=6)
+    k = 20
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+    pc.plant_kdtree(k)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        cloud = pdist.SharedHostArray(f"pct_gpu_test_{port}_in", pts.shape, create=True)
+        out = pdist.SharedHostArray(f"pct_gpu_test_{port}_out", (2, len(pts)), create=True)
+        cloud.array[:] = pts
+        out.array[:] = np.nan
+        pdist.curvature_knn_shared(cloud, out, k)
+        assert np.allclose(out.array[0], K, rtol=1e-5, atol=1e-6, equal_nan=True)
+        assert np.allclose(out.array[1], H, rtol=1e-5, atol=1e-6, equal_nan=True)
+        cloud.close()
+        out.close()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_errors_mirror_reference(pct):
     with pytest.raises(ValueError, match="Either file_path or points and normals"):
         pct.PointCloud()
