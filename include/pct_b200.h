@@ -191,6 +191,10 @@ int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uin
                     void* stream);
 int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream);
 
+/* Frees the per-stream scratch arenas the library keeps for the temporaries of its calls (they grow to the
+ * largest call seen on a stream: about 37 bytes per point for an index build).  Synchronises those streams. */
+int pct_release_scratch(void);
+
 /* Host-buffer convenience for callers without PyTorch: H2D + build + fused kNN
  * curvature + D2H, synchronous.  K, H: N fp32 host arrays. */
 int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_host, float* H_host);

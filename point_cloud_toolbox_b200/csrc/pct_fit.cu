@@ -35,7 +35,7 @@ fit_rows_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, 
         nb.qx = __ldg(xyz + 3 * qi); nb.qy = __ldg(xyz + 3 * qi + 1); nb.qz = __ldg(xyz + 3 * qi + 2);
         FitResult res;
         res.status = 0;
-        fit_neighbourhood(nb, res);
+        fit_neighbourhood<true>(nb, res);
         store_fit(out, r, res);
     }
 }

@@ -174,25 +174,32 @@ __global__ void __launch_bounds__(kThreads) fill_tables_kernel(const unsigned lo
     }
 }
 
+// a temporary of the build: from the call's scratch session, else from the stream-ordered pool
 struct DeviceTemp {
     void* p = nullptr;
     cudaStream_t s;
-    explicit DeviceTemp(cudaStream_t st) : s(st) {}
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
-    ~DeviceTemp() { if (p) cudaFreeAsync(p, s); }
+    ScratchSession* scratch;
+    bool pooled = false;
+    DeviceTemp(cudaStream_t st, ScratchSession* ss) : s(st), scratch(ss) {}
+    cudaError_t alloc(size_t bytes) {
+        if (scratch && (p = scratch->take(bytes ? bytes : 16))) return cudaSuccess;
+        pooled = true;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, s);
+    }
+    ~DeviceTemp() { if (p && pooled) cudaFreeAsync(p, s); }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
 }  // namespace
 
 static int choose_cell_size(const float* xyz, long long n, int stride, const float lo[3], float extent_max,
-                            int k_hint, cudaStream_t s, float* h_out, float* dim_out) {
+                            int k_hint, cudaStream_t s, ScratchSession* ss, float* h_out, float* dim_out) {
     *dim_out = 2.f;
     if (!(extent_max > 0.f)) { *h_out = 1.f; return PCT_OK; }
     const int samples = (int)std::min<long long>(n, kPilotSample);
     const long long step = std::max<long long>(1, n / samples);
     const float cell = extent_max * (1.0f + 1e-6f) / (float)(1 << kPilotBits);
-    DeviceTemp keys_a(s), keys_b(s), tmp(s), hist(s);
+    DeviceTemp keys_a(s, ss), keys_b(s, ss), tmp(s, ss), hist(s, ss);
     PCT_CUDA(keys_a.alloc(sizeof(uint32_t) * samples));
     PCT_CUDA(keys_b.alloc(sizeof(uint32_t) * samples));
     PCT_CUDA(hist.alloc(sizeof(unsigned long long) * kMaxLevels));
@@ -238,9 +245,10 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
 }
 
 // min xyz, max xyz of the cloud; PCT_ERR_NONFINITE if any coordinate is NaN / Inf.  Synchronises `s`.
-static int bounding_box(const float* xyz, long long n, int stride, int sm_count, cudaStream_t s, float h_bbox[6]) {
+static int bounding_box(const float* xyz, long long n, int stride, int sm_count, cudaStream_t s, ScratchSession* ss,
+                        float h_bbox[6]) {
     const int bb_blocks = std::max(1, std::min<int>(sm_count * 8, (int)((n + kThreads - 1) / kThreads)));
-    DeviceTemp bbox(s);
+    DeviceTemp bbox(s, ss);
     PCT_CUDA(bbox.alloc(sizeof(unsigned int) * 8));
     PCT_CUDA(cudaMemsetAsync(bbox.p, 0xFF, sizeof(unsigned int) * 3, s));
     PCT_CUDA(cudaMemsetAsync(bbox.as<unsigned int>() + 3, 0, sizeof(unsigned int) * 5, s));
@@ -272,10 +280,13 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
         PCT_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
 
+    // keys and values twice, radix-sort workspace (about its input again), pilot and small buffers
+    ScratchSession scratch(s, (size_t)n * 24 + (size_t)n * 13 + ((size_t)32 << 20));
+
     // 1. bounding box + finiteness
     float h_bbox[6];
     {
-        const int rc = bounding_box(xyz, n, stride, ix->sm_count, s, h_bbox);
+        const int rc = bounding_box(xyz, n, stride, ix->sm_count, s, &scratch, h_bbox);
         if (rc != PCT_OK) return rc;
     }
     const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
@@ -285,7 +296,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     // 2. cell size
     float h = cell_hint, est_dim = 2.f;
     if (!(h > 0.f)) {
-        const int rc = choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &h, &est_dim);
+        const int rc = choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &scratch, &h, &est_dim);
         if (rc != PCT_OK) return rc;
     }
     if (!(h > 0.f) || !std::isfinite(h)) h = 1.f;
@@ -318,7 +329,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     }
 
     // 3. keys, sort, gather
-    DeviceTemp keys_a(s), keys_b(s), vals_a(s), vals_b(s), sort_tmp(s), hist(s);
+    DeviceTemp keys_a(s, &scratch), keys_b(s, &scratch), vals_a(s, &scratch), vals_b(s, &scratch), sort_tmp(s, &scratch), hist(s, &scratch);
     PCT_CUDA(keys_a.alloc(sizeof(unsigned long long) * n));
     PCT_CUDA(keys_b.alloc(sizeof(unsigned long long) * n));
     PCT_CUDA(vals_a.alloc(sizeof(uint32_t) * n));
@@ -417,12 +428,13 @@ int pct_estimate_cell_size(const float* xyz, int64_t n, int stride, int k_hint, 
     PCT_CUDA(cudaGetDevice(&device));
     PCT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     float h_bbox[6];
-    int rc = pct::bounding_box(xyz, n, stride, sm_count, s, h_bbox);
+    pct::ScratchSession scratch(s, (size_t)32 << 20);
+    int rc = pct::bounding_box(xyz, n, stride, sm_count, s, &scratch, h_bbox);
     if (rc != PCT_OK) return rc;
     const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
     const float extent_max = std::max(h_bbox[3] - h_bbox[0], std::max(h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]));
     float h = 1.f, dim = 2.f;
-    rc = pct::choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &h, &dim);
+    rc = pct::choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &scratch, &h, &dim);
     if (rc != PCT_OK) return rc;
     *cell_size = h;
     if (bbox_min_max)

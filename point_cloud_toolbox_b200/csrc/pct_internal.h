@@ -45,6 +45,20 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         }                                      \
     } while (0)
 
+// Bump allocation out of the calling stream's scratch arena for the duration of one call
+// (pct_scratch.cu).  take() returns nullptr when the arena is exhausted or could not be allocated;
+// callers then fall back to cudaMallocAsync.
+class ScratchSession {
+ public:
+    ScratchSession(cudaStream_t s, size_t bytes);
+    void* take(size_t bytes);
+
+ private:
+    char* p_ = nullptr;
+    size_t left_ = 0;
+};
+void release_scratch();
+
 // per-row output pointers of the fit (any may be null)
 struct FitOutputs {
     float* normals;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void emit_query(const Source& src, const ListRef<type
         nb.src = &src; nb.list = list; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
         FitResult r;
         r.status = 0;
-        fit_neighbourhood(nb, r);
+        fit_neighbourhood<false>(nb, r);
         store_fit(out, row, r);
     } else {
         // ordered rows: successive minima of (d2, index) over the k members

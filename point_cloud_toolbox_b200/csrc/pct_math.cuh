@@ -522,7 +522,11 @@ PCT_HD_NOINLINE void fit_few_rows(Nbr& nb, const Frame& fr, FitResult& out) {
 // Whole per-point pipeline over an abstract neighbourhood.
 //   nb.pass(fn)  calls fn(cx, cy, cz) for every neighbour (fp32, centred)
 //   nb.reference(rx, ry, rz) gives c_last - c_first in fp32, valid after the first pass
-template <class Nbr>
+// FEW_ROWS: neighbourhoods of fewer than 6 rows get lstsq's minimum-norm solution (the fit-from-rows
+// entry points, i.e. the neighbour study).  The search kernels instantiate it with false -- the row
+// buffers of that path would cost them a 1.2 KB stack frame and 8 % of their speed -- and report such
+// neighbourhoods as rank deficient; the host layer sends k < 6 through the rows path instead.
+template <bool FEW_ROWS, class Nbr>
 PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     Moments mom;
     mom.reset();
@@ -533,7 +537,7 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     nb.reference(rx, ry, rz);
     Frame fr;
     plane_frame(mom, rx, ry, rz, fr);
-    if (mom.n < 6) {
+    if (FEW_ROWS && mom.n < 6) {
         fit_few_rows(nb, fr, out);
         return;
     }

@@ -161,7 +161,7 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             nb.src = &src; nb.list.base = mine; nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
             FitResult r;
             r.status = ST_EXACT_PATH;
-            fit_neighbourhood(nb, r);
+            fit_neighbourhood<false>(nb, r);
             store_fit(out, qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx), r);
         }
         __syncwarp();
@@ -207,7 +207,7 @@ ball_kernel(const IndexView ix, const int level, const QueryRange qr, const doub
         } else if (MODE == BALL_FUSED) {
             FitResult r;
             r.status = 0;
-            fit_neighbourhood(nb, r);
+            fit_neighbourhood<false>(nb, r);
             if (counts) counts[row] = nb.count;
             store_fit(out, row, r);
         } else {
@@ -262,10 +262,15 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     const long long nq = q_end - q_begin;
     if (nq == 0) return PCT_OK;
     const int cap = k + PCT_TIE_SLACK;
-    uint32_t* queues = nullptr;
-    unsigned int* counters = nullptr;
-    PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 3 * (size_t)nq, s));
-    PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 4, s));
+    // three work queues of up to nq entries each, from the stream's scratch arena
+    ScratchSession scratch(s, sizeof(uint32_t) * 3 * (size_t)nq + 4096);
+    uint32_t* queues = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * 3 * (size_t)nq));
+    unsigned int* counters = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
+    const bool pooled = !queues || !counters;
+    if (pooled) {
+        PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 3 * (size_t)nq, s));
+        PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 4, s));
+    }
     PCT_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, s));
     uint32_t* retry1 = queues;
     uint32_t* exactq = queues + nq;
@@ -286,8 +291,10 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     ++launches;
     publish_stats_kernel<<<1, 1, 0, s>>>(counters, ix->stats, (unsigned int)nq, launches);
     PCT_CUDA(cudaGetLastError());
-    PCT_CUDA(cudaFreeAsync(queues, s));
-    PCT_CUDA(cudaFreeAsync(counters, s));
+    if (pooled) {
+        PCT_CUDA(cudaFreeAsync(queues, s));
+        PCT_CUDA(cudaFreeAsync(counters, s));
+    }
     return PCT_OK;
 }
 

@@ -255,6 +255,9 @@ class PointCloud:
     def fit_explicit_quadratic_surfaces_to_neighborhoods(self):
         if self.kdtree is None and self._lists is None:
             raise AttributeError("'PointCloud' object has no attribute 'neighbor_indices'")
+        if self.kdtree is not None and self._ball_radius is None and self.k_neighbors < 6 and self._lists is None:
+            # fewer rows than coefficients: lstsq's minimum-norm solution (ref :359) lives in the rows path
+            self._materialise_lists()
         if self._lists is not None and self._lists[0] is not None:
             # rows were read or assigned: fit exactly those rows (ref :640)
             d_points = self._d_points if self._d_points is not None else self._upload()
@@ -302,7 +305,8 @@ class PointCloud:
 
     def compute_pointwise_explicit_quadratic_curvature(self):
         """Compute explicit quadratic curvature and return pointwise values (ref :505-509)."""
-        if (self._lists is None or self._lists[0] is None) and self.kdtree is not None:
+        if (self._lists is None or self._lists[0] is None) and self.kdtree is not None and \
+                (self.k_neighbors >= 6 or self._ball_radius is not None):
             # throughput path: one fused kernel, and only K and H have to come back to the host
             with trace.stage("fused_kernel"):
                 fit = self._fused_fit(want_coeffs=False)

@@ -15,6 +15,8 @@ def main():
     with_query = len(sys.argv) > 2 and sys.argv[2] == "q"
     pts = torus(n)
     print("cpus", os.cpu_count(), "load", os.getloadavg(), flush=True)
+    nosync = len(sys.argv) > 3 and sys.argv[3] == "nosync"
+    evs = []
     last = None
     for rep in range(14):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -28,8 +30,14 @@ def main():
         if last is not None:
             last[0].close()
         last = (ix, fit)
+        if nosync:
+            evs.append((e0, e1, e2, t0, t1))
+            continue
         torch.cuda.synchronize()
         print(f"rep{rep} build dev={e0.elapsed_time(e1):.2f}ms host={1e3 * (t1 - t0):.2f}ms query dev={e1.elapsed_time(e2):.2f}ms", flush=True)
+    torch.cuda.synchronize()
+    for rep, (e0, e1, e2, t0, t1) in enumerate(evs):
+        print(f"rep{rep} nosync build dev={e0.elapsed_time(e1):.2f}ms host={1e3 * (t1 - t0):.2f}ms query dev={e1.elapsed_time(e2):.2f}ms", flush=True)
 
 
 if __name__ == "__main__":

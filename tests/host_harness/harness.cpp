@@ -247,7 +247,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
             nb.src = &gsrc; nb.list.base = list.data(); nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
             FitResult r;
             r.status = exact ? ST_EXACT_PATH : 0;
-            fit_neighbourhood(nb, r);
+            fit_neighbourhood<false>(nb, r);
             for (int c = 0; c < 3; ++c) normals[row * 3 + c] = r.normal[c];
             for (int c = 0; c < 6; ++c) coeffs[row * 6 + c] = r.coeffs[c];
             for (int c = 0; c < 5; ++c) curv[row * 5 + c] = r.curv[c];
@@ -283,7 +283,7 @@ void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const
         nb.qx = xyz[3 * qi]; nb.qy = xyz[3 * qi + 1]; nb.qz = xyz[3 * qi + 2];
         FitResult o;
         o.status = 0;
-        fit_neighbourhood(nb, o);
+        fit_neighbourhood<true>(nb, o);
         for (int c = 0; c < 3; ++c) normals[r * 3 + c] = o.normal[c];
         for (int c = 0; c < 6; ++c) coeffs[r * 6 + c] = o.coeffs[c];
         for (int c = 0; c < 5; ++c) curv[r * 5 + c] = o.curv[c];
@@ -304,7 +304,7 @@ void h_ball(void* p, double radius, int32_t* counts, float* normals, float* coef
         make_stencil(v, level, nb.q.x, nb.q.y, nb.q.z, nb.st);
         FitResult o;
         o.status = 0;
-        fit_neighbourhood(nb, o);
+        fit_neighbourhood<true>(nb, o);
         const long long row = nb.q.idx;
         counts[row] = nb.count;
         for (int c = 0; c < 3; ++c) normals[row * 3 + c] = o.normal[c];
