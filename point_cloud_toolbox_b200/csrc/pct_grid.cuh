@@ -726,14 +726,30 @@ struct BallTest {
     }
 };
 
-// Neighbourhood adaptor that re-walks the stencil (fused ball path).  The first
-// pass also finds the nearest / farthest member by (d2, index).
-struct BallNeighbourhood {
+// Candidates of a stencil through L1/L2, cell by cell (ball queries at any grid level).
+struct StencilSource {
+    typedef uint32_t Pos;
     const IndexView* ix;
     Stencil st;
+    template <class F>
+    PCT_HD void scan(F& fn) const {
+        struct Each {
+            F* f;
+            PCT_HD void operator()(uint32_t j, const Pt& p) { (*f)(j, p, true); }
+        } each;
+        each.f = &fn;
+        for_each_candidate(*ix, st, each);
+    }
+};
+
+// Neighbourhood adaptor that re-walks the candidates (fused ball path): the members of the ball are
+// whatever passes the radius test, in both passes of the fit.  The first pass also finds the
+// nearest / farthest member by (d2, index).
+template <class Source>
+struct BallNeighbourhood {
+    const Source* src;
     BallTest test;
     Pt q;
-    uint32_t self;
     // tracking
     double dmin, dmax;
     uint32_t imin, imax;
@@ -746,8 +762,8 @@ struct BallNeighbourhood {
         BallNeighbourhood* nb;
         F* fn;
         bool track;
-        PCT_HD void operator()(uint32_t j, const Pt& p) {
-            if (j == nb->self || !nb->test.inside(nb->q, p)) return;
+        PCT_HD void operator()(typename Source::Pos, const Pt& p, bool valid) {
+            if (!valid || p.idx == nb->q.idx || !nb->test.inside(nb->q, p)) return;
             fn->add(fsub_rn(p.x, nb->q.x), fsub_rn(p.y, nb->q.y), fsub_rn(p.z, nb->q.z));
             if (track) {
                 const double d = dist2_f64(nb->q.x, nb->q.y, nb->q.z, p.x, p.y, p.z);
@@ -762,7 +778,7 @@ struct BallNeighbourhood {
         Visit<F> v;
         v.nb = this; v.fn = &fn; v.track = !tracked;
         if (!tracked) count = 0;
-        for_each_candidate(*ix, st, v);
+        src->scan(v);
         tracked = true;
     }
     PCT_HD void reference(float& rx, float& ry, float& rz) const {
@@ -771,6 +787,45 @@ struct BallNeighbourhood {
         rz = fsub_rn(fsub_rn(pmax.z, q.z), fsub_rn(pmin.z, q.z));
     }
 };
+
+// Nearest and farthest member of a listed neighbourhood by (d2 fp64, original index) -- ref :286 needs
+// them for the orientation of the normal.  Decided in fp32 when the runner-up is more than 1e-5
+// (relative) away, which is 30 times the fp32 error of the distance; otherwise in fp64 with the index
+// as tie-break.
+template <class Source>
+PCT_HD void list_extremes(const Source& src, const ListRef<typename Source::Pos>& list, int n, const Pt& q,
+                          typename Source::Pos& first, typename Source::Pos& last) {
+    typedef typename Source::Pos Pos;
+    float d_min = 3.4e38f, d_min2 = 3.4e38f, d_max = -1.f, d_max2 = -1.f;
+    Pos j_min = 0, j_max = 0;
+#pragma unroll 1
+    for (int m = 0; m < n; ++m) {
+        const Pos j = list.at(m);
+        const Pt p = src.load(j);
+        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        const bool closer = d < d_min, farther = d > d_max;
+        d_min2 = closer ? d_min : fminf(d_min2, d);
+        j_min = closer ? j : j_min;
+        d_min = closer ? d : d_min;
+        d_max2 = farther ? d_max : fmaxf(d_max2, d);
+        j_max = farther ? j : j_max;
+        d_max = farther ? d : d_max;
+    }
+    first = j_min;
+    last = j_max;
+    const bool min_clear = d_min2 > d_min * 1.00001f && d_min > 1.0e-30f;
+    const bool max_clear = d_max2 * 1.00001f < d_max;
+    if (min_clear && max_clear) return;
+    double bd = 0.0, wd = 0.0;
+    uint32_t bi = 0, wi = 0;
+    for (int m = 0; m < n; ++m) {
+        const Pos j = list.at(m);
+        const Pt p = src.load(j);
+        const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (!min_clear && (m == 0 || key_less(d, p.idx, bd, bi))) { bd = d; bi = p.idx; first = j; }
+        if (!max_clear && (m == 0 || key_less(wd, wi, d, p.idx))) { wd = d; wi = p.idx; last = j; }
+    }
+}
 
 // Neighbourhood adaptor over caller-provided index rows on the ORIGINAL cloud
 // (packed xyz, stride 3): the fit of fit_explicit_quadratic_surfaces_to_neighborhoods

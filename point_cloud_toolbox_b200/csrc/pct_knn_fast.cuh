@@ -169,10 +169,23 @@ __host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool c
 }
 
 #if defined(__CUDACC__)
-template <int U, bool FUSED, bool COLLECT>
-__global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
-knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
-                  int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
+// What staging leaves a thread with: its query, the staged source positioned on the query's region,
+// and the block's per-query scratch area (the staging temporaries in it are dead).
+struct StagedQuery {
+    uint32_t i;      // sorted position of the query
+    Pt q;
+    StagedSource src;
+    char* scratch;   // start of the block's scratch area
+};
+
+// Steps A-D of the staged kernels: block-cooperative copy of the cells the chunk's queries can reach.
+// Returns false for threads that have nothing to do afterwards: threads beyond the range, queries the
+// index does not own (slabs), and every thread of a chunk that does not fit the staging buffer (its
+// queries are appended to `fallback`).  All threads of the block must call it.
+template <int U>
+__device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRange& qr, const int cap_pts,
+                                            uint32_t* __restrict__ fallback, unsigned int* __restrict__ fallback_count,
+                                            StagedQuery& sq) {
     typedef StageShape<U> Shape;
     constexpr int S = Shape::kSide, C = Shape::kCells, B = kStagedBlock, W = kStagedWarps;
     extern __shared__ uint4 smem_u4[];
@@ -273,10 +286,10 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         // the chunk goes to the L1/L2 kernel as a whole; active threads are a prefix of the block
         const long long left = total - (long long)blockIdx.x * B;
         const unsigned int n_active = left < B ? (unsigned int)left : (unsigned int)B;
-        if (t == 0) hdr[Shape::kHdrQueue] = (int)atomicAdd(&qu.counters[2], n_active);
+        if (t == 0) hdr[Shape::kHdrQueue] = (int)atomicAdd(fallback_count, n_active);
         __syncthreads();
-        if (active) qu.fallback[(unsigned int)hdr[Shape::kHdrQueue] + (unsigned int)t] = i;
-        return;
+        if (active) fallback[(unsigned int)hdr[Shape::kHdrQueue] + (unsigned int)t] = i;
+        return false;
     }
 #pragma unroll
     for (int u = 0; u < Shape::kItemsPerThread; ++u) {
@@ -304,14 +317,31 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
         }
     }
     __syncthreads();  // temporaries are dead, the per-query scratch may be written
-    if (!active || !query_owned(ix, q.x, q.y, q.z)) return;
+    if (!active || !query_owned(ix, q.x, q.y, q.z)) return false;
+    const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
+    sq.i = i;
+    sq.q = q;
+    sq.src.tab = (uint32_t)__cvta_generic_to_shared(tab + region * C);
+    sq.src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
+    sq.src.side = S;
+    sq.scratch = scratch;
+    return true;
+}
+
+template <int U, bool FUSED, bool COLLECT>
+__global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
+knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
+                  int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
+    constexpr int B = kStagedBlock;
+    StagedQuery sq;
+    if (!stage_chunk<U>(ix, qr, cap_pts, qu.fallback, qu.counters + 2, sq)) return;
+    const int t = threadIdx.x;
+    const uint32_t i = sq.i;
+    const Pt q = sq.q;
+    const StagedSource& src = sq.src;
+    char* const scratch = sq.scratch;
 
     // ---- E. select out of the staged copy
-    const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
-    StagedSource src;
-    src.tab = (uint32_t)__cvta_generic_to_shared(tab + region * C);
-    src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
-    src.side = S;
     SelectScratch<uint16_t> sel;
     sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
     sel.list.stride = 2 * B;

@@ -190,13 +190,15 @@ __global__ void __launch_bounds__(kBlock)
 ball_kernel(const IndexView ix, const int level, const QueryRange qr, const double radius, int32_t* __restrict__ counts,
             const long long* __restrict__ offsets, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
             double* __restrict__ scratch_d2, const FitOutputs out) {
-    const long long total = qr.q_end - qr.q_begin;
+    const long long total = qr.list ? (long long)*qr.count : qr.q_end - qr.q_begin;
     for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += (long long)gridDim.x * kBlock) {
-        const uint32_t i = (uint32_t)(qr.q_begin + t);
-        BallNeighbourhood nb;
-        nb.ix = &ix; nb.q = load_pt(ix.pts + i); nb.self = i; nb.tracked = false; nb.count = 0;
+        const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
+        StencilSource src;
+        src.ix = &ix;
+        BallNeighbourhood<StencilSource> nb;
+        nb.src = &src; nb.q = load_pt(ix.pts + i); nb.tracked = false; nb.count = 0;
         nb.test.set(radius);
-        make_stencil(ix, level, nb.q.x, nb.q.y, nb.q.z, nb.st);
+        make_stencil(ix, level, nb.q.x, nb.q.y, nb.q.z, src.st);
         const long long row = out_row(qr, i, nb.q.idx);
         if (MODE == BALL_COUNT) {
             CountOnly c;
@@ -215,13 +217,13 @@ ball_kernel(const IndexView ix, const int level, const QueryRange qr, const doub
             const long long o = offsets[row];
             int n = 0;
             struct Walk {
-                BallNeighbourhood* nb;
+                BallNeighbourhood<StencilSource>* nb;
                 long long o;
                 int* n;
                 int32_t* idx;
                 double* d2;
-                __device__ __forceinline__ void operator()(uint32_t j, const Pt& p) {
-                    if (j == nb->self || !nb->test.inside(nb->q, p)) return;
+                __device__ __forceinline__ void operator()(uint32_t, const Pt& p, bool) {
+                    if (p.idx == nb->q.idx || !nb->test.inside(nb->q, p)) return;
                     const double d = dist2_f64(nb->q.x, nb->q.y, nb->q.z, p.x, p.y, p.z);
                     int m = (*n)++;
                     // insertion from the back keeps the row ordered as it grows
@@ -235,11 +237,58 @@ ball_kernel(const IndexView ix, const int level, const QueryRange qr, const doub
                 }
             } wk;
             wk.nb = &nb; wk.o = o; wk.n = &n; wk.idx = out_idx; wk.d2 = scratch_d2;
-            for_each_candidate(ix, nb.st, wk);
+            src.scan(wk);
             if (out_dist)
                 for (int m = 0; m < n; ++m) out_dist[o + m] = (float)sqrt(scratch_d2[o + m]);
         }
     }
+}
+
+// Fused ball fit out of the staged copy (level 0: the cell edge is at least the radius, so the 3x3x3 block
+// holds the ball).  Same staging as the kNN kernel; one pass over the candidates lists the members of the
+// ball in shared memory, then the fit runs over that list exactly like the kNN fit.  Balls with more
+// members than the list holds and chunks that do not fit the staging buffer go to ball_kernel (which
+// streams the candidates twice) through a queue.
+constexpr int kBallListSlots = 64;
+
+template <int U>
+__global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
+ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius, const int cap_pts,
+                   int32_t* __restrict__ counts, const FitOutputs out, uint32_t* __restrict__ fallback,
+                   unsigned int* __restrict__ fallback_count) {
+    StagedQuery sq;
+    if (!stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sq)) return;
+    const Pt q = sq.q;
+    ListRef<uint16_t> list;
+    list.base = reinterpret_cast<uint16_t*>(sq.scratch) + 2 * threadIdx.x;
+    list.stride = 2 * kStagedBlock;
+    struct Collect {
+        ListRef<uint16_t> list;
+        BallTest test;
+        Pt q;
+        int n;
+        __device__ __forceinline__ void operator()(uint16_t j, const Pt& p, bool valid) {
+            if (!valid || p.idx == q.idx || !test.inside(q, p)) return;
+            if (n < kBallListSlots) list.at(n) = j;
+            ++n;
+        }
+    } col;
+    col.list = list; col.q = q; col.n = 0;
+    col.test.set(radius);
+    sq.src.scan(col);
+    if (col.n > kBallListSlots) {  // a ball larger than the list: streamed by ball_kernel
+        fallback[atomicAdd(fallback_count, 1u)] = sq.i;
+        return;
+    }
+    const long long row = out_row(qr, sq.i, q.idx);
+    FitResult r;
+    r.status = 0;
+    ListNeighbourhood<StagedSource> nb;
+    nb.src = &sq.src; nb.list = list; nb.count = col.n; nb.q = q; nb.first = 0; nb.last = 0;
+    if (col.n >= 2) list_extremes(sq.src, list, col.n, q, nb.first, nb.last);
+    fit_neighbourhood<false>(nb, r);
+    if (counts) counts[row] = col.n;
+    store_fit(out, row, r);
 }
 
 int ball_level(const IndexView& v, double radius) {
@@ -342,7 +391,28 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
     if (mode == BALL_COUNT) {
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
     } else if (mode == BALL_FUSED) {
-        ball_kernel<BALL_FUSED><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+        constexpr int U = 2;
+        const size_t fixed = staged_smem_bytes<U>(kBallListSlots, 0, false);
+        const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
+        const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
+        ScratchSession scratch(s, sizeof(uint32_t) * (size_t)nq + 4096);
+        uint32_t* fallback = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * (size_t)nq));
+        unsigned int* fb_count = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
+        if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
+            // staged kernel over the whole range, L1/L2 kernel over the chunks that did not fit
+            const size_t smem = staged_smem_bytes<U>(kBallListSlots, cap_pts, false);
+            PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PCT_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int) * 4, s));
+            const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
+            ball_staged_kernel<U><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(v, qr, radius, cap_pts, counts, out, fallback, fb_count);
+            QueryRange ql = qr;
+            ql.list = fallback;
+            ql.count = fb_count;
+            const int grid_list = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)ix->sm_count * 8);
+            ball_kernel<BALL_FUSED><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+        } else {
+            ball_kernel<BALL_FUSED><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+        }
     } else {
         double* scratch = nullptr;
         PCT_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));

@@ -298,10 +298,12 @@ void h_ball(void* p, double radius, int32_t* counts, float* normals, float* coef
     int level = 0;
     while (level + 1 < v.num_levels && (double)v.h * (double)(1 << level) * (1.0 - 1e-4) - (double)v.slack * v.h < radius) ++level;
     for (long long i = 0; i < v.n; ++i) {
-        BallNeighbourhood nb;
-        nb.ix = &v; nb.q = v.pts[i]; nb.self = (uint32_t)i; nb.tracked = false; nb.count = 0;
+        StencilSource src;
+        src.ix = &v;
+        BallNeighbourhood<StencilSource> nb;
+        nb.src = &src; nb.q = v.pts[i]; nb.tracked = false; nb.count = 0;
         nb.test.set(radius);
-        make_stencil(v, level, nb.q.x, nb.q.y, nb.q.z, nb.st);
+        make_stencil(v, level, nb.q.x, nb.q.y, nb.q.z, src.st);
         FitResult o;
         o.status = 0;
         fit_neighbourhood<true>(nb, o);
