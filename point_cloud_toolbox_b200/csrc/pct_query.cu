@@ -251,10 +251,11 @@ ball_kernel(const IndexView ix, const int level, const QueryRange qr, const doub
 // streams the candidates twice) through a queue.
 constexpr int kBallListSlots = 64;
 
-template <int U>
+template <int U, int MODE>
 __global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
 ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius, const int cap_pts,
-                   int32_t* __restrict__ counts, const FitOutputs out, uint32_t* __restrict__ fallback,
+                   int32_t* __restrict__ counts, const FitOutputs out, const long long* __restrict__ offsets,
+                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist, uint32_t* __restrict__ fallback,
                    unsigned int* __restrict__ fallback_count) {
     StagedQuery sq;
     if (!stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sq)) return;
@@ -281,6 +282,25 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
         return;
     }
     const long long row = out_row(qr, sq.i, q.idx);
+    if (MODE == BALL_FILL) {
+        // CSR row ordered by (d2, index): successive minima over the listed members
+        const long long o = offsets[row];
+        double pd = -1.0;
+        uint32_t pi = 0;
+        for (int m = 0; m < col.n; ++m) {
+            double bd = 1.0e300;
+            uint32_t bi = 0xffffffffu;
+            for (int c = 0; c < col.n; ++c) {
+                const Pt p = sq.src.load(list.at(c));
+                const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
+            }
+            out_idx[o + m] = (int32_t)bi;
+            if (out_dist) out_dist[o + m] = (float)sqrt(bd);
+            pd = bd; pi = bi;
+        }
+        return;
+    }
     FitResult r;
     r.status = 0;
     ListNeighbourhood<StagedSource> nb;
@@ -390,8 +410,10 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
     const int grid = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)ix->sm_count * 64);
     if (mode == BALL_COUNT) {
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
-    } else if (mode == BALL_FUSED) {
+    } else {
         constexpr int U = 2;
+        double* scratch_d2 = nullptr;
+        if (mode == BALL_FILL) PCT_CUDA(cudaMallocAsync(&scratch_d2, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));
         const size_t fixed = staged_smem_bytes<U>(kBallListSlots, 0, false);
         const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
         const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
@@ -399,25 +421,31 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         uint32_t* fallback = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * (size_t)nq));
         unsigned int* fb_count = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
         if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
-            // staged kernel over the whole range, L1/L2 kernel over the chunks that did not fit
+            // staged kernel over the whole range, L1/L2 kernel over the chunks and balls that did not fit
             const size_t smem = staged_smem_bytes<U>(kBallListSlots, cap_pts, false);
-            PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PCT_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int) * 4, s));
             const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
-            ball_staged_kernel<U><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(v, qr, radius, cap_pts, counts, out, fallback, fb_count);
             QueryRange ql = qr;
             ql.list = fallback;
             ql.count = fb_count;
             const int grid_list = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)ix->sm_count * 8);
-            ball_kernel<BALL_FUSED><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
-        } else {
+            if (mode == BALL_FUSED) {
+                PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U, BALL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ball_staged_kernel<U, BALL_FUSED><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(
+                    v, qr, radius, cap_pts, counts, out, nullptr, nullptr, nullptr, fallback, fb_count);
+                ball_kernel<BALL_FUSED><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+            } else {
+                PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U, BALL_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ball_staged_kernel<U, BALL_FILL><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(
+                    v, qr, radius, cap_pts, nullptr, out, offsets, idx, dist, fallback, fb_count);
+                ball_kernel<BALL_FILL><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, nullptr, offsets, idx, dist, scratch_d2, out);
+            }
+        } else if (mode == BALL_FUSED) {
             ball_kernel<BALL_FUSED><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+        } else {
+            ball_kernel<BALL_FILL><<<grid, kBlock, 0, s>>>(v, level, qr, radius, nullptr, offsets, idx, dist, scratch_d2, out);
         }
-    } else {
-        double* scratch = nullptr;
-        PCT_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));
-        ball_kernel<BALL_FILL><<<grid, kBlock, 0, s>>>(v, level, qr, radius, nullptr, offsets, idx, dist, scratch, out);
-        PCT_CUDA(cudaFreeAsync(scratch, s));
+        if (scratch_d2) PCT_CUDA(cudaFreeAsync(scratch_d2, s));
     }
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
