@@ -280,6 +280,43 @@ def test_slab_mode_equals_whole_cloud_index(pct, world):
     whole.close()
 
 
+def test_slab_mode_keeps_the_tie_order_of_the_whole_cloud(pct):
+    """A lattice is nothing but ties: slab indices must break them by the WHOLE cloud's index order."""
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    g = np.arange(24, dtype=np.float32)
+    pts = np.stack(np.meshgrid(g, g * 0.5, g * 0.25, indexing="ij"), -1).reshape(-1, 3)
+    pts = np.ascontiguousarray(pts[np.random.default_rng(2).permutation(len(pts))])
+    k = 12
+    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+    cloud = torch.from_numpy(pts).cuda()
+    for rank in range(3):
+        part = pdist.curvature_knn_slab(cloud, k, rank, 3)
+        idx_local, dist_local = part.index.knn(k)
+        sel, own = pdist.slab_select(cloud[:, part.axis], part.bounds)
+        owned = sel[own].cpu().numpy()
+        assert np.array_equal(sel[idx_local.long()].cpu().numpy(), ref_idx[owned])
+        assert np.array_equal(dist_local.cpu().numpy(), ref_dist[owned])
+        part.index.close()
+
+
+def test_fewer_neighbours_than_coefficients_through_the_class(pct, bunny):
+    """k < 6: lstsq's minimum-norm solution (ref :359), served by the rows path."""
+    pts = np.ascontiguousarray(bunny[::5])
+    k = 4
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+    pc.plant_kdtree(k)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    rows = np.arange(0, len(pts), 7)
+    ref = oracle.knn_curvature(pts, k, rows=rows)
+    ok = np.isfinite(ref["K"]) & np.isfinite(K[rows])
+    assert ok.mean() > 0.99
+    scale = np.abs(ref["coeffs"]).max(axis=1)
+    err = np.abs(np.asarray(pc.quadratic_coefficients)[rows] - ref["coeffs"]).max(axis=1) / scale
+    assert np.quantile(err[ok], 0.99) < 1e-4
+    assert pct._lib.lib.pct_release_scratch() == 0
+
+
 def test_unresolved_slab_queries_fall_back_to_the_whole_cloud(pct):
     """A cloud with far outliers: their k-th neighbour lies beyond any margin; the slab index says so
     (PCT_STATUS_UNRESOLVED) and the rank answers them from a whole-cloud index."""
