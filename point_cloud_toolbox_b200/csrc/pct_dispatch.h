@@ -19,3 +19,13 @@
 #ifndef PCT_SCAN_WIDTH
 #define PCT_SCAN_WIDTH 2
 #endif
+
+// pass 1 of the selection without a branch around the histogram update
+#ifndef PCT_BRANCHFREE_HIST
+#define PCT_BRANCHFREE_HIST 1
+#endif
+
+// pass 2 of the selection with one predicated store instead of nested branches
+#ifndef PCT_BRANCHFREE_PART
+#define PCT_BRANCHFREE_PART 1
+#endif

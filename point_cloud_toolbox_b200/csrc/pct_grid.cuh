@@ -327,7 +327,7 @@ enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 //   hist  kHistBins byte counters = 16 words, word w at hist[w * hist_stride]   (distance histogram);
 //         with hist_stride = threads of the block every thread stays in its own bank
 static constexpr int kHistBins = 64;
-static constexpr int kHistRowBytes = kHistBins;
+static constexpr int kHistRowBytes = kHistBins + 4;  // + the word of the overflow counter (candidates beyond the range)
 
 // Where the candidates of a query come from.  knn_select() and the fit only need
 //   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
@@ -509,7 +509,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     }
 
 #pragma unroll
-    for (int w = 0; w < kHistBins / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
+    for (int w = 0; w < kHistRowBytes / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
 
     // The bodies of both passes are executed by the whole warp whenever one lane needs them,
     // so they are kept short; everything that can wait is done on the list afterwards.
@@ -523,6 +523,17 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         float qx, qy, qz, range2, inv_w, cut2;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
+#if PCT_BRANCHFREE_HIST
+            // no branch: candidates beyond the range land in the overflow counter (bin kHistBins)
+            const int b = (int)fminf(d * inv_w, (float)kHistBins);
+            uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
+            *c = (uint8_t)(*c + 1);
+            seen += b < kHistBins ? 1u : 0u;  // (a candidate within 1e-5 of range2 may land in the last bin: still inside safe2)
+            if (COLLECT && d < cut2) {
+                if (n_coll < coll_slots) list.at((int)n_coll) = j;
+                ++n_coll;
+            }
+#else
             if (d < range2) {
                 const int b = (int)(d * inv_w);
                 uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
@@ -533,6 +544,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
                     ++n_coll;
                 }
             }
+#endif
         }
     } p1;
     p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.seen = 0; p1.n_coll = 0;
@@ -580,6 +592,14 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         float qx, qy, qz, lo, hi;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
+#if PCT_BRANCHFREE_PART
+            const bool in = d <= hi && p.idx != self, front = d < lo;
+            const bool is_front = in && front, is_zone = in && !front;
+            const int slot = front ? (int)n_front : zone_top - (int)n_zone;
+            if (is_front || (is_zone && (int)n_zone < zone_slots)) list.at(slot) = j;
+            n_front += is_front ? 1u : 0u;
+            n_zone += is_zone ? 1u : 0u;
+#else
             if (d <= hi && p.idx != self) {
                 if (d < lo) {
                     list.at((int)n_front) = j;  // n_front < k: always room
@@ -589,6 +609,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
                     ++n_zone;
                 }
             }
+#endif
         }
     } p2;
     p2.list = sc.list; p2.zone_top = sc.cap - 1; p2.zone_slots = zone_slots;
