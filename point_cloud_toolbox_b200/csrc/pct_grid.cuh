@@ -443,13 +443,23 @@ struct StagedSource {
 // A per-query list of positions inside an array shared by the threads of a block.  Every thread owns
 // one 32-bit word of each row of `threads` words, so rows never make two threads share a bank and a
 // thread's words can be reused for another per-thread structure (the histogram) without any
-// synchronisation: 32-bit positions take one row per slot, 16-bit positions one row per slot PAIR.
+// synchronisation.  The list has `rows` LOW slots (slot m < rows) and, behind them, HIGH slots
+// (slot rows + z): 32-bit positions take one row per slot; 16-bit positions keep low slot m in the
+// lower half of row m and high slot z in the upper half of row z, so the neighbours (always low
+// slots) are addressed with one multiply and the boundary zone (high slots) costs no extra rows.
 template <class PosT>
 struct ListRef {
     PosT* base;  // the thread's first element
     int stride;  // elements of PosT between consecutive rows
-    PCT_HD PosT& at(int m) const {
-        return sizeof(PosT) == 2 ? base[(size_t)(m >> 1) * stride + (m & 1)] : base[(size_t)m * stride];
+    int rows;    // number of low slots
+    PCT_HD PosT& lo(int m) const { return base[(size_t)m * stride]; }
+    PCT_HD PosT& hi(int z) const {
+        return sizeof(PosT) == 2 ? base[(size_t)z * stride + 1] : base[(size_t)(rows + z) * stride];
+    }
+    PCT_HD PosT& at(int m) const { return m < rows ? lo(m) : hi(m - rows); }
+    // bytes one thread needs for `slots` slots of which `rows` are low
+    PCT_HD static size_t bytes(int rows, int slots) {
+        return sizeof(PosT) == 2 ? 4 * (size_t)(rows > slots - rows ? rows : slots - rows) : sizeof(PosT) * (size_t)slots;
     }
 };
 
@@ -458,7 +468,7 @@ struct SelectScratch {
     ListRef<PosT> list;
     uint32_t* hist; // word w of the byte histogram at hist[w * hist_stride]
     int hist_stride;
-    int cap;        // list slots; the last PCT_TIE_SLACK of them hold the boundary zone (COLLECT needs cap well above k + that)
+    int cap;        // list slots = list.rows low slots (neighbours, pre-collected candidates) + PCT_TIE_SLACK high slots (boundary zone)
 };
 
 // Finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
@@ -530,7 +540,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
             *c = (uint8_t)(*c + 1);
             seen += b < kHistBins ? 1u : 0u;  // (a candidate within 1e-5 of range2 may land in the last bin: still inside safe2)
             if (COLLECT && d < cut2) {
-                if (n_coll < coll_slots) list.at((int)n_coll) = j;
+                if (n_coll < coll_slots) list.lo((int)n_coll) = j;
                 ++n_coll;
             }
 #else
@@ -540,7 +550,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
                 *c = (uint8_t)(*c + 1);
                 ++seen;
                 if (COLLECT && d < cut2) {
-                    if (n_coll < coll_slots) list.at((int)n_coll) = j;
+                    if (n_coll < coll_slots) list.lo((int)n_coll) = j;
                     ++n_coll;
                 }
             }
@@ -587,7 +597,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 
     struct P2 {
         ListRef<Pos> list;
-        int zone_top, zone_slots;
+        int zone_slots;
         uint32_t self, n_front, n_zone;
         float qx, qy, qz, lo, hi;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
@@ -595,24 +605,24 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 #if PCT_BRANCHFREE_PART
             const bool in = d <= hi && p.idx != self, front = d < lo;
             const bool is_front = in && front, is_zone = in && !front;
-            const int slot = front ? (int)n_front : zone_top - (int)n_zone;
-            if (is_front || (is_zone && (int)n_zone < zone_slots)) list.at(slot) = j;
+            Pos* const slot = front ? &list.lo((int)n_front) : &list.hi((int)n_zone);  // n_front < k: always room
+            if (is_front || (is_zone && (int)n_zone < zone_slots)) *slot = j;
             n_front += is_front ? 1u : 0u;
             n_zone += is_zone ? 1u : 0u;
 #else
             if (d <= hi && p.idx != self) {
                 if (d < lo) {
-                    list.at((int)n_front) = j;  // n_front < k: always room
+                    list.lo((int)n_front) = j;  // n_front < k: always room
                     ++n_front;
                 } else {
-                    if ((int)n_zone < zone_slots) list.at(zone_top - (int)n_zone) = j;
+                    if ((int)n_zone < zone_slots) list.hi((int)n_zone) = j;
                     ++n_zone;
                 }
             }
 #endif
         }
     } p2;
-    p2.list = sc.list; p2.zone_top = sc.cap - 1; p2.zone_slots = zone_slots;
+    p2.list = sc.list; p2.zone_slots = zone_slots;
     p2.self = self; p2.n_front = 0; p2.n_zone = 0;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi;
     PCT_SELECT_TRACE(hi < cut2 && p1.n_coll <= (uint32_t)coll_slots);
@@ -621,7 +631,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         // position of the front never passes the read position)
 #pragma unroll 1
         for (uint32_t m = 0; m < p1.n_coll; ++m) {
-            const Pos j = sc.list.at((int)m);
+            const Pos j = sc.list.lo((int)m);
             p2(j, src.load(j), true);
         }
     } else {
@@ -638,11 +648,10 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     Pos j_min = 0;
     {
         const int n_list = n_front + n_zone;
-        const int skip = sc.cap - n_list;  // the unused slots between the front and the zone
 #pragma unroll 1
         for (int m = 0; m < n_list; ++m) {
             const bool is_front = m < n_front;
-            const Pos j = sc.list.at(is_front ? m : m + skip);
+            const Pos j = is_front ? sc.list.lo(m) : sc.list.hi(m - n_front);
             const Pt p = src.load(j);
             const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
             front_max = is_front ? fmaxf(front_max, d) : front_max;
@@ -661,23 +670,23 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     if (need < 1 || need > n_zone) return SEL_EXACT;   // (a saturated histogram bin can break the invariant)
 
     // exact choice inside the boundary zone: `need` successive minima of (d2, index)
-    int zone0 = sc.cap - n_zone;  // first occupied zone slot
+    int zone0 = 0;  // first occupied zone slot
     for (int t = 0; t < need; ++t) {
         double bd = 0.0;
         uint32_t bi = 0;
         Pos bj = 0;
         int bm = 0;
         for (int m = 0; m < n_zone; ++m) {
-            const Pos j = sc.list.at(zone0 + m);
+            const Pos j = sc.list.hi(zone0 + m);
             const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
         }
-        // zone entries sit at the back in reverse order of arrival: remove bm by moving entry 0 into it
-        sc.list.at(zone0 + bm) = sc.list.at(zone0);
+        // remove entry bm from the zone by moving the zone's first entry into its place
+        sc.list.hi(zone0 + bm) = sc.list.hi(zone0);
         ++zone0;
         --n_zone;
-        sc.list.at(n_front + t) = bj;
+        sc.list.lo(n_front + t) = bj;
         last = bj;
         d2_last = bd;
     }
@@ -689,7 +698,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         double bd = 0.0;
         uint32_t bi = 0;
         for (int m = 0; m < k; ++m) {
-            const Pos j = sc.list.at(m);
+            const Pos j = sc.list.lo(m);
             const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
@@ -698,8 +707,9 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     return SEL_OK;
 }
 
-// Neighbourhood adaptor over a list of candidate positions (fused kNN path).
-template <class Source>
+// Neighbourhood adaptor over a list of candidate positions (fused kNN path: the neighbours sit in
+// the low slots; the ball path fills low and high slots, LOW_ONLY = false).
+template <class Source, bool LOW_ONLY = true>
 struct ListNeighbourhood {
     typedef typename Source::Pos Pos;
     const Source* src;
@@ -710,11 +720,11 @@ struct ListNeighbourhood {
     template <class F>
     PCT_HD void pass(F& fn) const {
         if (count <= 0) return;
-        Pt p = src->load(list.at(0));
+        Pt p = src->load(list.lo(0));
 #pragma unroll 1
         for (int m = 0; m < count; ++m) {
             const int mn = m + 1 < count ? m + 1 : m;
-            const Pt nxt = src->load(list.at(mn));  // in flight during the fp64 work below
+            const Pt nxt = src->load(LOW_ONLY ? list.lo(mn) : list.at(mn));  // in flight during the fp64 work below
             fn.add(fsub_rn(p.x, q.x), fsub_rn(p.y, q.y), fsub_rn(p.z, q.z));
             p = nxt;
         }

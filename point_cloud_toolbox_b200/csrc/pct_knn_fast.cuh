@@ -67,7 +67,7 @@ __device__ __forceinline__ void emit_query(const Source& src, const ListRef<type
             double bd = 1.0e300;
             uint32_t bi = 0xffffffffu;
             for (int c = 0; c < k; ++c) {
-                const Pt p = src.load(list.at(c));
+                const Pt p = src.load(list.lo(c));
                 const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
                 if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
             }
@@ -98,6 +98,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
     SelectScratch<uint32_t> sc;
     sc.list.base = smem_words + 54 * kBlock + threadIdx.x;
     sc.list.stride = kBlock;
+    sc.list.rows = cap - PCT_TIE_SLACK;
     sc.hist = smem_words + (54 + cap) * kBlock + threadIdx.x;
     sc.hist_stride = kBlock;
     sc.cap = cap;
@@ -160,7 +161,7 @@ struct StagedCell {
 //       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
 __host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool collect) {
-    const size_t list = (size_t)((cap + 1) & ~1) * sizeof(uint16_t), hist = kHistRowBytes;
+    const size_t list = ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap), hist = kHistRowBytes;
     const size_t per_query = (collect ? list + hist : (list > hist ? list : hist)) * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
@@ -345,7 +346,8 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     SelectScratch<uint16_t> sel;
     sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
     sel.list.stride = 2 * B;
-    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? sizeof(uint16_t) * (size_t)((cap + 1) & ~1) * B : 0)) + t;
+    sel.list.rows = cap - PCT_TIE_SLACK;
+    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap) * B : 0)) + t;
     sel.hist_stride = B;
     sel.cap = cap;
     Stencil st;
@@ -404,7 +406,8 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const double lambda = expected_collected(v, a.k);
     const int cap_collect = (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK;
     const bool collect = cap_collect >= 2 * a.k + PCT_TIE_SLACK;  // cut_gain == 0 switches it off
-    const int cap_staged = collect ? cap_collect : a.cap;
+    // at least PCT_TIE_SLACK low slots: the zone lives in the upper halves of the first rows
+    const int cap_staged = (collect ? cap_collect : std::max(a.k, PCT_TIE_SLACK) + PCT_TIE_SLACK);
     // staging buffer: what is left of this CTA's share of the SM's shared memory after the fixed parts.
     // The kernel is compiled for PCT_STAGED_CTAS resident CTAs; when the regions of a chunk are expected
     // to be larger than that share (large k: cells hold 0.4 k points), fewer, larger CTAs are resident.

@@ -158,7 +158,7 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             GlobalSource src;
             src.pts = ix.pts;
             ListNeighbourhood<GlobalSource> nb;
-            nb.src = &src; nb.list.base = mine; nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
+            nb.src = &src; nb.list.base = mine; nb.list.stride = 1; nb.list.rows = k; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
             FitResult r;
             r.status = ST_EXACT_PATH;
             fit_neighbourhood<false>(nb, r);
@@ -263,6 +263,7 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
     ListRef<uint16_t> list;
     list.base = reinterpret_cast<uint16_t*>(sq.scratch) + 2 * threadIdx.x;
     list.stride = 2 * kStagedBlock;
+    list.rows = kBallListSlots / 2;  // both halves of every row are used
     struct Collect {
         ListRef<uint16_t> list;
         BallTest test;
@@ -303,7 +304,7 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
     }
     FitResult r;
     r.status = 0;
-    ListNeighbourhood<StagedSource> nb;
+    ListNeighbourhood<StagedSource, false> nb;
     nb.src = &sq.src; nb.list = list; nb.count = col.n; nb.q = q; nb.first = 0; nb.last = 0;
     if (col.n >= 2) list_extremes(sq.src, list, col.n, q, nb.first, nb.last);
     fit_neighbourhood<false>(nb, r);
@@ -414,7 +415,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         constexpr int U = 2;
         double* scratch_d2 = nullptr;
         if (mode == BALL_FILL) PCT_CUDA(cudaMallocAsync(&scratch_d2, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));
-        const size_t fixed = staged_smem_bytes<U>(kBallListSlots, 0, false);
+        const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, 0, false);
         const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
         const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
         ScratchSession scratch(s, sizeof(uint32_t) * (size_t)nq + 4096);
@@ -422,7 +423,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         unsigned int* fb_count = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
         if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
             // staged kernel over the whole range, L1/L2 kernel over the chunks and balls that did not fit
-            const size_t smem = staged_smem_bytes<U>(kBallListSlots, cap_pts, false);
+            const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, cap_pts, false);
             PCT_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int) * 4, s));
             const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
             QueryRange ql = qr;

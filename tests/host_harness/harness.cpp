@@ -172,10 +172,10 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK + coll_extra;  // coll_extra > 0 switches the pre-collection of pass 1 on
     std::vector<uint32_t> list(cap), runs(54);
-    std::vector<uint16_t> list16(cap + 1);
+    std::vector<uint16_t> list16(2 * cap + 2);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
-    SelectScratch<uint32_t> sc{{list.data(), 1}, hist.data(), 1, cap};
-    SelectScratch<uint16_t> sc16{{list16.data(), 2}, hist.data(), 1, cap};  // 16-bit slots come in pairs: row stride 2
+    SelectScratch<uint32_t> sc{{list.data(), 1, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};
+    SelectScratch<uint16_t> sc16{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // 16-bit: two slots per row
     const bool collect = coll_extra > 0;
     GlobalSource gsrc;
     gsrc.pts = v.pts;
@@ -210,7 +210,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                              : knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
-                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[list16[m]].idx];
+                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[sc16.list.lo(m)].idx];
                     first = ix->pos_of[stage.pts[f16].idx];
                     last = ix->pos_of[stage.pts[l16].idx];
                     staged = true;
@@ -244,7 +244,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
         }
         if (curv) {
             ListNeighbourhood<GlobalSource> nb;
-            nb.src = &gsrc; nb.list.base = list.data(); nb.list.stride = 1; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
+            nb.src = &gsrc; nb.list.base = list.data(); nb.list.stride = 1; nb.list.rows = k; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
             FitResult r;
             r.status = exact ? ST_EXACT_PATH : 0;
             fit_neighbourhood<false>(nb, r);
