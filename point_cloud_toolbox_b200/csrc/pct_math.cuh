@@ -167,33 +167,13 @@ PCT_HD_NOINLINE void smallest_eigenvector_sym3_jacobi(double a00, double a01, do
     else                          { n[0] = v02; n[1] = v12; n[2] = v22; }
 }
 
-// fp32 rotation of the same cyclic Jacobi (used to get a starting vector cheaply)
-PCT_HD void jacobi_rotate_f32(float& app, float& aqq, float& apq, float& arp, float& arq,
-                              float& v0p, float& v0q, float& v1p, float& v1q, float& v2p, float& v2q) {
-    if (apq == 0.f) return;
-    const float theta = (aqq - app) / (2.f * apq);
-    const float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
-    const float c = 1.f / sqrtf(t * t + 1.f);
-    const float s = t * c;
-    const float tau = s / (1.f + c);
-    app -= t * apq;
-    aqq += t * apq;
-    apq = 0.f;
-    const float rp = arp, rq = arq;
-    arp = rp - s * (rq + tau * rp);
-    arq = rq + s * (rp - tau * rq);
-    float a, b;
-    a = v0p; b = v0q; v0p = a - s * (b + tau * a); v0q = b + s * (a - tau * b);
-    a = v1p; b = v1q; v1p = a - s * (b + tau * a); v1q = b + s * (a - tau * b);
-    a = v2p; b = v2q; v2p = a - s * (b + tau * a); v2q = b + s * (a - tau * b);
-}
-
-// Smallest eigenvector in fp64 accuracy for a fraction of the fp64 Jacobi's cost (its
-// rotations are serial chains of fp64 divisions and square roots): an fp32 Jacobi gives
-// the eigenvector to ~1e-7 / gap, two Rayleigh-quotient iterations in fp64 -- each a
-// multiplication by the adjugate of (A - lambda I), no division -- converge cubically
-// from there.  When the two smallest eigenvalues are closer than 1e-4 of the trace the
-// start may be poor and the fp64 Jacobi is used instead.
+// Smallest eigenvector in fp64 accuracy for a fraction of the fp64 Jacobi's cost (its rotations are
+// serial chains of fp64 divisions and square roots): the closed form of the eigenvalues of a symmetric
+// 3x3 (trigonometric solution of the characteristic cubic) in fp32 gives the smallest eigenvalue to
+// ~1e-7 of the trace, the cross product of two rows of (A - lambda I) its eigenvector to ~1e-7 / gap,
+// and two Rayleigh-quotient iterations in fp64 -- each a multiplication by the adjugate of
+// (A - lambda I), no division -- converge cubically from there.  When the two smallest eigenvalues are
+// closer than 1e-4 of the trace the start may be poor and the fp64 Jacobi is used instead.
 PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double a11, double a12, double a22,
                                       double n[3]) {
     const double tr = a00 + a11 + a22;
@@ -203,22 +183,36 @@ PCT_HD void smallest_eigenvector_sym3(double a00, double a01, double a02, double
     }
     const double inv = 1.0 / tr;
     a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
-    float b00 = (float)a00, b01 = (float)a01, b02 = (float)a02, b11 = (float)a11, b12 = (float)a12, b22 = (float)a22;
-    float v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
-#pragma unroll 1
-    for (int sweep = 0; sweep < 6; ++sweep) {
-        const float off = b01 * b01 + b02 * b02 + b12 * b12;
-        if (off < 1e-15f) break;  // relative to trace^2 == 1
-        jacobi_rotate_f32(b00, b11, b01, b02, b12, v00, v01, v10, v11, v20, v21);
-        jacobi_rotate_f32(b00, b22, b02, b01, b12, v00, v02, v10, v12, v20, v22);
-        jacobi_rotate_f32(b11, b22, b12, b01, b02, v01, v02, v11, v12, v21, v22);
+    // eigenvalues of A (trace 1): q + 2 p cos(phi + 2 pi j / 3), q = 1/3
+    const float f01 = (float)a01, f02 = (float)a02, f12 = (float)a12;
+    const float q = 1.f / 3.f;
+    const float b00 = (float)a00 - q, b11 = (float)a11 - q, b22 = (float)a22 - q;
+    const float p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.f * (f01 * f01 + f02 * f02 + f12 * f12);
+    const float p = sqrtf(p2 * (1.f / 6.f));
+    bool good = p > 1e-6f;
+    double x = 0.0, y = 0.0, z = 1.0;
+    if (good) {
+        const float ip = 1.f / p;
+        const float c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = f01 * ip, c02 = f02 * ip, c12 = f12 * ip;
+        float r = 0.5f * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+        r = fminf(1.f, fmaxf(-1.f, r));
+        const float phi = acosf(r) * (1.f / 3.f);
+        const float e1 = q + 2.f * p * cosf(phi);
+        const float e3 = q + 2.f * p * cosf(phi + 2.0943951f);  // smallest
+        const float e2 = 1.f - e1 - e3;
+        good = e2 - e3 > 1e-4f;
+        // null vector of A - e3 I: the largest of the three cross products of its rows
+        const float m00 = (float)a00 - e3, m11 = (float)a11 - e3, m22 = (float)a22 - e3;
+        const float u0 = f01 * f12 - f02 * m11, u1 = f02 * f01 - m00 * f12, u2 = m00 * m11 - f01 * f01;   // row0 x row1
+        const float v0 = f01 * m22 - f02 * f12, v1 = f02 * f02 - m00 * m22, v2 = m00 * f12 - f01 * f02;   // row0 x row2
+        const float w0 = m11 * m22 - f12 * f12, w1 = f12 * f02 - f01 * m22, w2 = f01 * f12 - m11 * f02;   // row1 x row2
+        const float nu = u0 * u0 + u1 * u1 + u2 * u2, nv = v0 * v0 + v1 * v1 + v2 * v2, nw = w0 * w0 + w1 * w1 + w2 * w2;
+        if (nu >= nv && nu >= nw) { x = u0; y = u1; z = u2; }
+        else if (nv >= nw)        { x = v0; y = v1; z = v2; }
+        else                      { x = w0; y = w1; z = w2; }
+        good = good && fmaxf(nu, fmaxf(nv, nw)) > 1e-20f;
     }
-    float lmin, lmid;
-    double x, y, z;
-    if (b00 <= b11 && b00 <= b22) { lmin = b00; lmid = fminf(b11, b22); x = v00; y = v10; z = v20; }
-    else if (b11 <= b22)          { lmin = b11; lmid = fminf(b00, b22); x = v01; y = v11; z = v21; }
-    else                          { lmin = b22; lmid = fminf(b00, b11); x = v02; y = v12; z = v22; }
-    if (!(lmid - lmin > 1e-4f)) {
+    if (!good) {
         smallest_eigenvector_sym3_jacobi(a00, a01, a02, a11, a12, a22, n);
         return;
     }

@@ -413,14 +413,20 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
     } else {
         constexpr int U = 2;
-        double* scratch_d2 = nullptr;
-        if (mode == BALL_FILL) PCT_CUDA(cudaMallocAsync(&scratch_d2, sizeof(double) * (size_t)std::max<long long>(nnz, 1), s));
         const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, 0, false);
         const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
         const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
-        ScratchSession scratch(s, sizeof(uint32_t) * (size_t)nq + 4096);
+        const size_t d2_bytes = mode == BALL_FILL ? sizeof(double) * (size_t)std::max<long long>(nnz, 1) : 0;
+        ScratchSession scratch(s, sizeof(uint32_t) * (size_t)nq + 8192 + d2_bytes);
         uint32_t* fallback = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * (size_t)nq));
         unsigned int* fb_count = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
+        // squared distances of the rows ball_kernel<fill> sorts by insertion
+        double* scratch_d2 = d2_bytes ? static_cast<double*>(scratch.take(d2_bytes)) : nullptr;
+        bool d2_pooled = false;
+        if (d2_bytes && !scratch_d2) {
+            PCT_CUDA(cudaMallocAsync(&scratch_d2, d2_bytes, s));
+            d2_pooled = true;
+        }
         if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
             // staged kernel over the whole range, L1/L2 kernel over the chunks and balls that did not fit
             const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, cap_pts, false);
@@ -446,7 +452,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         } else {
             ball_kernel<BALL_FILL><<<grid, kBlock, 0, s>>>(v, level, qr, radius, nullptr, offsets, idx, dist, scratch_d2, out);
         }
-        if (scratch_d2) PCT_CUDA(cudaFreeAsync(scratch_d2, s));
+        if (d2_pooled) PCT_CUDA(cudaFreeAsync(scratch_d2, s));
     }
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
