@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 METRIC = "points/sec for kNN+SVD+quadric curvature"
 ALG_BYTES_QUERY = 44   # per point: 16 B own record read + 28 B result written; 32 B are actually written
 ALG_BYTES_E2E = 76     # + 12 B raw read + 16 B sorted record + 4 B permutation
-# our kernels per step (profiles/launches_r01s.txt): bbox, pilot keys, 2 x level hist, Morton keys, gather, table fill,
+# our kernels per step (profiles/launches_r01t.txt): bbox, pilot keys, 2 x level hist, Morton keys, gather, table fill,
 # staged kNN+fit, L1/L2 kNN+fit x2 (unstaged chunks, level-1 retries), exact tail, stats; CUB's sort kernels not counted
 OUR_KERNELS_PER_STEP = 12
 
@@ -478,7 +478,7 @@ def ours(args):
             "bound": "hbm", "kernel": "knn_staged_kernel<2,true,false> (+ unstaged chunks, level-1 retries and exact tail: one call, CUDA events on its stream)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": profiled_traffic(pts_per_launch, k), "peak_source": peak_src,
-            "note": "algorithmic 44 B/point; the kernel is instruction-issue bound (64 % of issue slots, profiles/staged_full_r01s.txt), not HBM bound (DESIGN.md 5)",
+            "note": "algorithmic 44 B/point; the kernel is instruction-issue bound (72 % of issue slots, profiles/staged_full_r01t.txt), not HBM bound (DESIGN.md 5)",
         },
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
                 "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "step_wall_ms": step_walls, "host_io": e2e_host_io},
