@@ -377,6 +377,39 @@ def test_shared_host_path_single_rank_group(pct):
         dist.destroy_process_group()
 
 
+def test_tiny_and_degenerate_clouds(pct):
+    """Edge cases of the staged kernel: clouds smaller than a chunk, k = 1, k = N - 1, coincident points,
+    points on a line and on a plane.  Neighbour rows stay bit-exact; fits of degenerate geometry are NaN + status."""
+    rng = np.random.default_rng(12)
+    cases = {
+        "seven": (rng.normal(size=(7, 3)).astype(np.float32), [1, 5, 6]),
+        "chunk_edge": (rng.normal(size=(257, 3)).astype(np.float32), [1, 20]),
+        "line": (np.stack((np.linspace(0, 1, 400), np.zeros(400), np.zeros(400)), 1).astype(np.float32), [8]),
+        "plane": (np.concatenate((rng.uniform(size=(3000, 2)), np.zeros((3000, 1))), 1).astype(np.float32), [20]),
+        "coincident": (np.repeat(rng.normal(size=(5, 3)).astype(np.float32), 40, axis=0), [10]),
+    }
+    for name, (pts, ks) in cases.items():
+        for k in ks:
+            ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+            pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+            pc.plant_kdtree(k)
+            assert np.array_equal(pc.neighbor_indices, ref_idx), (name, k)
+            assert np.array_equal(pc.dists, ref_dist), (name, k)
+            pc2 = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+            pc2.plant_kdtree(k)
+            K, H = pc2.compute_pointwise_explicit_quadratic_curvature()     # fused kernel, never raises on these
+            assert K.shape == (len(pts),) and H.shape == (len(pts),)
+            if name == "plane":
+                ok = np.isfinite(K)
+                assert ok.mean() > 0.99 and np.abs(K[ok]).max() < 1e-3 and np.abs(H[ok]).max() < 1e-2
+            if name in ("line", "coincident"):
+                assert not np.isfinite(K).any()                              # rank-deficient designs: NaN, like a failed lstsq
+                assert (pc2.fit_status != 0).all()
+    with pytest.raises(IndexError):
+        pc = pct.PointCloud(points=cases["seven"][0], normals=_empty_normals(7), k_neighbors=7)
+        pc.plant_kdtree(7)
+
+
 def test_errors_mirror_reference(pct):
     with pytest.raises(ValueError, match="Either file_path or points and normals"):
         pct.PointCloud()
