@@ -109,6 +109,16 @@ int pct_estimate_cell_size(const float* xyz, int64_t n, int stride, int k_hint, 
  * axis = -1 removes the restriction.  kNN entry points only. */
 int pct_index_set_slab(pct_index* index, int axis, float complete_lo, float complete_hi,
                        float own_lo, float own_hi, const int32_t* row_map);
+/* Slab selection on the device (new, multi-GPU): pct_slab_select writes to `sel` (device, capacity N int32)
+ * the ASCENDING original indices of the points with complete_lo <= coordinate[axis] <= complete_hi and
+ * returns their number; pct_slab_gather copies those points to `local_xyz` (m x 3 packed) and writes
+ * `row_map` (m int32): for a point with own_lo <= coordinate[axis] < own_hi its rank among the owned
+ * points (the compact output row pct_index_set_slab expects), and returns the number of owned points.
+ * Both synchronise `stream`. */
+int pct_slab_select(const float* xyz, int64_t n, int stride, int axis, float complete_lo, float complete_hi,
+                    int32_t* sel, int64_t* num_selected, void* stream);
+int pct_slab_gather(const float* xyz, int stride, int axis, const int32_t* sel, int64_t m, float own_lo,
+                    float own_hi, float* local_xyz, int32_t* row_map, int64_t* num_owned, void* stream);
 /* frees the index in the order of the stream it was built on (no device synchronisation);
  * queries issued on OTHER streams must have completed */
 int pct_index_destroy(pct_index* index);

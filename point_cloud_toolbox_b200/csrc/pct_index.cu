@@ -6,6 +6,9 @@
 // streaming passes; the sort uses CUB's radix sort (library code, 8-bit digits
 // over 3*bits key bits).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -460,6 +463,111 @@ int pct_index_destroy(pct_index* ix) {
 int pct_index_get_info(const pct_index* ix, pct_index_info* info) {
     PCT_REQUIRE(ix && info, "pct_index_get_info: NULL argument");
     *info = ix->info;
+    return PCT_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// slab selection (multi-GPU): which points of the replicated cloud does one rank index, which does it own
+// ---------------------------------------------------------------------------
+namespace pct {
+namespace {
+
+struct InComplete {
+    const float* xyz;
+    int stride, axis;
+    float c_lo, c_hi;
+    __device__ __forceinline__ bool operator()(const int i) const {
+        const float v = xyz[(size_t)i * stride + axis];
+        return v >= c_lo && v <= c_hi;
+    }
+};
+
+// local cloud (packed xyz) of the selected points and the flag "owned" per local point
+__global__ void slab_gather_kernel(const float* __restrict__ xyz, int stride, int axis, const int32_t* __restrict__ sel,
+                                   long long m, float own_lo, float own_hi, float* __restrict__ local,
+                                   int32_t* __restrict__ own_flag) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const float* p = xyz + (size_t)sel[r] * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    local[3 * r] = x; local[3 * r + 1] = y; local[3 * r + 2] = z;
+    const float v = axis == 0 ? x : (axis == 1 ? y : z);
+    own_flag[r] = v >= own_lo && v < own_hi ? 1 : 0;
+}
+
+__global__ void slab_rows_kernel(const int32_t* __restrict__ incl, long long m, int32_t* __restrict__ row_map) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r < m) row_map[r] = incl[r] - 1;
+}
+
+}  // namespace
+}  // namespace pct
+
+extern "C" {
+
+int pct_slab_select(const float* xyz, int64_t n, int stride, int axis, float complete_lo, float complete_hi,
+                    int32_t* sel, int64_t* num_selected, void* stream) {
+    PCT_REQUIRE(xyz && sel && num_selected && n >= 1 && n < (1ll << 31) && (stride == 3 || stride == 4) && axis >= 0 && axis <= 2,
+                "pct_slab_select: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    pct::InComplete pred{xyz, stride, axis, complete_lo, complete_hi};
+    cub::CountingInputIterator<int> ids(0);
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, ids, sel, (int*)nullptr, (int)n, pred, s));
+    pct::ScratchSession scratch(s, tmp_bytes + 4096);
+    void* tmp = scratch.take(tmp_bytes);
+    int* d_num = static_cast<int*>(scratch.take(sizeof(int)));
+    const bool pooled = !tmp || !d_num;
+    if (pooled) {
+        PCT_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+        PCT_CUDA(cudaMallocAsync(&d_num, sizeof(int), s));
+    }
+    PCT_CUDA(cub::DeviceSelect::If(tmp, tmp_bytes, ids, sel, d_num, (int)n, pred, s));
+    int h_num = 0;
+    PCT_CUDA(cudaMemcpyAsync(&h_num, d_num, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    if (pooled) {
+        PCT_CUDA(cudaFreeAsync(tmp, s));
+        PCT_CUDA(cudaFreeAsync(d_num, s));
+    }
+    *num_selected = h_num;
+    return PCT_OK;
+}
+
+int pct_slab_gather(const float* xyz, int stride, int axis, const int32_t* sel, int64_t m, float own_lo, float own_hi,
+                    float* local_xyz, int32_t* row_map, int64_t* num_owned, void* stream) {
+    PCT_REQUIRE(xyz && sel && local_xyz && row_map && num_owned && m >= 0 && (stride == 3 || stride == 4), "pct_slab_gather: bad argument");
+    *num_owned = 0;
+    if (m == 0) return PCT_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)m, s));
+    pct::ScratchSession scratch(s, tmp_bytes + 2 * sizeof(int32_t) * (size_t)m + 8192);
+    void* tmp = scratch.take(tmp_bytes);
+    int32_t* flag = static_cast<int32_t*>(scratch.take(sizeof(int32_t) * (size_t)m));
+    int32_t* incl = static_cast<int32_t*>(scratch.take(sizeof(int32_t) * (size_t)m));
+    const bool pooled = !tmp || !flag || !incl;
+    if (pooled) {
+        PCT_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+        PCT_CUDA(cudaMallocAsync(&flag, sizeof(int32_t) * (size_t)m, s));
+        PCT_CUDA(cudaMallocAsync(&incl, sizeof(int32_t) * (size_t)m, s));
+    }
+    const int blocks = (int)((m + 255) / 256);
+    pct::slab_gather_kernel<<<blocks, 256, 0, s>>>(xyz, stride, axis, sel, m, own_lo, own_hi, local_xyz, flag);
+    PCT_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, flag, incl, (int)m, s));
+    pct::slab_rows_kernel<<<blocks, 256, 0, s>>>(incl, m, row_map);
+    int32_t h_last = 0;
+    PCT_CUDA(cudaMemcpyAsync(&h_last, incl + (m - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    PCT_CUDA(cudaGetLastError());
+    if (pooled) {
+        PCT_CUDA(cudaFreeAsync(tmp, s));
+        PCT_CUDA(cudaFreeAsync(flag, s));
+        PCT_CUDA(cudaFreeAsync(incl, s));
+    }
+    *num_owned = h_last;
     return PCT_OK;
 }
 

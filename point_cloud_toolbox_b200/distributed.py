@@ -160,24 +160,24 @@ def curvature_knn_slab(cloud: torch.Tensor, k: int, rank: int, world: int, event
     axis = max(range(3), key=lambda a: hi[a] - lo[a])
     x = cloud[:, axis]
     bounds = slab_bounds(slab_cuts(x, world), rank, SLAB_MARGIN_CELLS * h)
-    sel, own = slab_select(x, bounds)
+    sel, local, row_map, n_own = engine.slab_select(cloud, axis, bounds)
     if int(sel.numel()) <= k + 1:
         # degenerate slab (tiny cloud): index the whole cloud, still answer only what this rank owns
         bounds = (float("-inf"), float("inf"), bounds[2], bounds[3])
-        sel, own = slab_select(x, bounds)
-    # compact outputs: row of an owned point = its rank among the owned points
-    row_map = torch.cumsum(own, 0, dtype=torch.int32) - 1
-    n_own = int(row_map[-1]) + 1 if row_map.numel() else 0
+        sel, local, row_map, n_own = engine.slab_select(cloud, axis, bounds)
     if n_own == 0:
         empty = torch.empty((0,), dtype=torch.int64, device=cloud.device)
         return SlabFit(empty, torch.empty((0, 8), dtype=torch.float32, device=cloud.device), 0, None, h, bounds, axis)
-    local = cloud.index_select(0, sel).contiguous()
     index = engine.GridIndex(local, cell_hint=h, k_hint=k)
     index.set_slab(axis, *bounds, row_map=row_map, mapped_rows=n_own)  # rows of points it does not own are never written
     for ev in events:
         ev.record()
     records = index.curvature_knn(k, want_coeffs=False).records   # (n_own, 8)
-    ids = sel[own]
+    # original indices of the owned points, ascending: row_map steps by one exactly at an owned point
+    own = torch.ones_like(row_map, dtype=torch.bool)
+    own[1:] = row_map[1:] != row_map[:-1]
+    own[0] = bool(row_map[0] == 0)
+    ids = sel[own].to(torch.int64)
     n_bad = int(index.last_stats().unresolved)
     if n_bad:
         bad = (records[:, 7].contiguous().view(torch.int32) & STATUS_UNRESOLVED) != 0

@@ -300,6 +300,28 @@ def estimate_cell_size(points_dev, k_hint=20):
     return float(h.value), [box[0], box[1], box[2]], [box[3], box[4], box[5]]
 
 
+def slab_select(points_dev, axis, bounds):
+    """Device-side slab selection (pct_slab_select + pct_slab_gather).
+
+    Returns ``(sel int32 (m,), local (m, 3), row_map int32 (m,), n_own)``: ascending original indices of the
+    points inside the slab's complete range, those points, the compact output row of every owned point."""
+    c_lo, c_hi, own_lo, own_hi = bounds
+    n = int(points_dev.shape[0])
+    stride = int(points_dev.shape[1])
+    sel = torch.empty((n,), dtype=torch.int32, device=points_dev.device)
+    m = ctypes.c_int64()
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_slab_select(ptr(points_dev), n, stride, int(axis), float(c_lo), float(c_hi), ptr(sel), ctypes.byref(m), _stream()))
+        m = int(m.value)
+        sel = sel[:m]
+        local = torch.empty((m, 3), dtype=torch.float32, device=points_dev.device)
+        row_map = torch.empty((m,), dtype=torch.int32, device=points_dev.device)
+        n_own = ctypes.c_int64()
+        check(lib.pct_slab_gather(ptr(points_dev), stride, int(axis), ptr(sel), m, float(own_lo), float(own_hi), ptr(local),
+                                  ptr(row_map), ctypes.byref(n_own), _stream()))
+    return sel, local, row_map, int(n_own.value)
+
+
 def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:
     """Fit rows of original-index neighbour lists (nq, k) on an (N, 3) cloud."""
     if points_dev.shape[1] != 3 or not points_dev.is_contiguous():

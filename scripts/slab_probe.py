@@ -30,11 +30,12 @@ def main():
             axis = max(range(3), key=lambda a: hi[a] - lo[a])
             x = cloud[:, axis]
             bounds = pdist.slab_bounds(pdist.slab_cuts(x, world), rank, pdist.SLAB_MARGIN_CELLS * h); e.append(ev())
-            sel, own = pdist.slab_select(x, bounds); row_map = torch.cumsum(own, 0, dtype=torch.int32) - 1; n_own = int(row_map[-1]) + 1; e.append(ev())
-            local = cloud.index_select(0, sel).contiguous(); e.append(ev())
+            sel, local, row_map, n_own = engine.slab_select(cloud, axis, bounds); e.append(ev())
+            e.append(ev())
             index = GridIndex(local, cell_hint=h, k_hint=k); e.append(ev())
             index.set_slab(axis, *bounds, row_map=row_map, mapped_rows=n_own)
             fit = index.curvature_knn(k, want_coeffs=False); e.append(ev())
+            own = torch.ones_like(row_map, dtype=torch.bool); own[1:] = row_map[1:] != row_map[:-1]; own[0] = bool(row_map[0] == 0)
             ids = sel[own]; records = fit.records; e.append(ev())
             torch.cuda.synchronize()
             st = index.last_stats()
