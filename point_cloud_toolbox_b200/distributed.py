@@ -208,7 +208,14 @@ class SharedHostArray:
         nbytes = 4
         for d in shape:
             nbytes *= int(d)
-        self._shm = shared_memory.SharedMemory(name=name, create=create, size=max(nbytes, 4))
+        try:
+            self._shm = shared_memory.SharedMemory(name=name, create=create, size=max(nbytes, 4))
+        except FileExistsError:
+            # a segment of that name left behind by a run that did not finish: replace it
+            stale = shared_memory.SharedMemory(name=name, create=False)
+            stale.close()
+            stale.unlink()
+            self._shm = shared_memory.SharedMemory(name=name, create=True, size=max(nbytes, 4))
         self._owner = create
         if not create:
             # Python < 3.13 registers attached segments for unlinking at exit as well; only the creator unlinks
