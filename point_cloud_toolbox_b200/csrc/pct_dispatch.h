@@ -17,7 +17,7 @@
 
 // candidates per trip of the staged candidate loop
 #ifndef PCT_SCAN_WIDTH
-#define PCT_SCAN_WIDTH 2
+#define PCT_SCAN_WIDTH 4
 #endif
 
 // pass 1 of the selection without a branch around the histogram update
