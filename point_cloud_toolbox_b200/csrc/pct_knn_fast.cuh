@@ -414,10 +414,11 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     constexpr int U = 2;
     auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
     const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect);
-    // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide,
-    // but a few percent of unstaged chunks cost less than a third of the resident warps (scripts/gain_sweep.py)
+    // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide:
+    // with a buffer of 2.1 times that mean about 4 % of the chunks do not fit, which still beats giving up a
+    // third of the resident warps; below that the unstaged share explodes (k = 40: 26 %; scripts/qbench.py)
     const double per_parent = (double)v.n / (double)std::max<long long>(1, a.ix->cells_level[std::min(U, v.num_levels - 1)]);
-    const double wanted = 1.3 * (per_parent + kStagedBlock) * std::pow(1.5, (double)std::min(3.f, std::max(1.f, a.ix->est_dimension)));
+    const double wanted = 2.1 * (per_parent + kStagedBlock) * std::pow(1.5, (double)std::min(3.f, std::max(1.f, a.ix->est_dimension)));
     int cap_pts = 0;
     int ctas_max = PCT_STAGED_CTAS;
     if (const char* e = std::getenv("PCT_STAGED_RESIDENT")) ctas_max = std::max(1, std::min(PCT_STAGED_CTAS, std::atoi(e)));  // experiments
