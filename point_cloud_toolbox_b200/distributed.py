@@ -12,7 +12,7 @@ One process per GPU (torchrun), ``torch.distributed`` for the plumbing:
                           k-th neighbour could lie beyond it comes back PCT_STATUS_UNRESOLVED and is
                           answered from a whole-cloud index built on demand.  The build, the serial
                           fraction of the replicated form, shrinks with the number of ranks.
-       "replicated"       every rank builds the same whole-cloud index; rank g answers Morton-sorted
+       "replicated"       (kept for comparison) every rank builds the same whole-cloud index; rank g answers Morton-sorted
                           positions [g*N/G, (g+1)*N/G) in slice layout (PCT_LAYOUT_SLICE)
   3. ``gather`` to rank 0, which puts the rows in original order
 
@@ -137,9 +137,14 @@ def gather_scattered(ids: torch.Tensor, rows: torch.Tensor, n: int, group=None, 
 
 
 def default_mode(world: int) -> str:
-    """Slabs pay once the replicated whole-cloud build (10 ms at 100 M points) outweighs the cut / select /
-    smaller-build work of a rank (3.6 ms at 8 ranks); measured break-even is between 2 and 4 ranks."""
-    return "slab" if world >= 3 else "replicated"
+    """Slabs replace the replicated whole-cloud build (10 ms at 100 M points) by the cut / select / smaller-build
+    work of a rank (6.5 ms at 2 ranks, 2.7 ms at 8); measured faster from 2 ranks up (2 GPUs: 36.9 vs 38.1 ms)."""
+    import os
+
+    forced = os.environ.get("PCT_MULTI_MODE")  # experiments
+    if forced in ("slab", "replicated"):
+        return forced
+    return "slab" if world >= 2 else "replicated"
 
 
 class SlabFit:
