@@ -239,7 +239,7 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
     // points per cell, tuned on B200 with the staged kernel (scripts/ppc_sweep.py): small k wants few
     // level-1 retries, large k cells small enough for the staging buffer
     const double kh = (double)(k_hint > 0 ? k_hint : 20);
-    const double target = kh <= 24.0 ? 0.46 * kh : (kh <= 40.0 ? 0.42 * kh : 0.35 * kh);
+    const double target = kh <= 24.0 ? 0.46 * kh : (kh <= 40.0 ? 0.42 * kh : 0.37 * kh);
     double h = (double)cell * std::ldexp(1.0, Ls) * std::pow(target / ppc_full, 1.0 / dim);
     h = std::min(h, 2.0 * (double)extent_max);
     *h_out = (float)h;
