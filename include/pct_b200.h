@@ -201,6 +201,18 @@ int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uin
                     void* stream);
 int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream);
 
+/* Text loader: replaces `np.loadtxt(file_path)` of read_from_file (ref :51) with a memory-mapped,
+ * multi-threaded parser (host code).  One row per line; values separated by blanks, tabs or commas; '#'
+ * starts a comment; empty lines are skipped; every row has the same number of columns
+ * (PCT_ERR_INVALID_ARGUMENT otherwise, np.loadtxt raises ValueError).  Values are converted like Python's
+ * float() (correctly rounded), so the table equals np.loadtxt's bit for bit.
+ * pct_text_shape: rows and columns; pct_text_load: the rows x cols float64 table, `threads` <= 0 = all cores;
+ * pct_text_load_f32: the same table rounded to float32 (`.astype(np.float32)` of ref :52-53) without the
+ * float64 intermediate in memory -- what read_from_file keeps.  `out` may be pinned host memory. */
+int pct_text_shape(const char* path, int64_t* rows, int64_t* cols);
+int pct_text_load(const char* path, int64_t rows, int64_t cols, double* out, int threads);
+int pct_text_load_f32(const char* path, int64_t rows, int64_t cols, float* out, int threads);
+
 /* Frees the per-stream scratch arenas the library keeps for the temporaries of its calls (they grow to the
  * largest call seen on a stream: about 37 bytes per point for an index build).  Synchronises those streams. */
 int pct_release_scratch(void);

@@ -94,6 +94,30 @@ def to_host(t: torch.Tensor):
     return h.numpy()
 
 
+def load_text_f32(path, threads=0) -> torch.Tensor:
+    """Whitespace-separated numeric text file -> (rows, cols) float32 tensor in pinned host memory.
+
+    Values equal ``np.loadtxt(path).astype(np.float32)`` bit for bit (ref :51-53); a file of one row
+    comes back one-dimensional and an empty file as shape (0,), like ``np.loadtxt``.  Raises
+    ``ValueError`` on a malformed token or a ragged row and ``FileNotFoundError`` like ``np.loadtxt``.
+    """
+    import os
+
+    path = os.fspath(path)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found.")
+    rows, cols = ctypes.c_int64(), ctypes.c_int64()
+    check(lib.pct_text_shape(path.encode(), ctypes.byref(rows), ctypes.byref(cols)))
+    pin = torch.cuda.is_available()
+    out = torch.empty((rows.value, cols.value), dtype=torch.float32, pin_memory=pin)
+    check(lib.pct_text_load_f32(path.encode(), rows.value, cols.value, ctypes.c_void_p(out.data_ptr()), int(threads)))
+    if rows.value == 0:
+        return out.reshape(0)
+    if rows.value == 1:
+        return out.reshape(cols.value)
+    return out
+
+
 class FitOutputs:
     """Per-point results of a fit, resident on the device.
 

@@ -132,12 +132,17 @@ class PointCloud:
     # loading                                                   ref :50-66
     # ------------------------------------------------------------------
     def read_from_file(self):
-        table = np.loadtxt(self.file_path)
         engine.require_cuda()
+        # np.loadtxt (ref :51) replaced by the library's memory-mapped multi-threaded parser; the table is
+        # rounded to float32 (ref :52-53) straight into pinned memory and goes to the device from there
+        table = engine.load_text_f32(self.file_path)
+        if table.ndim != 2:
+            # np.loadtxt squeezes a one-row (or empty) file to one dimension and ref :52 fails on it
+            raise IndexError(f"too many indices for array: array is {table.ndim}-dimensional, but 2 were indexed")
         dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
-        t = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-        pts = t[:, 0:3].to(torch.float32).contiguous()        # ref :52
-        nrm = t[:, 3:6].to(torch.float32).contiguous()        # ref :53
+        t = table.to(dev, non_blocking=True)
+        pts = t[:, 0:3].contiguous()                          # ref :52
+        nrm = t[:, 3:6].contiguous()                          # ref :53
         pts[:, 0] -= pts[:, 0].max()                          # ref :56 (fp32)
         pts[:, 1] -= pts[:, 1].max()                          # ref :57
         if self.downsample:

@@ -271,3 +271,79 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+# ---------------------------------------------------------------------------
+# text loader (host code of the library; ref :51-53 np.loadtxt + astype(float32))
+# ---------------------------------------------------------------------------
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64 if a.dtype == np.float64 else np.uint32)
+
+
+def _load_f64(path, threads=0):
+    from point_cloud_toolbox_b200 import _lib
+
+    r, c = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(_lib.lib.pct_text_shape(str(path).encode(), ctypes.byref(r), ctypes.byref(c)))
+    out = np.empty((r.value, c.value), np.float64)
+    _lib.check(_lib.lib.pct_text_load(str(path).encode(), r.value, c.value, P(out), threads))
+    return out
+
+
+@pytest.mark.parametrize("fmt,threads", [("%.18e", 0), ("%.6f", 3), ("%.9g", 1)])
+def test_text_loader_equals_loadtxt_bit_for_bit(tmp_path, fmt, threads):
+    from point_cloud_toolbox_b200 import engine
+
+    rng = np.random.default_rng(5)
+    table = rng.standard_normal((60_000, 6)) * 10.0 ** rng.integers(-20, 20, (60_000, 6))
+    path = tmp_path / "t.txt"
+    np.savetxt(path, table, fmt=fmt)
+    want = np.loadtxt(path)
+    got = _load_f64(path, threads)
+    assert got.shape == want.shape and np.array_equal(_bits(got), _bits(want))
+    got32 = engine.load_text_f32(path, threads).numpy()
+    assert got32.dtype == np.float32 and np.array_equal(_bits(got32), _bits(want.astype(np.float32)))
+
+
+def test_text_loader_format_corners(tmp_path):
+    from point_cloud_toolbox_b200 import engine
+
+    path = tmp_path / "c.txt"
+    path.write_text("# header\n1 2 3\n\n   \n  4\t5 6 # trailing comment\r\n+7 -8e-400 1e400\nnan inf -Infinity")
+    want = np.loadtxt(path)
+    got = _load_f64(path)
+    assert np.array_equal(_bits(got), _bits(want))           # signed zero, inf, nan payloads included
+    path.write_text("1 2 3\n4 5\n")
+    with pytest.raises(ValueError, match="row 2"):
+        _load_f64(path)
+    with pytest.raises(ValueError):
+        np.loadtxt(path)
+    for bad in ("1,2,3\n", "1 2 x\n", "1 2 3abc\n"):
+        path.write_text(bad)
+        with pytest.raises(ValueError):
+            engine.load_text_f32(path)
+        with pytest.raises(ValueError):
+            np.loadtxt(path)
+    path.write_text("1 2 3\n")                                 # np.loadtxt squeezes one row
+    assert engine.load_text_f32(path).shape == (3,) and np.loadtxt(path).shape == (3,)
+    path.write_text("")
+    assert engine.load_text_f32(path).shape == (0,)
+    with pytest.raises(FileNotFoundError):
+        engine.load_text_f32(tmp_path / "missing.txt")
+
+
+def test_text_loader_on_the_reference_scan_fixture():
+    # the fp32 cloud of the golden fixture came from the unmodified reference's np.loadtxt (oracle/make_golden.py)
+    g = load_golden("loader_case")
+    import tempfile
+
+    from point_cloud_toolbox_b200 import engine
+
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "cloud.txt")
+        np.savetxt(path, g["table"], fmt="%.5f")
+        t = engine.load_text_f32(path).numpy()
+    pts = t[:, 0:3].copy()
+    pts[:, 0] -= pts[:, 0].max()
+    pts[:, 1] -= pts[:, 1].max()
+    assert np.array_equal(pts, g["points"]) and np.array_equal(t[:, 3:6], g["normals"])
