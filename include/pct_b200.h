@@ -213,6 +213,42 @@ int pct_text_shape(const char* path, int64_t* rows, int64_t* cols);
 int pct_text_load(const char* path, int64_t rows, int64_t cols, double* out, int threads);
 int pct_text_load_f32(const char* path, int64_t rows, int64_t cols, float* out, int threads);
 
+/* PCA estimators on given neighbour rows: replaces the per-point body of
+ * principal_curvatures_via_principal_component_analysis (ref :901-945): covariance (np.cov, ddof = 1, fp64) of the
+ * k listed points of every row (plus the query point itself when include_self != 0, as sklearn's
+ * kneighbors(points) lists it, utils.py:812-815), its eigen-decomposition, and what the reference derives:
+ * values nq x 6 = [l1 >= l2 >= l3, K = l1 * l2, H = (l1 + l2) / 2 (ref :935-936), l3 / (l1 + l2 + l3 + 1e-10)];
+ * directions nq x 3 x 2 = eigenvectors of l1 and l2 as columns (ref :933; sign is arbitrary, as in eigh); may be NULL.
+ * Rows come from pct_knn (the reference ranks all N points by fp32 distance per query, O(N^2)). */
+int pct_pca_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, int include_self,
+                           const int32_t* query_ids, double* values, double* directions, void* stream);
+
+/* Energy integration over a triangle mesh whose vertices carry the path's K and H: replaces
+ * load_mesh_compute_energies (utils.py:702-765).  vertices n x 3 fp32, triangles t x 3 int32 (negative indices
+ * count from the end like numpy's), gaussian / mean fp32 per vertex (NULL = zeros, utils.py:744-748), all on the
+ * device.  out (device, 4 doubles): bending = nansum(mean(H^2 at the corners) * area), stretching =
+ * nansum(mean(K at the corners) * area), total area, number of triangles with an index out of range (the
+ * reference raises IndexError; such triangles contribute nothing here). */
+int pct_mesh_energies(const float* vertices, int64_t n_vertices, const int32_t* triangles, int64_t n_triangles,
+                      const float* gaussian, const float* mean, double* out, void* stream);
+
+/* PLY body reader: replaces parse_ply (utils.py:979-1004) -- skip to the line "end_header", then float() of the
+ * first three tokens of EVERY following line (extra columns are ignored, face lines are read as points, exactly
+ * like the reference), rounded to float32.  A line with fewer than three numbers is an error (the reference
+ * prints it and returns None).  pct_ply_shape: number of body lines and the byte offset of the body. */
+int pct_ply_shape(const char* path, int64_t* rows, int64_t* body_offset);
+int pct_ply_load_f32(const char* path, int64_t body_offset, int64_t rows, float* out /* rows x 3 */, int threads);
+
+/* Writers (host code, all threads format blocks of rows, pwrite at each block's offset).
+ * pct_write_points_ply: save_points_to_ply (utils.py:963-976): ASCII PLY header + np.savetxt '%.6f %.6f %.6f';
+ *   `points` is n x 3 float32 (is_f64 = 0) or float64 (is_f64 = 1), host memory.
+ * pct_write_curvature_ply: the output block of validate_shape (utils.py:538-551): header with
+ *   gaussian_curvature / mean_curvature properties, rows f'{x} {y} {z} {K} {H}' of float32 scalars, i.e.
+ *   repr(float(v)) of every value.  Both files are byte-identical to the reference's. */
+int pct_write_points_ply(const char* path, const void* points, int is_f64, int64_t n, int threads);
+int pct_write_curvature_ply(const char* path, const float* points, const float* gaussian, const float* mean, int64_t n,
+                            int threads);
+
 /* Frees the per-stream scratch arenas the library keeps for the temporaries of its calls (they grow to the
  * largest call seen on a stream: about 37 bytes per point for an index build).  Synchronises those streams. */
 int pct_release_scratch(void);

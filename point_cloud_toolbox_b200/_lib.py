@@ -75,6 +75,12 @@ SIGNATURES = {
     "pct_text_shape": (c_int, [c_char_p, POINTER(c_int64), POINTER(c_int64)]),
     "pct_text_load": (c_int, [c_char_p, c_int64, c_int64, c_void_p, c_int]),
     "pct_text_load_f32": (c_int, [c_char_p, c_int64, c_int64, c_void_p, c_int]),
+    "pct_pca_from_neighbors": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pct_mesh_energies": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pct_ply_shape": (c_int, [c_char_p, POINTER(c_int64), POINTER(c_int64)]),
+    "pct_ply_load_f32": (c_int, [c_char_p, c_int64, c_int64, c_void_p, c_int]),
+    "pct_write_points_ply": (c_int, [c_char_p, c_void_p, c_int, c_int64, c_int]),
+    "pct_write_curvature_ply": (c_int, [c_char_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),
     "pct_slab_select": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_void_p, POINTER(c_int64), c_void_p]),
     "pct_slab_gather": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
                                 POINTER(c_int64), c_void_p]),

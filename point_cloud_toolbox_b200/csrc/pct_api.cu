@@ -197,6 +197,12 @@ int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* st
     return launch_quadric_curvature(coeffs, nq, curv, (cudaStream_t)stream);
 }
 
+int pct_pca_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, int include_self,
+                           const int32_t* query_ids, double* values, double* directions, void* stream) {
+    PCT_REQUIRE(xyz && idx && values && n >= 1 && nq >= 0 && k >= 1, "pct_pca_from_neighbors: bad argument");
+    return launch_pca_rows(xyz, idx, nq, k, include_self, query_ids, values, directions, (cudaStream_t)stream);
+}
+
 int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_host, float* H_host) {
     PCT_REQUIRE(xyz_host && K_host && H_host && n >= 1, "pct_curvature_knn_host: bad argument");
     cudaStream_t s;

@@ -6,6 +6,7 @@
 //   plane_rotate_kernel                get_best_fit_plane_and_rotate            (:270-321)
 //   quadric_fit_kernel                 fit_quadratic_surface                    (:331-360)
 //   quadric_curvature_kernel           calculate_explicit_quadratic_curvatures  (:398-431)
+//   pca_rows_kernel                    principal_curvatures_via_principal_component_analysis (:901-945)
 //
 // One thread per neighbourhood; rows are gathered from the original cloud (L2).
 #include <algorithm>
@@ -133,6 +134,40 @@ quadric_curvature_kernel(const float* __restrict__ coeffs, long long nq, float* 
     }
 }
 
+// PCA of every neighbourhood row: covariance (np.cov, ddof = 1, fp64) of the k listed points (plus the query
+// point itself when include_self), eigen-decomposition, and the quantities the reference derives from it.
+// values (nq x 6): l1 >= l2 >= l3, K = l1 * l2, H = (l1 + l2) / 2 (ref :935-936), l3 / (l1 + l2 + l3 + 1e-10)
+// (the surface variation utils.py:778-829 describes); directions (nq x 3 x 2): eigenvectors of l1 and l2.
+__global__ void __launch_bounds__(kBlock)
+pca_rows_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, long long nq, int k, int include_self,
+                const int32_t* __restrict__ qids, double* __restrict__ values, double* __restrict__ directions) {
+    for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < nq; r += (long long)gridDim.x * kBlock) {
+        const long long qi = qids ? (long long)qids[r] : r;
+        const double qx = __ldg(xyz + 3 * qi), qy = __ldg(xyz + 3 * qi + 1), qz = __ldg(xyz + 3 * qi + 2);
+        PcaMoments m;
+        m.reset();
+        if (include_self) m.add(0.0, 0.0, 0.0);
+        const int32_t* row = idx + r * k;
+        for (int j = 0; j < k; ++j) {
+            const long long p = row[j];
+            m.add((double)__ldg(xyz + 3 * p) - qx, (double)__ldg(xyz + 3 * p + 1) - qy, (double)__ldg(xyz + 3 * p + 2) - qz);
+        }
+        double c[6], w[3], v[3][3];
+        m.covariance(c);
+        eig_sym3_descending(c[0], c[1], c[2], c[3], c[4], c[5], w, v);
+        double* o = values + 6 * r;
+        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        o[3] = w[0] * w[1];
+        o[4] = (w[0] + w[1]) / 2.0;
+        o[5] = w[2] / (w[0] + w[1] + w[2] + 1e-10);
+        if (directions) {
+            double* d = directions + 6 * r;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { d[2 * a] = v[a][0]; d[2 * a + 1] = v[a][1]; }
+        }
+    }
+}
+
 int grid_for(long long n) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -169,6 +204,14 @@ int launch_plane_rotate(const float* centered, long long nq, int k, double* rota
 int launch_quadric_fit(const double* rotated, long long nq, int k, float* coeffs, uint8_t* status, cudaStream_t s) {
     if (nq == 0) return PCT_OK;
     quadric_fit_kernel<<<grid_for(nq), kBlock, 0, s>>>(rotated, nq, k, coeffs, status);
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+int launch_pca_rows(const float* xyz, const int32_t* idx, long long nq, int k, int include_self, const int32_t* qids,
+                    double* values, double* directions, cudaStream_t s) {
+    if (nq == 0) return PCT_OK;
+    pca_rows_kernel<<<grid_for(nq), kBlock, 0, s>>>(xyz, idx, nq, k, include_self, qids, values, directions);
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
 }

@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <charconv>
+#include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -91,13 +93,34 @@ inline bool is_data_line(const char* b, const char* e) {
     return b < e && *b != '#';
 }
 
+// first `want` tokens of a PLY body line as float(); the rest of the line is not looked at (ref utils.py:993-994)
+template <typename T>
+bool parse_prefix(const char* b, const char* e, T* out, int want) {
+    for (int i = 0; i < want; ++i) {
+        while (b < e && is_sep(*b)) ++b;
+        if (b >= e) return false;
+        const char* t = b;
+        if (*t == '+') ++t;
+        double v = 0.0;
+        const std::from_chars_result r = std::from_chars(t, e, v);
+        if (r.ec == std::errc::invalid_argument || r.ptr == t) return false;
+        if (r.ec == std::errc::result_out_of_range) v = std::strtod(std::string(t, r.ptr).c_str(), nullptr);
+        if (r.ptr < e && !is_sep(*r.ptr)) return false;
+        out[i] = (T)v;
+        b = r.ptr;
+    }
+    return true;
+}
+
 // cut the file at line boundaries, count the data lines of every piece in parallel
-void count_rows(const Mapped& f, int threads, std::vector<Piece>& pieces) {
-    threads = (int)std::min<size_t>((size_t)std::max(threads, 1), std::max<size_t>(1, f.n >> 16));
+// (every_line: PLY body, where each line is a row; begin0: offset of the first byte of the body)
+void count_rows(const Mapped& f, int threads, std::vector<Piece>& pieces, bool every_line = false, size_t begin0 = 0) {
+    const size_t span = f.n - begin0;
+    threads = (int)std::min<size_t>((size_t)std::max(threads, 1), std::max<size_t>(1, span >> 16));
     pieces.assign((size_t)threads, Piece());
     for (int t = 0; t < threads; ++t) {
-        size_t b = f.n * (size_t)t / (size_t)threads;
-        if (t > 0 && b > 0) {  // advance to the next line start
+        size_t b = begin0 + span * (size_t)t / (size_t)threads;
+        if (t > 0 && b > begin0) {  // advance to the next line start
             const char* nl = static_cast<const char*>(memchr(f.p + b - 1, '\n', f.n - (b - 1)));
             b = nl ? (size_t)(nl - f.p) + 1 : f.n;
         }
@@ -112,7 +135,7 @@ void count_rows(const Mapped& f, int threads, std::vector<Piece>& pieces) {
         while (p < end) {
             const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
             const char* e = nl ? nl : end;
-            r += is_data_line(p, e) ? 1 : 0;
+            r += (every_line || is_data_line(p, e)) ? 1 : 0;
             p = nl ? nl + 1 : end;
         }
         pc.rows = r;
@@ -203,6 +226,245 @@ int pct_text_load(const char* path, int64_t rows, int64_t cols, double* out, int
 
 int pct_text_load_f32(const char* path, int64_t rows, int64_t cols, float* out, int threads) {
     return text_load(path, rows, cols, out, threads);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// PLY body reader: parse_ply of /root/reference/utils.py:979-1004 (skip to the line "end_header", then
+// float() of the first three tokens of EVERY following line, rounded to float32).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// offset of the first byte after the line whose stripped text is "end_header"; SIZE_MAX when absent
+size_t ply_body_offset(const Mapped& f) {
+    const char* p = f.p;
+    const char* end = f.p + f.n;
+    while (p < end) {
+        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+        const char* b = p;
+        const char* e = nl ? nl : end;
+        while (b < e && (is_sep(*b))) ++b;
+        while (e > b && (is_sep(e[-1]))) --e;
+        if (e - b == 10 && memcmp(b, "end_header", 10) == 0) return nl ? (size_t)(nl + 1 - f.p) : f.n;
+        p = nl ? nl + 1 : end;
+    }
+    return SIZE_MAX;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pct_ply_shape(const char* path, int64_t* rows, int64_t* body_offset) {
+    PCT_REQUIRE(path && rows && body_offset, "pct_ply_shape: NULL argument");
+    Mapped f;
+    if (!f.open_file(path)) { set_error(std::string("pct_ply_shape: cannot open ") + path); return PCT_ERR_INVALID_ARGUMENT; }
+    const size_t off = ply_body_offset(f);
+    if (off == SIZE_MAX) { set_error("pct_ply_shape: no end_header line"); return PCT_ERR_INVALID_ARGUMENT; }
+    std::vector<Piece> pieces;
+    count_rows(f, default_threads(0), pieces, true, off);
+    *rows = pieces.back().first_row + pieces.back().rows;
+    *body_offset = (int64_t)off;
+    return PCT_OK;
+}
+
+int pct_ply_load_f32(const char* path, int64_t body_offset, int64_t rows, float* out, int threads) {
+    PCT_REQUIRE(path && body_offset >= 0 && rows >= 0 && (out || rows == 0), "pct_ply_load_f32: bad argument");
+    Mapped f;
+    if (!f.open_file(path)) { set_error(std::string("pct_ply_load_f32: cannot open ") + path); return PCT_ERR_INVALID_ARGUMENT; }
+    PCT_REQUIRE((size_t)body_offset <= f.n, "pct_ply_load_f32: body offset beyond the end of the file");
+    std::vector<Piece> pieces;
+    count_rows(f, default_threads(threads), pieces, true, (size_t)body_offset);
+    const long total = pieces.back().first_row + pieces.back().rows;
+    if (total != rows) { set_error("pct_ply_load_f32: the body holds " + std::to_string(total) + " lines"); return PCT_ERR_INVALID_ARGUMENT; }
+    auto walk = [&](Piece& pc) {
+        const char* p = f.p + pc.begin;
+        const char* end = f.p + pc.end;
+        long r = 0;
+        while (p < end) {
+            const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+            const char* e = nl ? nl : end;
+            if (!parse_prefix(p, e, out + (pc.first_row + r) * 3, 3) && pc.bad_line < 0) pc.bad_line = r;
+            ++r;
+            p = nl ? nl + 1 : end;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < pieces.size(); ++t) pool.emplace_back([&, t] { walk(pieces[t]); });
+    walk(pieces[0]);
+    for (auto& th : pool) th.join();
+    for (auto& pc : pieces)
+        if (pc.bad_line >= 0) {
+            set_error("body line " + std::to_string(pc.first_row + pc.bad_line + 1) + " does not start with three numbers");
+            return PCT_ERR_INVALID_ARGUMENT;
+        }
+    return PCT_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Writers on the output side of the path.  Rows are formatted by all host threads, a block of rows per
+// thread and wave, and every block is written at its own file offset (pwrite) -- the per-line Python
+// loop of utils.py:538-551 takes ~1 us per value.
+//   * points PLY: save_points_to_ply (utils.py:963-976), np.savetxt with '%.6f %.6f %.6f'
+//   * curvature PLY: utils.py:538-551, f'{x} {y} {z} {K} {H}' with numpy float32 scalars -- their
+//     __format__ goes through Python's float, so every value is repr(float(v)): the shortest digits that
+//     round-trip the DOUBLE image of the float32, fixed notation for 1e-4 <= |v| < 1e16
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// repr(float(v)) of CPython (Python/pystrtod.c format_float_short, mode 'r')
+inline char* py_repr(char* o, double v) {
+    if (v != v) { memcpy(o, "nan", 3); return o + 3; }
+    if (std::signbit(v)) { *o++ = '-'; v = -v; }
+    if (v > 1.7976931348623157e308) { memcpy(o, "inf", 3); return o + 3; }
+    if (v == 0.0) { memcpy(o, "0.0", 3); return o + 3; }
+    char t[40];
+    const std::to_chars_result r = std::to_chars(t, t + sizeof t, v, std::chars_format::scientific);  // d[.ddd]e+XX, shortest
+    char digits[24];
+    int nd = 0;
+    const char* q = t;
+    for (; q < r.ptr && *q != 'e'; ++q)
+        if (*q != '.') digits[nd++] = *q;
+    int ex = 0;
+    {
+        const char* x = q + 1;
+        const bool neg = *x == '-';
+        ++x;
+        for (; x < r.ptr; ++x) ex = ex * 10 + (*x - '0');
+        if (neg) ex = -ex;
+    }
+    const int decpt = ex + 1;  // value = 0.d1d2... * 10^decpt
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) {
+            *o++ = '0'; *o++ = '.';
+            for (int i = 0; i < -decpt; ++i) *o++ = '0';
+            memcpy(o, digits, (size_t)nd); o += nd;
+        } else if (decpt >= nd) {
+            memcpy(o, digits, (size_t)nd); o += nd;
+            for (int i = nd; i < decpt; ++i) *o++ = '0';
+            *o++ = '.'; *o++ = '0';
+        } else {
+            memcpy(o, digits, (size_t)decpt); o += decpt;
+            *o++ = '.';
+            memcpy(o, digits + decpt, (size_t)(nd - decpt)); o += nd - decpt;
+        }
+    } else {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, (size_t)(nd - 1)); o += nd - 1; }
+        *o++ = 'e';
+        int e10 = decpt - 1;
+        *o++ = e10 < 0 ? '-' : '+';
+        if (e10 < 0) e10 = -e10;
+        if (e10 >= 100) { *o++ = (char)('0' + e10 / 100); e10 %= 100; *o++ = (char)('0' + e10 / 10); *o++ = (char)('0' + e10 % 10); }
+        else { *o++ = (char)('0' + e10 / 10); *o++ = (char)('0' + e10 % 10); }
+    }
+    return o;
+}
+
+// '%.6f' of C (what np.savetxt applies to a float64)
+inline char* fixed6(char* o, double v) {
+    if (v != v) { memcpy(o, "nan", 3); return o + 3; }  // Python's '%.6f' never prints a sign for nan
+    if (v > 1.7976931348623157e308) { memcpy(o, "inf", 3); return o + 3; }
+    if (v < -1.7976931348623157e308) { memcpy(o, "-inf", 4); return o + 4; }
+    return std::to_chars(o, o + 330, v, std::chars_format::fixed, 6).ptr;
+}
+
+// rows [0, n) formatted by `fmt(row, out) -> end`, at most `max_row` bytes each, appended to `fd` at `offset`
+template <typename F>
+int write_rows(int fd, size_t offset, int64_t n, size_t max_row, int threads, F fmt) {
+    threads = default_threads(threads);
+    const int64_t block = 1 << 15;
+    const int64_t blocks = (n + block - 1) / block;
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, blocks));
+    std::vector<std::vector<char>> buf((size_t)threads);
+    std::vector<size_t> len((size_t)threads);
+    std::vector<int> err((size_t)threads, 0);
+    for (int64_t wave = 0; wave < blocks; wave += threads) {
+        const int live = (int)std::min<int64_t>(threads, blocks - wave);
+        auto work = [&](int t) {
+            const int64_t b = (wave + t) * block, e = std::min(n, b + block);
+            std::vector<char>& v = buf[(size_t)t];
+            v.resize((size_t)(e - b) * max_row);
+            char* o = v.data();
+            for (int64_t i = b; i < e; ++i) o = fmt(i, o);
+            len[(size_t)t] = (size_t)(o - v.data());
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < live; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        pool.clear();
+        std::vector<size_t> at((size_t)live);
+        for (int t = 0; t < live; ++t) { at[(size_t)t] = offset; offset += len[(size_t)t]; }
+        auto put = [&](int t) {
+            const char* p = buf[(size_t)t].data();
+            size_t left = len[(size_t)t], pos = at[(size_t)t];
+            while (left) {
+                const ssize_t w = pwrite(fd, p, left, (off_t)pos);
+                if (w <= 0) { err[(size_t)t] = 1; return; }
+                p += w; pos += (size_t)w; left -= (size_t)w;
+            }
+        };
+        for (int t = 1; t < live; ++t) pool.emplace_back(put, t);
+        put(0);
+        for (auto& th : pool) th.join();
+        for (int t = 0; t < live; ++t)
+            if (err[(size_t)t]) { set_error("write failed"); return PCT_ERR_INVALID_ARGUMENT; }
+    }
+    return PCT_OK;
+}
+
+int open_with_header(const char* path, const std::string& header) {
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return -1;
+    if (pwrite(fd, header.data(), header.size(), 0) != (ssize_t)header.size()) { close(fd); return -1; }
+    return fd;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pct_write_points_ply(const char* path, const void* points, int is_f64, int64_t n, int threads) {
+    PCT_REQUIRE(path && n >= 0 && (points || n == 0), "pct_write_points_ply: bad argument");
+    const std::string header = "ply\nformat ascii 1.0\nelement vertex " + std::to_string(n) +
+                               "\nproperty float x\nproperty float y\nproperty float z\nend_header\n";
+    const int fd = open_with_header(path, header);
+    if (fd < 0) { set_error(std::string("pct_write_points_ply: cannot write ") + path); return PCT_ERR_INVALID_ARGUMENT; }
+    const float* pf = static_cast<const float*>(points);
+    const double* pd = static_cast<const double*>(points);
+    const int rc = write_rows(fd, header.size(), n, 3 * 332, threads, [=](int64_t i, char* o) {
+        for (int c = 0; c < 3; ++c) {
+            o = fixed6(o, is_f64 ? pd[3 * i + c] : (double)pf[3 * i + c]);
+            *o++ = c < 2 ? ' ' : '\n';
+        }
+        return o;
+    });
+    close(fd);
+    return rc;
+}
+
+int pct_write_curvature_ply(const char* path, const float* points, const float* gaussian, const float* mean, int64_t n,
+                            int threads) {
+    PCT_REQUIRE(path && n >= 0 && ((points && gaussian && mean) || n == 0), "pct_write_curvature_ply: bad argument");
+    const std::string header = "ply\nformat ascii 1.0\nelement vertex " + std::to_string(n) +
+                               "\nproperty float x\nproperty float y\nproperty float z\n"
+                               "property float gaussian_curvature\nproperty float mean_curvature\nend_header\n";
+    const int fd = open_with_header(path, header);
+    if (fd < 0) { set_error(std::string("pct_write_curvature_ply: cannot write ") + path); return PCT_ERR_INVALID_ARGUMENT; }
+    const int rc = write_rows(fd, header.size(), n, 5 * 26, threads, [=](int64_t i, char* o) {
+        o = py_repr(o, (double)points[3 * i]);     *o++ = ' ';
+        o = py_repr(o, (double)points[3 * i + 1]); *o++ = ' ';
+        o = py_repr(o, (double)points[3 * i + 2]); *o++ = ' ';
+        o = py_repr(o, (double)gaussian[i]);       *o++ = ' ';
+        o = py_repr(o, (double)mean[i]);           *o++ = '\n';
+        return o;
+    });
+    close(fd);
+    return rc;
 }
 
 }  // extern "C"

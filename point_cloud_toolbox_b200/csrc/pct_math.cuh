@@ -167,6 +167,60 @@ PCT_HD_NOINLINE void smallest_eigenvector_sym3_jacobi(double a00, double a01, do
     else                          { n[0] = v02; n[1] = v12; n[2] = v22; }
 }
 
+// All three eigenpairs of a symmetric 3x3 (fp64 cyclic Jacobi), eigenvalues in DESCENDING order, column j of
+// v = eigenvector of w[j].  For the PCA estimators (/root/reference/pointCloudToolbox.py:901-945).
+PCT_HD_NOINLINE void eig_sym3_descending(double a00, double a01, double a02, double a11, double a12, double a22,
+                                         double w[3], double v[3][3]) {
+    const double tr = fabs(a00) + fabs(a11) + fabs(a22);
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+    if (tr > 0.0 && tr <= 1.7e308) {
+        const double inv = 1.0 / tr;
+        a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+#pragma unroll 1
+        for (int sweep = 0; sweep < 12; ++sweep) {
+            const double off = a01 * a01 + a02 * a02 + a12 * a12;
+            if (off < 1e-40) break;
+            jacobi_rotate(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21);
+            jacobi_rotate(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22);
+            jacobi_rotate(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22);
+        }
+        a00 *= tr; a11 *= tr; a22 *= tr;
+    }
+    double ev[3] = {a00, a11, a22};
+    double vec[3][3] = {{v00, v01, v02}, {v10, v11, v12}, {v20, v21, v22}};
+    int o0 = 0, o1 = 1, o2 = 2, t;
+    if (ev[o0] < ev[o1]) { t = o0; o0 = o1; o1 = t; }
+    if (ev[o1] < ev[o2]) { t = o1; o1 = o2; o2 = t; }
+    if (ev[o0] < ev[o1]) { t = o0; o0 = o1; o1 = t; }
+    const int ord[3] = {o0, o1, o2};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        w[j] = ev[ord[j]];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) v[r][j] = vec[r][ord[j]];
+    }
+}
+
+// Covariance (ddof = 1, np.cov) of a neighbourhood from its raw fp64 moments about ANY origin: np.cov
+// subtracts the mean, so the origin drops out; the query point is used because the fp64 differences of
+// fp32 coordinates are exact and small.
+struct PcaMoments {
+    double sx, sy, sz, sxx, sxy, sxz, syy, syz, szz;
+    int n;
+    PCT_HD void reset() { sx = sy = sz = sxx = sxy = sxz = syy = syz = szz = 0.0; n = 0; }
+    PCT_HD void add(double x, double y, double z) {
+        sx += x; sy += y; sz += z;
+        sxx = fma(x, x, sxx); sxy = fma(x, y, sxy); sxz = fma(x, z, sxz);
+        syy = fma(y, y, syy); syz = fma(y, z, syz); szz = fma(z, z, szz);
+        ++n;
+    }
+    PCT_HD void covariance(double c[6]) const {  // c00 c01 c02 c11 c12 c22; n = 1 gives nan like np.cov
+        const double inv_n = 1.0 / (double)n, inv = 1.0 / (double)(n - 1);
+        c[0] = (sxx - sx * sx * inv_n) * inv; c[1] = (sxy - sx * sy * inv_n) * inv; c[2] = (sxz - sx * sz * inv_n) * inv;
+        c[3] = (syy - sy * sy * inv_n) * inv; c[4] = (syz - sy * sz * inv_n) * inv; c[5] = (szz - sz * sz * inv_n) * inv;
+    }
+};
+
 // Smallest eigenvector in fp64 accuracy for a fraction of the fp64 Jacobi's cost (its rotations are
 // serial chains of fp64 divisions and square roots): the closed form of the eigenvalues of a symmetric
 // 3x3 (trigonometric solution of the characteristic cubic) in fp32 gives the smallest eigenvalue to

@@ -399,3 +399,37 @@ def quadric_curvature(coeffs_dev):
     with torch.cuda.device(c.device):
         check(lib.pct_quadric_curvature(ptr(c), int(c.shape[0]), ptr(curv), _stream()))
     return curv
+
+
+def pca_from_neighbors(points_dev, idx_dev, include_self=False, query_ids=None, want_directions=True):
+    """PCA of the neighbourhood rows (nq, k): ``values (nq, 6)`` float64 = [l1, l2, l3, l1*l2, (l1+l2)/2,
+    l3/(l1+l2+l3+1e-10)] and ``directions (nq, 3, 2)`` float64 (ref :901-945)."""
+    if points_dev.shape[1] != 3 or not points_dev.is_contiguous():
+        raise ValueError("pca_from_neighbors needs packed (N, 3) points")
+    idx_dev = idx_dev.to(torch.int32).contiguous()
+    nq, k = idx_dev.shape
+    values = torch.empty((nq, 6), dtype=torch.float64, device=points_dev.device)
+    directions = torch.empty((nq, 3, 2), dtype=torch.float64, device=points_dev.device) if want_directions else None
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_pca_from_neighbors(ptr(points_dev), int(points_dev.shape[0]), ptr(idx_dev), nq, k, int(bool(include_self)),
+                                         ptr(query_ids), ptr(values), ptr(directions), _stream()))
+    return values, directions
+
+
+def mesh_energies(vertices_dev, triangles_dev, gaussian_dev=None, mean_dev=None):
+    """Device tensor of 4 float64: bending, stretching, total area, triangles with an index out of range
+    (utils.py:702-765)."""
+    require_cuda()
+    v = vertices_dev.to(torch.float32).contiguous()
+    t = triangles_dev.to(torch.int32).contiguous()
+    if v.ndim != 2 or v.shape[1] != 3 or t.ndim != 2 or t.shape[1] != 3:
+        raise ValueError("vertices must be (V, 3) and triangles (T, 3)")
+    g = None if gaussian_dev is None else gaussian_dev.to(torch.float32).contiguous()
+    m = None if mean_dev is None else mean_dev.to(torch.float32).contiguous()
+    for c in (g, m):
+        if c is not None and c.numel() < v.shape[0]:
+            raise IndexError(f"index {c.numel()} is out of bounds for axis 0 with size {c.numel()}")
+    out = torch.empty(4, dtype=torch.float64, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib.pct_mesh_energies(ptr(v), int(v.shape[0]), ptr(t), int(t.shape[0]), ptr(g), ptr(m), ptr(out), _stream()))
+    return out

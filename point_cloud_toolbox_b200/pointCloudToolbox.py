@@ -402,6 +402,42 @@ class PointCloud:
             converged.append(best)
         return int(np.mean(converged)) + 1                                       # ref :800
 
+    # ------------------------------------------------------------------
+    # PCA "principal curvatures"                                ref :901-945
+    # ------------------------------------------------------------------
+    def principal_curvatures_via_principal_component_analysis(self, k_neighbors):
+        """Eigenvalues of every neighbourhood's covariance as the reference reports them (ref :901-945).
+
+        The reference ranks all N points by distance for every point (O(N^2)); here the rows come from the grid
+        index (exact kNN, the point itself dropped like ``sorted_indices[1:k + 1]``) and one kernel does
+        ``np.cov`` + ``eigh`` per row in fp64.  Sets the same five float64 attributes; the sign of each
+        direction is arbitrary, as it is in ``eigh``.
+        """
+        k = int(k_neighbors)
+        if k < 1 or k > MAX_K:
+            raise ValueError(f"k_neighbors must be in [1, {MAX_K}]")
+        n = len(self.points)
+        d_points = self._upload()
+        if d_points.shape[1] != 3 or not d_points.is_contiguous():
+            d_points = d_points[:, :3].contiguous()
+        if self.kdtree is not None and self._ball_radius is None and self.kdtree.index.n == n:
+            index = self.kdtree.index
+        else:
+            index = engine.GridIndex(d_points, k_hint=k)
+        kk = min(k, n - 1)                                   # a slice past the end just ends (ref :916)
+        if kk < 1:
+            values = torch.full((n, 6), float("nan"), dtype=torch.float64)
+            directions = torch.full((n, 3, 2), float("nan"), dtype=torch.float64)
+        else:
+            idx, _ = index.knn(kk, want_dist=False)
+            values, directions = engine.pca_from_neighbors(d_points, idx)
+        v = engine.to_host(values)
+        self.pca_principal_curvature_values_1 = v[:, 0].copy()
+        self.pca_principal_curvature_values_2 = v[:, 1].copy()
+        self.principal_curvature_directions = engine.to_host(directions).copy()
+        self.pca_K_values = v[:, 3].copy()
+        self.pca_H_values = v[:, 4].copy()
+
     def __getattr__(self, name):
         # outputs of the fused call are copied to the host only when somebody asks for them
         lazy = ("quadratic_coefficients", "normals_quadratic", "fit_status", "K_H_sq_quadratic", "k1_quadratic", "k2_quadratic")

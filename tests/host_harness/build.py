@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libharness.so")
 def build():
     src = os.path.join(HERE, "harness.cpp")
     inc = os.path.join(ROOT, "point_cloud_toolbox_b200", "csrc")
-    deps = [src] + [os.path.join(inc, f) for f in ("pct_math.cuh", "pct_grid.cuh", "pct_dispatch.h")]
+    deps = [src] + [os.path.join(inc, f) for f in ("pct_math.cuh", "pct_grid.cuh", "pct_dispatch.h", "pct_energy.cuh")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I", inc, src, "-o", LIB], check=True)

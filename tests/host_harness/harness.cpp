@@ -317,3 +317,49 @@ void h_ball(void* p, double radius, int32_t* counts, float* normals, float* coef
 }
 
 }  // extern "C"
+
+// ---- energy integration and PCA rows: the same __host__ __device__ arithmetic the kernels of
+// ---- csrc/pct_energy.cu and csrc/pct_fit.cu (pca_rows_kernel) run, serially
+#include "pct_energy.cuh"
+
+extern "C" {
+
+void h_mesh_energies(const float* xyz, long long nv, const int32_t* tri, long long nt, const float* K, const float* H,
+                     double* out) {
+    double acc[4] = {0, 0, 0, 0};
+    for (long long t = 0; t < nt; ++t) {
+        long long a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        a += a < 0 ? nv : 0; b += b < 0 ? nv : 0; c += c < 0 ? nv : 0;
+        if (a < 0 || b < 0 || c < 0 || a >= nv || b >= nv || c >= nv) { acc[3] += 1.0; continue; }
+        const TriangleTerms tt = triangle_terms(xyz + 3 * a, xyz + 3 * b, xyz + 3 * c, K ? K[a] : 0.f, K ? K[b] : 0.f,
+                                                K ? K[c] : 0.f, H ? H[a] : 0.f, H ? H[b] : 0.f, H ? H[c] : 0.f);
+        acc[0] += tt.bending; acc[1] += tt.stretching; acc[2] += tt.area;
+    }
+    for (int i = 0; i < 4; ++i) out[i] = acc[i];
+}
+
+void h_pca_rows(const float* xyz, const int32_t* idx, long long nq, int k, int include_self, double* values,
+                double* directions) {
+    for (long long r = 0; r < nq; ++r) {
+        const double qx = xyz[3 * r], qy = xyz[3 * r + 1], qz = xyz[3 * r + 2];
+        PcaMoments m;
+        m.reset();
+        if (include_self) m.add(0.0, 0.0, 0.0);
+        for (int j = 0; j < k; ++j) {
+            const long long p = idx[r * k + j];
+            m.add((double)xyz[3 * p] - qx, (double)xyz[3 * p + 1] - qy, (double)xyz[3 * p + 2] - qz);
+        }
+        double c[6], w[3], v[3][3];
+        m.covariance(c);
+        eig_sym3_descending(c[0], c[1], c[2], c[3], c[4], c[5], w, v);
+        double* o = values + 6 * r;
+        o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        o[3] = w[0] * w[1];
+        o[4] = (w[0] + w[1]) / 2.0;
+        o[5] = w[2] / (w[0] + w[1] + w[2] + 1e-10);
+        double* d = directions + 6 * r;
+        for (int a = 0; a < 3; ++a) { d[2 * a] = v[a][0]; d[2 * a + 1] = v[a][1]; }
+    }
+}
+
+}  // extern "C"

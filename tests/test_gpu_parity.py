@@ -550,3 +550,103 @@ def test_large_cloud_properties(pct):
     sel = torch.from_numpy(crop[inner]).cuda()
     assert np.array_equal(crop[ref_idx], gi[sel].cpu().numpy())
     assert np.array_equal(ref_dist, gd[sel].cpu().numpy())
+
+
+# ---------------------------------------------------------------------------
+# either side of the path: energies, PCA estimators, file round trip
+# ---------------------------------------------------------------------------
+def test_mesh_energies_against_the_reference_numbers(pct):
+    from oracle import around_path as ap
+    from point_cloud_toolbox_b200 import utils as U
+
+    g = load_golden("io_energy_pca")
+    v, t, K, H = g["energy_vertices"], g["energy_triangles"], g["energy_K"], g["energy_H"]
+    got = U.compute_energies(v, t, K, H)
+    assert np.allclose(got, g["energy_result"], rtol=1e-12, atol=1e-13)          # fp64 sums in another order
+    assert np.allclose(U.compute_energies(v, t), g["energy_result_no_curvature"], rtol=1e-12, atol=0)
+
+    class Mesh:  # pyvista-like
+        points = v
+        faces = np.concatenate([np.full((len(t), 1), 3, np.int64), t.astype(np.int64)], 1).ravel()
+        point_data = {"gaussian_curvature": K, "mean_curvature": H}
+
+    assert np.allclose(U.load_mesh_compute_energies(Mesh), g["energy_result"], rtol=1e-12, atol=1e-13)
+    assert U.compute_energies(v, np.zeros((0, 3), np.int32), K, H) == (0, 0, 0)
+    assert U.compute_energies(v * 0, t, K, H) == (0, 0, 0)
+    with pytest.raises(IndexError):
+        U.compute_energies(v, np.array([[0, 1, len(v)]], np.int32), K, H)
+    # a mesh of 2 M triangles (more than one wave of the persistent grid) with the path's own K and H
+    n = 1001
+    from oracle.make_golden_io import grid_mesh
+
+    verts, tris = grid_mesh(n, 5)
+    pc = pct.PointCloud(points=verts, normals=_empty_normals(len(verts)), k_neighbors=20)
+    pc.plant_kdtree(20)
+    Kq, Hq = pc.compute_pointwise_explicit_quadratic_curvature()
+    got = U.compute_energies(verts, tris, Kq, Hq)
+    want = ap.mesh_energies(verts, tris, Kq, Hq)
+    assert np.allclose(got, want, rtol=1e-11, atol=0)
+    # determinism: the two-stage reduction has a fixed order
+    assert got == U.compute_energies(verts, tris, Kq, Hq)
+
+
+def test_pca_principal_curvatures_against_the_reference(pct):
+    from oracle import around_path as ap
+
+    g = load_golden("io_energy_pca")
+    pts, k = g["pca_points"], int(g["pca_k"])
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+    pc.principal_curvatures_via_principal_component_analysis(k)
+    l1, l2 = pc.pca_principal_curvature_values_1, pc.pca_principal_curvature_values_2
+    assert l1.dtype == np.float64 and pc.principal_curvature_directions.shape == (len(pts), 3, 2)
+    assert np.all(np.abs(l1 - g["pca_l1"]) <= 1e-12 * g["pca_l1"])
+    assert np.all(np.abs(l2 - g["pca_l2"]) <= 1e-12 * g["pca_l1"])
+    assert np.allclose(pc.pca_K_values, g["pca_K"], rtol=1e-9, atol=0)
+    assert np.allclose(pc.pca_H_values, g["pca_H"], rtol=1e-12, atol=0)
+    vals, _ = ap.pca_from_rows(pts, oracle.knn_canonical(pts, k)[0])
+    gap = np.minimum(vals[:, 0] - vals[:, 1], vals[:, 1] - vals[:, 2]) / vals[:, 0]
+    ok = gap > 1e-3
+    dots = np.abs(np.einsum("nij,nij->nj", pc.principal_curvature_directions, g["pca_directions"]))
+    assert np.all(dots[ok] > 1 - 1e-9)
+    # with a planted tree of the same cloud the index is reused; other k
+    pc.plant_kdtree(20)
+    pc.principal_curvatures_via_principal_component_analysis(25)
+    vals, _ = ap.pca_from_rows(pts, oracle.knn_canonical(pts, 25)[0])
+    assert np.all(np.abs(pc.pca_principal_curvature_values_1 - vals[:, 0]) <= 1e-12 * vals[:, 0])
+    assert np.allclose(pc.pca_H_values, vals[:, 4], rtol=1e-12, atol=0)
+
+
+def test_surface_variation_estimate(pct):
+    from oracle import around_path as ap
+    from point_cloud_toolbox_b200 import utils as U
+
+    pts = _cloud("bunny")[::4].copy()
+    got = U.estimate_curvature(pts, k_fraction=0.002)           # k = max(5, 17) = 17, the point itself included
+    k = min(max(5, int(0.002 * len(pts))), 100)
+    want, _ = ap.pca_from_rows(pts, oracle.knn_canonical(pts, k - 1)[0], include_self=True)
+    assert got.shape == (len(pts),) and np.allclose(got, want[:, 5], rtol=1e-7, atol=1e-12)
+    assert 0 <= got.min() and got.max() <= 1 / 3 + 1e-12
+
+
+def test_file_in_file_out_round_trip(pct, tmp_path):
+    """Text scan in (library parser), curvature out (library writers), read back with the PLY reader."""
+    from oracle import around_path as ap
+    from point_cloud_toolbox_b200 import utils as U
+
+    pts = _cloud("bunny")
+    src = tmp_path / "scan.txt"
+    np.savetxt(src, pts.astype(np.float64), fmt="%.9g")
+    pc = pct.PointCloud(str(src), k_neighbors=20)
+    shifted = pts.copy()
+    shifted[:, 0] -= shifted[:, 0].max()
+    shifted[:, 1] -= shifted[:, 1].max()
+    assert np.array_equal(pc.points, shifted) and pc.normals.shape == (len(pts), 0)
+    pc.plant_kdtree(20)
+    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    out = tmp_path / "output_with_curvatures.ply"
+    U.save_curvatures_to_ply(pc.points, K, H, str(out))
+    assert out.read_bytes() == ap.curvature_ply_bytes(pc.points, K, H)
+    back = U.parse_ply(str(out))
+    assert np.array_equal(back, pc.points)
+    fg, fm = U.save_curvature_arrays(K, H, "bunny", "scan", 1, str(tmp_path / "curvature_data"))
+    assert np.array_equal(np.load(fg), K) and np.array_equal(np.load(fm), H)

@@ -347,3 +347,105 @@ def test_text_loader_on_the_reference_scan_fixture():
     pts[:, 0] -= pts[:, 0].max()
     pts[:, 1] -= pts[:, 1].max()
     assert np.array_equal(pts, g["points"]) and np.array_equal(t[:, 3:6], g["normals"])
+
+
+# ---------------------------------------------------------------------------
+# PLY reader and the two writers (host code of the library): byte- / bit-identical to the reference
+# ---------------------------------------------------------------------------
+def test_ply_writers_and_reader_reproduce_the_reference_files(tmp_path):
+    from point_cloud_toolbox_b200 import utils as U
+
+    g = load_golden("io_energy_pca")
+    for tag in ("f64", "f32"):
+        path = tmp_path / f"p_{tag}.ply"
+        U.save_points_to_ply(g[f"points_ply_in_{tag}"], str(path))
+        assert path.read_bytes() == g[f"points_ply_bytes_{tag}"].tobytes()
+    path = tmp_path / "c.ply"
+    U.save_curvatures_to_ply(g["curv_ply_points"], g["curv_ply_K"], g["curv_ply_H"], str(path))
+    assert path.read_bytes() == g["curv_ply_bytes"].tobytes()
+    path = tmp_path / "in.ply"
+    path.write_bytes(g["parse_ply_text"].tobytes())
+    got = U.parse_ply(str(path))
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), g["parse_ply_points"].view(np.uint32))
+    # the reference's error behaviour: None for a missing file, a short line, no header
+    assert U.parse_ply(str(tmp_path / "missing.ply")) is None
+    path.write_text("ply\nend_header\n1 2 3\n4 5\n")
+    assert U.parse_ply(str(path)) is None
+    path.write_text("1 2 3\n")
+    assert U.parse_ply(str(path)) is None
+    path.write_text("ply\nend_header\n")
+    assert U.parse_ply(str(path)).shape == (0,)
+
+
+def test_float_formatting_against_python_on_random_bit_patterns(tmp_path):
+    from oracle import around_path as ap
+    from point_cloud_toolbox_b200 import utils as U
+
+    rng = np.random.default_rng(8)
+    n = 70_001                                            # more than one block of rows per thread
+    bits = rng.integers(0, 2 ** 32, (n, 5), dtype=np.uint64).astype(np.uint32)
+    vals = bits.view(np.float32)
+    vals[:, 3] = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 17, n)).astype(np.float32)   # the fixed-notation band
+    path = tmp_path / "c.ply"
+    U.save_curvatures_to_ply(vals[:, :3], vals[:, 3], vals[:, 4], str(path))
+    assert path.read_bytes() == ap.curvature_ply_bytes(vals[:, :3], vals[:, 3], vals[:, 4])
+    pts = (rng.standard_normal((n, 3)) * 10.0 ** rng.integers(-9, 12, (n, 3)))
+    pts[::97] = np.round(pts[::97] * 2e6) / 2e6           # exact ties of the sixth decimal
+    path = tmp_path / "p.ply"
+    U.save_points_to_ply(pts, str(path))
+    assert path.read_bytes() == ap.points_ply_bytes(pts)
+    back = U.parse_ply(str(path))                          # and the reader on what the writer wrote
+    assert np.array_equal(back, ap.parse_ply(path.read_text()))
+
+
+# ---------------------------------------------------------------------------
+# energy integration and PCA rows: the kernels' __host__ __device__ arithmetic against the oracle
+# ---------------------------------------------------------------------------
+def test_energy_terms_against_reference_numbers(harness):
+    from oracle import around_path as ap
+
+    harness.h_mesh_energies.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    g = load_golden("io_energy_pca")
+    v, t = np.ascontiguousarray(g["energy_vertices"]), np.ascontiguousarray(g["energy_triangles"])
+    K, H = np.ascontiguousarray(g["energy_K"]), np.ascontiguousarray(g["energy_H"])
+    out = np.zeros(4)
+    harness.h_mesh_energies(P(v), len(v), P(t), len(t), P(K), P(H), P(out))
+    assert out[3] == 0 and np.allclose(out[:3], g["energy_result"], rtol=1e-13, atol=1e-14)   # summation order only
+    harness.h_mesh_energies(P(v), len(v), P(t), len(t), None, None, P(out))
+    assert np.allclose(out[:3], g["energy_result_no_curvature"], rtol=1e-13, atol=0)
+    # per-triangle terms are exact: one triangle at a time equals the oracle bit for bit
+    for i in range(0, len(t), 37):
+        ti = np.ascontiguousarray(t[i:i + 1])
+        harness.h_mesh_energies(P(v), len(v), P(ti), 1, P(K), P(H), P(out))
+        want = ap.mesh_energies(v, ti, K, H)
+        assert tuple(out[:3]) == tuple(float(x) for x in want)
+    bad = np.array([[0, 1, len(v)], [0, 1, -1], [0, 1, -len(v) - 1]], np.int32)
+    harness.h_mesh_energies(P(v), len(v), P(bad), 3, P(K), P(H), P(out))
+    assert out[3] == 2
+
+
+def test_pca_rows_against_reference_numbers(harness):
+    harness.h_pca_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_void_p]
+    from oracle import around_path as ap
+
+    g = load_golden("io_energy_pca")
+    pts, k = np.ascontiguousarray(g["pca_points"]), int(g["pca_k"])
+    idx = np.ascontiguousarray(oracle.knn_canonical(pts, k)[0])
+    vals, dirs = np.zeros((len(pts), 6)), np.zeros((len(pts), 3, 2))
+    harness.h_pca_rows(P(pts), P(idx), len(pts), k, 0, P(vals), P(dirs))
+    scale = g["pca_l1"]                                   # errors of an eigenvalue are relative to the largest
+    assert np.all(np.abs(vals[:, 0] - g["pca_l1"]) <= 1e-12 * scale)
+    assert np.all(np.abs(vals[:, 1] - g["pca_l2"]) <= 1e-12 * scale)
+    assert np.allclose(vals[:, 3], g["pca_K"], rtol=1e-9, atol=0) and np.allclose(vals[:, 4], g["pca_H"], rtol=1e-12, atol=0)
+    # directions up to sign, where the eigenvalues are separated
+    ref = g["pca_directions"]
+    gap = np.minimum(vals[:, 0] - vals[:, 1], vals[:, 1] - vals[:, 2]) / vals[:, 0]
+    ok = gap > 1e-3
+    dots = np.abs(np.einsum("nij,nij->nj", dirs, ref))
+    assert ok.mean() > 0.9 and np.all(dots[ok] > 1 - 1e-9)
+    want, _ = ap.pca_from_rows(pts, idx, include_self=True)
+    harness.h_pca_rows(P(pts), P(idx), len(pts), k, 1, P(vals), P(dirs))
+    assert np.all(np.abs(vals[:, :3] - want[:, :3]) <= 1e-12 * want[:, :1])
+    assert np.allclose(vals[:, 5], want[:, 5], rtol=1e-7, atol=1e-12)

@@ -157,3 +157,30 @@ def test_neighbor_study_reproduces_reference_returns(bunny):
         for b, tol in enumerate(g["tols"]):
             if tol in (1e-7, 500.0):  # the two ends: nothing converges / most converge early (keeps the CPU suite short)
                 assert oracle.neighbor_study(bunny, g["samples"][a], tol=float(tol), tree=tree) == int(g["results"][a, b])
+
+
+# ---------------------------------------------------------------------------
+# either side of the path: the restatements of oracle/around_path.py reproduce what the
+# unmodified reference functions produced (tests/golden/io_energy_pca.npz, oracle/make_golden_io.py)
+# ---------------------------------------------------------------------------
+def test_around_path_oracle_is_pinned_to_the_reference():
+    from oracle import around_path as ap
+
+    g = load_golden("io_energy_pca")
+    for tag in ("f64", "f32"):
+        assert ap.points_ply_bytes(g[f"points_ply_in_{tag}"]) == g[f"points_ply_bytes_{tag}"].tobytes()
+    assert ap.curvature_ply_bytes(g["curv_ply_points"], g["curv_ply_K"], g["curv_ply_H"]) == g["curv_ply_bytes"].tobytes()
+    p = ap.parse_ply(g["parse_ply_text"].tobytes().decode())
+    assert p.dtype == np.float32 and np.array_equal(p.view(np.uint32), g["parse_ply_points"].view(np.uint32))
+    e = ap.mesh_energies(g["energy_vertices"], g["energy_triangles"], g["energy_K"], g["energy_H"])
+    assert np.allclose(e, g["energy_result"], rtol=1e-14, atol=1e-15)
+    e0 = ap.mesh_energies(g["energy_vertices"], g["energy_triangles"])
+    assert np.allclose(e0, g["energy_result_no_curvature"], rtol=1e-14, atol=0)
+    l1, l2, K, H, d = ap.pca_principal_curvatures(g["pca_points"], int(g["pca_k"]))
+    assert np.array_equal(l1, g["pca_l1"]) and np.array_equal(l2, g["pca_l2"])
+    assert np.array_equal(K, g["pca_K"]) and np.array_equal(H, g["pca_H"]) and np.array_equal(d, g["pca_directions"])
+    # the vectorised form on canonical kNN rows gives the same numbers (what the GPU tests compare against)
+    idx = oracle.knn_canonical(g["pca_points"], int(g["pca_k"]))[0]
+    vals, dirs = ap.pca_from_rows(g["pca_points"], idx)
+    assert np.allclose(vals[:, 0], l1, rtol=1e-9, atol=1e-18) and np.allclose(vals[:, 1], l2, rtol=1e-9, atol=1e-18)
+    assert np.allclose(vals[:, 3], K, rtol=1e-9, atol=1e-30) and np.allclose(vals[:, 4], H, rtol=1e-9, atol=1e-18)
