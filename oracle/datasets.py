@@ -137,3 +137,16 @@ def scanned_sheet(n=332_757, seed=2, noise=1e-3, half_width=2 * np.pi):
 def interior_mask_xy(points, half_width, margin):
     """Points farther than ``margin`` from the open boundary of an (x, y) patch."""
     return (np.abs(points[:, 0]) < half_width - margin) & (np.abs(points[:, 1]) < half_width - margin)
+
+
+def grid_mesh(n, seed):
+    """Triangulated n x n jittered grid on z = sin x sin y: (vertices (n*n, 3) float32, triangles int32)."""
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.linspace(-2, 2, n), np.linspace(-2, 2, n), indexing="ij")
+    u = u + rng.uniform(-0.02, 0.02, u.shape)
+    v = v + rng.uniform(-0.02, 0.02, v.shape)
+    verts = np.stack([u, v, np.sin(u) * np.sin(v)], -1).reshape(-1, 3).astype(np.float32)
+    i, j = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
+    a = (i * n + j).ravel()
+    tris = np.concatenate([np.stack([a, a + 1, a + n], 1), np.stack([a + 1, a + n + 1, a + n], 1)]).astype(np.int32)
+    return verts, tris

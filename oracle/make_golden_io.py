@@ -28,6 +28,7 @@ import tempfile
 
 import numpy as np
 
+from .datasets import grid_mesh
 from .make_golden import GOLDEN_DIR, REFERENCE_ROOT, import_reference
 
 
@@ -70,18 +71,6 @@ class _FakeO3dMesh:  # what convert_pv_to_o3d returns, reduced to what load_mesh
 class _FakePvMesh:
     def __init__(self, vertices, triangles, point_data):
         self.vertices, self.triangles, self.point_data = vertices, triangles, point_data
-
-
-def grid_mesh(n, seed):
-    rng = np.random.default_rng(seed)
-    u, v = np.meshgrid(np.linspace(-2, 2, n), np.linspace(-2, 2, n), indexing="ij")
-    u = u + rng.uniform(-0.02, 0.02, u.shape)
-    v = v + rng.uniform(-0.02, 0.02, v.shape)
-    verts = np.stack([u, v, np.sin(u) * np.sin(v)], -1).reshape(-1, 3).astype(np.float32)
-    i, j = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
-    a = (i * n + j).ravel()
-    tris = np.concatenate([np.stack([a, a + 1, a + n], 1), np.stack([a + 1, a + n + 1, a + n], 1)]).astype(np.int32)
-    return verts, tris
 
 
 def main():

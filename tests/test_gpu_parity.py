@@ -577,9 +577,7 @@ def test_mesh_energies_against_the_reference_numbers(pct):
         U.compute_energies(v, np.array([[0, 1, len(v)]], np.int32), K, H)
     # a mesh of 2 M triangles (more than one wave of the persistent grid) with the path's own K and H
     n = 1001
-    from oracle.make_golden_io import grid_mesh
-
-    verts, tris = grid_mesh(n, 5)
+    verts, tris = datasets.grid_mesh(n, 5)
     pc = pct.PointCloud(points=verts, normals=_empty_normals(len(verts)), k_neighbors=20)
     pc.plant_kdtree(20)
     Kq, Hq = pc.compute_pointwise_explicit_quadratic_curvature()
