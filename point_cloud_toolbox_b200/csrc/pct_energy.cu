@@ -4,6 +4,8 @@
 // streaming pass: thread per triangle, fp64 partial sums per block, a second one-block kernel adds the
 // partials in a fixed order, so the result does not depend on scheduling.
 // Algorithmic bytes per triangle: 12 (indices); the nine coordinate and six curvature gathers hit L2.
+#include <cstdlib>
+
 #include "pct_energy.cuh"
 #include "pct_internal.h"
 
@@ -36,20 +38,64 @@ __device__ __forceinline__ void block_sum4(double v[4], double* out) {
     }
 }
 
-__global__ void __launch_bounds__(kEnergyBlock)
+// one triangle: gathers first (all 15 loads of a triangle are independent), then the arithmetic
+struct Corner {
+    float x, y, z, k, h;
+};
+
+__device__ __forceinline__ bool load_corner(const float* __restrict__ xyz, const float* __restrict__ K,
+                                            const float* __restrict__ H, long long n_vertices, long long i, Corner& c) {
+    i += i < 0 ? n_vertices : 0;  // numpy indexing: negative indices count from the end
+    const bool ok = i >= 0 && i < n_vertices;
+    const long long j = ok ? i : 0;
+    c.x = __ldg(xyz + 3 * j); c.y = __ldg(xyz + 3 * j + 1); c.z = __ldg(xyz + 3 * j + 2);
+    c.k = K ? __ldg(K + j) : 0.f;
+    c.h = H ? __ldg(H + j) : 0.f;
+    return ok;
+}
+
+// kTrisPerThread triangles per thread and trip: their index loads, then all their gathers, are independent
+template <int kTrisPerThread, int kMinBlocks>
+__global__ void __launch_bounds__(kEnergyBlock, kMinBlocks)
 energy_partials_kernel(const float* __restrict__ xyz, long long n_vertices, const int32_t* __restrict__ tri,
                        long long n_triangles, const float* __restrict__ K, const float* __restrict__ H,
                        double* __restrict__ partials) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};  // bending, stretching, area, triangles with an index out of range
-    for (long long t = (long long)blockIdx.x * kEnergyBlock + threadIdx.x; t < n_triangles;
-         t += (long long)gridDim.x * kEnergyBlock) {
-        long long a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
-        // numpy indexing: negative indices count from the end
-        a += a < 0 ? n_vertices : 0; b += b < 0 ? n_vertices : 0; c += c < 0 ? n_vertices : 0;
-        if (a < 0 || b < 0 || c < 0 || a >= n_vertices || b >= n_vertices || c >= n_vertices) { acc[3] += 1.0; continue; }
-        const TriangleTerms tt = triangle_terms(xyz + 3 * a, xyz + 3 * b, xyz + 3 * c, K ? K[a] : 0.f, K ? K[b] : 0.f,
-                                                K ? K[c] : 0.f, H ? H[a] : 0.f, H ? H[b] : 0.f, H ? H[c] : 0.f);
-        acc[0] += tt.bending; acc[1] += tt.stretching; acc[2] += tt.area;
+    const long long groups = (n_triangles + kTrisPerThread - 1) / kTrisPerThread;
+    const bool aligned = (reinterpret_cast<uintptr_t>(tri) & 15) == 0;
+    for (long long g = (long long)blockIdx.x * kEnergyBlock + threadIdx.x; g < groups;
+         g += (long long)gridDim.x * kEnergyBlock) {
+        const long long t0 = g * kTrisPerThread;
+        int32_t id[3 * kTrisPerThread];
+        if (kTrisPerThread % 4 == 0 && aligned && t0 + kTrisPerThread <= n_triangles) {
+            const int4* p = reinterpret_cast<const int4*>(tri + 3 * t0);
+#pragma unroll
+            for (int q = 0; q < 3 * kTrisPerThread / 4; ++q) {
+                const int4 v = __ldg(p + q);
+                id[4 * q] = v.x; id[4 * q + 1] = v.y; id[4 * q + 2] = v.z; id[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3 * kTrisPerThread; ++q)
+                id[q] = 3 * t0 + q < 3 * n_triangles ? __ldg(tri + 3 * t0 + q) : 0;
+        }
+        Corner c[3 * kTrisPerThread];
+        bool ok[kTrisPerThread];
+#pragma unroll
+        for (int u = 0; u < kTrisPerThread; ++u) {
+            const bool a = load_corner(xyz, K, H, n_vertices, id[3 * u], c[3 * u]);
+            const bool b = load_corner(xyz, K, H, n_vertices, id[3 * u + 1], c[3 * u + 1]);
+            const bool d = load_corner(xyz, K, H, n_vertices, id[3 * u + 2], c[3 * u + 2]);
+            ok[u] = a && b && d;
+        }
+#pragma unroll
+        for (int u = 0; u < kTrisPerThread; ++u) {
+            if (t0 + u >= n_triangles) break;
+            if (!ok[u]) { acc[3] += 1.0; continue; }
+            const Corner &a = c[3 * u], &b = c[3 * u + 1], &d = c[3 * u + 2];
+            const TriangleTerms tt = triangle_terms(&a.x, &b.x, &d.x, a.k, b.k, d.k, a.h, b.h, d.h);
+            acc[0] += tt.bending; acc[1] += tt.stretching; acc[2] += tt.area;
+        }
     }
     block_sum4(acc, partials + 4 * (long long)blockIdx.x);
 }
@@ -74,14 +120,21 @@ int launch_mesh_energies(const float* xyz, long long n_vertices, const int32_t* 
     int dev = 0, sms = 148;
     PCT_CUDA(cudaGetDevice(&dev));
     PCT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // persistent grid: 8 blocks of 256 threads per SM (2048 resident threads), fewer for small meshes
-    const long long want = (n_triangles + kEnergyBlock - 1) / kEnergyBlock;
-    const int blocks = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+    // persistent grid: up to 8 blocks of 256 threads per SM, four triangles per thread and trip
+    static const int variant = [] { const char* e = getenv("PCT_ENERGY_VARIANT"); return e ? atoi(e) : 2; }();
+    const int tpt = variant == 1 ? 1 : variant == 2 ? 2 : 4;
+    const int resident = variant == 1 ? 8 : variant == 2 ? 4 : variant == 3 ? 3 : 2;
+    const long long per_block = (long long)kEnergyBlock * tpt;
+    const long long want = (n_triangles + per_block - 1) / per_block;
+    const int blocks = (int)(want < (long long)sms * resident ? want : (long long)sms * resident);
     ScratchSession scratch(s, (size_t)blocks * 4 * sizeof(double) + 256);
     double* partials = static_cast<double*>(scratch.take((size_t)blocks * 4 * sizeof(double)));
     const bool own = partials == nullptr;
     if (own) PCT_CUDA(cudaMallocAsync(&partials, (size_t)blocks * 4 * sizeof(double), s));
-    energy_partials_kernel<<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
+    if (variant == 1) energy_partials_kernel<1, 8><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
+    else if (variant == 2) energy_partials_kernel<2, 4><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
+    else if (variant == 3) energy_partials_kernel<4, 3><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
+    else energy_partials_kernel<4, 2><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
     energy_final_kernel<<<1, kEnergyBlock, 0, s>>>(partials, blocks, out);
     const cudaError_t e = cudaGetLastError();
     if (own) cudaFreeAsync(partials, s);

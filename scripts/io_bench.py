@@ -33,8 +33,10 @@ def cuda_ms(fn, reps=5):
     fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")    # 4 x L2: every timed call starts cold
     ts = []
     for _ in range(reps):
+        flush.fill_(1)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     return float(np.median(ts))
