@@ -4,8 +4,6 @@
 // streaming pass: thread per triangle, fp64 partial sums per block, a second one-block kernel adds the
 // partials in a fixed order, so the result does not depend on scheduling.
 // Algorithmic bytes per triangle: 12 (indices); the nine coordinate and six curvature gathers hit L2.
-#include <cstdlib>
-
 #include "pct_energy.cuh"
 #include "pct_internal.h"
 
@@ -13,6 +11,8 @@ namespace pct {
 namespace {
 
 constexpr int kEnergyBlock = 256;
+constexpr int kTrisPerThread = 2;   // triangles per thread and trip
+constexpr int kEnergyResident = 4;  // blocks per SM the kernel is compiled for (64 registers)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -43,25 +43,27 @@ struct Corner {
     float x, y, z, k, h;
 };
 
+// 32-bit index arithmetic (n_vertices < 2^31 because the indices are int32): one wide multiply-add per address
 __device__ __forceinline__ bool load_corner(const float* __restrict__ xyz, const float* __restrict__ K,
-                                            const float* __restrict__ H, long long n_vertices, long long i, Corner& c) {
-    i += i < 0 ? n_vertices : 0;  // numpy indexing: negative indices count from the end
-    const bool ok = i >= 0 && i < n_vertices;
-    const long long j = ok ? i : 0;
-    c.x = __ldg(xyz + 3 * j); c.y = __ldg(xyz + 3 * j + 1); c.z = __ldg(xyz + 3 * j + 2);
+                                            const float* __restrict__ H, uint32_t n_vertices, int32_t i, Corner& c) {
+    const uint32_t u = (uint32_t)i + (i < 0 ? n_vertices : 0u);  // numpy indexing: negative indices count from the end
+    const bool ok = u < n_vertices;                              // (a negative index below -n wraps to a large value)
+    const uint32_t j = ok ? u : 0u;
+    const float* p = xyz + (size_t)j * 3;
+    c.x = __ldg(p); c.y = __ldg(p + 1); c.z = __ldg(p + 2);
     c.k = K ? __ldg(K + j) : 0.f;
     c.h = H ? __ldg(H + j) : 0.f;
     return ok;
 }
 
 // kTrisPerThread triangles per thread and trip: their index loads, then all their gathers, are independent
-template <int kTrisPerThread, int kMinBlocks>
-__global__ void __launch_bounds__(kEnergyBlock, kMinBlocks)
+__global__ void __launch_bounds__(kEnergyBlock, kEnergyResident)
 energy_partials_kernel(const float* __restrict__ xyz, long long n_vertices, const int32_t* __restrict__ tri,
                        long long n_triangles, const float* __restrict__ K, const float* __restrict__ H,
                        double* __restrict__ partials) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};  // bending, stretching, area, triangles with an index out of range
     const long long groups = (n_triangles + kTrisPerThread - 1) / kTrisPerThread;
+    const uint32_t nv = (uint32_t)n_vertices;
     const bool aligned = (reinterpret_cast<uintptr_t>(tri) & 15) == 0;
     for (long long g = (long long)blockIdx.x * kEnergyBlock + threadIdx.x; g < groups;
          g += (long long)gridDim.x * kEnergyBlock) {
@@ -83,9 +85,9 @@ energy_partials_kernel(const float* __restrict__ xyz, long long n_vertices, cons
         bool ok[kTrisPerThread];
 #pragma unroll
         for (int u = 0; u < kTrisPerThread; ++u) {
-            const bool a = load_corner(xyz, K, H, n_vertices, id[3 * u], c[3 * u]);
-            const bool b = load_corner(xyz, K, H, n_vertices, id[3 * u + 1], c[3 * u + 1]);
-            const bool d = load_corner(xyz, K, H, n_vertices, id[3 * u + 2], c[3 * u + 2]);
+            const bool a = load_corner(xyz, K, H, nv, id[3 * u], c[3 * u]);
+            const bool b = load_corner(xyz, K, H, nv, id[3 * u + 1], c[3 * u + 1]);
+            const bool d = load_corner(xyz, K, H, nv, id[3 * u + 2], c[3 * u + 2]);
             ok[u] = a && b && d;
         }
 #pragma unroll
@@ -121,20 +123,17 @@ int launch_mesh_energies(const float* xyz, long long n_vertices, const int32_t* 
     PCT_CUDA(cudaGetDevice(&dev));
     PCT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // persistent grid: up to 8 blocks of 256 threads per SM, four triangles per thread and trip
-    static const int variant = [] { const char* e = getenv("PCT_ENERGY_VARIANT"); return e ? atoi(e) : 2; }();
-    const int tpt = variant == 1 ? 1 : variant == 2 ? 2 : 4;
-    const int resident = variant == 1 ? 8 : variant == 2 ? 4 : variant == 3 ? 3 : 2;
-    const long long per_block = (long long)kEnergyBlock * tpt;
+    // Two triangles per thread, four blocks per SM.  Measured on a B200 (scripts/energy_probe.py, cold L2, 32 M
+    // triangles of a grid mesh / 18 M triangles with shuffled vertex numbering): 1 x 8 blocks 0.35 / 1.11 ms,
+    // 2 x 4 blocks 0.30 / 0.79 ms, 4 x 3 blocks 0.38 / 0.98 ms, 4 x 2 blocks 0.37 / 0.74 ms.
+    const long long per_block = (long long)kEnergyBlock * kTrisPerThread;
     const long long want = (n_triangles + per_block - 1) / per_block;
-    const int blocks = (int)(want < (long long)sms * resident ? want : (long long)sms * resident);
+    const int blocks = (int)(want < (long long)sms * kEnergyResident ? want : (long long)sms * kEnergyResident);
     ScratchSession scratch(s, (size_t)blocks * 4 * sizeof(double) + 256);
     double* partials = static_cast<double*>(scratch.take((size_t)blocks * 4 * sizeof(double)));
     const bool own = partials == nullptr;
     if (own) PCT_CUDA(cudaMallocAsync(&partials, (size_t)blocks * 4 * sizeof(double), s));
-    if (variant == 1) energy_partials_kernel<1, 8><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
-    else if (variant == 2) energy_partials_kernel<2, 4><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
-    else if (variant == 3) energy_partials_kernel<4, 3><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
-    else energy_partials_kernel<4, 2><<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
+    energy_partials_kernel<<<blocks, kEnergyBlock, 0, s>>>(xyz, n_vertices, tri, n_triangles, K, H, partials);
     energy_final_kernel<<<1, kEnergyBlock, 0, s>>>(partials, blocks, out);
     const cudaError_t e = cudaGetLastError();
     if (own) cudaFreeAsync(partials, s);
@@ -146,7 +145,8 @@ int launch_mesh_energies(const float* xyz, long long n_vertices, const int32_t* 
 
 extern "C" int pct_mesh_energies(const float* vertices, int64_t n_vertices, const int32_t* triangles, int64_t n_triangles,
                                  const float* gaussian, const float* mean, double* out, void* stream) {
-    PCT_REQUIRE(out && n_vertices >= 0 && n_triangles >= 0 && ((vertices && triangles) || n_triangles == 0),
+    PCT_REQUIRE(out && n_vertices >= 0 && n_vertices < (1ll << 31) && n_triangles >= 0 &&
+                    ((vertices && triangles) || n_triangles == 0),
                 "pct_mesh_energies: bad argument");
     return pct::launch_mesh_energies(vertices, n_vertices, triangles, n_triangles, gaussian, mean, out, (cudaStream_t)stream);
 }
