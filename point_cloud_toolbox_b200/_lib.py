@@ -106,7 +106,8 @@ def _load():
 
     try:
         _build.build()
-    except Exception:
+    except _build.NvccMissing:
+        # a box without the toolkit runs the library that travelled with the tree; a failed COMPILE always raises
         if not os.path.exists(LIB_PATH):
             raise
     lib = ctypes.CDLL(LIB_PATH)

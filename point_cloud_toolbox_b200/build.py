@@ -28,10 +28,14 @@ NVCC_FLAGS = [
 ] + os.environ.get("PCT_NVCC_EXTRA", "").split()  # experiments only (e.g. -DPCT_STAGED_CTAS=5)
 
 
+class NvccMissing(RuntimeError):
+    pass
+
+
 def _nvcc():
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
-        raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+        raise NvccMissing("nvcc not found: the CUDA library cannot be built")
     return exe
 
 

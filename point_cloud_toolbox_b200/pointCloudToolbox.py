@@ -150,8 +150,9 @@ class PointCloud:
             raise AttributeError("'PointCloud' object has no attribute 'downsample_point_cloud_by_grid'")
         lo = pts.min(0).values.cpu().numpy()
         hi = pts.max(0).values.cpu().numpy()
-        self.points = pts.cpu().numpy()
-        self.normals = nrm.cpu().numpy()
+        # host copies live in page-locked memory, so the upload of plant_kdtree runs at PCIe speed
+        self.points = engine.to_host(pts)
+        self.normals = engine.to_host(nrm) if nrm.numel() else np.zeros(tuple(nrm.shape), np.float32)
         self.x_domain = [lo[0], hi[0]]                        # ref :64-66
         self.y_domain = [lo[1], hi[1]]
         self.z_domain = [lo[2], hi[2]]

@@ -94,6 +94,26 @@ def main():
         t, ref = timed(lambda: np.loadtxt(small), 1)
         res["np_loadtxt_rows_per_s"] = len(ref) / t
         assert np.array_equal(ref.astype(np.float32), tab.numpy()[:len(ref)])
+    # the whole caller-side sequence, file in -> file out (validate_shape's order, utils.py:475-551)
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "scan.txt")
+        U.save_points_to_ply(pts, src)           # rows in the scan text format, after a PLY header
+        body = open(src, "rb").read()
+        open(src, "wb").write(body[body.index(b"end_header\n") + 11:])
+        stages = {}
+        t0 = time.perf_counter()
+        pc2 = pct.PointCloud(src, k_neighbors=20)
+        stages["load_s"] = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        pc2.plant_kdtree(20)
+        K2, H2 = pc2.compute_pointwise_explicit_quadratic_curvature()
+        stages["curvature_s"] = time.perf_counter() - t1
+        t2 = time.perf_counter()
+        U.save_curvatures_to_ply(pc2.points, K2, H2, os.path.join(d, "output_with_curvatures.ply"))
+        stages["write_s"] = time.perf_counter() - t2
+        stages["total_s"] = time.perf_counter() - t0
+        stages["rows_per_s"] = rows / stages["total_s"]
+        res["file_to_file"] = stages
     # energy kernel
     i, j = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
     a = (i * n + j).ravel()
