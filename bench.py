@@ -485,6 +485,22 @@ def ours(args):
         "gpu_launches": OUR_KERNELS_PER_STEP * args.steps * 2,
         "clocks": clocks,
     }
+    # secondary roofline: algorithmic flops per point -- search 8c + selection 2c with
+    # c = 2.9 k candidates, covariance 15 k, rotation 18 k, normal equations 59 k, fixed 600 -- against the FMA
+    # rate of the CUDA cores measured here, after the timed regions
+    try:
+        from point_cloud_toolbox_b200 import _lib
+        import ctypes
+
+        f32, f64 = ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.lib.pct_measure_fma_peaks(ctypes.byref(f32), ctypes.byref(f64), None))
+        flops_pt = 121.0 * k + 600.0
+        ach = pts_per_launch * flops_pt / (query_ms * 1e-3) / 1e12
+        line["roofline_fp32"] = {"algorithmic_flops_per_point": flops_pt, "achieved": ach, "peak": f32.value, "unit": "TFLOP/s",
+                                 "frac": ach / f32.value if f32.value > 0 else None, "fp64_peak": f64.value,
+                                 "peak_source": "pct_measure_fma_peaks (FMA chains on this GPU, this run)"}
+    except Exception as e:  # diagnostics must not cost the bench line
+        line["roofline_fp32"] = {"error": str(e)}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

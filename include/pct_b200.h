@@ -249,6 +249,10 @@ int pct_write_points_ply(const char* path, const void* points, int is_f64, int64
 int pct_write_curvature_ply(const char* path, const float* points, const float* gaussian, const float* mean, int64_t n,
                             int threads);
 
+/* Diagnostics: measured FP32 and FP64 FMA throughput (TFLOP/s, 2 flops per FMA) of the current device -- the
+ * secondary roofline of SURVEY.md section 8(d); MEASURED_PEAKS.json has no CUDA-core figure.  Synchronises `stream`. */
+int pct_measure_fma_peaks(double* fp32_tflops, double* fp64_tflops, void* stream);
+
 /* Frees the per-stream scratch arenas the library keeps for the temporaries of its calls (they grow to the
  * largest call seen on a stream: about 37 bytes per point for an index build).  Synchronises those streams. */
 int pct_release_scratch(void);

@@ -11,6 +11,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
@@ -372,48 +374,48 @@ inline char* fixed6(char* o, double v) {
     return std::to_chars(o, o + 330, v, std::chars_format::fixed, 6).ptr;
 }
 
-// rows [0, n) formatted by `fmt(row, out) -> end`, at most `max_row` bytes each, appended to `fd` at `offset`
+// rows [0, n) formatted by `fmt(row, out) -> end`, at most `max_row` bytes each, appended to `fd` at `offset`.
+// Blocks of rows are claimed in order from a counter; a block's file offset is the end of the block before it, so
+// its owner waits until the previous owner has FORMATTED (not written) its block and published where it ends --
+// a chained scan: formatting and writing of different blocks overlap and no thread waits at a barrier.
 template <typename F>
 int write_rows(int fd, size_t offset, int64_t n, size_t max_row, int threads, F fmt) {
     threads = default_threads(threads);
-    const int64_t block = 1 << 15;
+    const int64_t block = 1 << 14;
     const int64_t blocks = (n + block - 1) / block;
+    if (blocks == 0) return PCT_OK;
     threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, blocks));
-    std::vector<std::vector<char>> buf((size_t)threads);
-    std::vector<size_t> len((size_t)threads);
-    std::vector<int> err((size_t)threads, 0);
-    for (int64_t wave = 0; wave < blocks; wave += threads) {
-        const int live = (int)std::min<int64_t>(threads, blocks - wave);
-        auto work = [&](int t) {
-            const int64_t b = (wave + t) * block, e = std::min(n, b + block);
-            std::vector<char>& v = buf[(size_t)t];
-            v.resize((size_t)(e - b) * max_row);
-            char* o = v.data();
-            for (int64_t i = b; i < e; ++i) o = fmt(i, o);
-            len[(size_t)t] = (size_t)(o - v.data());
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < live; ++t) pool.emplace_back(work, t);
-        work(0);
-        for (auto& th : pool) th.join();
-        pool.clear();
-        std::vector<size_t> at((size_t)live);
-        for (int t = 0; t < live; ++t) { at[(size_t)t] = offset; offset += len[(size_t)t]; }
-        auto put = [&](int t) {
-            const char* p = buf[(size_t)t].data();
-            size_t left = len[(size_t)t], pos = at[(size_t)t];
-            while (left) {
+    std::unique_ptr<std::atomic<int64_t>[]> start(new std::atomic<int64_t>[(size_t)blocks + 1]);
+    for (int64_t b = 0; b <= blocks; ++b) start[(size_t)b].store(-1, std::memory_order_relaxed);
+    start[0].store((int64_t)offset, std::memory_order_release);
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        std::vector<char> buf((size_t)block * max_row);
+        for (;;) {
+            const int64_t b = next.fetch_add(1, std::memory_order_relaxed);
+            if (b >= blocks) return;
+            const int64_t r0 = b * block, r1 = std::min(n, r0 + block);
+            char* o = buf.data();
+            for (int64_t i = r0; i < r1; ++i) o = fmt(i, o);
+            const size_t len = (size_t)(o - buf.data());
+            int64_t at;
+            while ((at = start[(size_t)b].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+            start[(size_t)b + 1].store(at + (int64_t)len, std::memory_order_release);
+            const char* p = buf.data();
+            size_t left = len, pos = (size_t)at;
+            while (left && !failed.load(std::memory_order_relaxed)) {
                 const ssize_t w = pwrite(fd, p, left, (off_t)pos);
-                if (w <= 0) { err[(size_t)t] = 1; return; }
+                if (w <= 0) { failed.store(1); break; }
                 p += w; pos += (size_t)w; left -= (size_t)w;
             }
-        };
-        for (int t = 1; t < live; ++t) pool.emplace_back(put, t);
-        put(0);
-        for (auto& th : pool) th.join();
-        for (int t = 0; t < live; ++t)
-            if (err[(size_t)t]) { set_error("write failed"); return PCT_ERR_INVALID_ARGUMENT; }
-    }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (failed.load()) { set_error("write failed"); return PCT_ERR_INVALID_ARGUMENT; }
     return PCT_OK;
 }
 
