@@ -489,6 +489,8 @@ def ours(args):
     # c = 2.9 k candidates, covariance 15 k, rotation 18 k, normal equations 59 k, fixed 600 -- against the FMA
     # rate of the CUDA cores measured here, after the timed regions
     try:
+        if world > 1:
+            raise RuntimeError("measured at N = 1 only (like cpu_baseline)")
         from point_cloud_toolbox_b200 import _lib
         import ctypes
 
@@ -500,7 +502,8 @@ def ours(args):
                                  "frac": ach / f32.value if f32.value > 0 else None, "fp64_peak": f64.value,
                                  "peak_source": "pct_measure_fma_peaks (FMA chains on this GPU, this run)"}
     except Exception as e:  # diagnostics must not cost the bench line
-        line["roofline_fp32"] = {"error": str(e)}
+        if world == 1:
+            line["roofline_fp32"] = {"error": str(e)}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
