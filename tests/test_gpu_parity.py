@@ -648,3 +648,36 @@ def test_file_in_file_out_round_trip(pct, tmp_path):
     assert np.array_equal(back, pc.points)
     fg, fm = U.save_curvature_arrays(K, H, "bunny", "scan", 1, str(tmp_path / "curvature_data"))
     assert np.array_equal(np.load(fg), K) and np.array_equal(np.load(fm), H)
+
+
+def test_energy_and_pca_corner_cases(pct):
+    from oracle import around_path as ap
+    from point_cloud_toolbox_b200 import engine
+
+    v = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3]], dtype=torch.float32, device="cuda")
+    K = torch.tensor([1.0, 2.0, 4.0, float("nan")], device="cuda")
+    H = torch.tensor([1.0, -2.0, 3.0, 5.0], device="cuda")
+    # no triangles: zeros; one triangle; numpy-style negative indices; an index out of range is counted, not read
+    assert engine.mesh_energies(v, torch.zeros((0, 3), dtype=torch.int32, device="cuda"), K, H).tolist() == [0, 0, 0, 0]
+    t = torch.tensor([[0, 1, 2]], dtype=torch.int32, device="cuda")
+    got = engine.mesh_energies(v, t, K, H).cpu().numpy()
+    want = ap.mesh_energies(v.cpu().numpy(), t.cpu().numpy(), K.cpu().numpy(), H.cpu().numpy())
+    assert got[3] == 0 and tuple(got[:3]) == tuple(float(x) for x in want)       # a single triangle is exact
+    neg = torch.tensor([[0, 1, -2], [0, 1, -1], [0, 4, 1], [0, -5, 1]], dtype=torch.int32, device="cuda")
+    got = engine.mesh_energies(v, neg, K, H).cpu().numpy()
+    want = ap.mesh_energies(v.cpu().numpy(), np.array([[0, 1, 2], [0, 1, 3]]), K.cpu().numpy(), H.cpu().numpy())
+    assert got[3] == 2 and np.allclose(got[:3], want, rtol=1e-15)                # the NaN corner drops out of stretching only
+    assert np.isfinite(got[:3]).all()
+    # PCA: one neighbour gives np.cov's NaN, n - 1 neighbours use every other point
+    pts = _cloud("bunny")[:500].copy()
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=5)
+    with np.errstate(all="ignore"):
+        pc.principal_curvatures_via_principal_component_analysis(1)
+    assert np.isnan(pc.pca_K_values).all()
+    small = pts[:60].copy()
+    pc = pct.PointCloud(points=small, normals=_empty_normals(60), k_neighbors=5)
+    pc.principal_curvatures_via_principal_component_analysis(59)
+    idx = oracle.knn_canonical(small, 59)[0]
+    vals, _ = ap.pca_from_rows(small, idx)
+    assert np.all(np.abs(pc.pca_principal_curvature_values_1 - vals[:, 0]) <= 1e-12 * vals[:, 0])
+    assert np.all(np.abs(pc.pca_principal_curvature_values_2 - vals[:, 1]) <= 1e-12 * vals[:, 0])
