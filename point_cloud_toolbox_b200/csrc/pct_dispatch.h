@@ -29,3 +29,10 @@
 #ifndef PCT_BRANCHFREE_PART
 #define PCT_BRANCHFREE_PART 1
 #endif
+
+// pass 2 of the selection skips the cells of the staged block that lie beyond the boundary bin.  Off: 41 % of the
+// pass-2 candidates go away on the benchmark surface, but the warp pays whole 4-wide trips of its slowest lane and
+// the per-row bound tests of every lane, and the kernel got 9 % slower (12.5 vs 11.4 ms at 20 M points, k = 20)
+#ifndef PCT_CULL_PASS2
+#define PCT_CULL_PASS2 0
+#endif

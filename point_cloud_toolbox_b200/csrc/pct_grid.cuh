@@ -335,12 +335,42 @@ static constexpr int kHistRowBytes = kHistBins + 4;  // + the word of the overfl
 //   src.count()    number of points in the 27 cells
 // GlobalSource reads the Morton-sorted cloud through L1/L2 (positions = sorted positions);
 // StagedSource reads the copy a CTA has made in shared memory (positions = 16-bit).
+// Lower bounds of the squared distance from a query to the cells of its 3x3x3 block, per axis: [0] the cells
+// one below the query's, [1] its own (0), [2] the cells one above.  A point of the cell below has a cell
+// coordinate smaller than the query's cell number, one of the cell above at least that number + 1
+// (cell_of() clamps only downwards from beyond the grid); the coordinates themselves carry the rounding
+// slack of make_stencil().  A cell whose three bounds add up to more than a limit holds no point closer.
+struct BlockBounds {
+    float x0, x2, y0, y2, z0, z2;
+    PCT_HD float y(int i) const { return i == 0 ? y0 : (i == 1 ? 0.f : y2); }
+    PCT_HD float z(int i) const { return i == 0 ? z0 : (i == 1 ? 0.f : z2); }
+};
+
+PCT_HD BlockBounds block_bounds(const IndexView& ix, const Stencil& st, int level, float qx, float qy, float qz) {
+    const float sc = ldexpf(1.f, -level);
+    const float cell = ix.h * ldexpf(1.f, level);
+    const float fx = cell_coord(qx, ix.ox, ix.inv_h) * sc - (float)st.lx;
+    const float fy = cell_coord(qy, ix.oy, ix.inv_h) * sc - (float)st.ly;
+    const float fz = cell_coord(qz, ix.oz, ix.inv_h) * sc - (float)st.lz;
+    BlockBounds b;
+    float t;
+    t = fmaxf(fx - ix.slack, 0.f) * cell; b.x0 = t * t;
+    t = fmaxf(1.f - fx - ix.slack, 0.f) * cell; b.x2 = t * t;
+    t = fmaxf(fy - ix.slack, 0.f) * cell; b.y0 = t * t;
+    t = fmaxf(1.f - fy - ix.slack, 0.f) * cell; b.y2 = t * t;
+    t = fmaxf(fz - ix.slack, 0.f) * cell; b.z0 = t * t;
+    t = fmaxf(1.f - fz - ix.slack, 0.f) * cell; b.z2 = t * t;
+    return b;
+}
+
 struct GlobalSource {
     typedef uint32_t Pos;
     const Pt* pts;
     CellRuns runs;
     template <class F>
     PCT_HD void scan(F& fn) const { runs.scan(pts, fn); }
+    template <class F>
+    PCT_HD void scan_within(F& fn, const BlockBounds&, float) const { runs.scan(pts, fn); }  // merged runs: no cell culling
     PCT_HD Pt load(uint32_t pos) const { return load_pt(pts + pos); }
     PCT_HD uint32_t count() const {
         uint32_t c = 0;
@@ -426,6 +456,40 @@ struct StagedSource {
             for (int u = 0; u < kScanWidth; ++u) fn((uint16_t)((a >> 4) + u), p[u], u == 0 || (uint32_t)u < left);
             a += left < (uint32_t)kScanWidth ? (e - a) : 16u * kScanWidth;
         }
+    }
+    // The same walk over the cells that can hold a point closer than sqrt(lim2): a row of cells (run) beyond the
+    // limit is skipped, and a row loses its first / last cell when that one is beyond it (the cells of a row are
+    // contiguous, so this only moves the run's ends).
+    template <class F>
+    PCT_HD void scan_within(F& fn, const BlockBounds& bb, float lim2) const {
+#if PCT_CULL_PASS2
+        int r = 0, c0 = corner;
+        uint32_t a = 0, e = 0;
+#pragma unroll 1
+        for (;;) {
+            if (a == e) {
+                do {
+                    if (r == 9) return;
+                    const int ry = r < 3 ? r : (r < 6 ? r - 3 : r - 6), rz = r < 3 ? 0 : (r < 6 ? 1 : 2);
+                    const float dyz = bb.y(ry) + bb.z(rz);
+                    const int first = dyz + bb.x0 > lim2 ? 1 : 0, last = dyz + bb.x2 > lim2 ? 2 : 3;
+                    a = cell_begin(c0 + first);
+                    e = dyz > lim2 ? a : cell_begin(c0 + last);
+                    ++r;
+                    c0 += (r == 3 || r == 6) ? side * side - 2 * side : side;
+                } while (a == e);
+            }
+            Pt p[kScanWidth];
+#pragma unroll
+            for (int u = 0; u < kScanWidth; ++u) p[u] = load_at(a + 16u * u);
+            const uint32_t left = (e - a) >> 4;
+#pragma unroll
+            for (int u = 0; u < kScanWidth; ++u) fn((uint16_t)((a >> 4) + u), p[u], u == 0 || (uint32_t)u < left);
+            a += left < (uint32_t)kScanWidth ? (e - a) : 16u * kScanWidth;
+        }
+#else
+        scan(fn);
+#endif
     }
     PCT_HD Pt load(uint16_t pos) const { return load_at((uint32_t)pos << 4); }
     PCT_HD uint32_t count() const {
@@ -635,7 +699,9 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
             p2(j, src.load(j), true);
         }
     } else {
-        src.scan(p2);
+        // cells of the block that lie entirely beyond hi hold nothing pass 2 would keep (the margin of
+        // 1e-4 covers the rounding of the bounds and the 3e-7 of d32)
+        src.scan_within(p2, block_bounds(ix, st, level, q.x, q.y, q.z), hi * 1.0001f);
     }
 
     const int n_front = (int)p2.n_front;
@@ -771,6 +837,8 @@ struct StencilSource {
         each.f = &fn;
         for_each_candidate(*ix, st, each);
     }
+    template <class F>
+    PCT_HD void scan_within(F& fn, const BlockBounds&, float) const { scan(fn); }
 };
 
 // Neighbourhood adaptor that re-walks the candidates (fused ball path): the members of the ball are
