@@ -249,6 +249,12 @@ int pct_write_points_ply(const char* path, const void* points, int is_f64, int64
 int pct_write_curvature_ply(const char* path, const float* points, const float* gaussian, const float* mean, int64_t n,
                             int threads);
 
+/* Host -> device copy on `stream` that does not depend on the source being page-locked: a pageable source (a plain
+ * numpy array given to PointCloud(points=...), ref :26-47) is staged by several host threads through page-locked
+ * double buffers, piece by piece, each piece's DMA queued as soon as it is staged.  Like cudaMemcpyAsync from
+ * pageable memory, the call returns once the source has been read; the transfer completes in stream order. */
+int pct_upload(void* dst_device, const void* src_host, int64_t bytes, void* stream);
+
 /* Diagnostics: measured FP32 and FP64 FMA throughput (TFLOP/s, 2 flops per FMA) of the current device -- the
  * secondary roofline of SURVEY.md section 8(d); MEASURED_PEAKS.json has no CUDA-core figure.  Synchronises `stream`. */
 int pct_measure_fma_peaks(double* fp32_tflops, double* fp64_tflops, void* stream);

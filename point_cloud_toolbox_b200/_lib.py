@@ -72,6 +72,7 @@ SIGNATURES = {
     "pct_estimate_cell_size": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
     "pct_index_set_slab": (c_int, [c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),
     "pct_release_scratch": (c_int, []),
+    "pct_upload": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pct_measure_fma_peaks": (c_int, [POINTER(c_double), POINTER(c_double), c_void_p]),
     "pct_text_shape": (c_int, [c_char_p, POINTER(c_int64), POINTER(c_int64)]),
     "pct_text_load": (c_int, [c_char_p, c_int64, c_int64, c_void_p, c_int]),

@@ -227,7 +227,8 @@ int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_hos
     PCT_TRY(cudaMalloc(&d_xyz, sizeof(float) * 3 * (size_t)n));
     PCT_TRY(cudaMalloc(&d_curv, sizeof(float) * 5 * (size_t)n));
     PCT_TRY(cudaMallocHost(&h_curv, sizeof(float) * 5 * (size_t)n));
-    PCT_TRY(cudaMemcpyAsync(d_xyz, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+    rc = pct_upload(d_xyz, xyz_host, (int64_t)(sizeof(float) * 3 * (size_t)n), s);  // staged when the source is pageable
+    if (rc != PCT_OK) { cleanup(); return rc; }
     rc = pct_index_build(d_xyz, n, 3, 0.f, k, s, &ix);
     if (rc == PCT_OK) rc = pct_curvature_fused_knn(ix, 0, n, k, nullptr, nullptr, d_curv, nullptr, PCT_LAYOUT_ORIGINAL, s);
     if (rc != PCT_OK) { cleanup(); return rc; }

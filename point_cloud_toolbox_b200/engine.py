@@ -38,6 +38,13 @@ def to_device_points(points, device=None):
     if t.shape[1] != 3:
         t = t[:, :3]
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[1] == 3
+            and t.numel() >= (8 << 20) and not t.is_pinned()):
+        # a large pageable array: staged by several host threads (pct_upload) instead of the driver's single one
+        out = torch.empty(t.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pct_upload(ptr(out), ctypes.c_void_p(t.data_ptr()), t.numel() * 4, _stream()))
+        return out
     return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 

@@ -681,3 +681,19 @@ def test_energy_and_pca_corner_cases(pct):
     vals, _ = ap.pca_from_rows(small, idx)
     assert np.all(np.abs(pc.pca_principal_curvature_values_1 - vals[:, 0]) <= 1e-12 * vals[:, 0])
     assert np.all(np.abs(pc.pca_principal_curvature_values_2 - vals[:, 1]) <= 1e-12 * vals[:, 0])
+
+
+def test_pageable_upload_is_staged_and_exact(pct):
+    from point_cloud_toolbox_b200 import engine
+
+    rng = np.random.default_rng(12)
+    a = rng.random((3_000_001, 3), dtype=np.float32)                 # 36 MB, pageable: goes through pct_upload
+    d = engine.to_device_points(a)
+    assert d.is_cuda and d.dtype == torch.float32 and torch.equal(d.cpu(), torch.from_numpy(a))
+    d2 = engine.to_device_points(a)                                   # the staging buffers are reused
+    assert torch.equal(d2, d)
+    pinned = torch.from_numpy(a).pin_memory()
+    assert torch.equal(engine.to_device_points(pinned), d)            # page-locked source: direct copy
+    assert torch.equal(engine.to_device_points(a[:1000]), d[:1000])   # small: direct copy
+    six = np.concatenate([a[:50000], a[:50000]], 1)                   # (N, 6): the first three columns
+    assert torch.equal(engine.to_device_points(six), d[:50000])
