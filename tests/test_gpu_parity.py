@@ -697,3 +697,23 @@ def test_pageable_upload_is_staged_and_exact(pct):
     assert torch.equal(engine.to_device_points(a[:1000]), d[:1000])   # small: direct copy
     six = np.concatenate([a[:50000], a[:50000]], 1)                   # (N, 6): the first three columns
     assert torch.equal(engine.to_device_points(six), d[:50000])
+
+
+def test_host_buffer_entry_of_the_c_abi(pct):
+    """pct_curvature_knn_host: plain host pointers in and out, what a binding without a device allocator calls."""
+    import ctypes
+
+    from point_cloud_toolbox_b200 import _lib
+
+    for pts in (_cloud("bunny"), np.ascontiguousarray(np.tile(_cloud("bunny"), (80, 1)) +
+                                                      np.repeat(np.arange(80, dtype=np.float32), 35947)[:, None])):
+        # the second cloud (2.9 M points, 34 MB) is large enough for the staged upload
+        n, k = len(pts), 20
+        K = np.empty(n, np.float32)
+        H = np.empty(n, np.float32)
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        _lib.check(_lib.lib.pct_curvature_knn_host(P(pts), n, k, P(K), P(H)))
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+        pc.plant_kdtree(k)
+        K2, H2 = pc.compute_pointwise_explicit_quadratic_curvature()
+        assert np.array_equal(K, K2, equal_nan=True) and np.array_equal(H, H2, equal_nan=True)
