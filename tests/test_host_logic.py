@@ -449,3 +449,66 @@ def test_pca_rows_against_reference_numbers(harness):
     harness.h_pca_rows(P(pts), P(idx), len(pts), k, 1, P(vals), P(dirs))
     assert np.all(np.abs(vals[:, :3] - want[:, :3]) <= 1e-12 * want[:, :1])
     assert np.allclose(vals[:, 5], want[:, 5], rtol=1e-7, atol=1e-12)
+
+
+def test_text_loader_fuzz_against_loadtxt(tmp_path):
+    """Random small files in the dialect np.loadtxt reads by default: the table is the same bit for bit, or both refuse."""
+    from point_cloud_toolbox_b200 import engine
+
+    rng = np.random.default_rng(21)
+
+    def token():
+        kind = rng.integers(0, 9)
+        v = float(rng.standard_normal() * 10.0 ** rng.integers(-12, 12))
+        if kind == 0:
+            return str(int(rng.integers(-10 ** 6, 10 ** 6)))
+        if kind == 1:
+            return f"{v:.{rng.integers(0, 18)}e}"
+        if kind == 2:
+            return f"{v:.{rng.integers(0, 12)}f}"
+        if kind == 3:
+            return repr(float(np.float32(v)))
+        if kind == 4:
+            return "+" + repr(abs(v))
+        if kind == 5:
+            return rng.choice(["nan", "inf", "-inf", "NaN", "Infinity", "1e400", "-1e-400", "0", "-0.0", ".5", "5.", "1E5"])
+        if kind == 6:
+            return f"{v:.3g}".upper()
+        return repr(v)
+
+    path = tmp_path / "f.txt"
+    agree = 0
+    for case in range(150):
+        cols = int(rng.integers(1, 7))
+        rows = int(rng.integers(2, 40))
+        lines = []
+        for r in range(rows):
+            sep = rng.choice([" ", "  ", "\t", " \t "])
+            line = sep.join(token() for _ in range(cols))
+            if rng.random() < 0.1:
+                line = "   " + line
+            if rng.random() < 0.1:
+                line += "  # note " + token()
+            if rng.random() < 0.08:
+                lines.append(rng.choice(["", "   ", "# only a comment", "\t"]))
+            lines.append(line)
+        if case % 10 == 9:                                  # a broken file now and then
+            lines[int(rng.integers(0, len(lines)))] += rng.choice([" 1", " x", ",2"])
+        eol = "\r\n" if case % 7 == 3 else "\n"
+        text = eol.join(lines) + (eol if case % 3 else "")
+        path.write_bytes(text.encode())
+        try:
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = np.loadtxt(path, ndmin=2)
+        except ValueError:
+            with pytest.raises(ValueError):
+                engine.load_text_f32(path)
+            continue
+        got = _load_f64(path)
+        assert got.shape == want.shape, (case, text)
+        assert np.array_equal(_bits(got), _bits(want)), (case, text)
+        agree += 1
+    assert agree > 100
