@@ -504,6 +504,20 @@ def ours(args):
     except Exception as e:  # diagnostics must not cost the bench line
         if world == 1:
             line["roofline_fp32"] = {"error": str(e)}
+    # the bound that actually holds: warp instructions issued per second against the schedulers' peak.
+    # Instructions per point come from the committed ncu capture of the staged kernel, the time is this run's.
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            prof = json.load(f)
+        if int(prof.get("k", -1)) == k and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_inst = sms * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9
+            ach_inst = pts_per_launch * float(prof["warp_inst_per_point"]) / (query_ms * 1e-3) / 1e9
+            line["roofline_issue"] = {"bound": "instruction issue", "warp_inst_per_point": prof["warp_inst_per_point"],
+                                      "achieved": ach_inst, "peak": peak_inst, "unit": "G warp-inst/s", "frac": ach_inst / peak_inst,
+                                      "source": prof.get("source_inst")}
+    except Exception:
+        pass
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
