@@ -1,7 +1,7 @@
 // Thread-per-query kNN kernels: histogram selection, exact neighbour set in shared
 // memory, fused fp64 fit.  One kernel for every k (the selection is O(candidates)).
 //
-//   knn_staged_kernel<U, FUSED>  the throughput path.  A CTA owns 128 consecutive
+//   knn_staged_kernel<U, FUSED>  the throughput path.  A CTA owns PCT_STAGED_BLOCK (256) consecutive
 //       Morton-sorted queries, copies the cells they can reach (their parent cubes plus
 //       a one-cell halo) into shared memory with coalesced 16-byte loads, and every
 //       thread then selects and fits its own query out of that copy.  The cloud is read
