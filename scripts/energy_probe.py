@@ -1,5 +1,5 @@
-"""Mesh energy kernel alone: `python scripts/energy_probe.py [grid_n]` -> ms per call (cold L2) and GB/s.
-PCT_ENERGY_VARIANT selects the experiment variants of csrc/pct_energy.cu."""
+"""Mesh energy kernel alone: `python scripts/energy_probe.py [grid_n] [shuffle]` -> ms per call (cold L2) and GB/s;
+`shuffle` renumbers the vertices at random (a mesh without locality)."""
 import json
 import os
 import sys
@@ -34,6 +34,6 @@ for _ in range(7):
     ts.append(ev[0].elapsed_time(ev[1]))
 ms = float(np.median(ts))
 T, V = tris.shape[0], verts.shape[0]
-print(json.dumps({"variant": os.environ.get("PCT_ENERGY_VARIANT", "0"), "triangles": T, "vertices": V, "shuffled": shuffle,
+print(json.dumps({"triangles": T, "vertices": V, "shuffled": shuffle,
                   "ms": ms, "GBps_indices": T * 12 / ms / 1e6, "GBps_indices_and_vertex_arrays": (T * 12 + V * 20) / ms / 1e6,
                   "out": [float(x) for x in out.cpu()]}))
