@@ -16,6 +16,11 @@ Parity status
 * neighbour study (ref :732-800): **pinned** -- return values of the unmodified reference's
   ``explicit_quadratic_neighbor_study`` on ``bunny.txt`` for seeded samples and several tolerances
   (``tests/golden/neighbor_study.npz``).
+* rows either side of the path (text / PLY I/O, mesh energies, PCA estimators; ``oracle/around_path.py``):
+  **pinned** -- ``oracle/make_golden_io.py`` compiles the unmodified function definitions out of
+  ``/root/reference/utils.py`` (the file itself needs open3d / pyvista to import) and stores their outputs in
+  ``tests/golden/io_energy_pca.npz``; ``estimate_curvature`` is the exception (the reference's output is rounding
+  noise, see its docstring in the product), **parity unpinned** for it.
 * epsilon-ball query: **parity unpinned** -- the reference never implemented it
   (README.md:8 advertises it, pointCloudToolbox.py:101-102 only lists scipy's
   API).  The oracle composes ``scipy.spatial.cKDTree.query_ball_point`` with the
