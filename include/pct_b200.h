@@ -260,7 +260,8 @@ int pct_upload(void* dst_device, const void* src_host, int64_t bytes, void* stre
 int pct_measure_fma_peaks(double* fp32_tflops, double* fp64_tflops, void* stream);
 
 /* Frees the per-stream scratch arenas the library keeps for the temporaries of its calls (they grow to the
- * largest call seen on a stream: about 37 bytes per point for an index build).  Synchronises those streams. */
+ * largest call seen on a stream: about 37 bytes per point for an index build) and the page-locked staging buffers
+ * of pct_upload.  Synchronises those streams. */
 int pct_release_scratch(void);
 
 /* Host-buffer convenience for callers without PyTorch: H2D + build + fused kNN

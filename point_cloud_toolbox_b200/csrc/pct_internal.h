@@ -58,6 +58,7 @@ class ScratchSession {
     size_t left_ = 0;
 };
 void release_scratch();
+void release_upload_stage();  // pct_transfer.cu
 
 // per-row output pointers of the fit (any may be null)
 struct FitOutputs {

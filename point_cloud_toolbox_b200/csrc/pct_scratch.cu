@@ -80,5 +80,6 @@ void release_scratch() {
 
 extern "C" int pct_release_scratch(void) {
     pct::release_scratch();
+    pct::release_upload_stage();
     return PCT_OK;
 }

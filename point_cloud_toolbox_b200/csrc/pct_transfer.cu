@@ -45,6 +45,18 @@ int ensure_stage(int device) {
 }
 
 }  // namespace
+
+// page-locked staging buffers of pct_upload (64 MB) go with the scratch arenas (pct_release_scratch)
+void release_upload_stage() {
+    std::lock_guard<std::mutex> lock(g_stage.mutex);
+    for (int w = 0; w < kWorkers; ++w)
+        for (int b = 0; b < kSlots; ++b) {
+            if (g_stage.done[w][b]) { cudaEventSynchronize(g_stage.done[w][b]); cudaEventDestroy(g_stage.done[w][b]); g_stage.done[w][b] = nullptr; }
+            if (g_stage.buf[w][b]) { cudaFreeHost(g_stage.buf[w][b]); g_stage.buf[w][b] = nullptr; }
+        }
+    g_stage.device = -1;
+}
+
 }  // namespace pct
 
 extern "C" int pct_upload(void* dst_device, const void* src_host, int64_t bytes, void* stream) {

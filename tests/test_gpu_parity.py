@@ -692,6 +692,11 @@ def test_pageable_upload_is_staged_and_exact(pct):
     assert d.is_cuda and d.dtype == torch.float32 and torch.equal(d.cpu(), torch.from_numpy(a))
     d2 = engine.to_device_points(a)                                   # the staging buffers are reused
     assert torch.equal(d2, d)
+    from point_cloud_toolbox_b200 import _lib
+
+    torch.cuda.synchronize()
+    assert _lib.lib.pct_release_scratch() == 0                        # frees the staging buffers too
+    assert torch.equal(engine.to_device_points(a), d)                 # ... and they come back on demand
     pinned = torch.from_numpy(a).pin_memory()
     assert torch.equal(engine.to_device_points(pinned), d)            # page-locked source: direct copy
     assert torch.equal(engine.to_device_points(a[:1000]), d[:1000])   # small: direct copy
