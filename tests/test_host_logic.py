@@ -512,3 +512,29 @@ def test_text_loader_fuzz_against_loadtxt(tmp_path):
         assert np.array_equal(_bits(got), _bits(want)), (case, text)
         agree += 1
     assert agree > 100
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/pct_b200.h compiles as C99 and a C program links against the library."""
+    import shutil
+    import subprocess
+
+    from point_cloud_toolbox_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pct_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    long long rows = -1, cols = -1;\n'
+                   '    if (pct_version() != 100) return 1;\n'
+                   '    if (pct_text_shape("/nonexistent/file", (int64_t*)&rows, (int64_t*)&cols) == PCT_OK) return 2;\n'
+                   '    printf("%s\\n", pct_last_error());\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lpct_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "cannot open" in out
