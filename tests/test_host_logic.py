@@ -538,3 +538,27 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     "-o", str(exe), "-L", libdir, "-lpct_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "cannot open" in out
+
+
+def test_io_code_under_address_and_ub_sanitizers(tmp_path):
+    """csrc/pct_io.cu built alone with -fsanitize=address,undefined; random bit patterns through the writers and readers,
+    garbage files through the parsers (tests/host_harness/io_sanitize)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    here = os.path.join(ROOT, "tests", "host_harness", "io_sanitize")
+    exe = tmp_path / "io_sanitize"
+    cmd = [gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           "-x", "c++", "-D__uint_as_float(x)=(0.f)", "-I", cuda_inc, "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "point_cloud_toolbox_b200", "csrc", "pct_io.cu"), os.path.join(here, "stub.cpp"),
+           os.path.join(here, "main.cpp"), "-o", str(exe), "-pthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0 and "sanitize" in res.stderr and "cannot find" in res.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert res.returncode == 0, res.stderr[-2000:]
+    run = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
+    assert run.returncode == 0 and "asan run done" in run.stdout, (run.stdout[-500:], run.stderr[-3000:])
