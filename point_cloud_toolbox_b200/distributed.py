@@ -251,6 +251,52 @@ class SharedHostArray:
             pass
 
 
+def shared_cloud_from_text(path, name: str, group=None) -> SharedHostArray:
+    """The scan file of ``PointCloud(file_path)`` as the (N, 3) shared host array ``curvature_knn_shared`` reads.
+
+    Rank 0 parses the text with the library's loader (all host threads) straight into the segment, applies the
+    reference's shift of x and y by their maxima in float32 (ref :56-57), and the other ranks map the segment
+    afterwards.  Collective over ``group``; the caller closes the array (rank 0 unlinks it)."""
+    import ctypes
+
+    import numpy as np
+
+    from ._lib import check, lib
+
+    rank = dist.get_rank(group)
+    shape = torch.zeros(2, dtype=torch.int64)
+    if rank == 0:
+        rows, cols = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.pct_text_shape(str(path).encode(), ctypes.byref(rows), ctypes.byref(cols)))
+        shape[0], shape[1] = rows.value, cols.value
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dev_shape = shape.cuda()
+        dist.broadcast(dev_shape, src=0, group=group)
+        shape = dev_shape.cpu()
+    else:
+        dist.broadcast(shape, src=0, group=group)
+    n, cols = int(shape[0]), int(shape[1])
+    if n < 2 or cols < 3:
+        raise ValueError(f"{path}: {n} rows of {cols} columns is not a point cloud")
+    shared = None
+    if rank == 0:
+        shared = SharedHostArray(name, (n, 3), create=True)
+        if cols == 3:
+            check(lib.pct_text_load_f32(str(path).encode(), n, 3, ctypes.c_void_p(shared.tensor.data_ptr()), 0))
+        else:
+            table = np.empty((n, cols), np.float32)
+            check(lib.pct_text_load_f32(str(path).encode(), n, cols, table.ctypes.data_as(ctypes.c_void_p), 0))
+            shared.array[:] = table[:, 0:3]                                  # ref :52
+        shared.array[:, 0] -= shared.array[:, 0].max()                       # ref :56 (fp32)
+        shared.array[:, 1] -= shared.array[:, 1].max()                       # ref :57
+    dist.barrier(group=group)
+    if rank != 0:
+        shared = SharedHostArray(name, (n, 3), create=False)
+    dist.barrier(group=group)
+    return shared
+
+
 def exchange_by_owner(ids: torch.Tensor, rows: torch.Tensor, n: int, group=None):
     """All-to-all of per-point rows to the ranks that own their ORIGINAL index ranges.
 

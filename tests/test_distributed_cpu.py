@@ -128,3 +128,34 @@ def test_gather_and_unpermute_world2(tmp_path, n):
     mp.spawn(_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
     res = np.load(out)
     assert res[0] == 1.0 and res[1] == n
+
+
+def _text_worker(rank, world, port, path, out):
+    import torch.distributed as dist
+
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shared = pdist.shared_cloud_from_text(path, f"pct_text_{port}")
+        np.save(out + f".{rank}.npy", np.array(shared.array))
+        dist.barrier()
+        shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cols", [3, 6])
+def test_shared_cloud_from_text_world2(tmp_path, cols):
+    """Every rank sees the file's cloud exactly as the reference's loader leaves it (golden loader case)."""
+    from conftest import load_golden
+
+    g = load_golden("loader_case")
+    path = str(tmp_path / "cloud.txt")
+    np.savetxt(path, g["table"][:, :cols], fmt="%.5f")
+    out = str(tmp_path / "seen")
+    mp.spawn(_text_worker, args=(2, _free_port(), path, out), nprocs=2, join=True)
+    for rank in range(2):
+        assert np.array_equal(np.load(out + f".{rank}.npy"), g["points"])
