@@ -36,3 +36,9 @@
 #ifndef PCT_CULL_PASS2
 #define PCT_CULL_PASS2 0
 #endif
+
+// pass 1 updates its byte histogram with one shared-memory reduction per candidate instead of a byte
+// load-add-store (not measured yet: profiles/README.md, end of r01u).  Only for kernels whose scratch is shared memory.
+#ifndef PCT_HIST_RED
+#define PCT_HIST_RED 0
+#endif

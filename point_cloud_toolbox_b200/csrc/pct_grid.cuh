@@ -591,6 +591,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     // bytes that may wrap; `seen` detects that afterwards.
     struct P1 {
         uint8_t* hist;
+        uint32_t hist_s;   // the same as a shared-window address (PCT_HIST_RED)
         int hist_stride4;  // bytes between consecutive words
         ListRef<Pos> list;
         uint32_t seen, n_coll, coll_slots;
@@ -600,8 +601,17 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 #if PCT_BRANCHFREE_HIST
             // no branch: candidates beyond the range land in the overflow counter (bin kHistBins)
             const int b = (int)fminf(d * inv_w, (float)kHistBins);
+#if PCT_HIST_RED && defined(__CUDA_ARCH__)
+            // one reduction on the counter's word instead of load-add-store of its byte: nothing comes back, so the
+            // updates of a trip do not wait for one another (a byte that wraps carries into its neighbour, which
+            // the total-count check below still sees)
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + (uint32_t)((b >> 2) * hist_stride4)),
+                         "r"(1u << ((b & 3) * 8))
+                         : "memory");
+#else
             uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
             *c = (uint8_t)(*c + 1);
+#endif
             seen += b < kHistBins ? 1u : 0u;  // (a candidate within 1e-5 of range2 may land in the last bin: still inside safe2)
             if (COLLECT && d < cut2) {
                 if (n_coll < coll_slots) list.lo((int)n_coll) = j;
@@ -622,6 +632,11 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         }
     } p1;
     p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.seen = 0; p1.n_coll = 0;
+#if PCT_HIST_RED && defined(__CUDA_ARCH__)
+    p1.hist_s = (uint32_t)__cvta_generic_to_shared(sc.hist);
+#else
+    p1.hist_s = 0;
+#endif
     p1.coll_slots = (uint32_t)coll_slots;
     p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
     src.scan(p1);
