@@ -42,3 +42,9 @@
 #ifndef PCT_HIST_RED
 #define PCT_HIST_RED 0
 #endif
+
+// bins of the distance histogram of pass 1 (a multiple of 4): fewer bins = fewer words to clear and to prefix-sum
+// per query, a wider boundary bin = more candidates for the fp64 re-rank
+#ifndef PCT_HIST_BINS
+#define PCT_HIST_BINS 64
+#endif

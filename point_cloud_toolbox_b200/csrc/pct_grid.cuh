@@ -326,7 +326,8 @@ enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 //   list  cap entries, addressed through ListRef           (neighbour positions)
 //   hist  kHistBins byte counters = 16 words, word w at hist[w * hist_stride]   (distance histogram);
 //         with hist_stride = threads of the block every thread stays in its own bank
-static constexpr int kHistBins = 64;
+static constexpr int kHistBins = PCT_HIST_BINS;
+static_assert(kHistBins % 4 == 0 && kHistBins >= 8 && kHistBins <= 252, "byte counters, four bins to a word");
 static constexpr int kHistRowBytes = kHistBins + 4;  // + the word of the overflow counter (candidates beyond the range)
 
 // Where the candidates of a query come from.  knn_select() and the fit only need

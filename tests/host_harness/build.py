@@ -11,10 +11,12 @@ def build():
     src = os.path.join(HERE, "harness.cpp")
     inc = os.path.join(ROOT, "point_cloud_toolbox_b200", "csrc")
     deps = [src] + [os.path.join(inc, f) for f in ("pct_math.cuh", "pct_grid.cuh", "pct_dispatch.h", "pct_energy.cuh")]
-    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
-        return LIB
-    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I", inc, src, "-o", LIB], check=True)
-    return LIB
+    extra = os.environ.get("PCT_HARNESS_EXTRA", "").split()  # e.g. -DPCT_HIST_BINS=32: the logic tests against a knob setting
+    lib = LIB if not extra else LIB.replace(".so", "_variant.so")
+    if not extra and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps):
+        return lib
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", *extra, "-I", inc, src, "-o", lib], check=True)
+    return lib
 
 
 if __name__ == "__main__":
