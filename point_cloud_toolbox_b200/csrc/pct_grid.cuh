@@ -319,7 +319,8 @@ struct CellRuns {
 // ---------------------------------------------------------------------------
 // kNN selection, thread per query
 // ---------------------------------------------------------------------------
-enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
+enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2,
+                        SEL_TWOPASS = 3 };  // ONEPASS only: the cut missed, redo with the two-pass selection
 
 // Selection scratch of one query.  On the GPU all of it lives in shared memory:
 //   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
@@ -559,7 +560,13 @@ struct SelectScratch {
 //
 // On SEL_OK, list.at(m) (m < k) holds the neighbours' positions (unordered),
 // `first` / `last` the nearest / farthest by (d2 fp64, original index).
-template <bool COLLECT, class Source>
+//
+// ONEPASS (experiment, needs COLLECT): pass 1 only lists the candidates below the estimated cut -- no
+// histogram over all candidates -- and the histogram is then built from the list alone, over
+// [0, 0.999 cut2) so that the boundary bin ends below the cut.  When the list overflows or holds fewer
+// than k + 1 candidates the estimate missed: SEL_TWOPASS, and the caller redoes the query with the
+// two-pass selection.  The exactness argument is the same: every candidate below cut2 is listed.
+template <bool COLLECT, bool ONEPASS = false, class Source>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
                       const SelectScratch<typename Source::Pos>& sc, typename Source::Pos& first,
                       typename Source::Pos& last, double& d2_last) {
@@ -569,8 +576,9 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     // everything closer than sqrt(range2) is certain to be among the candidates
     const float cell = ix.h * ldexpf(1.f, level);
     const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
-    const float inv_w = (float)kHistBins / range2 * 0.99999f;  // rounded down: bin < kHistBins for d < range2
-    if (!(range2 > 1.0e-30f) || !(inv_w < 3.0e38f)) return SEL_EXACT;
+    static_assert(!ONEPASS || COLLECT, "ONEPASS lists the candidates below the cut: it needs COLLECT");
+    const float inv_w_range = (float)kHistBins / range2 * 0.99999f;  // rounded down: bin < kHistBins for d < range2
+    if (!(range2 > 1.0e-30f) || !(inv_w_range < 3.0e38f)) return SEL_EXACT;
 
     // estimated squared distance of the k-th neighbour, with head-room (cut_gain): on a surface the
     // population C of the 3x3 block of cells is density * 9 cell^2 * tilt, in a volume density * 27 cell^3
@@ -582,6 +590,10 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         const float f = ix.volumetric ? cbrtf(frac * frac) : frac;
         cut2 = fminf(ix.cut_gain * f * cell * cell, range2);
     }
+    // ONEPASS: histogram over [0, 0.999 cut2): candidates in the last 0.1 % below the cut are listed but land in the
+    // overflow counter, so the boundary bin (widened by 1e-5) always ends below cut2
+    const float inv_w = ONEPASS ? (float)kHistBins / (cut2 * 0.999f) * 0.99999f : inv_w_range;
+    if (ONEPASS && (!(cut2 > 1.0e-30f) || !(inv_w < 3.0e38f))) return SEL_EXACT;
 
 #pragma unroll
     for (int w = 0; w < kHistRowBytes / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
@@ -599,6 +611,13 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         float qx, qy, qz, range2, inv_w, cut2;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
+            if (ONEPASS) {  // list only; the histogram is built from the list afterwards
+                if (d < cut2) {
+                    if (n_coll < coll_slots) list.lo((int)n_coll) = j;
+                    ++n_coll;
+                }
+                return;
+            }
 #if PCT_BRANCHFREE_HIST
             // no branch: candidates beyond the range land in the overflow counter (bin kHistBins)
             const int b = (int)fminf(d * inv_w, (float)kHistBins);
@@ -641,6 +660,22 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     p1.coll_slots = (uint32_t)coll_slots;
     p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
     src.scan(p1);
+    if (ONEPASS) {
+        if (p1.n_coll > (uint32_t)coll_slots) return SEL_TWOPASS;  // more below the cut than the list holds
+        // histogram of the listed candidates (the query among them, bin 0); a byte that wraps (more than 255 listed
+        // candidates in one bin, large k only) is caught by the total-count check below
+        uint8_t* const hb = reinterpret_cast<uint8_t*>(sc.hist);
+        const int stride4 = 4 * sc.hist_stride;
+#pragma unroll 1
+        for (uint32_t m = 0; m < p1.n_coll; ++m) {
+            const Pt p = src.load(sc.list.lo((int)m));
+            const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+            const int b = (int)fminf(d * inv_w, (float)kHistBins);
+            uint8_t* const c = hb + (b >> 2) * stride4 + (b & 3);
+            *c = (uint8_t)(*c + 1);
+            p1.seen += b < kHistBins ? 1u : 0u;
+        }
+    }
 
     // bin of the k-th neighbour: word-wise byte sums first (one dp4a per four bins), then the
     // four bins of the word in which the running count passes k
@@ -668,7 +703,11 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         }
     }
     if (cum != p1.seen) return SEL_EXACT;  // a counter wrapped (> 255 candidates in one bin)
-    if (b < 0) return SEL_RETRY_COARSER;   // fewer than k points within the certain radius
+    if (b < 0) {
+        // fewer than k points within the histogram's range: the certain radius (-> one level coarser), or only the
+        // estimated cut of ONEPASS (-> two-pass selection over the same block)
+        return ONEPASS && cut2 < range2 ? SEL_TWOPASS : SEL_RETRY_COARSER;
+    }
 
     // bin b is [b, b + 1) / inv_w; widened by 1e-5 relative on both sides
     const float bin_w = 1.f / inv_w;

@@ -326,6 +326,9 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     v.slab_axis = -1;
     v.volumetric = est_dim > 2.5f ? 1 : 0;
     v.cut_gain = 0.f;  // off: at 24 warps/SM the list space is worth more as staging buffer (profiles/README.md)
+#if PCT_ONEPASS
+    v.cut_gain = 6.3f;  // 2.2 * 9 / pi: the margin at which the simulated cut misses 0 - 0.3 % of the queries
+#endif
     if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
         const float gv = (float)std::atof(g);
         if (gv >= 0.f) v.cut_gain = gv;

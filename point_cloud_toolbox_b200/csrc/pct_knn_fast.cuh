@@ -329,7 +329,7 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
     return true;
 }
 
-template <int U, bool FUSED, bool COLLECT>
+template <int U, bool FUSED, bool COLLECT, bool ONEPASS = false>
 __global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
 knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
@@ -354,9 +354,11 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     make_stencil(ix, 0, q.x, q.y, q.z, st);
     uint16_t first = 0, last = 0;
     double d2_last = 0.0;
-    const int rc = knn_select<COLLECT>(ix, st, 0, src, q, k, sel, first, last, d2_last);
+    const int rc = knn_select<COLLECT, ONEPASS>(ix, st, 0, src, q, k, sel, first, last, d2_last);
     if (rc != SEL_OK) {
-        if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
+        if (ONEPASS && rc == SEL_TWOPASS) {
+            qu.fallback[atomicAdd(&qu.counters[2], 1u)] = i;  // the L1/L2 kernel redoes it with both passes
+        } else if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
             qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
         } else {
             qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
@@ -412,7 +414,12 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     // The kernel is compiled for PCT_STAGED_CTAS resident CTAs; when the regions of a chunk are expected
     // to be larger than that share (large k: cells hold 0.4 k points), fewer, larger CTAs are resident.
     constexpr int U = 2;
+#if PCT_ONEPASS
+    // experiment: pass 1 only lists the candidates below the estimated cut (IndexView::cut_gain must be set)
+    auto staged = collect ? knn_staged_kernel<U, FUSED, true, true> : knn_staged_kernel<U, FUSED, false>;
+#else
     auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
+#endif
     const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect);
     // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide:
     // with a buffer of 2.1 times that mean about 4 % of the chunks do not fit, which still beats giving up a

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <vector>
 
+static long long g_twopass;  // one-pass selections whose cut missed (redone with both passes)
+static int g_onepass;       // knn_impl uses knn_select<true, true> on the staged source
 static long long g_pass2[2];  // [0] = pass 2 walked all candidates, [1] = pass 2 read the pre-collected list
 #define PCT_SELECT_TRACE(used_list) (++g_pass2[(used_list) ? 1 : 0])
 #include "pct_grid.cuh"
@@ -206,8 +208,16 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
-                rc = collect ? knn_select<true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last)
-                             : knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                if (collect && g_onepass) {
+                    rc = knn_select<true, true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                    if (rc == SEL_TWOPASS) {  // what the L1/L2 kernel does with the queued query
+                        ++g_twopass;
+                        rc = knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                    }
+                } else {
+                    rc = collect ? knn_select<true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last)
+                                 : knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                }
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
                     for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[sc16.list.lo(m)].idx];
@@ -257,6 +267,9 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
 }
 
 extern "C" {
+
+// one-pass selection on the staged source (with coll_extra > 0 and a cut_gain); returns the number of redone queries so far
+long long h_set_onepass(int on) { g_onepass = on; const long long r = g_twopass; if (on) g_twopass = 0; return r; }
 
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {

@@ -562,3 +562,50 @@ def test_io_code_under_address_and_ub_sanitizers(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     run = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True)
     assert run.returncode == 0 and "asan run done" in run.stdout, (run.stdout[-500:], run.stderr[-3000:])
+
+
+def test_one_pass_selection_gives_the_same_rows(harness, bunny):
+    """knn_select<COLLECT, ONEPASS> (the experiment behind PCT_ONEPASS): rows equal the oracle's whatever the cut --
+    the margin of DESIGN.md 7, a cut that misses often (redone with both passes), a list too short for the cut."""
+    harness.h_set_onepass.restype = ctypes.c_longlong
+    harness.h_set_onepass.argtypes = [ctypes.c_int]
+    pts = bunny[::3]
+    k = 20
+    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+    h = 1.25 * float(np.median(ref_dist[:, -1]))
+    base = run_knn(harness, pts, k, h, staged_u=2)
+    staged = np.mean(base["code"] == 50)
+    assert staged > 0.8
+    seen = {}
+    for gain, extra in ((6.3, 48), (2.5, 48), (12.0, 12)):
+        harness.h_set_onepass(1)
+        try:
+            got = run_knn(harness, pts, k, h, staged_u=2, coll_extra=extra, cut_gain=gain)
+        finally:
+            redone = harness.h_set_onepass(0)
+        assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (gain, extra)
+        assert np.array_equal(got["dist"], ref_dist), (gain, extra)
+        # (a k-th neighbour in the last 0.1 % of the certain radius is found one level coarser: the list's
+        # histogram stops at 0.999 of the cut)
+        moved = got["code"] != base["code"]
+        assert moved.mean() < 1e-3 and (got["code"][moved] == 1).all() and (base["code"][moved] == 50).all(), (gain, extra)
+        seen[(gain, extra)] = redone / (staged * len(pts))
+    assert seen[(6.3, 48)] < 0.02, seen            # the cut rarely misses ...
+    assert seen[(2.5, 48)] > 0.2, seen             # ... a tight one often does ...
+    assert seen[(12.0, 12)] > 0.2, seen            # ... and a generous one overflows a short list
+    # ties, duplicates of the query, tiny clouds
+    rng = np.random.default_rng(5)
+    g = np.arange(9, dtype=np.float32)
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    cloud = rng.normal(size=(1200, 3)).astype(np.float32)
+    dup = np.concatenate((cloud, cloud[:150]))
+    tiny = rng.normal(size=(23, 3)).astype(np.float32)
+    for name, p3, kk, hh in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
+        want_idx, want_dist, _ = oracle.knn_canonical(p3, kk)
+        harness.h_set_onepass(1)
+        try:
+            got = run_knn(harness, p3, kk, hh, staged_u=2, coll_extra=3 * kk, cut_gain=6.3)
+        finally:
+            harness.h_set_onepass(0)
+        assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0, name
+        assert np.array_equal(got["dist"], want_dist), name
