@@ -330,6 +330,12 @@ enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2,
 static constexpr int kHistBins = PCT_HIST_BINS;
 static_assert(kHistBins % 4 == 0 && kHistBins >= 8 && kHistBins <= 252, "byte counters, four bins to a word");
 static constexpr int kHistRowBytes = kHistBins + 4;  // + the word of the overflow counter (candidates beyond the range)
+static constexpr int kOnePassBins = 16;               // ONEPASS: bins of the histogram of the ~40 LISTED candidates
+static constexpr int kOnePassRowBytes = kOnePassBins + 4;
+template <bool ONEPASS>
+struct SelectBins {  // bins of the histogram a knn_select() call builds
+    static constexpr int value = ONEPASS ? kOnePassBins : kHistBins;
+};
 
 // Where the candidates of a query come from.  knn_select() and the fit only need
 //   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
@@ -513,25 +519,33 @@ struct StagedSource {
 // (slot rows + z): 32-bit positions take one row per slot; 16-bit positions keep low slot m in the
 // lower half of row m and high slot z in the upper half of row z, so the neighbours (always low
 // slots) are addressed with one multiply and the boundary zone (high slots) costs no extra rows.
-template <class PosT>
+// PACKED (16-bit positions only, the one-pass experiment): two slots per row -- low slot m in half (m & 1) of row
+// m >> 1, the high slots behind the low rows the same way; half the rows, a shift and a mask more per access.
+template <class PosT, bool PACKED = false>
 struct ListRef {
     PosT* base;  // the thread's first element
     int stride;  // elements of PosT between consecutive rows
     int rows;    // number of low slots
-    PCT_HD PosT& lo(int m) const { return base[(size_t)m * stride]; }
+    PCT_HD PosT& lo(int m) const {
+        return PACKED ? base[(size_t)(m >> 1) * stride + (m & 1)] : base[(size_t)m * stride];
+    }
     PCT_HD PosT& hi(int z) const {
+        if (PACKED) return base[(size_t)(((rows + 1) >> 1) + (z >> 1)) * stride + (z & 1)];
         return sizeof(PosT) == 2 ? base[(size_t)z * stride + 1] : base[(size_t)(rows + z) * stride];
     }
     PCT_HD PosT& at(int m) const { return m < rows ? lo(m) : hi(m - rows); }
     // bytes one thread needs for `slots` slots of which `rows` are low
     PCT_HD static size_t bytes(int rows, int slots) {
+        if (PACKED) return 4 * (size_t)(((rows + 1) >> 1) + ((slots - rows + 1) >> 1));
         return sizeof(PosT) == 2 ? 4 * (size_t)(rows > slots - rows ? rows : slots - rows) : sizeof(PosT) * (size_t)slots;
     }
 };
+static_assert(sizeof(ListRef<uint16_t, true>) == sizeof(ListRef<uint16_t>), "same members");
 
-template <class PosT>
+template <class PosT, bool PACKED = false>
 struct SelectScratch {
-    ListRef<PosT> list;
+    typedef ListRef<PosT, PACKED> List;
+    List list;
     uint32_t* hist; // word w of the byte histogram at hist[w * hist_stride]
     int hist_stride;
     int cap;        // list slots = list.rows low slots (neighbours, pre-collected candidates) + PCT_TIE_SLACK high slots (boundary zone)
@@ -566,9 +580,9 @@ struct SelectScratch {
 // [0, 0.999 cut2) so that the boundary bin ends below the cut.  When the list overflows or holds fewer
 // than k + 1 candidates the estimate missed: SEL_TWOPASS, and the caller redoes the query with the
 // two-pass selection.  The exactness argument is the same: every candidate below cut2 is listed.
-template <bool COLLECT, bool ONEPASS = false, class Source>
+template <bool COLLECT, bool ONEPASS = false, class Source, class Scratch>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
-                      const SelectScratch<typename Source::Pos>& sc, typename Source::Pos& first,
+                      const Scratch& sc, typename Source::Pos& first,
                       typename Source::Pos& last, double& d2_last) {
     typedef typename Source::Pos Pos;
     const uint32_t self = q.idx;  // original indices are unique: identifies the query among the candidates
@@ -592,11 +606,11 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     }
     // ONEPASS: histogram over [0, 0.999 cut2): candidates in the last 0.1 % below the cut are listed but land in the
     // overflow counter, so the boundary bin (widened by 1e-5) always ends below cut2
-    const float inv_w = ONEPASS ? (float)kHistBins / (cut2 * 0.999f) * 0.99999f : inv_w_range;
+    const float inv_w = ONEPASS ? (float)SelectBins<ONEPASS>::value / (cut2 * 0.999f) * 0.99999f : inv_w_range;
     if (ONEPASS && (!(cut2 > 1.0e-30f) || !(inv_w < 3.0e38f))) return SEL_EXACT;
 
 #pragma unroll
-    for (int w = 0; w < kHistRowBytes / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
+    for (int w = 0; w < (SelectBins<ONEPASS>::value + 4) / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
 
     // The bodies of both passes are executed by the whole warp whenever one lane needs them,
     // so they are kept short; everything that can wait is done on the list afterwards.
@@ -606,7 +620,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         uint8_t* hist;
         uint32_t hist_s;   // the same as a shared-window address (PCT_HIST_RED)
         int hist_stride4;  // bytes between consecutive words
-        ListRef<Pos> list;
+        typename Scratch::List list;
         uint32_t seen, n_coll, coll_slots;
         float qx, qy, qz, range2, inv_w, cut2;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
@@ -670,10 +684,10 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         for (uint32_t m = 0; m < p1.n_coll; ++m) {
             const Pt p = src.load(sc.list.lo((int)m));
             const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
-            const int b = (int)fminf(d * inv_w, (float)kHistBins);
+            const int b = (int)fminf(d * inv_w, (float)SelectBins<ONEPASS>::value);
             uint8_t* const c = hb + (b >> 2) * stride4 + (b & 3);
             *c = (uint8_t)(*c + 1);
-            p1.seen += b < kHistBins ? 1u : 0u;
+            p1.seen += b < SelectBins<ONEPASS>::value ? 1u : 0u;
         }
     }
 
@@ -685,7 +699,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         int w_hit = -1;
         uint32_t cum_hit = 0;
 #pragma unroll
-        for (int w = 0; w < kHistBins / 4; ++w) {
+        for (int w = 0; w < SelectBins<ONEPASS>::value / 4; ++w) {
             const uint32_t s4 = byte_sum4(sc.hist[(size_t)w * sc.hist_stride]);
             const bool hit = w_hit < 0 && cum + s4 > (uint32_t)k;
             w_hit = hit ? w : w_hit;
@@ -715,7 +729,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
 
     struct P2 {
-        ListRef<Pos> list;
+        typename Scratch::List list;
         int zone_slots;
         uint32_t self, n_front, n_zone;
         float qx, qy, qz, lo, hi;
@@ -830,11 +844,11 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
 
 // Neighbourhood adaptor over a list of candidate positions (fused kNN path: the neighbours sit in
 // the low slots; the ball path fills low and high slots, LOW_ONLY = false).
-template <class Source, bool LOW_ONLY = true>
+template <class Source, bool LOW_ONLY = true, class List = ListRef<typename Source::Pos>>
 struct ListNeighbourhood {
     typedef typename Source::Pos Pos;
     const Source* src;
-    ListRef<Pos> list;
+    List list;
     int count;
     Pt q;
     Pos first, last;

@@ -47,13 +47,13 @@ __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, u
 
 // What a query does once its k neighbours sit in list[m * stride]: the fused fit, or the
 // ordered (index, distance) rows of plant_kdtree (ref :78-85).
-template <bool FUSED, class Source>
-__device__ __forceinline__ void emit_query(const Source& src, const ListRef<typename Source::Pos>& list, int k,
+template <bool FUSED, class Source, class List>
+__device__ __forceinline__ void emit_query(const Source& src, const List& list, int k,
                                            const Pt& q, typename Source::Pos first, typename Source::Pos last,
                                            long long row, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
                                            const FitOutputs& out) {
     if (FUSED) {
-        ListNeighbourhood<Source> nb;
+        ListNeighbourhood<Source, true, List> nb;
         nb.src = &src; nb.list = list; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
         FitResult r;
         r.status = 0;
@@ -160,8 +160,10 @@ struct StagedCell {
 //                    list is first written after the histogram has been read, so the two share their memory
 //       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
-__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool collect) {
-    const size_t list = ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap), hist = kHistRowBytes;
+__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool collect, bool onepass = false) {
+    // (one-pass experiment: packed list, 16-bin histogram of the listed candidates)
+    const size_t list = onepass ? ListRef<uint16_t, true>::bytes(cap - PCT_TIE_SLACK, cap) : ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap);
+    const size_t hist = onepass ? kOnePassRowBytes : kHistRowBytes;
     const size_t per_query = (collect ? list + hist : (list > hist ? list : hist)) * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
@@ -343,11 +345,11 @@ knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const in
     char* const scratch = sq.scratch;
 
     // ---- E. select out of the staged copy
-    SelectScratch<uint16_t> sel;
+    SelectScratch<uint16_t, ONEPASS> sel;  // (the one-pass experiment packs two list slots into a row)
     sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
     sel.list.stride = 2 * B;
     sel.list.rows = cap - PCT_TIE_SLACK;
-    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap) * B : 0)) + t;
+    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? ListRef<uint16_t, ONEPASS>::bytes(cap - PCT_TIE_SLACK, cap) * B : 0)) + t;
     sel.hist_stride = B;
     sel.cap = cap;
     Stencil st;
@@ -420,12 +422,15 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
 #else
     auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
 #endif
-    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect);
+    const bool onepass = PCT_ONEPASS && collect;
+    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect, onepass);
     // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide:
     // with a buffer of 2.1 times that mean about 4 % of the chunks do not fit, which still beats giving up a
     // third of the resident warps; below that the unstaged share explodes (k = 40: 26 %; scripts/qbench.py)
     const double per_parent = (double)v.n / (double)std::max<long long>(1, a.ix->cells_level[std::min(U, v.num_levels - 1)]);
-    const double wanted = 2.1 * (per_parent + kStagedBlock) * std::pow(1.5, (double)std::min(3.f, std::max(1.f, a.ix->est_dimension)));
+    double wanted_gain = 2.1;
+    if (const char* e = std::getenv("PCT_STAGED_WANTED")) wanted_gain = std::max(0.5, std::atof(e));  // experiments
+    const double wanted = wanted_gain * (per_parent + kStagedBlock) * std::pow(1.5, (double)std::min(3.f, std::max(1.f, a.ix->est_dimension)));
     int cap_pts = 0;
     int ctas_max = PCT_STAGED_CTAS;
     if (const char* e = std::getenv("PCT_STAGED_RESIDENT")) ctas_max = std::max(1, std::min(PCT_STAGED_CTAS, std::atoi(e)));  // experiments
@@ -435,7 +440,7 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
         if ((double)cap_pts >= wanted) break;
     }
     if (cap_pts > 0xffff) cap_pts = 0xffff;
-    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts, collect);
+    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts, collect, onepass);
     if (cap_pts >= 512 && smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;

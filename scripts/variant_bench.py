@@ -26,7 +26,6 @@ def build(specs):
     keep = os.path.join(VARIANTS, "_shipping.so")
     stamp = os.path.join(PKG, "build", "stamp")
     shutil.copy(LIB, keep)
-    stamp_text = open(stamp).read() if os.path.exists(stamp) else None
     try:
         for name, flags in [("base", "")] + specs:
             env = dict(os.environ, PCT_NVCC_EXTRA=flags.replace(",", " "))
@@ -37,8 +36,10 @@ def build(specs):
     finally:
         shutil.copy(keep, LIB)
         os.remove(keep)
-        if stamp_text is not None:
-            open(stamp, "w").write(stamp_text)
+        # the object files now belong to the last variant: drop the stamp so that the next import / build() recompiles
+        # the shipping configuration (scripts/sass_hash.py reads the objects)
+        if os.path.exists(stamp):
+            os.remove(stamp)
 
 
 def run(argv):

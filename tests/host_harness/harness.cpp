@@ -178,6 +178,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
     std::vector<uint32_t> hist(kHistRowBytes / 4);
     SelectScratch<uint32_t> sc{{list.data(), 1, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};
     SelectScratch<uint16_t> sc16{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // 16-bit: two slots per row
+    SelectScratch<uint16_t, true> sc16p{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // packed rows (one-pass experiment)
     const bool collect = coll_extra > 0;
     GlobalSource gsrc;
     gsrc.pts = v.pts;
@@ -208,8 +209,10 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
+                bool packed = false;
                 if (collect && g_onepass) {
-                    rc = knn_select<true, true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                    rc = knn_select<true, true>(v, st, level, ssrc, q, k, sc16p, f16, l16, d2_last);
+                    packed = rc == SEL_OK;
                     if (rc == SEL_TWOPASS) {  // what the L1/L2 kernel does with the queued query
                         ++g_twopass;
                         rc = knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
@@ -220,7 +223,7 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 }
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
-                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[sc16.list.lo(m)].idx];
+                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[packed ? sc16p.list.lo(m) : sc16.list.lo(m)].idx];
                     first = ix->pos_of[stage.pts[f16].idx];
                     last = ix->pos_of[stage.pts[l16].idx];
                     staged = true;
