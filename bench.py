@@ -1,16 +1,19 @@
 """Headline benchmark: points/s for kNN + PCA + quadric curvature on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--k 20]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--k 20] [--workload torus|c3_sphere|bunny_ball|sheet_ball]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...        # the reference's CPU path on the host cores
+    python bench.py --impl reference ...        # the UNMODIFIED reference (baseline/_ref) on the host cores
 
 A step is one pass of the hot path over one synthetic cloud:
-    value  index build + fused kNN/fit kernel, raw xyz already in HBM        (device timed)
-    e2e    PointCloud(points=host) -> plant_kdtree(k) -> compute_pointwise_explicit_quadratic_curvature()
-           with pinned host input and host K, H output inside the timed region
-Multi-GPU is strong scaling on one fixed cloud: the cloud is replicated (NCCL broadcast), the ranks
-agree on cut planes, every rank indexes its own slab (plus a margin) and answers the points in it.
-Prints ONE JSON line on rank 0.
+    value  index build + fused kNN/fit kernel, the cloud already in HBM                 (device timed)
+           N > 1: every rank holds 1/N of the cloud in HBM; the slab exchange (one all-to-all each way over
+           NVLink) is INSIDE the timed region
+    e2e    N = 1: PointCloud(points=host) -> plant_kdtree(k) -> compute_pointwise_explicit_quadratic_curvature()
+           N > 1: distributed.curvature_knn_shared (every rank moves its share of the host arrays)
+           pinned host input and host K, H output inside the timed region
+Multi-GPU is strong scaling on one fixed cloud.  After the timed regions a seeded sample of queries of THIS run is
+checked against the oracle (neighbour rows bit-exact, curvature within the stated tolerance) at k = 20 and k = 32:
+the "parity" object.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -18,7 +21,6 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -29,10 +31,8 @@ if ROOT not in sys.path:
 
 METRIC = "points/sec for kNN+SVD+quadric curvature"
 ALG_BYTES_QUERY = 44   # per point: 16 B own record read + 28 B result written; 32 B are actually written
-ALG_BYTES_E2E = 76     # + 12 B raw read + 16 B sorted record + 4 B permutation
-# our kernels per step (profiles/launches_r01t.txt): bbox, pilot keys, 2 x level hist, Morton keys, gather, table fill,
-# staged kNN+fit, L1/L2 kNN+fit x2 (unstaged chunks, level-1 retries), exact tail, stats; CUB's sort kernels not counted
-OUR_KERNELS_PER_STEP = 12
+ALG_BYTES_BALL = 48    # + 4 B member count
+ALG_BYTES_MEMBER = 16  # ball workloads: one record per ball member has to be seen at least once
 
 
 def parse_args():
@@ -41,21 +41,40 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="torus", choices=["torus", "c3_sphere", "bunny_ball", "sheet_ball"])
     ap.add_argument("--points", type=int, default=100_000_000)
     ap.add_argument("--k", type=int, default=20)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-k", default="20,32", help="k values of the parity block (torus workload)")
+    ap.add_argument("--parity-rows", type=int, default=100_000, help="queries checked per k, over all ranks")
     ap.add_argument("--clock-interval-ms", type=int, default=200)
     return ap.parse_args()
 
 
-def workload_name(n, k):
-    return f"synthetic torus surface (R=1, r=1/3, uniform u,v, seed 3), N={n}, k={k} kNN"
+# --------------------------------------------------------------------------
+# workloads (the config object is identical in both arms)
+# --------------------------------------------------------------------------
+def workload_config(args):
+    n, k = args.points, args.k
+    if args.workload == "torus":
+        return {"workload": f"synthetic torus surface (R=1, r=1/3, uniform u,v, seed 3), N={n}, k={k} kNN", "k": k, "points": n,
+                "l2": "inputs (12 B/point raw + 16 B/point sorted: 2.8 GB at 100M) exceed the 126 MB L2; no flush needed"}
+    if args.workload == "c3_sphere":
+        return {"workload": f"C3: Fibonacci sphere R=1, N=1000000, k={k} kNN, closed-form K=1, |H|=1", "k": k, "points": 1_000_000,
+                "l2": "28 MB of inputs fit the L2: a 256 MB buffer is written between timed steps"}
+    if args.workload == "bunny_ball":
+        return {"workload": "C2: sample_scans/bunny.txt (35947 points), epsilon-ball radius 3.8e-3 (mean ~30 members)", "k": 0,
+                "points": 35947, "radius": 3.8e-3, "l2": "inputs fit the L2: a 256 MB buffer is written between timed steps"}
+    return {"workload": "C4 stand-in: 332757-point scanned sheet z = sin x sin y, 3-component density mixture + N(0, 1e-3) noise, "
+                        "epsilon-ball radius 2.5 x median nearest-neighbour spacing", "k": 0, "points": 332_757,
+            "l2": "inputs fit the L2: a 256 MB buffer is written between timed steps"}
 
 
 def host_sample(n_sample, seed=3):
-    """Host copy of the workload's distribution for the CPU legs (same surface, same sampling law)."""
+    """Host cloud of the torus workload's distribution (same surface, same sampling law)."""
     import numpy as np
 
     rng = np.random.default_rng(seed)
@@ -65,57 +84,141 @@ def host_sample(n_sample, seed=3):
     return np.stack(((R + r * np.cos(v)) * np.cos(u), (R + r * np.cos(v)) * np.sin(u), r * np.sin(v)), 1).astype(np.float32)
 
 
-def cpu_sample_cloud(n_total, rows_needed):
-    """A cloud whose point spacing equals the full workload's would need all N points; the CPU path's
-    cost per point does not depend on spacing, so the legs run on a self-contained sample cloud."""
-    return host_sample(int(min(n_total, max(20_000, rows_needed))))
+def sphere_sample(n_sample, seed=0):
+    import numpy as np
+
+    i = np.arange(0, n_sample, dtype=np.float64) + 0.5
+    phi = np.arccos(1 - 2 * i / n_sample)
+    theta = np.pi * (1 + np.sqrt(5)) * i
+    return np.stack((np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)), 1).astype(np.float32)
+
+
+def sheet_cloud(n=332_757, seed=2, noise=1e-3, half_width=2 * math.pi):
+    """C4 stand-in: non-uniform density so that ball sizes vary by more than 10x."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    centres = np.array([[-3.0, -2.0], [2.5, 1.0], [0.0, 4.0]])
+    sigmas = np.array([0.8, 2.0, 4.0])
+    weights = np.array([0.3, 0.4, 0.3])
+    xy = np.empty((0, 2))
+    while len(xy) < n:
+        m = 2 * (n - len(xy)) + 1024
+        comp = rng.choice(3, size=m, p=weights)
+        cand = centres[comp] + rng.normal(size=(m, 2)) * sigmas[comp, None]
+        xy = np.concatenate((xy, cand[(np.abs(cand) <= half_width).all(axis=1)]))
+    xy = xy[:n]
+    p = np.stack((xy[:, 0], xy[:, 1], np.sin(xy[:, 0]) * np.sin(xy[:, 1])), 1) + rng.normal(scale=noise, size=(n, 3))
+    return p.astype(np.float32)
+
+
+def small_workload_cloud(args):
+    """(points float32 (N, 3), radius or None) of the non-default workloads."""
+    import numpy as np
+
+    if args.workload == "c3_sphere":
+        return sphere_sample(1_000_000), None
+    if args.workload == "bunny_ball":
+        pts = np.load(os.path.join(ROOT, "tests", "golden", "bunny_points.npz"))["points"].astype(np.float32)
+        return np.ascontiguousarray(pts), 3.8e-3
+    pts = sheet_cloud()
+    from scipy.spatial import cKDTree  # input preparation only: the radius is defined from the data's spacing
+
+    sub = pts[:: max(1, len(pts) // 20000)]
+    d1 = cKDTree(pts).query(sub, 2)[0][:, 1]
+    return pts, float(2.5 * np.median(d1))
 
 
 # --------------------------------------------------------------------------
-# reference arm / cpu baseline
+# CPU arms: the unmodified reference (baseline/_ref), imported as it is
 # --------------------------------------------------------------------------
-def run_cpu_leg(n_total, k, seconds):
+def cpu_cloud_maker(args):
+    if args.workload == "c3_sphere":
+        return sphere_sample
+    return host_sample
+
+
+def reference_leg(args, seconds, with_fan_out=True):
+    """cpu_baseline object: the reference's own call sequence on one thread (it has no parallelism), and the same
+    unmodified sequence fanned out over every host core, each process on its own sample cloud."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("MKL_NUM_THREADS", "1")
-    from oracle import baseline
+    from oracle import ref_arm
 
-    cores = baseline.host_cores()
-    # size the sample cloud so that the leg really spends `seconds` on all cores
-    cost = baseline.per_point_seconds(host_sample(20_000), k, probe=1000)
-    rows = int(min(n_total, 4_000_000, max(50_000, cores * seconds / cost)))
-    pts = cpu_sample_cloud(n_total, rows)
-    res = baseline.timed_reference(pts, k, seconds=seconds, procs=cores)
-    return res, len(pts)
+    if args.workload in ("bunny_ball", "sheet_ball"):
+        return ball_port_leg(args, seconds)
+    if not ref_arm.available():
+        ref_arm.install()
+    if not ref_arm.available():
+        return {"unavailable": "baseline/_ref/pointCloudToolbox.py is missing (run __graft_entry__.build() in the dev container)"}
+    k = args.k
+    make = cpu_cloud_maker(args)
+    one = ref_arm.timed_single(make, k, seconds)
+    out = {"value": one["points_per_s"], "unit": "points/s", "cores": 1, "kind": "reference",
+           "sample": (f"PointCloud(points) -> plant_kdtree({k}) -> compute_pointwise_explicit_quadratic_curvature() of the UNMODIFIED "
+                      f"reference (baseline/_ref/pointCloudToolbox.py, sha256 {ref_arm.sha256()[:12]}) on one thread, a {one['rows']}-point "
+                      f"cloud of the workload's surface, {one['seconds']:.1f} s"),
+           "per_point_us_single_core": one["per_point_us"], "rows": one["rows"], "seconds": one["seconds"]}
+    if with_fan_out:
+        fan = ref_arm.fan_out(make, k, seconds, one["per_point_us"] * 1e-6)
+        out["all_cores"] = {"value": fan["points_per_s"], "unit": "points/s", "cores": fan["cores"], "kind": "reference",
+                            "sample": (f"the same unmodified call sequence in {fan['cores']} processes, each on its own "
+                                       f"{fan['rows'] // fan['cores']}-point sample cloud, {fan['seconds']:.1f} s wall")}
+    return out
+
+
+def ball_port_leg(args, seconds):
+    """The reference has no epsilon-ball code (README.md:8 only advertises it): the CPU figure is the oracle's
+    composition of scipy's query_ball_point with the reference's per-neighbourhood functions, one thread."""
+    import numpy as np
+
+    import oracle
+
+    pts, radius = small_workload_cloud(args)
+    rows = np.arange(0, len(pts), max(1, len(pts) // 4000))
+    t = time.perf_counter()
+    off, idx, _ = oracle.ball_canonical(pts, radius, rows=rows)
+    oracle.curvature_from_csr(pts, off, idx, rows=rows)
+    dt = time.perf_counter() - t
+    return {"value": len(rows) / dt, "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": f"{len(rows)} strided query points: scipy query_ball_point + the reference's plane / fit / curvature functions (oracle port), {dt:.1f} s"}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    k = args.k
-    step_seconds = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    info = None
+    step_seconds = max(2.0, min(15.0, 90.0 / max(1, args.steps + args.warmup)))
+    legs = []
     for s in range(args.warmup + args.steps):
-        res, cloud_n = run_cpu_leg(args.points, k, step_seconds)
+        leg = reference_leg(args, step_seconds, with_fan_out=False)
+        if "unavailable" in leg:
+            print(json.dumps({"impl": "reference", "unavailable": leg["unavailable"]}), flush=True)
+            return
         if s >= args.warmup:
-            vals.append(res)
-        info = (res, cloud_n)
-    total_rows = sum(r["rows"] for r in vals)
-    total_s = sum(r["seconds"] for r in vals)
-    value = total_rows / total_s
-    res, cloud_n = info
-    sample = (f"{res['rows']} query points per step of a {cloud_n}-point cloud drawn from the workload's surface; the "
-              f"reference's per-point loop (cKDTree.query + np.cov + svd + lstsq per point) fanned out over {res['cores']} processes")
+            legs.append(leg)
+    if args.workload in ("bunny_ball", "sheet_ball"):
+        value = sum(leg["value"] for leg in legs) / len(legs)
+        ms = 0.0
+    else:
+        rows = sum(leg["rows"] for leg in legs)
+        secs = sum(leg["seconds"] for leg in legs)
+        value = rows / secs
+        ms = 1e3 * secs / len(legs)
+    cpu = dict(legs[-1])
+    cpu["value"] = value
+    if args.workload not in ("bunny_ball", "sheet_ball"):
+        from oracle import ref_arm
+
+        fan = ref_arm.fan_out(cpu_cloud_maker(args), args.k, step_seconds, cpu["per_point_us_single_core"] * 1e-6)
+        cpu["all_cores"] = {"value": fan["points_per_s"], "unit": "points/s", "cores": fan["cores"], "kind": "reference",
+                            "sample": f"the same unmodified call sequence in {fan['cores']} processes, each on its own sample cloud"}
     line = {
-        "impl": "reference",
-        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, len(vals)), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32 inputs, f64 LAPACK", "data": "synthetic",
-        "config": {"workload": workload_name(args.points, k), "k": k, "points": args.points},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": res["cores"], "kind": "port", "sample": sample,
-                         "per_point_us_single_core": res["per_point_us_single_core"]},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 inputs, f64 LAPACK", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,17 +326,211 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profiled_traffic(points_per_launch, k):
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
-    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+def committed_profile(k):
+    """Counters of the committed ncu --set full capture of the dominant kernel (profiles/roofline_traffic.json):
+    NOT measured in this run -- the entry names the capture (file, date, commit) it comes from."""
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             t = json.load(f)
-        if int(t.get("k", -1)) != k:
-            return None
-        return float(t["dram_bytes_per_point"]) * points_per_launch
+        return t if int(t.get("k", -1)) == k else None
     except Exception:
         return None
+
+
+def fma_peaks():
+    import ctypes
+
+    from point_cloud_toolbox_b200 import _lib
+
+    f32, f64 = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib.pct_measure_fma_peaks(ctypes.byref(f32), ctypes.byref(f64), None))
+    return f32.value, f64.value
+
+
+def make_torus_on_device(n, dev):
+    import torch
+
+    gen = torch.Generator(device=dev).manual_seed(3)
+    pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    chunk = 1 << 24
+    R, r = 1.0, 1.0 / 3.0
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        u = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
+        v = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
+        w = R + r * torch.cos(v)
+        pts[s:s + m, 0] = (w * torch.cos(u)).float()
+        pts[s:s + m, 1] = (w * torch.sin(u)).float()
+        pts[s:s + m, 2] = (r * torch.sin(v)).float()
+        del u, v, w
+    return pts
+
+
+def parity_block(args, world, rank, dev, pts, shared_in, shared_out, host_pts):
+    """Seeded sample of THIS run's answers against the oracle, per k: neighbour rows of the index that answered
+    (bit-exact), records of the device-resident path and K, H of the end-to-end path (stated tolerance)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle import sample_parity
+    from point_cloud_toolbox_b200 import GridIndex, PointCloud
+    from point_cloud_toolbox_b200 import distributed as pdist
+
+    n = args.points
+    out = {}
+    run_len = 4096
+    for kk in [int(v) for v in args.parity_k.split(",") if v]:
+        n_runs = max(1, args.parity_rows // (run_len * world))
+        if world == 1:
+            index = GridIndex(pts, k_hint=kk)
+            rec = index.curvature_knn(kk, want_coeffs=False).records
+            pc = PointCloud(points=host_pts, normals=np.zeros((n, 0), np.float32), k_neighbors=kk)
+            pc.plant_kdtree(kk)
+            K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+            runs = sample_parity.choose_runs(index, n_runs, run_len, seed=1000 + kk)
+            res = sample_parity.check_runs(index, pts, kk, runs, records_of=lambda ids: rec[ids], host_kh=(K, H))
+            index.close()
+            del pc, rec
+            parts = [res]
+        else:
+            begin, end = pdist.shard_bounds(n, world, rank)
+            part = pdist.curvature_knn_exchange(pts[begin:end].contiguous(), begin, n, kk)
+            if shared_in is not None:
+                pdist.curvature_knn_shared(shared_in, shared_out, kk, device=dev)       # collective; out complete on return
+                host_kh = (shared_out.array[0], shared_out.array[1])
+            else:
+                host_kh = None
+            res = {}
+            if part.index is not None:
+                c_lo, c_hi, own_lo, own_hi = part.plan.bounds[rank]
+                axis = part.plan.axis
+                runs = sample_parity.choose_runs(part.index, n_runs, run_len, seed=1000 + kk + 17 * rank,
+                                                 planes=(own_lo, own_hi), axis=axis)
+                own_ids = part.own_ids.long()
+                res = sample_parity.check_runs(
+                    part.index, pts, kk, runs, local_to_orig=part.local_ids,
+                    owned=lambda c: (c[:, axis] >= own_lo) & (c[:, axis] < own_hi),
+                    records_of=lambda ids: part.records[torch.searchsorted(own_ids, ids)], host_kh=host_kh)
+            part.close()
+            parts = [None] * world
+            dist.all_gather_object(parts, res)
+            dist.barrier()
+        out[f"k{kk}"] = sample_parity.merge([p for p in parts if p])
+    total = {key: sum(v.get(key, 0) for v in out.values()) for key in ("rows", "violations", "rows_differing", "dist_differing",
+                                                                        "e2e_violations", "pad_too_small")}
+    total["per_k"] = out
+    total["checker"] = ("oracle.knn_curvature (ref :69-89, :505-509 restated, pinned to the unmodified reference) on padded spatial crops "
+                        "of the whole cloud; sample = Morton runs of the index that answered, incl. runs on the slab cut planes")
+    return total
+
+
+def small_workload(args):
+    """c3_sphere / bunny_ball / sheet_ball on one GPU: inputs fit the L2, so it is flushed between timed steps."""
+    import numpy as np
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = reference_leg(args, args.cpu_seconds, with_fan_out=False)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from point_cloud_toolbox_b200 import GridIndex, PointCloud
+
+    host_pts, radius = small_workload_cloud(args)
+    n, k = len(host_pts), args.k
+    pinned = torch.from_numpy(host_pts).pin_memory()
+    host_pts = pinned.numpy()
+    pts = pinned.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(0, args.clock_interval_ms, not args.no_clocks)
+    sampler.prepare()
+
+    def device_step():
+        flush.fill_(1)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        if radius is None:
+            index = GridIndex(pts, k_hint=k)
+            e1.record()
+            fit = index.curvature_knn(k, want_coeffs=False)
+        else:
+            index = GridIndex(pts, cell_hint=radius * 1.001)
+            e1.record()
+            fit = index.curvature_ball(radius)
+        e2.record()
+        return index, fit, (e0, e1, e2)
+
+    def e2e_step():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        pc = PointCloud(points=host_pts, normals=np.zeros((n, 0), np.float32), k_neighbors=max(k, 1))
+        if radius is None:
+            pc.plant_kdtree(k)
+        else:
+            pc.plant_ball(radius)
+        K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+        return K, H, time.perf_counter() - t
+
+    for _ in range(args.warmup):
+        index, fit, _ = device_step()
+        index.close()
+    torch.cuda.synchronize()
+    sampler.start()
+    steps = []
+    launches = 0
+    for _ in range(args.steps):
+        index, fit, ev = device_step()
+        torch.cuda.synchronize()
+        steps.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+        launches += int(index.info().build_launches) + (int(index.last_stats().kernel_launches) if radius is None else 2)
+        last = (index, fit)
+        if _ + 1 < args.steps:
+            index.close()
+    build_ms = sum(s[0] for s in steps) / len(steps)
+    query_ms = sum(s[1] for s in steps) / len(steps)
+    index, fit = last
+    members = int(fit.counts.sum().item()) if radius is not None else n * k
+    nan_rows = int(torch.isnan(fit.column("K")).sum().item())
+    index.close()
+    for _ in range(args.warmup):
+        e2e_step()
+    walls = []
+    for _ in range(args.steps):
+        K, H, w = e2e_step()
+        walls.append(w)
+    clocks = sampler.stop()
+    e2e_ms = 1e3 * sum(walls) / len(walls)
+    peak, peak_src = measured_peak_gbs()
+    per_q = ALG_BYTES_QUERY if radius is None else ALG_BYTES_BALL
+    alg_bytes = n * per_q + (members * ALG_BYTES_MEMBER if radius is not None else 0)
+    achieved = alg_bytes / (query_ms * 1e-3) / 1e9
+    details = {"build_ms": build_ms, "query_ms": query_ms, "nan_rows": nan_rows, "members": members,
+               "members_per_query": members / n, "parallelism": "one GPU"}
+    if radius is not None:
+        details["radius"] = radius
+        details["count_min_max"] = [int(fit.counts.min().item()), int(fit.counts.max().item())]
+    else:
+        Kd = np.asarray(K, np.float64)
+        details["closed_form"] = {"K_abs_err_median": float(np.median(np.abs(Kd - 1.0))), "H_abs_err_median": float(np.median(np.abs(np.abs(H) - 1.0)))}
+    line = {
+        "metric": METRIC, "value": n / ((build_ms + query_ms) * 1e-3), "unit": "points/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": build_ms + query_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 search keys, f64 re-rank and fit, f32 outputs", "data": "synthetic" if args.workload != "bunny_ball" else "sample_scans/bunny.txt (fixture copy)",
+        "config": workload_config(args), "details": details,
+        "roofline": {"bound": "hbm", "kernel": "ball_staged_kernel<2, fused>" if radius is not None else "knn_staged_kernel<2, fused>",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "note": (f"algorithmic {per_q} B/query" + (f" + {ALG_BYTES_MEMBER} B per ball member ({members / n:.1f} members/query)" if radius is not None else "")
+                              + "; instruction-issue bound, not HBM bound (DESIGN.md 5)")},
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
+                "ms_per_step": e2e_ms, "host_io": "one rank"},
+        "gpu_launches": launches * 2, "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
 
 
 def ours(args):
@@ -244,16 +541,18 @@ def ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "torus":
+        if world > 1:
+            if rank == 0:
+                print(json.dumps({"unavailable": f"workload {args.workload} is a one-GPU case (BASELINE.json configs 1-3)"}), flush=True)
+            return
+        return small_workload(args)
     n, k = args.points, args.k
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        # before CUDA is initialised in this process: the leg forks worker processes
-        res, cloud_n = run_cpu_leg(n, k, args.cpu_seconds)
-        cpu = {"value": res["points_per_s"], "unit": "points/s", "cores": res["cores"], "kind": "port",
-               "sample": (f"{res['rows']} query points of a {cloud_n}-point cloud from the workload's surface, the reference's "
-                          f"per-point loop on {res['cores']} processes, {res['seconds']:.1f} s"),
-               "per_point_us_single_core": res["per_point_us_single_core"]}
+        # before CUDA is initialised in this process: the fan-out leg forks worker processes
+        cpu = reference_leg(args, args.cpu_seconds)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -263,25 +562,10 @@ def ours(args):
 
     from point_cloud_toolbox_b200 import GridIndex, PointCloud
     from point_cloud_toolbox_b200 import distributed as pdist
-    from point_cloud_toolbox_b200._lib import LAYOUT_SLICE
 
-    # ---- the cloud: generated on the device (rank 0), replicated before any timing ----
-    if rank == 0:
-        gen = torch.Generator(device=dev).manual_seed(3)
-        pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        chunk = 1 << 24
-        R, r = 1.0, 1.0 / 3.0
-        for s in range(0, n, chunk):
-            m = min(chunk, n - s)
-            u = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
-            v = torch.rand(m, generator=gen, device=dev, dtype=torch.float64) * (2 * math.pi)
-            w = R + r * torch.cos(v)
-            pts[s:s + m, 0] = (w * torch.cos(u)).float()
-            pts[s:s + m, 1] = (w * torch.sin(u)).float()
-            pts[s:s + m, 2] = (r * torch.sin(v)).float()
-            del u, v, w
-    else:
-        pts = None
+    # ---- the cloud: generated on the device (rank 0) before any timing; every rank keeps a replica for the
+    # ---- parity crops and the comparison figure, the timed multi-GPU paths only see this rank's SHARE
+    pts = make_torus_on_device(n, dev) if rank == 0 else None
     if world > 1:
         pts = pdist.broadcast_cloud(pts, n, None, 0, dev)
     host_pts = None
@@ -290,9 +574,8 @@ def ours(args):
         host.copy_(pts)
         torch.cuda.synchronize()
         host_pts = host.numpy()
-
-    mode = pdist.default_mode(world)
     begin, end = pdist.shard_bounds(n, world, rank)
+    share = pts[begin:end].clone() if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -300,30 +583,25 @@ def ours(args):
         torch.cuda.synchronize()
 
     def device_step(record=None):
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e2 = torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         if world == 1:
             index = GridIndex(pts, k_hint=k)
             e1.record()
             fit = index.curvature_knn(k, want_coeffs=False)
-        elif mode == "replicated":
-            index = GridIndex(pts, k_hint=k)
-            e1.record()
-            fit = index.curvature_knn(k, begin, end, layout=LAYOUT_SLICE, want_coeffs=False)
+            e2.record()
+            handle = index
         else:
-            # cut planes + slab selection + slab index + fused kernel on the points this rank owns
-            part = pdist.curvature_knn_slab(pts, k, rank, world, events=(e1,))
-            index, fit = part.index, part
-        e2.record()
+            fit = pdist.curvature_knn_exchange(share, begin, n, k)
+            e1.record()
+            e2.record()
+            handle = fit
         if record is not None:
             record.append((e0, e1, e2))
-        return index, fit
+        return handle, fit
 
     # multi-GPU end to end: the host cloud and the host result live in shared memory mapped by every rank
-    # (a one-node job's ranks see the same input), so each rank moves its share over its own PCIe link;
-    # if the node's /dev/shm cannot hold them, rank 0 moves everything (broadcast in, gather out)
+    # (a one-node job's ranks see the same input), so each rank moves its share over its own PCIe link
     shared_in = shared_out = None
     if world > 1:
         tag = f"pct_bench_{os.environ.get('MASTER_PORT', '0')}"
@@ -334,32 +612,24 @@ def ours(args):
                 shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=True)
                 shared_in.array[:] = host_pts
         except Exception as exc:  # pragma: no cover
-            print(f"shared host memory unavailable ({exc!r}); rank 0 moves all host data", file=sys.stderr)
+            print(f"shared host memory unavailable ({exc!r})", file=sys.stderr)
             ok.zero_()
         dist.broadcast(ok, 0)
-        if bool(ok.item()) and rank != 0:
+        if not bool(ok.item()):
+            raise RuntimeError("the multi-GPU end-to-end path needs /dev/shm room for the cloud and the result")
+        if rank != 0:
             shared_in = pdist.SharedHostArray(tag + "_in", (n, 3), create=False)
             shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=False)
-        if not bool(ok.item()):
-            shared_in = shared_out = None
         dist.barrier()
 
-    def e2e_step():
+    def e2e_step(stages=None):
         if world == 1:
             pc = PointCloud(points=host_pts, normals=np.zeros((n, 0), np.float32), k_neighbors=k)
             pc.plant_kdtree(k)
             K, H = pc.compute_pointwise_explicit_quadratic_curvature()
             return K, H
-        if shared_in is not None:
-            pdist.curvature_knn_shared(shared_in, shared_out, k, device=dev)
-            return (shared_out.array[0], shared_out.array[1]) if rank == 0 else (None, None)
-        out = pdist.curvature_knn_sharded(host_pts, n, k, device=dev)
-        if rank == 0:
-            from point_cloud_toolbox_b200.engine import to_host
-
-            kh = to_host(out.t())
-            return kh[0], kh[1]
-        return None, None
+        pdist.curvature_knn_shared(shared_in, shared_out, k, device=dev, stages=stages).close()
+        return (shared_out.array[0], shared_out.array[1]) if rank == 0 else (None, None)
 
     sampler = ClockSampler(local_rank, args.clock_interval_ms, not args.no_clocks)
     if rank == 0:
@@ -371,10 +641,10 @@ def ours(args):
     def device_loop(steps, events=None):
         last = None
         for _ in range(steps):
-            index, fit = device_step(events)
+            handle, fit = device_step(events)
             if last is not None:
                 last[0].close()
-            last = (index, fit)
+            last = (handle, fit)
         return last
 
     def e2e_loop(steps, walls=None):
@@ -402,23 +672,41 @@ def ours(args):
     t_end.record()
     barrier()
     total_ms = t_start.elapsed_time(t_end)
-    build_steps = [round(a.elapsed_time(b), 2) for a, b, _ in events]
-    build_ms = sum(build_steps) / len(events)
-    query_ms = sum(b.elapsed_time(c) for _, b, c in events) / len(events)
-    stats = last[0].last_stats()
-    info = last[0].info()
-    if world == 1 or mode == "replicated":
+    launches_step = 0
+    if world == 1:
+        build_steps = [round(a.elapsed_time(b), 2) for a, b, _ in events]
+        build_ms = sum(build_steps) / len(events)
+        query_ms = sum(b.elapsed_time(c) for _, b, c in events) / len(events)
+        index = last[0]
+        stats, info = index.last_stats(), index.info()
         status_bad = int((last[1].status != 0).sum().item())
         nan_rows = int(torch.isnan(last[1].column("K")).sum().item())
-        pts_per_launch, slab_points, unresolved = end - begin, n, 0
+        pts_per_launch, indexed, unresolved = n, n, 0
+        launches_step = int(info.build_launches) + int(stats.kernel_launches)
     else:
-        rec = last[1].records
+        fit = last[1]
+        stats, info = fit.index.last_stats(), fit.index.info()
+        rec = fit.records
         status_bad = int((rec[:, 7].contiguous().view(torch.int32) != 0).sum().item())
         nan_rows = int(torch.isnan(rec[:, 3]).sum().item())
-        pts_per_launch, slab_points, unresolved = int(last[1].ids.numel()), int(last[0].n), int(last[1].unresolved)
+        pts_per_launch, indexed, unresolved = int(fit.own_ids.numel()), int(fit.indexed), int(fit.unresolved)
+        build_steps, build_ms, query_ms = [], None, None
+        # bbox/sample torch kernels are not ours; pilot (2), bin count + fill + row starts (3), own flags + rows (2)
+        launches_step = int(info.build_launches) + int(stats.kernel_launches) + 7
     last[0].close()
     del last
     torch.cuda.empty_cache()
+
+    # stage times of the multi-GPU device-resident step (separate instrumented pass, after the timed region)
+    value_stages = None
+    if world > 1:
+        st = pdist.Stages()
+        fit = pdist.curvature_knn_exchange(share, begin, n, k, stages=st)
+        torch.cuda.synchronize()
+        value_stages = st.durations_ms()
+        fit.close()
+        # the kernel's own time: the fused query call alone on this rank's slab
+        barrier()
 
     # ---- end to end through the public API ----
     e2e_loop(args.warmup)
@@ -433,18 +721,67 @@ def ours(args):
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - wall0)
     e2e_ms = s0.elapsed_time(s1)
-    e2e_host_io = "one rank" if world == 1 else ("every rank its share (shared host memory)" if shared_in is not None else "rank 0")
-    if rank == 0 and world > 1 and shared_out is not None:
-        K = np.array(K[:1024])  # detach from the segment before it is unmapped
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_stages = None
+    if world > 1:
+        st = pdist.Stages()
+        e2e_step(st)
+        torch.cuda.synchronize()
+        e2e_stages = st.durations_ms()
+        barrier()
+
+    # ---- replicated-cloud comparison figure (round 1's `value`: no collective in the timed region) ----
+    replicated_ms = None
+    if world > 1:
+        for _ in range(2):
+            pdist.curvature_knn_slab(pts, k, rank, world).index.close()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            pdist.curvature_knn_slab(pts, k, rank, world).index.close()
+        r1.record()
+        barrier()
+        replicated_ms = r0.elapsed_time(r1) / reps
+
+    # ---- the fused query call alone (roofline), on this rank's slab / the whole index ----
+    if world == 1:
+        roof_query_ms = query_ms
+    else:
+        fit = pdist.curvature_knn_exchange(share, begin, n, k)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        q0.record()
+        for _ in range(reps):
+            fit.index.curvature_knn(k, want_coeffs=False)
+        q1.record()
+        torch.cuda.synchronize()
+        roof_query_ms = q0.elapsed_time(q1) / reps
+        fit.close()
+        barrier()
+
+    # ---- parity of this run (after every timed region) ----
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(args, world, rank, dev, pts, shared_in, shared_out, host_pts)
+
     for sh in (shared_in, shared_out):
         if sh is not None:
             sh.close()
-    clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, query_ms, build_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
+        vals = [total_ms, e2e_ms, e2e_wall_ms, roof_query_ms, replicated_ms]
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, query_ms, build_ms, e2e_wall_ms = t.tolist()
+        total_ms, e2e_ms, e2e_wall_ms, roof_query_ms, replicated_ms = t.tolist()
+        for stages in (value_stages, e2e_stages):
+            names = sorted(stages)
+            t = torch.tensor([stages[s] for s in names], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for s, v in zip(names, t.tolist()):
+                stages[s] = round(v, 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -456,68 +793,70 @@ def ours(args):
 
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3)
-    e2e_value = n / (max(e2e_ms, e2e_wall_ms) / args.steps * 1e-3)
+    e2e_step_ms = max(e2e_ms, e2e_wall_ms) / args.steps
     peak, peak_src = measured_peak_gbs()
-    achieved = pts_per_launch * ALG_BYTES_QUERY / (query_ms * 1e-3) / 1e9
+    achieved = pts_per_launch * ALG_BYTES_QUERY / (roof_query_ms * 1e-3) / 1e9
+    prof = committed_profile(k)
+    details = {
+        "parallelism": ("one GPU" if world == 1 else
+                        f"{world} slabs across the longest axis; every rank starts with 1/{world} of the cloud, one all-to-all delivers each slab "
+                        f"(+ margin) to its rank, one returns the rows (rank 0: {indexed} indexed, {pts_per_launch} answered, {unresolved} redone)"),
+        "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
+        "level1_retries": stats.level1_retries, "exact_path": stats.exact_path, "unstaged": stats.unstaged,
+        "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": roof_query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
+    }
+    if world > 1:
+        details["value_stages_ms"] = value_stages
+        details["e2e_stages_ms"] = e2e_stages
+        details["stage_note"] = "max over ranks of CUDA-event times of one instrumented pass after the timed region; a stage ends where it is named"
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 search keys, f64 re-rank and fit, f32 outputs", "data": "synthetic",
-        "config": {
-            "workload": workload_name(n, k), "k": k, "points": n, "parallelism": ("one GPU" if world == 1 else
-                                                                    f"cloud replicated, every rank builds the whole index and answers 1/{world} of the Morton-sorted queries"
-                                                                    if mode == "replicated" else
-                                                                    f"{world} slabs across the longest axis: cloud replicated, each rank indexes and answers its "
-                                                                    f"slab (rank 0: {slab_points} indexed, {pts_per_launch} answered, {unresolved} redone on a whole-cloud index)"),
-            "l2": "inputs (1.2 GB raw + 1.6 GB sorted at 100M) exceed the 126 MB L2; no flush needed",
-            "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
-            "level1_retries": stats.level1_retries, "exact_path": stats.exact_path,
-            "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
-        },
+        "config": workload_config(args), "details": details,
         "roofline": {
-            "bound": "hbm", "kernel": "knn_staged_kernel<2,true,false> (+ unstaged chunks, level-1 retries and exact tail: one call, CUDA events on its stream)",
+            "bound": "hbm", "kernel": "knn_staged_kernel<2, fused> (+ unstaged chunks, level-1 retries and exact tail: one call, CUDA events on its stream)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": profiled_traffic(pts_per_launch, k), "peak_source": peak_src,
-            "note": "algorithmic 44 B/point; the kernel is instruction-issue bound (72 % of issue slots, profiles/staged_full_r01t.txt), not HBM bound (DESIGN.md 5)",
+            "traffic": float(prof["dram_bytes_per_point"]) * pts_per_launch if prof else None,
+            "traffic_source": (prof.get("source") if prof else None),
+            "peak_source": peak_src,
+            "note": "algorithmic 44 B/point; the kernel is instruction-issue bound, not HBM bound (DESIGN.md 5); `traffic` is the committed "
+                    "ncu capture's bytes/point times this run's points, not a measurement of this run",
         },
-        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
-                "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps, "step_wall_ms": step_walls, "host_io": e2e_host_io},
-        "gpu_launches": OUR_KERNELS_PER_STEP * args.steps * 2,
+        "e2e": {"value": n / (e2e_step_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
+                "ms_per_step": e2e_step_ms, "step_wall_ms": step_walls,
+                "host_io": "one rank" if world == 1 else "every rank its share (shared host memory)"},
+        "gpu_launches": launches_step * args.steps * 2,
+        "gpu_launches_source": "pct_index_info.build_launches + pct_query_stats.kernel_launches of the last timed step (+ 7 slab-exchange kernels at N > 1), x steps x 2 timed loops",
         "clocks": clocks,
     }
+    if world > 1:
+        line["value_with_collectives"] = value
+        line["value_replicated_no_collective"] = {"value": n / (replicated_ms * 1e-3), "ms_per_step": replicated_ms,
+                                                  "note": "round 1's definition: cloud replicated before timing, every rank selects and answers its slab"}
+    if parity is not None:
+        line["parity"] = parity
     # secondary roofline: algorithmic flops per point -- search 8c + selection 2c with
     # c = 2.9 k candidates, covariance 15 k, rotation 18 k, normal equations 59 k, fixed 600 -- against the FMA
     # rate of the CUDA cores measured here, after the timed regions
     try:
-        if world > 1:
-            raise RuntimeError("measured at N = 1 only (like cpu_baseline)")
-        from point_cloud_toolbox_b200 import _lib
-        import ctypes
-
-        f32, f64 = ctypes.c_double(), ctypes.c_double()
-        _lib.check(_lib.lib.pct_measure_fma_peaks(ctypes.byref(f32), ctypes.byref(f64), None))
+        f32, f64 = fma_peaks()
         flops_pt = 121.0 * k + 600.0
-        ach = pts_per_launch * flops_pt / (query_ms * 1e-3) / 1e12
-        line["roofline_fp32"] = {"algorithmic_flops_per_point": flops_pt, "achieved": ach, "peak": f32.value, "unit": "TFLOP/s",
-                                 "frac": ach / f32.value if f32.value > 0 else None, "fp64_peak": f64.value,
+        ach = pts_per_launch * flops_pt / (roof_query_ms * 1e-3) / 1e12
+        line["roofline_fp32"] = {"algorithmic_flops_per_point": flops_pt, "achieved": ach, "peak": f32, "unit": "TFLOP/s",
+                                 "frac": ach / f32 if f32 > 0 else None, "fp64_peak": f64,
                                  "peak_source": "pct_measure_fma_peaks (FMA chains on this GPU, this run)"}
     except Exception as e:  # diagnostics must not cost the bench line
-        if world == 1:
-            line["roofline_fp32"] = {"error": str(e)}
+        line["roofline_fp32"] = {"error": str(e)}
     # the bound that actually holds: warp instructions issued per second against the schedulers' peak.
-    # Instructions per point come from the committed ncu capture of the staged kernel, the time is this run's.
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            prof = json.load(f)
-        if int(prof.get("k", -1)) == k and clocks and clocks.get("sm_mhz"):
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            peak_inst = sms * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9
-            ach_inst = pts_per_launch * float(prof["warp_inst_per_point"]) / (query_ms * 1e-3) / 1e9
-            line["roofline_issue"] = {"bound": "instruction issue", "warp_inst_per_point": prof["warp_inst_per_point"],
-                                      "achieved": ach_inst, "peak": peak_inst, "unit": "G warp-inst/s", "frac": ach_inst / peak_inst,
-                                      "source": prof.get("source_inst")}
-    except Exception:
-        pass
+    # Instructions per point come from the committed ncu capture named in `source`; the time and the clock are this run's.
+    if prof and clocks and clocks.get("sm_mhz") and prof.get("warp_inst_per_point"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_inst = sms * 4 * float(clocks["sm_mhz"]) * 1e6 / 1e9
+        ach_inst = pts_per_launch * float(prof["warp_inst_per_point"]) / (roof_query_ms * 1e-3) / 1e9
+        line["roofline_issue"] = {"bound": "instruction issue", "warp_inst_per_point": prof["warp_inst_per_point"],
+                                  "achieved": ach_inst, "peak": peak_inst, "unit": "G warp-inst/s", "frac": ach_inst / peak_inst,
+                                  "source": prof.get("source"), "note": "instructions per point from the committed capture, not from this run"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

@@ -71,6 +71,7 @@ typedef struct pct_index_info {
     int64_t cells_level0; /* occupied cells */
     int64_t device_bytes; /* HBM held by the index */
     float est_dimension;  /* intrinsic dimension seen by the density pilot */
+    int32_t build_launches; /* kernels of this library the build launched (CUB's sort kernels not counted) */
 } pct_index_info;
 
 typedef struct pct_query_stats {
@@ -80,6 +81,7 @@ typedef struct pct_query_stats {
     int64_t kernel_launches;
     int64_t unstaged;       /* queries whose chunk did not fit the shared-memory staging buffer */
     int64_t unresolved;     /* slab index only: queries returned with PCT_STATUS_UNRESOLVED */
+    int64_t rank_deficient; /* fused kNN fit: neighbourhoods answered with lstsq's minimum-norm solution */
 } pct_query_stats;
 
 int pct_version(void);
@@ -119,6 +121,29 @@ int pct_slab_select(const float* xyz, int64_t n, int stride, int axis, float com
                     int32_t* sel, int64_t* num_selected, void* stream);
 int pct_slab_gather(const float* xyz, int stride, int axis, const int32_t* sel, int64_t m, float own_lo,
                     float own_hi, float* local_xyz, int32_t* row_map, int64_t* num_owned, void* stream);
+/* Slab exchange (new, multi-GPU): every rank holds a contiguous share of the cloud (original indices id_base ..
+ * id_base + n - 1) and the ranks trade points with ONE all-to-all instead of replicating the cloud.
+ * bounds (host, world x 4 floats): complete_lo, complete_hi, own_lo, own_hi of every slab, as pct_index_set_slab takes them.
+ * pct_estimate_cell_size_sample: the cell edge pct_index_build would choose for a cloud of n_total points of which
+ *   `sample` (device) holds n_sample; bbox_min_max (host, 6 floats) is the WHOLE cloud's box.  Synchronises `stream`.
+ * pct_slab_bin_count: counts (host, 2 x world int64) = number of the share's points inside every slab's complete range,
+ *   then the number every slab owns; block_pos (device, 2 * world * pct_slab_bin_blocks(n) + 1 int32) is working storage
+ *   that pct_slab_bin_fill reads.  Synchronises `stream`.
+ * pct_slab_bin_fill: records (device, total_complete x 4 floats {x, y, z, original index as int bits}) grouped by
+ *   destination slab, ascending index inside a group (distance ties keep the whole cloud's order at the receiver);
+ *   owned_local (device, n int32): the share's local indices grouped by OWNER slab, ascending -- the order in which the
+ *   owners return their rows.
+ * pct_slab_rows: row_map of pct_index_set_slab for a received slab cloud (m rows): rank of every owned point. */
+int pct_estimate_cell_size_sample(const float* sample, int64_t n_sample, int stride, int64_t n_total,
+                                  const float* bbox_min_max, int k_hint, void* stream, float* cell_size);
+int64_t pct_slab_bin_blocks(int64_t n);
+int pct_slab_bin_count(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                       int32_t* block_pos, int64_t* counts, void* stream);
+int pct_slab_bin_fill(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                      const int32_t* block_pos, int64_t total_complete, int64_t id_base, float* records,
+                      int32_t* owned_local, void* stream);
+int pct_slab_rows(const float* xyz, int64_t m, int stride, int axis, float own_lo, float own_hi, int32_t* row_map,
+                  void* stream);
 /* frees the index in the order of the stream it was built on (no device synchronisation);
  * queries issued on OTHER streams must have completed */
 int pct_index_destroy(pct_index* index);

@@ -43,6 +43,7 @@ class IndexInfo(ctypes.Structure):
         ("cells_level0", c_int64),
         ("device_bytes", c_int64),
         ("est_dimension", c_float),
+        ("build_launches", c_int32),
     ]
 
 
@@ -54,6 +55,7 @@ class QueryStats(ctypes.Structure):
         ("kernel_launches", c_int64),
         ("unstaged", c_int64),
         ("unresolved", c_int64),
+        ("rank_deficient", c_int64),
     ]
 
 
@@ -86,6 +88,11 @@ SIGNATURES = {
     "pct_slab_select": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_void_p, POINTER(c_int64), c_void_p]),
     "pct_slab_gather": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p,
                                 POINTER(c_int64), c_void_p]),
+    "pct_estimate_cell_size_sample": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(ctypes.c_float), c_int, c_void_p, POINTER(ctypes.c_float)]),
+    "pct_slab_bin_blocks": (c_int64, [c_int64]),
+    "pct_slab_bin_count": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(ctypes.c_float), c_void_p, POINTER(c_int64), c_void_p]),
+    "pct_slab_bin_fill": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(ctypes.c_float), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pct_slab_rows": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p]),
     "pct_ball_count": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int, c_void_p]),
     "pct_ball_fill": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_fit_from_neighbors": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -58,7 +58,7 @@ int pct_index_permutation(const pct_index* ix, int32_t* perm, void* stream) {
 
 int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* stats) {
     PCT_REQUIRE(ix && stats, "pct_index_last_stats: NULL argument");
-    unsigned int h[6];
+    unsigned int h[7];
     PCT_CUDA(cudaMemcpyAsync(h, ix->stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PCT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     stats->level1_retries = h[0];
@@ -67,6 +67,7 @@ int pct_index_last_stats(const pct_index* ix, void* stream, pct_query_stats* sta
     stats->queries = h[3];
     stats->unstaged = h[4];
     stats->unresolved = h[5];
+    stats->rank_deficient = h[6];
     return PCT_OK;
 }
 

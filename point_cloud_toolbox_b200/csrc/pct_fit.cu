@@ -103,21 +103,29 @@ quadric_fit_kernel(const double* __restrict__ rotated, long long nq, int k, floa
         double w[6];
         if (!q.finite() || !(max_abs <= 3.0e38f)) {
             st = ST_NONFINITE;  // ref :356-357
-        } else if (k < 6) {     // underdetermined: lstsq's minimum-norm solution
-            FewRows rows;
-            rows.reset();
-            for (int m = 0; m < k; ++m) rows.add(p[3 * m], p[3 * m + 1], p[3 * m + 2]);
-            if (solve_min_norm(rows, w)) {
-                for (int j = 0; j < 6; ++j) c[j] = (float)w[j];
-            } else {
-                st = ST_RANK;
-            }
-        } else if (solve_normal_equations(q, w)) {
-            unscale_coefficients(w, scale, c);
         } else {
-            st = ST_RANK;
+            bool solved = false;
+            if (k < 6) {        // underdetermined: lstsq's minimum-norm solution
+                FewRows rows;
+                rows.reset();
+                for (int m = 0; m < k; ++m) rows.add(p[3 * m], p[3 * m + 1], p[3 * m + 2]);
+                solved = solve_min_norm(rows, w);
+                if (solved)
+                    for (int j = 0; j < 6; ++j) c[j] = (float)w[j];
+            } else if (solve_normal_equations(q, w)) {
+                unscale_coefficients(w, scale, c);
+                solved = true;
+            }
+            if (!solved) {      // dependent rows: lstsq still answers, with the minimum-norm solution (ref :359)
+                GivensQR qr;
+                qr.reset();
+                for (int m = 0; m < k; ++m) qr.add(p[3 * m], p[3 * m + 1], p[3 * m + 2]);
+                solve_min_norm_svd(qr, w);
+                for (int j = 0; j < 6; ++j) c[j] = (float)w[j];
+                st = ST_RANK;   // informational
+            }
         }
-        if (st)
+        if (st & ST_NONFINITE)
             for (int j = 0; j < 6; ++j) c[j] = nanf("");
         for (int j = 0; j < 6; ++j) coeffs[6 * r + j] = c[j];
         if (status) status[r] = (uint8_t)st;

@@ -320,22 +320,16 @@ struct CellRuns {
 // kNN selection, thread per query
 // ---------------------------------------------------------------------------
 enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2,
-                        SEL_TWOPASS = 3 };  // ONEPASS only: the cut missed, redo with the two-pass selection
+                        SEL_RECUT = 3,    // listed selection only: the cut missed, `cut2` holds the cut to try next
+                        SEL_TWOPASS = 4 };  // listed selection only: hand the query to the two-pass selection
 
-// Selection scratch of one query.  On the GPU all of it lives in shared memory:
+// Selection scratch of one query (two-pass selection).  On the GPU all of it lives in shared memory:
 //   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
 //   list  cap entries, addressed through ListRef           (neighbour positions)
 //   hist  kHistBins byte counters = 16 words, word w at hist[w * hist_stride]   (distance histogram);
 //         with hist_stride = threads of the block every thread stays in its own bank
-static constexpr int kHistBins = PCT_HIST_BINS;
-static_assert(kHistBins % 4 == 0 && kHistBins >= 8 && kHistBins <= 252, "byte counters, four bins to a word");
+static constexpr int kHistBins = 64;                 // 32 and 128 measured the same or slower (profiles/variants_r02a.txt)
 static constexpr int kHistRowBytes = kHistBins + 4;  // + the word of the overflow counter (candidates beyond the range)
-static constexpr int kOnePassBins = 16;               // ONEPASS: bins of the histogram of the ~40 LISTED candidates
-static constexpr int kOnePassRowBytes = kOnePassBins + 4;
-template <bool ONEPASS>
-struct SelectBins {  // bins of the histogram a knn_select() call builds
-    static constexpr int value = ONEPASS ? kOnePassBins : kHistBins;
-};
 
 // Where the candidates of a query come from.  knn_select() and the fit only need
 //   src.scan(fn)   fn(pos, Pt) for every point of the query's 27 cells
@@ -343,42 +337,12 @@ struct SelectBins {  // bins of the histogram a knn_select() call builds
 //   src.count()    number of points in the 27 cells
 // GlobalSource reads the Morton-sorted cloud through L1/L2 (positions = sorted positions);
 // StagedSource reads the copy a CTA has made in shared memory (positions = 16-bit).
-// Lower bounds of the squared distance from a query to the cells of its 3x3x3 block, per axis: [0] the cells
-// one below the query's, [1] its own (0), [2] the cells one above.  A point of the cell below has a cell
-// coordinate smaller than the query's cell number, one of the cell above at least that number + 1
-// (cell_of() clamps only downwards from beyond the grid); the coordinates themselves carry the rounding
-// slack of make_stencil().  A cell whose three bounds add up to more than a limit holds no point closer.
-struct BlockBounds {
-    float x0, x2, y0, y2, z0, z2;
-    PCT_HD float y(int i) const { return i == 0 ? y0 : (i == 1 ? 0.f : y2); }
-    PCT_HD float z(int i) const { return i == 0 ? z0 : (i == 1 ? 0.f : z2); }
-};
-
-PCT_HD BlockBounds block_bounds(const IndexView& ix, const Stencil& st, int level, float qx, float qy, float qz) {
-    const float sc = ldexpf(1.f, -level);
-    const float cell = ix.h * ldexpf(1.f, level);
-    const float fx = cell_coord(qx, ix.ox, ix.inv_h) * sc - (float)st.lx;
-    const float fy = cell_coord(qy, ix.oy, ix.inv_h) * sc - (float)st.ly;
-    const float fz = cell_coord(qz, ix.oz, ix.inv_h) * sc - (float)st.lz;
-    BlockBounds b;
-    float t;
-    t = fmaxf(fx - ix.slack, 0.f) * cell; b.x0 = t * t;
-    t = fmaxf(1.f - fx - ix.slack, 0.f) * cell; b.x2 = t * t;
-    t = fmaxf(fy - ix.slack, 0.f) * cell; b.y0 = t * t;
-    t = fmaxf(1.f - fy - ix.slack, 0.f) * cell; b.y2 = t * t;
-    t = fmaxf(fz - ix.slack, 0.f) * cell; b.z0 = t * t;
-    t = fmaxf(1.f - fz - ix.slack, 0.f) * cell; b.z2 = t * t;
-    return b;
-}
-
 struct GlobalSource {
     typedef uint32_t Pos;
     const Pt* pts;
     CellRuns runs;
     template <class F>
     PCT_HD void scan(F& fn) const { runs.scan(pts, fn); }
-    template <class F>
-    PCT_HD void scan_within(F& fn, const BlockBounds&, float) const { runs.scan(pts, fn); }  // merged runs: no cell culling
     PCT_HD Pt load(uint32_t pos) const { return load_pt(pts + pos); }
     PCT_HD uint32_t count() const {
         uint32_t c = 0;
@@ -439,7 +403,7 @@ struct StagedSource {
     // kScanWidth candidates per trip: all records are loaded before any is used (loads may run
     // past the run; they stay inside the block's shared memory and are discarded through
     // `valid`), which overlaps their latencies and divides the loop control.
-    static constexpr int kScanWidth = PCT_SCAN_WIDTH;
+    static constexpr int kScanWidth = 4;
     template <class F>
     PCT_HD void scan(F& fn) const {
         int r = 0, c0 = corner;
@@ -465,40 +429,6 @@ struct StagedSource {
             a += left < (uint32_t)kScanWidth ? (e - a) : 16u * kScanWidth;
         }
     }
-    // The same walk over the cells that can hold a point closer than sqrt(lim2): a row of cells (run) beyond the
-    // limit is skipped, and a row loses its first / last cell when that one is beyond it (the cells of a row are
-    // contiguous, so this only moves the run's ends).
-    template <class F>
-    PCT_HD void scan_within(F& fn, const BlockBounds& bb, float lim2) const {
-#if PCT_CULL_PASS2
-        int r = 0, c0 = corner;
-        uint32_t a = 0, e = 0;
-#pragma unroll 1
-        for (;;) {
-            if (a == e) {
-                do {
-                    if (r == 9) return;
-                    const int ry = r < 3 ? r : (r < 6 ? r - 3 : r - 6), rz = r < 3 ? 0 : (r < 6 ? 1 : 2);
-                    const float dyz = bb.y(ry) + bb.z(rz);
-                    const int first = dyz + bb.x0 > lim2 ? 1 : 0, last = dyz + bb.x2 > lim2 ? 2 : 3;
-                    a = cell_begin(c0 + first);
-                    e = dyz > lim2 ? a : cell_begin(c0 + last);
-                    ++r;
-                    c0 += (r == 3 || r == 6) ? side * side - 2 * side : side;
-                } while (a == e);
-            }
-            Pt p[kScanWidth];
-#pragma unroll
-            for (int u = 0; u < kScanWidth; ++u) p[u] = load_at(a + 16u * u);
-            const uint32_t left = (e - a) >> 4;
-#pragma unroll
-            for (int u = 0; u < kScanWidth; ++u) fn((uint16_t)((a >> 4) + u), p[u], u == 0 || (uint32_t)u < left);
-            a += left < (uint32_t)kScanWidth ? (e - a) : 16u * kScanWidth;
-        }
-#else
-        scan(fn);
-#endif
-    }
     PCT_HD Pt load(uint16_t pos) const { return load_at((uint32_t)pos << 4); }
     PCT_HD uint32_t count() const {
         uint32_t c = 0;
@@ -518,69 +448,52 @@ struct StagedSource {
 // synchronisation.  The list has `rows` LOW slots (slot m < rows) and, behind them, HIGH slots
 // (slot rows + z): 32-bit positions take one row per slot; 16-bit positions keep low slot m in the
 // lower half of row m and high slot z in the upper half of row z, so the neighbours (always low
-// slots) are addressed with one multiply and the boundary zone (high slots) costs no extra rows.
-// PACKED (16-bit positions only, the one-pass experiment): two slots per row -- low slot m in half (m & 1) of row
-// m >> 1, the high slots behind the low rows the same way; half the rows, a shift and a mask more per access.
-template <class PosT, bool PACKED = false>
+// slots) are addressed with one multiply and the high slots cost no extra rows.
+template <class PosT>
 struct ListRef {
     PosT* base;  // the thread's first element
     int stride;  // elements of PosT between consecutive rows
     int rows;    // number of low slots
-    PCT_HD PosT& lo(int m) const {
-        return PACKED ? base[(size_t)(m >> 1) * stride + (m & 1)] : base[(size_t)m * stride];
-    }
+    PCT_HD PosT& lo(int m) const { return base[(size_t)m * stride]; }
     PCT_HD PosT& hi(int z) const {
-        if (PACKED) return base[(size_t)(((rows + 1) >> 1) + (z >> 1)) * stride + (z & 1)];
         return sizeof(PosT) == 2 ? base[(size_t)z * stride + 1] : base[(size_t)(rows + z) * stride];
     }
     PCT_HD PosT& at(int m) const { return m < rows ? lo(m) : hi(m - rows); }
     // bytes one thread needs for `slots` slots of which `rows` are low
     PCT_HD static size_t bytes(int rows, int slots) {
-        if (PACKED) return 4 * (size_t)(((rows + 1) >> 1) + ((slots - rows + 1) >> 1));
         return sizeof(PosT) == 2 ? 4 * (size_t)(rows > slots - rows ? rows : slots - rows) : sizeof(PosT) * (size_t)slots;
     }
 };
-static_assert(sizeof(ListRef<uint16_t, true>) == sizeof(ListRef<uint16_t>), "same members");
 
-template <class PosT, bool PACKED = false>
+template <class PosT>
 struct SelectScratch {
-    typedef ListRef<PosT, PACKED> List;
+    typedef ListRef<PosT> List;
     List list;
     uint32_t* hist; // word w of the byte histogram at hist[w * hist_stride]
     int hist_stride;
-    int cap;        // list slots = list.rows low slots (neighbours, pre-collected candidates) + PCT_TIE_SLACK high slots (boundary zone)
+    int cap;        // list slots = list.rows low slots (neighbours) + PCT_TIE_SLACK high slots (boundary zone)
 };
 
-// Finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
-// level-`level` stencil, in O(candidates) work:
+// Two-pass selection: finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
+// level-`level` stencil, in O(candidates) work.  The L1/L2 kernel runs it (queued queries); the staged kernel
+// uses knn_select_listed() below.
 //
 //   pass 1  histogram of the fp32 squared distances over kHistBins equal bins of
 //           [0, range2) (squared distance is uniform in area on a surface, so the
 //           bins are evenly filled); the bin b that holds the k-th neighbour follows
-//           from a prefix sum.  No sorted list, no dependence on k.  The same pass
-//           copies every candidate closer than an ESTIMATE of the k-th distance
-//           (local density from the population of the 27 cells) into the list.
+//           from a prefix sum.  No sorted list, no dependence on k.
 //   pass 2  candidates clearly below bin b (d32 < lo) are neighbours and go to the
 //           front of the list; candidates in the boundary zone [lo, hi] -- bin b widened
 //           by 1e-5 relative on both sides, far more than the 3e-7 fp32 error -- go
-//           to the last PCT_TIE_SLACK slots; everything above hi is out.  When the estimate
-//           covered bin b this pass reads the pre-collected list (about 2 k entries, in
-//           place); otherwise it walks all candidates again.  The estimate only ever
-//           decides how much work is done, never the result.
+//           to the last PCT_TIE_SLACK slots; everything above hi is out.
 //   exact   the k - |front| nearest of the boundary zone are chosen with scipy's fp64
 //           key (d2, index).  The zone holds one or two points on average.  If the
 //           farthest front point and the nearest zone point are closer than 2e-6
 //           relative the cut itself is ambiguous and the query goes to the exact kernel.
 //
-// On SEL_OK, list.at(m) (m < k) holds the neighbours' positions (unordered),
+// On SEL_OK, list.lo(m) (m < k) holds the neighbours' positions (unordered),
 // `first` / `last` the nearest / farthest by (d2 fp64, original index).
-//
-// ONEPASS (experiment, needs COLLECT): pass 1 only lists the candidates below the estimated cut -- no
-// histogram over all candidates -- and the histogram is then built from the list alone, over
-// [0, 0.999 cut2) so that the boundary bin ends below the cut.  When the list overflows or holds fewer
-// than k + 1 candidates the estimate missed: SEL_TWOPASS, and the caller redoes the query with the
-// two-pass selection.  The exactness argument is the same: every candidate below cut2 is listed.
-template <bool COLLECT, bool ONEPASS = false, class Source, class Scratch>
+template <class Source, class Scratch>
 PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const Source& src, const Pt& q, int k,
                       const Scratch& sc, typename Source::Pos& first,
                       typename Source::Pos& last, double& d2_last) {
@@ -590,106 +503,34 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     // everything closer than sqrt(range2) is certain to be among the candidates
     const float cell = ix.h * ldexpf(1.f, level);
     const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
-    static_assert(!ONEPASS || COLLECT, "ONEPASS lists the candidates below the cut: it needs COLLECT");
-    const float inv_w_range = (float)kHistBins / range2 * 0.99999f;  // rounded down: bin < kHistBins for d < range2
-    if (!(range2 > 1.0e-30f) || !(inv_w_range < 3.0e38f)) return SEL_EXACT;
-
-    // estimated squared distance of the k-th neighbour, with head-room (cut_gain): on a surface the
-    // population C of the 3x3 block of cells is density * 9 cell^2 * tilt, in a volume density * 27 cell^3
+    const float inv_w = (float)kHistBins / range2 * 0.99999f;  // rounded down: bin < kHistBins for d < range2
+    if (!(range2 > 1.0e-30f) || !(inv_w < 3.0e38f)) return SEL_EXACT;
     const int zone_slots = PCT_TIE_SLACK;
-    const int coll_slots = sc.cap - zone_slots;
-    float cut2 = 0.f;
-    if (COLLECT) {
-        const float frac = (float)k / (float)(src.count() + 1u);
-        const float f = ix.volumetric ? cbrtf(frac * frac) : frac;
-        cut2 = fminf(ix.cut_gain * f * cell * cell, range2);
-    }
-    // ONEPASS: histogram over [0, 0.999 cut2): candidates in the last 0.1 % below the cut are listed but land in the
-    // overflow counter, so the boundary bin (widened by 1e-5) always ends below cut2
-    const float inv_w = ONEPASS ? (float)SelectBins<ONEPASS>::value / (cut2 * 0.999f) * 0.99999f : inv_w_range;
-    if (ONEPASS && (!(cut2 > 1.0e-30f) || !(inv_w < 3.0e38f))) return SEL_EXACT;
 
 #pragma unroll
-    for (int w = 0; w < (SelectBins<ONEPASS>::value + 4) / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
+    for (int w = 0; w < (kHistBins + 4) / 4; ++w) sc.hist[(size_t)w * sc.hist_stride] = 0u;
 
     // The bodies of both passes are executed by the whole warp whenever one lane needs them,
-    // so they are kept short; everything that can wait is done on the list afterwards.
+    // so they are kept short and branch-free; everything that can wait is done on the list afterwards.
     // Pass 1 counts the query itself (bin 0): the k-th neighbour is entry k + 1.  Counters are
     // bytes that may wrap; `seen` detects that afterwards.
     struct P1 {
         uint8_t* hist;
-        uint32_t hist_s;   // the same as a shared-window address (PCT_HIST_RED)
         int hist_stride4;  // bytes between consecutive words
-        typename Scratch::List list;
-        uint32_t seen, n_coll, coll_slots;
-        float qx, qy, qz, range2, inv_w, cut2;
-        PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
+        uint32_t seen;
+        float qx, qy, qz, inv_w;
+        PCT_HD void operator()(Pos, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
-            if (ONEPASS) {  // list only; the histogram is built from the list afterwards
-                if (d < cut2) {
-                    if (n_coll < coll_slots) list.lo((int)n_coll) = j;
-                    ++n_coll;
-                }
-                return;
-            }
-#if PCT_BRANCHFREE_HIST
-            // no branch: candidates beyond the range land in the overflow counter (bin kHistBins)
+            // candidates beyond the range land in the overflow counter (bin kHistBins)
             const int b = (int)fminf(d * inv_w, (float)kHistBins);
-#if PCT_HIST_RED && defined(__CUDA_ARCH__)
-            // one reduction on the counter's word instead of load-add-store of its byte: nothing comes back, so the
-            // updates of a trip do not wait for one another (a byte that wraps carries into its neighbour, which
-            // the total-count check below still sees)
-            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + (uint32_t)((b >> 2) * hist_stride4)),
-                         "r"(1u << ((b & 3) * 8))
-                         : "memory");
-#else
             uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
             *c = (uint8_t)(*c + 1);
-#endif
             seen += b < kHistBins ? 1u : 0u;  // (a candidate within 1e-5 of range2 may land in the last bin: still inside safe2)
-            if (COLLECT && d < cut2) {
-                if (n_coll < coll_slots) list.lo((int)n_coll) = j;
-                ++n_coll;
-            }
-#else
-            if (d < range2) {
-                const int b = (int)(d * inv_w);
-                uint8_t* const c = hist + (b >> 2) * hist_stride4 + (b & 3);
-                *c = (uint8_t)(*c + 1);
-                ++seen;
-                if (COLLECT && d < cut2) {
-                    if (n_coll < coll_slots) list.lo((int)n_coll) = j;
-                    ++n_coll;
-                }
-            }
-#endif
         }
     } p1;
-    p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.list = sc.list; p1.seen = 0; p1.n_coll = 0;
-#if PCT_HIST_RED && defined(__CUDA_ARCH__)
-    p1.hist_s = (uint32_t)__cvta_generic_to_shared(sc.hist);
-#else
-    p1.hist_s = 0;
-#endif
-    p1.coll_slots = (uint32_t)coll_slots;
-    p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.range2 = range2; p1.inv_w = inv_w; p1.cut2 = cut2;
+    p1.hist = reinterpret_cast<uint8_t*>(sc.hist); p1.hist_stride4 = 4 * sc.hist_stride; p1.seen = 0;
+    p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.inv_w = inv_w;
     src.scan(p1);
-    if (ONEPASS) {
-        if (p1.n_coll > (uint32_t)coll_slots) return SEL_TWOPASS;  // more below the cut than the list holds
-        // histogram of the listed candidates (the query among them, bin 0); a byte that wraps (more than 255 listed
-        // candidates in one bin, large k only) is caught by the total-count check below
-        uint8_t* const hb = reinterpret_cast<uint8_t*>(sc.hist);
-        const int stride4 = 4 * sc.hist_stride;
-#pragma unroll 1
-        for (uint32_t m = 0; m < p1.n_coll; ++m) {
-            const Pt p = src.load(sc.list.lo((int)m));
-            const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
-            const int b = (int)fminf(d * inv_w, (float)SelectBins<ONEPASS>::value);
-            uint8_t* const c = hb + (b >> 2) * stride4 + (b & 3);
-            *c = (uint8_t)(*c + 1);
-            p1.seen += b < SelectBins<ONEPASS>::value ? 1u : 0u;
-        }
-    }
 
     // bin of the k-th neighbour: word-wise byte sums first (one dp4a per four bins), then the
     // four bins of the word in which the running count passes k
@@ -699,7 +540,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         int w_hit = -1;
         uint32_t cum_hit = 0;
 #pragma unroll
-        for (int w = 0; w < SelectBins<ONEPASS>::value / 4; ++w) {
+        for (int w = 0; w < kHistBins / 4; ++w) {
             const uint32_t s4 = byte_sum4(sc.hist[(size_t)w * sc.hist_stride]);
             const bool hit = w_hit < 0 && cum + s4 > (uint32_t)k;
             w_hit = hit ? w : w_hit;
@@ -717,11 +558,7 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         }
     }
     if (cum != p1.seen) return SEL_EXACT;  // a counter wrapped (> 255 candidates in one bin)
-    if (b < 0) {
-        // fewer than k points within the histogram's range: the certain radius (-> one level coarser), or only the
-        // estimated cut of ONEPASS (-> two-pass selection over the same block)
-        return ONEPASS && cut2 < range2 ? SEL_TWOPASS : SEL_RETRY_COARSER;
-    }
+    if (b < 0) return SEL_RETRY_COARSER;   // fewer than k points within the certain radius
 
     // bin b is [b, b + 1) / inv_w; widened by 1e-5 relative on both sides
     const float bin_w = 1.f / inv_w;
@@ -735,43 +572,18 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         float qx, qy, qz, lo, hi;
         PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
             const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
-#if PCT_BRANCHFREE_PART
             const bool in = d <= hi && p.idx != self, front = d < lo;
             const bool is_front = in && front, is_zone = in && !front;
             Pos* const slot = front ? &list.lo((int)n_front) : &list.hi((int)n_zone);  // n_front < k: always room
             if (is_front || (is_zone && (int)n_zone < zone_slots)) *slot = j;
             n_front += is_front ? 1u : 0u;
             n_zone += is_zone ? 1u : 0u;
-#else
-            if (d <= hi && p.idx != self) {
-                if (d < lo) {
-                    list.lo((int)n_front) = j;  // n_front < k: always room
-                    ++n_front;
-                } else {
-                    if ((int)n_zone < zone_slots) list.hi((int)n_zone) = j;
-                    ++n_zone;
-                }
-            }
-#endif
         }
     } p2;
     p2.list = sc.list; p2.zone_slots = zone_slots;
     p2.self = self; p2.n_front = 0; p2.n_zone = 0;
     p2.qx = q.x; p2.qy = q.y; p2.qz = q.z; p2.lo = lo; p2.hi = hi;
-    PCT_SELECT_TRACE(hi < cut2 && p1.n_coll <= (uint32_t)coll_slots);
-    if (COLLECT && hi < cut2 && p1.n_coll <= (uint32_t)coll_slots) {
-        // every candidate up to hi was collected: partition the list in place (the write
-        // position of the front never passes the read position)
-#pragma unroll 1
-        for (uint32_t m = 0; m < p1.n_coll; ++m) {
-            const Pos j = sc.list.lo((int)m);
-            p2(j, src.load(j), true);
-        }
-    } else {
-        // cells of the block that lie entirely beyond hi hold nothing pass 2 would keep (the margin of
-        // 1e-4 covers the rounding of the bounds and the 3e-7 of d32)
-        src.scan_within(p2, block_bounds(ix, st, level, q.x, q.y, q.z), hi * 1.0001f);
-    }
+    src.scan(p2);
 
     const int n_front = (int)p2.n_front;
     int n_zone = (int)p2.n_zone;
@@ -834,6 +646,198 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
         uint32_t bi = 0;
         for (int m = 0; m < k; ++m) {
             const Pos j = sc.list.lo(m);
+            const Pt p = src.load(j);
+            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
+        }
+    }
+    return SEL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// listed selection (the staged kernel): ONE pass over the candidates
+// ---------------------------------------------------------------------------
+// The two-pass selection visits every candidate twice and updates a shared-memory histogram per visit; of the
+// ~150 candidates of a query only k + 1 matter.  Here one pass lists the candidates below a CUT and everything
+// else runs over the list:
+//
+//   cut     squared radius expected to hold `target` candidates, from the population C of the query's 27 cells
+//           (a surface: C = density * 9 cell^2 * tilt; a volume: density * 27 cell^3).  The caller keeps it per
+//           query: a cut that lists fewer than k + 1 or more than the list holds is rescaled with the count it
+//           produced (count ~ cut2 on a surface) and the query is tried again -- by whichever thread of the
+//           block is free (the block compacts its retries, so a warp does not pay a second pass for one lane).
+//   pass 1  lists every candidate with d32 < cut2 (the query itself among them).  cut2 never exceeds the certain
+//           radius of the stencil, so everything closer than the cut IS listed.
+//   list    16-bin byte histogram of the listed distances over [0, 0.999 cut2), kept in registers -> bin b of
+//           the (k + 1)-th entry; in-place partition of the list into the front (d32 < lo, certain neighbours)
+//           and the boundary zone (bin b widened by 1e-5: at most 8 positions, in registers); the same walk
+//           finds the nearest entry and the front / zone gap.  The zone is resolved with the fp64 key.
+//
+// Exactness is the two-pass argument with range2 replaced by cut2: every candidate below cut2 is listed, the
+// boundary bin ends below cut2 (the histogram stops at 0.999 cut2), so every true neighbour is in front or zone.
+// The cut only decides how much work is done, never the result.
+//
+// Slots: the list has 2 * list.rows 16-bit slots (low halves, then high halves of its rows); the k neighbours
+// end up in the low slots, where the fit reads them.
+static constexpr int kListedBins = 16;
+static constexpr int kListedZone = 8;
+
+// entries a cut should list: the geometric middle of what is needed and what fits
+PCT_HD int listed_target(int k, int slots) {
+    const float t = sqrtf((float)(k + 1) * (float)slots);
+    const int ti = (int)t;
+    return ti < k + 2 ? k + 2 : ti;
+}
+
+// first cut of a query whose 27 cells hold `population` points
+PCT_HD float listed_first_cut(const IndexView& ix, int target, uint32_t population) {
+    const float cell2 = ix.h * ix.h;
+    const float frac = (float)target / (float)(population + 1u);
+    // surface: count = C * pi cut2 / (9 cell2 tilt); volume: count = C * (4/3) pi cut^3 / (27 cell^3)
+    return ix.volumetric ? cbrtf(frac * frac) * 3.46f * cell2 : ix.cut_gain * frac * cell2;
+}
+
+template <class Source, class List>
+PCT_HD int knn_select_listed(const IndexView& ix, const Stencil& st, const Source& src, const Pt& q, int k, int target,
+                             const List& list, float& cut2, typename Source::Pos& first, typename Source::Pos& last) {
+    typedef typename Source::Pos Pos;
+    static_assert(sizeof(Pos) == 2, "zone positions are packed four to a 64-bit register");
+    const uint32_t self = q.idx;
+    const int slots = 2 * list.rows;
+    const float cell = ix.h;
+    const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
+    if (!(range2 > 1.0e-30f)) return SEL_EXACT;
+    const bool at_range = !(cut2 < range2);
+    if (at_range) cut2 = range2;   // never beyond the radius within which every cloud point has been visited
+    if (!(cut2 > 1.0e-30f)) return SEL_EXACT;
+
+    struct P1 {
+        List list;
+        uint32_t n, slots;
+        float qx, qy, qz, cut2;
+        PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
+            const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
+            const bool in = d < cut2;
+            if (in && n < slots) list.at((int)n) = j;
+            n += in ? 1u : 0u;
+        }
+    } p1;
+    p1.list = list; p1.n = 0; p1.slots = (uint32_t)slots;
+    p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.cut2 = cut2;
+    src.scan(p1);
+    const int n = (int)p1.n;
+    if (n > slots || n < k + 1) {
+        if (n < k + 1 && at_range) return SEL_RETRY_COARSER;   // fewer than k + 1 points within the certain radius
+        float ratio = (float)target / (float)(n > 0 ? n : 1);
+        if (ix.volumetric) ratio = cbrtf(ratio * ratio);
+        ratio = fminf(fmaxf(ratio, 0.2f), 6.f);
+        cut2 *= ratio;
+        return SEL_RECUT;
+    }
+
+    // histogram of the n listed entries: bin = d / (0.999 cut2 / 16); entries in the last 0.1 % below the cut
+    // land in no bin, so the boundary bin (widened by 1e-5) always ends below cut2
+    const float inv_w = (float)kListedBins / (cut2 * 0.999f) * 0.99999f;
+    if (!(inv_w < 3.0e38f)) return SEL_EXACT;
+    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+#pragma unroll 1
+    for (int s = 0; s < n; ++s) {
+        const Pt p = src.load(list.at(s));
+        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        const int b = (int)fminf(d * inv_w, (float)kListedBins);
+        const uint32_t inc = 1u << ((b & 3) * 8);
+        const int w = b >> 2;
+        h0 += w == 0 ? inc : 0u;
+        h1 += w == 1 ? inc : 0u;
+        h2 += w == 2 ? inc : 0u;
+        h3 += w == 3 ? inc : 0u;
+    }
+    int b = -1;
+    uint32_t cum = 0, cum_before = 0;
+    {
+        const uint32_t words[4] = {h0, h1, h2, h3};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t c = (words[w] >> (8 * t)) & 255u;
+                if (b < 0 && cum + c > (uint32_t)k) { b = 4 * w + t; cum_before = cum; }
+                cum += c;
+            }
+        }
+    }
+    if (cum > (uint32_t)n) return SEL_EXACT;   // (cannot happen: a byte only wraps at 256 entries in one bin)
+    if (b < 0) {
+        // the (k + 1)-th entry lies in the last 0.1 % below the cut: a slightly larger cut settles it
+        if (at_range) return SEL_TWOPASS;
+        cut2 *= 1.05f;
+        return SEL_RECUT;
+    }
+    const float bin_w = 1.f / inv_w;
+    const float hi = (float)(b + 1) * bin_w * 1.00001f;
+    const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
+
+    // in-place partition: front entries move to the low slots 0 .. n_front-1 (the write position never passes
+    // the read position, and high slots are only read), zone entries into two registers of four positions
+    unsigned long long za = 0ull, zb = 0ull;
+    int n_front = 0, n_zone = 0;
+    float d_min = 3.4e38f, d_min2 = 3.4e38f, front_max = 0.f, zone_min = 3.4e38f;
+    Pos j_min = 0;
+#pragma unroll 1
+    for (int s = 0; s < n; ++s) {
+        const Pos j = list.at(s);
+        const Pt p = src.load(j);
+        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
+        const bool in = d <= hi && p.idx != self, front = d < lo;
+        const bool is_front = in && front, is_zone = in && !front;
+        if (is_front) list.lo(n_front) = j;
+        if (is_zone) {
+            const unsigned long long e = (unsigned long long)j << (16 * (n_zone & 3));
+            za |= n_zone < 4 ? e : 0ull;
+            zb |= (n_zone >= 4 && n_zone < kListedZone) ? e : 0ull;
+        }
+        n_front += is_front ? 1 : 0;
+        n_zone += is_zone ? 1 : 0;
+        front_max = is_front ? fmaxf(front_max, d) : front_max;
+        zone_min = is_zone ? fminf(zone_min, d) : zone_min;
+        const bool closer = in && d < d_min;
+        d_min2 = closer ? d_min : (in ? fminf(d_min2, d) : d_min2);
+        j_min = closer ? j : j_min;
+        d_min = closer ? d : d_min;
+    }
+    if (n_zone > kListedZone) return SEL_TWOPASS;      // a crowded boundary bin: the two-pass selection has 16 slots, then the exact kernel
+    if (!(d_min > 1.0e-30f)) return SEL_EXACT;         // duplicates of the query / denormal range: fp64 only
+    if (n_front > 0 && !(zone_min > front_max * 1.000002f)) return SEL_EXACT;
+    const int need = k - n_front;
+    if (need < 1 || need > n_zone) return SEL_EXACT;
+
+    // exact choice inside the boundary zone: `need` successive minima of (d2, index)
+    unsigned int taken = 0u;
+    for (int t = 0; t < need; ++t) {
+        double bd = 0.0;
+        uint32_t bi = 0;
+        Pos bj = 0;
+        int bm = -1;
+        for (int m = 0; m < n_zone; ++m) {
+            if ((taken >> m) & 1u) continue;
+            const Pos j = (Pos)(((m < 4 ? za : zb) >> (16 * (m & 3))) & 0xffffull);
+            const Pt p = src.load(j);
+            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (bm < 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
+        }
+        taken |= 1u << bm;
+        list.lo(n_front + t) = bj;
+        last = bj;
+    }
+
+    // nearest neighbour: decided in fp32 when the runner-up is clearly farther
+    if (d_min2 > d_min * 1.00001f) {
+        first = j_min;
+    } else {
+        double bd = 0.0;
+        uint32_t bi = 0;
+        for (int m = 0; m < k; ++m) {
+            const Pos j = list.lo(m);
             const Pt p = src.load(j);
             const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
             if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
@@ -906,8 +910,6 @@ struct StencilSource {
         each.f = &fn;
         for_each_candidate(*ix, st, each);
     }
-    template <class F>
-    PCT_HD void scan_within(F& fn, const BlockBounds&, float) const { scan(fn); }
 };
 
 // Neighbourhood adaptor that re-walks the candidates (fused ball path): the members of the ball are

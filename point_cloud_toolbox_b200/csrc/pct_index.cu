@@ -195,7 +195,8 @@ struct DeviceTemp {
 
 }  // namespace
 
-static int choose_cell_size(const float* xyz, long long n, int stride, const float lo[3], float extent_max,
+// `n_total`: size of the cloud the n rows of `xyz` were drawn from (n itself when xyz is the whole cloud)
+static int choose_cell_size(const float* xyz, long long n, int stride, long long n_total, const float lo[3], float extent_max,
                             int k_hint, cudaStream_t s, ScratchSession* ss, float* h_out, float* dim_out) {
     *dim_out = 2.f;
     if (!(extent_max > 0.f)) { *h_out = 1.f; return PCT_OK; }
@@ -235,7 +236,7 @@ static int choose_cell_size(const float* xyz, long long n, int stride, const flo
     double dim = 2.0;
     if (Ls + 1 <= kPilotBits && cells[Ls + 1] >= 8.0) dim = std::log2(cells[Ls] / cells[Ls + 1]);
     dim = std::min(3.0, std::max(1.0, dim));
-    const double ppc_full = (double)n / cells[Ls];
+    const double ppc_full = (double)n_total / cells[Ls];
     // points per cell, tuned on B200 with the staged kernel (scripts/ppc_sweep.py): small k wants few
     // level-1 retries, large k cells small enough for the staging buffer
     const double kh = (double)(k_hint > 0 ? k_hint : 20);
@@ -299,7 +300,7 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     // 2. cell size
     float h = cell_hint, est_dim = 2.f;
     if (!(h > 0.f)) {
-        const int rc = choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &scratch, &h, &est_dim);
+        const int rc = choose_cell_size(xyz, n, stride, n, lo, extent_max, k_hint, s, &scratch, &h, &est_dim);
         if (rc != PCT_OK) return rc;
     }
     if (!(h > 0.f) || !std::isfinite(h)) h = 1.f;
@@ -321,17 +322,14 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     while ((1 << v.bits) < maxdim) ++v.bits;
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
-    // k-th-distance estimate of knn_select(): cut^2 = gain * (k / C) cell^2 on a surface (C = population of the
-    // 3x3x3 block = density * 9 cell^2 * tilt), gain * (k / C)^(2/3) cell^2 in a volume.  Performance only.
+    // first cut of the listed selection (knn_select_listed): cut2 = gain * (target / C) cell^2 on a surface, where
+    // C = population of the 3x3x3 block = density * 9 cell^2 * tilt: gain = 9 tilt / pi.  Performance only.
     v.slab_axis = -1;
     v.volumetric = est_dim > 2.5f ? 1 : 0;
-    v.cut_gain = 0.f;  // off: at 24 warps/SM the list space is worth more as staging buffer (profiles/README.md)
-#if PCT_ONEPASS
-    v.cut_gain = 6.3f;  // 2.2 * 9 / pi: the margin at which the simulated cut misses 0 - 0.3 % of the queries
-#endif
+    v.cut_gain = 3.3f;
     if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
         const float gv = (float)std::atof(g);
-        if (gv >= 0.f) v.cut_gain = gv;
+        if (gv > 0.f) v.cut_gain = gv;
     }
 
     // 3. keys, sort, gather
@@ -403,6 +401,8 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     ix->est_dimension = est_dim;
     info.device_bytes = (int64_t)(sizeof(Pt) * (size_t)n + sizeof(HashSlot) * total_slots);
     info.est_dimension = est_dim;
+    // bbox, Morton keys, record gather, level histogram, table fill (+ pilot keys and its level histogram)
+    info.build_launches = cell_hint > 0.f ? 5 : 7;
     return PCT_OK;
 }
 
@@ -440,7 +440,7 @@ int pct_estimate_cell_size(const float* xyz, int64_t n, int stride, int k_hint, 
     const float lo[3] = {h_bbox[0], h_bbox[1], h_bbox[2]};
     const float extent_max = std::max(h_bbox[3] - h_bbox[0], std::max(h_bbox[4] - h_bbox[1], h_bbox[5] - h_bbox[2]));
     float h = 1.f, dim = 2.f;
-    rc = pct::choose_cell_size(xyz, n, stride, lo, extent_max, k_hint, s, &scratch, &h, &dim);
+    rc = pct::choose_cell_size(xyz, n, stride, n, lo, extent_max, k_hint, s, &scratch, &h, &dim);
     if (rc != PCT_OK) return rc;
     *cell_size = h;
     if (bbox_min_max)
@@ -571,6 +571,235 @@ int pct_slab_gather(const float* xyz, int stride, int axis, const int32_t* sel, 
         PCT_CUDA(cudaFreeAsync(incl, s));
     }
     *num_owned = h_last;
+    return PCT_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// slab exchange (multi-GPU): every rank holds a contiguous share of the cloud (original indices id_base ..
+// id_base + n), bins it by destination slab and the ranks trade the bins with ONE all-to-all.  A point goes to
+// every slab whose complete range [complete_lo, complete_hi] holds its coordinate (its owner, and the neighbours
+// whose margin it lies in).  Bins keep ascending original index, so the concatenation a slab receives in rank
+// order is ascending too and distance ties keep the whole cloud's order.
+// ---------------------------------------------------------------------------
+namespace pct {
+namespace {
+
+constexpr int kBinThreads = 256, kBinItems = 4, kBinWarps = kBinThreads / 32;
+constexpr int kBinBlockPoints = kBinThreads * kBinItems;
+constexpr int kMaxWorld = 32;
+
+struct SlabBounds {
+    float c_lo[kMaxWorld], c_hi[kMaxWorld], own_lo[kMaxWorld], own_hi[kMaxWorld];
+    int world;
+};
+
+// bit d of the result: the point belongs to slab d's complete range; `owner` = the slab that answers it (-1: none)
+__device__ __forceinline__ unsigned int slab_mask(const SlabBounds& b, float x, int& owner) {
+    unsigned int m = 0;
+    owner = -1;
+    for (int d = 0; d < b.world; ++d) {
+        if (x >= b.c_lo[d] && x <= b.c_hi[d]) m |= 1u << d;
+        if (x >= b.own_lo[d] && x < b.own_hi[d]) owner = d;
+    }
+    return m;
+}
+
+// counts[row][block], rows 0 .. world-1 = complete members per destination, rows world .. 2 world-1 = owned members.
+// FILL: `pos` = exclusive scan of the flattened counts, i.e. the output position of the block's first member of a row.
+template <bool FILL>
+__global__ void __launch_bounds__(kBinThreads)
+slab_bin_kernel(const float* __restrict__ xyz, const long long n, const int stride, const int axis, const SlabBounds b,
+                const long long blocks, int32_t* __restrict__ counts, const int32_t* __restrict__ pos,
+                const long long total_complete, const long long id_base, float4* __restrict__ records,
+                int32_t* __restrict__ owned_local) {
+    __shared__ int cnt[2 * kMaxWorld][kBinItems * kBinWarps + 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long base = (long long)blockIdx.x * kBinBlockPoints;
+    unsigned int mask[kBinItems];
+    int owner[kBinItems];
+#pragma unroll
+    for (int j = 0; j < kBinItems; ++j) {
+        const long long i = base + j * kBinThreads + t;
+        mask[j] = 0;
+        owner[j] = -1;
+        if (i < n) mask[j] = slab_mask(b, __ldg(xyz + i * stride + axis), owner[j]);
+    }
+    // per (row, item, warp) member counts; item-major then warp = ascending point index
+    for (int d = 0; d < b.world; ++d) {
+#pragma unroll
+        for (int j = 0; j < kBinItems; ++j) {
+            const unsigned int bc = __ballot_sync(0xffffffffu, (mask[j] >> d) & 1u);
+            const unsigned int bo = __ballot_sync(0xffffffffu, owner[j] == d);
+            if (lane == 0) {
+                cnt[d][j * kBinWarps + warp] = __popc(bc);
+                cnt[b.world + d][j * kBinWarps + warp] = __popc(bo);
+            }
+        }
+    }
+    __syncthreads();
+    if (t < 2 * b.world) {  // exclusive scan of the row's 32 entries; the total goes to the extra slot
+        int run = 0;
+        for (int e = 0; e < kBinItems * kBinWarps; ++e) {
+            const int c = cnt[t][e];
+            cnt[t][e] = run;
+            run += c;
+        }
+        cnt[t][kBinItems * kBinWarps] = run;
+        if (!FILL) counts[(long long)t * blocks + blockIdx.x] = run;
+    }
+    if (!FILL) return;
+    __syncthreads();
+    const unsigned int lt = (1u << lane) - 1u;
+    for (int d = 0; d < b.world; ++d) {
+        const long long p_c = pos[(long long)d * blocks + blockIdx.x];
+        const long long p_o = (long long)pos[(long long)(b.world + d) * blocks + blockIdx.x] - total_complete;
+#pragma unroll
+        for (int j = 0; j < kBinItems; ++j) {
+            const bool fc = (mask[j] >> d) & 1u, fo = owner[j] == d;
+            const unsigned int bc = __ballot_sync(0xffffffffu, fc);
+            const unsigned int bo = __ballot_sync(0xffffffffu, fo);
+            const long long i = base + j * kBinThreads + t;
+            if (fc) {
+                const float* p = xyz + i * stride;
+                float4 r;
+                r.x = __ldg(p); r.y = __ldg(p + 1); r.z = __ldg(p + 2);
+                r.w = __int_as_float((int)(id_base + i));
+                records[p_c + cnt[d][j * kBinWarps + warp] + __popc(bc & lt)] = r;
+            }
+            if (fo) owned_local[p_o + cnt[b.world + d][j * kBinWarps + warp] + __popc(bo & lt)] = (int32_t)i;
+        }
+    }
+}
+
+__global__ void slab_row_starts_kernel(const int32_t* __restrict__ pos, long long blocks, int rows, int32_t* __restrict__ out) {
+    const int r = threadIdx.x;
+    if (r < rows) out[r] = pos[(long long)r * blocks];
+}
+
+__global__ void slab_own_flag_kernel(const float* __restrict__ xyz, long long m, int stride, int axis, float own_lo,
+                                     float own_hi, int32_t* __restrict__ flag) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const float v = __ldg(xyz + r * stride + axis);
+    flag[r] = v >= own_lo && v < own_hi ? 1 : 0;
+}
+
+int fill_bounds(SlabBounds& b, int world, const float* bounds) {
+    if (world < 1 || world > kMaxWorld || !bounds) return PCT_ERR_INVALID_ARGUMENT;
+    b.world = world;
+    for (int d = 0; d < world; ++d) {
+        b.c_lo[d] = bounds[4 * d]; b.c_hi[d] = bounds[4 * d + 1];
+        b.own_lo[d] = bounds[4 * d + 2]; b.own_hi[d] = bounds[4 * d + 3];
+    }
+    return PCT_OK;
+}
+
+}  // namespace
+}  // namespace pct
+
+extern "C" {
+
+int pct_estimate_cell_size_sample(const float* sample, int64_t n_sample, int stride, int64_t n_total,
+                                  const float* bbox_min_max, int k_hint, void* stream, float* cell_size) {
+    PCT_REQUIRE(sample && cell_size && bbox_min_max && n_sample >= 1 && n_total >= n_sample && (stride == 3 || stride == 4),
+                "pct_estimate_cell_size_sample: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    pct::ScratchSession scratch(s, (size_t)32 << 20);
+    const float lo[3] = {bbox_min_max[0], bbox_min_max[1], bbox_min_max[2]};
+    const float extent_max = std::max(bbox_min_max[3] - lo[0], std::max(bbox_min_max[4] - lo[1], bbox_min_max[5] - lo[2]));
+    float h = 1.f, dim = 2.f;
+    const int rc = pct::choose_cell_size(sample, n_sample, stride, n_total, lo, extent_max, k_hint, s, &scratch, &h, &dim);
+    if (rc != PCT_OK) return rc;
+    *cell_size = h;
+    return PCT_OK;
+}
+
+int64_t pct_slab_bin_blocks(int64_t n) { return (n + pct::kBinBlockPoints - 1) / pct::kBinBlockPoints; }
+
+int pct_slab_bin_count(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                       int32_t* block_pos, int64_t* counts, void* stream) {
+    PCT_REQUIRE(xyz && block_pos && counts && n >= 1 && n < (1ll << 31) && (stride == 3 || stride == 4) && axis >= 0 && axis <= 2,
+                "pct_slab_bin_count: bad argument");
+    pct::SlabBounds b;
+    PCT_REQUIRE(pct::fill_bounds(b, world, bounds) == PCT_OK, "pct_slab_bin_count: world must be in [1, 32]");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long blocks = pct_slab_bin_blocks(n);
+    const long long cells = 2ll * world * blocks;
+    PCT_REQUIRE(cells + 1 < (1ll << 31), "pct_slab_bin_count: share too large");
+    pct::slab_bin_kernel<false><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, block_pos, nullptr, 0, 0,
+                                                                                  nullptr, nullptr);
+    // exclusive scan of the flattened counts in place (+ one closing entry = grand total)
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cudaMemsetAsync(block_pos + cells, 0, sizeof(int32_t), s));
+    PCT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, block_pos, block_pos, (int)(cells + 1), s));
+    pct::ScratchSession scratch(s, tmp_bytes + 4096);
+    void* tmp = scratch.take(tmp_bytes);
+    int32_t* starts = static_cast<int32_t*>(scratch.take(sizeof(int32_t) * (2 * pct::kMaxWorld + 1)));
+    const bool pooled = !tmp || !starts;
+    if (pooled) {
+        PCT_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+        PCT_CUDA(cudaMallocAsync(&starts, sizeof(int32_t) * (2 * pct::kMaxWorld + 1), s));
+    }
+    PCT_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, block_pos, block_pos, (int)(cells + 1), s));
+    pct::slab_row_starts_kernel<<<1, 2 * pct::kMaxWorld + 1, 0, s>>>(block_pos, blocks, 2 * world + 1, starts);
+    int32_t h_starts[2 * pct::kMaxWorld + 1];
+    PCT_CUDA(cudaMemcpyAsync(h_starts, starts, sizeof(int32_t) * (2 * world + 1), cudaMemcpyDeviceToHost, s));
+    PCT_CUDA(cudaStreamSynchronize(s));
+    PCT_CUDA(cudaGetLastError());
+    if (pooled) {
+        PCT_CUDA(cudaFreeAsync(tmp, s));
+        PCT_CUDA(cudaFreeAsync(starts, s));
+    }
+    for (int r = 0; r < 2 * world; ++r) counts[r] = (int64_t)h_starts[r + 1] - (int64_t)h_starts[r];
+    return PCT_OK;
+}
+
+int pct_slab_bin_fill(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                      const int32_t* block_pos, int64_t total_complete, int64_t id_base, float* records,
+                      int32_t* owned_local, void* stream) {
+    PCT_REQUIRE(xyz && block_pos && records && owned_local && n >= 1 && (stride == 3 || stride == 4) && axis >= 0 && axis <= 2 &&
+                    id_base >= 0 && id_base + n <= (1ll << 31),
+                "pct_slab_bin_fill: bad argument");
+    pct::SlabBounds b;
+    PCT_REQUIRE(pct::fill_bounds(b, world, bounds) == PCT_OK, "pct_slab_bin_fill: world must be in [1, 32]");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long blocks = pct_slab_bin_blocks(n);
+    pct::slab_bin_kernel<true><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, nullptr, block_pos,
+                                                                                 total_complete, id_base,
+                                                                                 reinterpret_cast<float4*>(records), owned_local);
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+int pct_slab_rows(const float* xyz, int64_t m, int stride, int axis, float own_lo, float own_hi, int32_t* row_map,
+                  void* stream) {
+    PCT_REQUIRE(xyz && row_map && m >= 1 && m < (1ll << 31) && (stride == 3 || stride == 4) && axis >= 0 && axis <= 2,
+                "pct_slab_rows: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t tmp_bytes = 0;
+    PCT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)m, s));
+    pct::ScratchSession scratch(s, tmp_bytes + 2 * sizeof(int32_t) * (size_t)m + 8192);
+    void* tmp = scratch.take(tmp_bytes);
+    int32_t* flag = static_cast<int32_t*>(scratch.take(sizeof(int32_t) * (size_t)m));
+    int32_t* incl = static_cast<int32_t*>(scratch.take(sizeof(int32_t) * (size_t)m));
+    const bool pooled = !tmp || !flag || !incl;
+    if (pooled) {
+        PCT_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+        PCT_CUDA(cudaMallocAsync(&flag, sizeof(int32_t) * (size_t)m, s));
+        PCT_CUDA(cudaMallocAsync(&incl, sizeof(int32_t) * (size_t)m, s));
+    }
+    const int blocks = (int)((m + 255) / 256);
+    pct::slab_own_flag_kernel<<<blocks, 256, 0, s>>>(xyz, m, stride, axis, own_lo, own_hi, flag);
+    PCT_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, flag, incl, (int)m, s));
+    pct::slab_rows_kernel<<<blocks, 256, 0, s>>>(incl, m, row_map);
+    PCT_CUDA(cudaGetLastError());
+    if (pooled) {
+        PCT_CUDA(cudaFreeAsync(tmp, s));
+        PCT_CUDA(cudaFreeAsync(flag, s));
+        PCT_CUDA(cudaFreeAsync(incl, s));
+    }
     return PCT_OK;
 }
 

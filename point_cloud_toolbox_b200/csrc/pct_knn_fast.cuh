@@ -37,7 +37,8 @@ struct Queues {
     uint32_t* retry;     // queries to redo one level coarser (may be null: go straight to exact)
     uint32_t* exact;     // queries for the exact kernel
     uint32_t* fallback;  // staged kernel only: queries of chunks that could not be staged
-    unsigned int* counters;  // [0] = retry count, [1] = exact count, [2] = fallback count
+    uint32_t* rank;      // fused fit only: queries whose design matrix is rank deficient (redone with the minimum-norm solver)
+    unsigned int* counters;  // [0] = retry count, [1] = exact count, [2] = fallback count, [3] = unresolved, [4] = rank count
 };
 
 __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, uint32_t orig) {
@@ -48,16 +49,20 @@ __device__ __forceinline__ long long out_row(const QueryRange& qr, uint32_t i, u
 // What a query does once its k neighbours sit in list[m * stride]: the fused fit, or the
 // ordered (index, distance) rows of plant_kdtree (ref :78-85).
 template <bool FUSED, class Source, class List>
-__device__ __forceinline__ void emit_query(const Source& src, const List& list, int k,
+__device__ __forceinline__ void emit_query(const Source& src, const List& list, int k, const uint32_t i,
                                            const Pt& q, typename Source::Pos first, typename Source::Pos last,
                                            long long row, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
-                                           const FitOutputs& out) {
+                                           const FitOutputs& out, const Queues& qu) {
     if (FUSED) {
         ListNeighbourhood<Source, true, List> nb;
         nb.src = &src; nb.list = list; nb.count = k; nb.q = q; nb.first = first; nb.last = last;
         FitResult r;
         r.status = 0;
         fit_neighbourhood<false>(nb, r);
+        if ((r.status & ST_RANK) && qu.rank) {
+            qu.rank[atomicAdd(&qu.counters[4], 1u)] = i;  // lstsq's minimum-norm answer comes from knn_exact_kernel<true, true>
+            return;
+        }
         store_fit(out, row, r);
     } else {
         // ordered rows: successive minima of (d2, index) over the k members
@@ -115,7 +120,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
         src.runs.collect(st);
         uint32_t first = 0, last = 0;
         double d2_last = 0.0;
-        const int rc = knn_select<false>(ix, st, level, src, q, k, sc, first, last, d2_last);  // no pre-collection: the list is k + PCT_TIE_SLACK wide
+        const int rc = knn_select(ix, st, level, src, q, k, sc, first, last, d2_last);
         if (rc != SEL_OK) {
             if (rc == SEL_RETRY_COARSER && qu.retry && level + 1 < ix.num_levels) {
                 qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
@@ -124,7 +129,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
             }
             continue;
         }
-        emit_query<FUSED>(src, sc.list, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
+        emit_query<FUSED>(src, sc.list, k, i, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out, qu);
     }
 }
 
@@ -133,6 +138,7 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
 // ---------------------------------------------------------------------------
 constexpr int kStagedBlock = PCT_STAGED_BLOCK;  // queries (= threads) of one CTA
 constexpr int kStagedWarps = kStagedBlock / 32;
+constexpr int kStagedRoundsMax = 4;             // attempts of a query inside its CTA (first cut + rescaled cuts)
 
 template <int U>
 struct StageShape : RegionShape<U> {
@@ -140,9 +146,13 @@ struct StageShape : RegionShape<U> {
     static constexpr int kMaxRegions = U >= 2 ? 2 + kStagedBlock / 64 : 4 + kStagedBlock / 16;
     static constexpr int kTable = kMaxRegions * RegionShape<U>::kCells;
     static constexpr int kItemsPerThread = (kTable + kStagedBlock - 1) / kStagedBlock;
-    // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, then the region origins
-    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrOrg = kHdrFlag + 2;
+    // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, the two retry-queue
+    // lengths, then the region origins
+    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrRetry = kHdrFlag + 2, kHdrOrg = kHdrFlag + 4;
     static constexpr int kHdrWords = (kHdrOrg + 3 * kMaxRegions + 3) & ~3;
+    // per-query words that outlive staging: cut of the next attempt (float), region | block corner (uint16),
+    // two retry queues of query numbers (uint16)
+    static constexpr int kQueryBytes = kStagedBlock * (4 + 2 + 2 + 2);
 };
 
 struct StagedCell {
@@ -151,52 +161,69 @@ struct StagedCell {
     uint16_t count;
 };
 
-// dynamic shared memory of the staged kernel, in this order (every part 16-byte aligned):
+// dynamic shared memory of the staged kernels, in this order (every part 16-byte aligned):
 //   Pt       pts[cap_pts]
 //   uint32   tab[kTable + 4]         shared address of the first record of every region cell
 //   int      hdr[kHdrWords]          block-scan partials, flags, region origins
+//   query    float cut[B], uint16 where[B], uint16 retry[2][B]      (kQueryBytes)
 //   scratch  max(per-query scratch, staging temporaries)
-//       per query  : uint16 list[cap][kStagedBlock], uint32 hist[16][kStagedBlock]; without pre-collection the
-//                    list is first written after the histogram has been read, so the two share their memory
+//       per query  : uint16 list[2 * rows][kStagedBlock] as `rows` 32-bit rows
 //       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
-__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts, bool collect, bool onepass = false) {
-    // (one-pass experiment: packed list, 16-bin histogram of the listed candidates)
-    const size_t list = onepass ? ListRef<uint16_t, true>::bytes(cap - PCT_TIE_SLACK, cap) : ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap);
-    const size_t hist = onepass ? kOnePassRowBytes : kHistRowBytes;
-    const size_t per_query = (collect ? list + hist : (list > hist ? list : hist)) * kStagedBlock;
+__host__ __device__ inline size_t staged_smem_bytes(int rows, int cap_pts) {
+    const size_t per_query = (size_t)4 * rows * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
     const size_t tab = (size_t)(StageShape<U>::kTable + 4) * sizeof(uint32_t);
-    return sizeof(Pt) * (size_t)cap_pts + tab + StageShape<U>::kHdrWords * sizeof(int) + ((scratch + 15) & ~(size_t)15);
+    return sizeof(Pt) * (size_t)cap_pts + tab + StageShape<U>::kHdrWords * sizeof(int) + StageShape<U>::kQueryBytes +
+           ((scratch + 15) & ~(size_t)15);
 }
 
+// list rows of the staged kNN kernel: 2 * rows slots for the listed candidates, the k neighbours end up in the low ones
+__host__ __device__ inline int staged_list_rows(int k) { return k > 12 ? k : 12; }
+
 #if defined(__CUDACC__)
-// What staging leaves a thread with: its query, the staged source positioned on the query's region,
-// and the block's per-query scratch area (the staging temporaries in it are dead).
-struct StagedQuery {
-    uint32_t i;      // sorted position of the query
-    Pt q;
-    StagedSource src;
-    char* scratch;   // start of the block's scratch area
+// What staging leaves a block with.
+template <int U>
+struct StagedBlock {
+    uint32_t tab;      // shared address of the cell table (region r starts at tab + 4 * r * kCells)
+    float* cut;        // [B] cut of the query's next attempt
+    uint16_t* where;   // [B] region * 256 + raster index of the lowest cell of the query's 3x3x3 block
+    uint16_t* retry;   // [2][B] retry queues
+    int* hdr;
+    char* scratch;     // start of the block's per-query scratch area
+    __device__ __forceinline__ StagedSource source(int t) const {
+        const uint32_t w = where[t];
+        StagedSource src;
+        src.tab = tab + 4u * (w >> 8) * (uint32_t)StageShape<U>::kCells;
+        src.corner = (int)(w & 255u);
+        src.side = StageShape<U>::kSide;
+        return src;
+    }
 };
 
+enum StageCode : int { STAGE_QUERY = 0,     // this thread's query is staged
+                       STAGE_IDLE = 1,      // no query (beyond the range, or another slab owns it); the thread still joins the block's barriers
+                       STAGE_UNSTAGED = 2 };  // the whole chunk went to the fallback queue: every thread of the block gets this
+
 // Steps A-D of the staged kernels: block-cooperative copy of the cells the chunk's queries can reach.
-// Returns false for threads that have nothing to do afterwards: threads beyond the range, queries the
-// index does not own (slabs), and every thread of a chunk that does not fit the staging buffer (its
-// queries are appended to `fallback`).  All threads of the block must call it.
+// All threads of the block must call it; the return value is STAGE_UNSTAGED for all of them or for none.
 template <int U>
-__device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRange& qr, const int cap_pts,
-                                            uint32_t* __restrict__ fallback, unsigned int* __restrict__ fallback_count,
-                                            StagedQuery& sq) {
+__device__ __forceinline__ int stage_chunk(const IndexView& ix, const QueryRange& qr, const int cap_pts,
+                                           uint32_t* __restrict__ fallback, unsigned int* __restrict__ fallback_count,
+                                           StagedBlock<U>& sb, uint32_t& query, Pt& q_out) {
     typedef StageShape<U> Shape;
     constexpr int S = Shape::kSide, C = Shape::kCells, B = kStagedBlock, W = kStagedWarps;
+    static_assert(C <= 256 && Shape::kMaxRegions <= 255, "`where` packs region and corner into 16 bits");
     extern __shared__ uint4 smem_u4[];
     Pt* const pts_s = reinterpret_cast<Pt*>(smem_u4);
     uint32_t* const tab = reinterpret_cast<uint32_t*>(pts_s + cap_pts);
     int* const hdr = reinterpret_cast<int*>(tab + Shape::kTable + 4);
     const uint32_t pts_addr = (uint32_t)__cvta_generic_to_shared(pts_s);
-    char* const scratch = reinterpret_cast<char*>(hdr + Shape::kHdrWords);
+    float* const cut = reinterpret_cast<float*>(hdr + Shape::kHdrWords);
+    uint16_t* const where = reinterpret_cast<uint16_t*>(cut + B);
+    uint16_t* const retry = where + B;
+    char* const scratch = reinterpret_cast<char*>(retry + 2 * B);
     int* const org = hdr + Shape::kHdrOrg;
     // staging temporaries (dead before the per-query scratch is first written)
     uint32_t* const t_first = reinterpret_cast<uint32_t*>(scratch);
@@ -217,7 +244,7 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
     const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
                                       ((unsigned long long)(cz >> U) << 42);
     t_parent[t] = parent;
-    if (t == 0) hdr[Shape::kHdrFlag] = 0;
+    if (t == 0) { hdr[Shape::kHdrFlag] = 0; hdr[Shape::kHdrRetry] = 0; hdr[Shape::kHdrRetry + 1] = 0; }
     __syncthreads();
     const bool head = t == 0 || t_parent[t - 1] != parent;
     const unsigned int heads = __ballot_sync(0xffffffffu, head);
@@ -292,7 +319,7 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
         if (t == 0) hdr[Shape::kHdrQueue] = (int)atomicAdd(fallback_count, n_active);
         __syncthreads();
         if (active) fallback[(unsigned int)hdr[Shape::kHdrQueue] + (unsigned int)t] = i;
-        return false;
+        return STAGE_UNSTAGED;
     }
 #pragma unroll
     for (int u = 0; u < Shape::kItemsPerThread; ++u) {
@@ -319,56 +346,91 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
             reinterpret_cast<float4*>(pts_s)[sc.slot + m] = v;
         }
     }
-    __syncthreads();  // temporaries are dead, the per-query scratch may be written
-    if (!active || !query_owned(ix, q.x, q.y, q.z)) return false;
     const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
-    sq.i = i;
-    sq.q = q;
-    sq.src.tab = (uint32_t)__cvta_generic_to_shared(tab + region * C);
-    sq.src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
-    sq.src.side = S;
-    sq.scratch = scratch;
+    where[t] = (uint16_t)((region << 8) | ((lx - 1) + S * (ly - 1) + S * S * (lz - 1)));
+    __syncthreads();  // temporaries are dead, the per-query scratch may be written
+    sb.tab = (uint32_t)__cvta_generic_to_shared(tab);
+    sb.cut = cut; sb.where = where; sb.retry = retry; sb.hdr = hdr; sb.scratch = scratch;
+    query = i;
+    q_out = q;
+    return active && query_owned(ix, q.x, q.y, q.z) ? STAGE_QUERY : STAGE_IDLE;
+}
+
+// One attempt at one query of the block (any thread may run it): listed selection with the cut stored for the
+// query, then the fit / the ordered rows.  Returns false when the query wants another attempt with the cut it left
+// in sb.cut[tq].
+template <int U, bool FUSED>
+__device__ __forceinline__ bool staged_attempt(const IndexView& ix, const QueryRange& qr, const StagedBlock<U>& sb, const int tq,
+                                               const uint32_t i, const Pt& q, const int k, const int rows, const int target, const bool last_round,
+                                               int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs& out,
+                                               const Queues& qu) {
+    const StagedSource src = sb.source(tq);
+    ListRef<uint16_t> list;
+    list.base = reinterpret_cast<uint16_t*>(sb.scratch) + 2 * tq;
+    list.stride = 2 * kStagedBlock;
+    list.rows = rows;
+    Stencil st;
+    make_stencil(ix, 0, q.x, q.y, q.z, st);
+    float cut2 = sb.cut[tq];
+    if (!(cut2 > 0.f)) cut2 = listed_first_cut(ix, target, src.count());
+    uint16_t first = 0, last = 0;
+    const int rc = knn_select_listed(ix, st, src, q, k, target, list, cut2, first, last);
+    if (rc == SEL_OK) {
+        emit_query<FUSED>(src, list, k, i, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out, qu);
+        return true;
+    }
+    if (rc == SEL_RECUT && !last_round) {
+        sb.cut[tq] = cut2;
+        return false;
+    }
+    if (rc == SEL_RECUT || rc == SEL_TWOPASS) {
+        qu.fallback[atomicAdd(&qu.counters[2], 1u)] = i;  // the L1/L2 kernel redoes it with the two-pass selection
+    } else if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
+        qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
+    } else {
+        qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
+    }
     return true;
 }
 
-template <int U, bool FUSED, bool COLLECT, bool ONEPASS = false>
+template <int U, bool FUSED>
 __global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
-knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
+knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int rows, const int target, const int rounds, const int cap_pts,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
     constexpr int B = kStagedBlock;
-    StagedQuery sq;
-    if (!stage_chunk<U>(ix, qr, cap_pts, qu.fallback, qu.counters + 2, sq)) return;
+    typedef StageShape<U> Shape;
+    StagedBlock<U> sb;
+    uint32_t i;
+    Pt q;  // (the rounds below reload the query they work on)
+    const int code = stage_chunk<U>(ix, qr, cap_pts, qu.fallback, qu.counters + 2, sb, i, q);
+    if (code == STAGE_UNSTAGED) return;  // (the whole block)
     const int t = threadIdx.x;
-    const uint32_t i = sq.i;
-    const Pt q = sq.q;
-    const StagedSource& src = sq.src;
-    char* const scratch = sq.scratch;
+    const uint32_t chunk0 = (uint32_t)(qr.q_begin + (long long)blockIdx.x * B);  // sorted position of the block's first query
 
-    // ---- E. select out of the staged copy
-    SelectScratch<uint16_t, ONEPASS> sel;  // (the one-pass experiment packs two list slots into a row)
-    sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
-    sel.list.stride = 2 * B;
-    sel.list.rows = cap - PCT_TIE_SLACK;
-    sel.hist = reinterpret_cast<uint32_t*>(scratch + (COLLECT ? ListRef<uint16_t, ONEPASS>::bytes(cap - PCT_TIE_SLACK, cap) * B : 0)) + t;
-    sel.hist_stride = B;
-    sel.cap = cap;
-    Stencil st;
-    make_stencil(ix, 0, q.x, q.y, q.z, st);
-    uint16_t first = 0, last = 0;
-    double d2_last = 0.0;
-    const int rc = knn_select<COLLECT, ONEPASS>(ix, st, 0, src, q, k, sel, first, last, d2_last);
-    if (rc != SEL_OK) {
-        if (ONEPASS && rc == SEL_TWOPASS) {
-            qu.fallback[atomicAdd(&qu.counters[2], 1u)] = i;  // the L1/L2 kernel redoes it with both passes
-        } else if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
-            qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
-        } else {
-            qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
+    // ---- E, F. round 0: every thread its own query with the cut from the local density; rounds 1..: the queries
+    // whose cut missed, compacted over the threads of the block, with the cut rescaled by the count it produced
+    sb.cut[t] = 0.f;
+    int n_items = B;
+#pragma unroll 1
+    for (int round = 0; round < rounds; ++round) {
+        const int from = (round - 1) & 1, to = round & 1;
+        if (round > 0) {
+            __syncthreads();
+            n_items = sb.hdr[Shape::kHdrRetry + from];
+            if (n_items == 0) return;  // (uniform)
+            __syncthreads();           // everybody has read the count before it is reset
+            if (t == 0) sb.hdr[Shape::kHdrRetry + from] = 0;  // it becomes the queue of round + 1, written after the next barrier
         }
-        return;
+#pragma unroll 1
+        for (int item = t; item < n_items; item += B) {
+            const int tq = round == 0 ? t : (int)sb.retry[from * B + item];
+            if (round == 0 && code != STAGE_QUERY) continue;
+            const uint32_t iq = chunk0 + (uint32_t)tq;
+            const Pt qq = load_pt(ix.pts + iq);
+            if (!staged_attempt<U, FUSED>(ix, qr, sb, tq, iq, qq, k, rows, target, round + 1 == rounds, out_idx, out_dist, out, qu))
+                sb.retry[to * B + atomicAdd(&sb.hdr[Shape::kHdrRetry + to], 1)] = (uint16_t)tq;
+        }
     }
-    // ---- F. fit (or ordered rows) out of the staged copy
-    emit_query<FUSED>(src, sel.list, k, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out);
 }
 #endif
 
@@ -383,15 +445,10 @@ struct FastLaunch {
     uint32_t* retry1;
     uint32_t* exactq;
     uint32_t* fallback0;
+    uint32_t* rankq;
     unsigned int* counters;
     cudaStream_t s;
 };
-
-// candidates the pre-collection of knn_select() expects below its cut (see IndexView::cut_gain)
-static double expected_collected(const IndexView& v, int k) {
-    if (v.volumetric) return (double)k * std::pow((double)v.cut_gain / 3.46, 1.5);
-    return 0.349 * (double)v.cut_gain * (double)k;  // pi / 9, tilt 1
-}
 
 // staged level 0 over the whole range; L1/L2 kernel at level 0 over the chunks that could
 // not be staged, then at level 1 over whatever level 0 queued
@@ -403,27 +460,20 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     const int grid_list = (int)std::min<long long>((nq + kBlock - 1) / kBlock, (long long)a.ix->sm_count * 8);
     auto kern = knn_fast_kernel<FUSED>;
     PCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.fallback0, a.counters};
+    Queues q0{v.num_levels > 1 ? a.retry1 : nullptr, a.exactq, a.fallback0, a.rankq, a.counters};
 
-    // list of the staged kernel: room for the candidates pre-collected below the estimated k-th distance
-    // (expected number + 3 sigma) and the boundary zone
-    const double lambda = expected_collected(v, a.k);
-    const int cap_collect = (int)std::ceil(lambda + 3.0 * std::sqrt(lambda)) + PCT_TIE_SLACK;
-    const bool collect = cap_collect >= 2 * a.k + PCT_TIE_SLACK;  // cut_gain == 0 switches it off
-    // at least PCT_TIE_SLACK low slots: the zone lives in the upper halves of the first rows
-    const int cap_staged = (collect ? cap_collect : std::max(a.k, PCT_TIE_SLACK) + PCT_TIE_SLACK);
     // staging buffer: what is left of this CTA's share of the SM's shared memory after the fixed parts.
     // The kernel is compiled for PCT_STAGED_CTAS resident CTAs; when the regions of a chunk are expected
     // to be larger than that share (large k: cells hold 0.4 k points), fewer, larger CTAs are resident.
     constexpr int U = 2;
-#if PCT_ONEPASS
-    // experiment: pass 1 only lists the candidates below the estimated cut (IndexView::cut_gain must be set)
-    auto staged = collect ? knn_staged_kernel<U, FUSED, true, true> : knn_staged_kernel<U, FUSED, false>;
-#else
-    auto staged = collect ? knn_staged_kernel<U, FUSED, true> : knn_staged_kernel<U, FUSED, false>;
-#endif
-    const bool onepass = PCT_ONEPASS && collect;
-    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0, collect, onepass);
+    auto staged = knn_staged_kernel<U, FUSED>;
+    int rows = staged_list_rows(a.k);
+    if (const char* e = std::getenv("PCT_LIST_ROWS")) rows = std::max(a.k, std::min(128, std::atoi(e)));        // experiments
+    int target = listed_target(a.k, 2 * rows);
+    if (const char* e = std::getenv("PCT_LIST_TARGET")) target = std::max(a.k + 1, std::min(2 * rows, std::atoi(e)));  // experiments
+    int rounds = 2;
+    if (const char* e = std::getenv("PCT_STAGED_ROUNDS")) rounds = std::max(1, std::min(kStagedRoundsMax, std::atoi(e)));  // experiments
+    const size_t fixed = staged_smem_bytes<U>(rows, 0);
     // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide:
     // with a buffer of 2.1 times that mean about 4 % of the chunks do not fit, which still beats giving up a
     // third of the resident warps; below that the unstaged share explodes (k = 40: 26 %; scripts/qbench.py)
@@ -440,11 +490,11 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
         if ((double)cap_pts >= wanted) break;
     }
     if (cap_pts > 0xffff) cap_pts = 0xffff;
-    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts, collect, onepass);
+    const size_t smem_staged = staged_smem_bytes<U>(rows, cap_pts);
     if (cap_pts >= 512 && smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
-        staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);
+        staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, rows, target, rounds, cap_pts, a.idx, a.dist, a.out, q0);
         ++*launches;
         QueryRange qf = a.qr;
         qf.list = a.fallback0;
@@ -460,7 +510,7 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
         QueryRange q1 = a.qr;
         q1.list = a.retry1;
         q1.count = a.counters;
-        Queues qq{nullptr, a.exactq, nullptr, a.counters};
+        Queues qq{nullptr, a.exactq, nullptr, a.rankq, a.counters};
         kern<<<grid_list, kBlock, smem, a.s>>>(v, 1, q1, a.k, a.cap, a.idx, a.dist, a.out, qq);
         ++*launches;
     }

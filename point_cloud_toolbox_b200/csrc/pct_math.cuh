@@ -484,6 +484,92 @@ PCT_HD_NOINLINE bool solve_min_norm(FewRows& f, double w[6]) {
     return true;
 }
 
+// Rank-deficient designs with any number of rows: `lstsq` (ref :359, LAPACK dgelsd, rcond = eps * max(M, N)) returns
+// the MINIMUM-NORM least-squares solution -- finite numbers for collinear scan lines, duplicated points and
+// neighbourhoods that lie on a conic.  Restated without storing the rows: a QR factorisation of the UNSCALED design
+// (the norm that is minimised is that of the unscaled coefficients) built row by row with Givens rotations, R 6 x 6
+// and c = Q^T z; then the SVD of R by one-sided Jacobi rotations (small singular values come out with high relative
+// accuracy), singular values up to rcond * s_max dropped like dgelsd does, w = V S^+ U^T c.
+struct GivensQR {
+    double r[6][6];  // upper triangle
+    double c[6];
+    int m;
+    PCT_HD void reset() {
+        for (int i = 0; i < 6; ++i) {
+            c[i] = 0.0;
+            for (int j = 0; j < 6; ++j) r[i][j] = 0.0;
+        }
+        m = 0;
+    }
+    // rotated coordinates in fp64, quantised to fp32 like ref :350; features in fp32 like ref :358
+    PCT_HD void add(double xr, double yr, double zr) {
+        const float a = (float)xr, b = (float)yr, z = (float)zr;
+        double v[6] = {(double)fmul_rn(a, a), (double)fmul_rn(b, b), (double)fmul_rn(a, b), (double)a, (double)b, 1.0};
+        double zz = (double)z;
+        for (int j = 0; j < 6; ++j) {
+            if (v[j] == 0.0) continue;
+            const double p = r[j][j], h = sqrt(p * p + v[j] * v[j]);
+            const double cs = p / h, sn = v[j] / h;
+            r[j][j] = h;
+            for (int l = j + 1; l < 6; ++l) {
+                const double t = r[j][l];
+                r[j][l] = cs * t + sn * v[l];
+                v[l] = cs * v[l] - sn * t;
+            }
+            const double t = c[j];
+            c[j] = cs * t + sn * zz;
+            zz = cs * zz - sn * t;
+        }
+        ++m;
+    }
+    PCT_HD bool finite() const {
+        double s = 0.0;
+        for (int i = 0; i < 6; ++i) s += fabs(r[i][i]) + fabs(c[i]);
+        return s <= 1.7e308;
+    }
+};
+
+PCT_HD_NOINLINE void solve_min_norm_svd(const GivensQR& f, double w[6]) {
+    double a[6][6], v[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { a[i][j] = j >= i ? f.r[i][j] : 0.0; v[i][j] = i == j ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < 5; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int i = 0; i < 6; ++i) { alpha += a[i][p] * a[i][p]; beta += a[i][q] * a[i][q]; gamma += a[i][p] * a[i][q]; }
+                if (gamma == 0.0 || !(fabs(gamma) > 1e-15 * sqrt(alpha * beta))) continue;
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (int i = 0; i < 6; ++i) {
+                    const double x = a[i][p], y = a[i][q];
+                    a[i][p] = cs * x - sn * y; a[i][q] = sn * x + cs * y;
+                    const double vx = v[i][p], vy = v[i][q];
+                    v[i][p] = cs * vx - sn * vy; v[i][q] = sn * vx + cs * vy;
+                }
+            }
+        if (!rotated) break;
+    }
+    double s2[6], s2_max = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        s2[j] = 0.0;
+        for (int i = 0; i < 6; ++i) s2[j] += a[i][j] * a[i][j];
+        s2_max = s2[j] > s2_max ? s2[j] : s2_max;
+    }
+    const double rcond = 2.220446049250313e-16 * (double)(f.m > 6 ? f.m : 6);
+    for (int i = 0; i < 6; ++i) w[i] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        if (!(s2[j] > rcond * rcond * s2_max) || !(s2[j] > 0.0)) continue;  // s_j <= rcond * s_max: dropped
+        double uc = 0.0;
+        for (int i = 0; i < 6; ++i) uc += a[i][j] * f.c[i];
+        const double g = uc / s2[j];
+        for (int i = 0; i < 6; ++i) w[i] += v[i][j] * g;
+    }
+}
+
 // scaled solution -> reference coefficients [A,B,C,D,E,F] in fp32 (ref :359 result dtype)
 PCT_HD void unscale_coefficients(const double w[6], float scale, float c[6]) {
     const double s = (double)scale;
@@ -538,29 +624,52 @@ PCT_HD void fit_fail(FitResult& o, uint32_t status) {
 // status bits (mirrors include/pct_b200.h)
 enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u, ST_UNRESOLVED = 16u };
 
-// fewer rows than coefficients: minimum-norm solution (kept out of line, it is rare and register hungry)
+// minimum-norm solution of a design that has no unique least-squares solution: fewer rows than coefficients, or
+// rows that are linearly dependent (kept out of line, it is rare and needs a stack frame)
 template <class Nbr>
-PCT_HD_NOINLINE void fit_few_rows(Nbr& nb, const Frame& fr, FitResult& out) {
-    struct Collect {
-        const Frame* f;
-        FewRows rows;
-        PCT_HD void add(float cx, float cy, float cz) {
-            double x, y, z;
-            rotate_point(*f, cx, cy, cz, x, y, z);
-            rows.add(x, y, z);
-        }
-    } col;
-    col.f = &fr;
-    col.rows.reset();
-    nb.pass(col);
+PCT_HD_NOINLINE void fit_min_norm(Nbr& nb, const Frame& fr, FitResult& out) {
     out.normal[0] = (float)fr.nx; out.normal[1] = (float)fr.ny; out.normal[2] = (float)fr.nz;
-    if (!col.rows.finite()) { fit_fail(out, ST_NONFINITE); return; }
     double w[6];
-    if (col.rows.m > 5 || !solve_min_norm(col.rows, w)) {
-        const float nx = out.normal[0], ny = out.normal[1], nz = out.normal[2];
-        fit_fail(out, ST_RANK);
-        out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;
-        return;
+    bool solved = false;
+    {
+        struct Collect {
+            const Frame* f;
+            FewRows rows;
+            PCT_HD void add(float cx, float cy, float cz) {
+                double x, y, z;
+                rotate_point(*f, cx, cy, cz, x, y, z);
+                rows.add(x, y, z);
+            }
+        } col;
+        col.f = &fr;
+        col.rows.reset();
+        nb.pass(col);
+        if (col.rows.m <= 5) {
+            if (!col.rows.finite()) { fit_fail(out, ST_NONFINITE); return; }
+            solved = solve_min_norm(col.rows, w);  // independent rows: X = R^T Q^T, w = Q R^-T z
+        }
+    }
+    if (!solved) {
+        struct Stream {
+            const Frame* f;
+            GivensQR qr;
+            PCT_HD void add(float cx, float cy, float cz) {
+                double x, y, z;
+                rotate_point(*f, cx, cy, cz, x, y, z);
+                qr.add(x, y, z);
+            }
+        } st;
+        st.f = &fr;
+        st.qr.reset();
+        nb.pass(st);
+        if (!st.qr.finite()) {
+            const float nx = out.normal[0], ny = out.normal[1], nz = out.normal[2];
+            fit_fail(out, ST_NONFINITE);
+            out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;
+            return;
+        }
+        solve_min_norm_svd(st.qr, w);
+        out.status |= ST_RANK;  // informational: the design was rank deficient, the coefficients are lstsq's minimum-norm ones
     }
 #pragma unroll
     for (int c = 0; c < 6; ++c) out.coeffs[c] = (float)w[c];
@@ -570,10 +679,10 @@ PCT_HD_NOINLINE void fit_few_rows(Nbr& nb, const Frame& fr, FitResult& out) {
 // Whole per-point pipeline over an abstract neighbourhood.
 //   nb.pass(fn)  calls fn(cx, cy, cz) for every neighbour (fp32, centred)
 //   nb.reference(rx, ry, rz) gives c_last - c_first in fp32, valid after the first pass
-// FEW_ROWS: neighbourhoods of fewer than 6 rows get lstsq's minimum-norm solution (the fit-from-rows
-// entry points, i.e. the neighbour study).  The search kernels instantiate it with false -- the row
-// buffers of that path would cost them a 1.2 KB stack frame and 8 % of their speed -- and report such
-// neighbourhoods as rank deficient; the host layer sends k < 6 through the rows path instead.
+// FEW_ROWS: neighbourhoods of fewer than 6 rows and rank-deficient ones get lstsq's minimum-norm solution
+// (fit_min_norm: the fit-from-rows entry points and the kernel that redoes such queries of the search kernels).
+// The search kernels instantiate it with false -- the buffers of that path would cost them a 1.2 KB stack frame
+// and 8 % of their speed -- and report such neighbourhoods as ST_RANK with NaN outputs, which queues them.
 template <bool FEW_ROWS, class Nbr>
 PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     Moments mom;
@@ -586,7 +695,7 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     Frame fr;
     plane_frame(mom, rx, ry, rz, fr);
     if (FEW_ROWS && mom.n < 6) {
-        fit_few_rows(nb, fr, out);
+        fit_min_norm(nb, fr, out);
         return;
     }
     struct Second {
@@ -607,7 +716,11 @@ PCT_HD void fit_neighbourhood(Nbr& nb, FitResult& out) {
     if (!sec.q.finite()) { fit_fail(out, ST_NONFINITE); return; }
     double w[6];
     const bool ok = solve_normal_equations(sec.q, w);
-    if (!ok) {
+    if (!ok && FEW_ROWS) {  // rank-deficient rows: lstsq's minimum-norm solution (ref :359)
+        fit_min_norm(nb, fr, out);
+        return;
+    }
+    if (!ok) {  // (search kernels: the query is redone by the kernel that carries the minimum-norm solver)
         const float nx = out.normal[0], ny = out.normal[1], nz = out.normal[2];
         fit_fail(out, ST_RANK);
         out.normal[0] = nx; out.normal[1] = ny; out.normal[2] = nz;

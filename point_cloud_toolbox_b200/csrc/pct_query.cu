@@ -68,11 +68,14 @@ __global__ void locate_kernel(const IndexView ix, const float* __restrict__ xyz,
     positions[r] = found;
 }
 
-template <bool FUSED>
+// MINNORM: the fit carries lstsq's minimum-norm solver for rank-deficient designs (a stack frame the throughput
+// kernels do not want); the other instances queue such queries in `rankq` for it.
+template <bool FUSED, bool MINNORM = false>
 __global__ void __launch_bounds__(kExactWarps * 32)
 knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* __restrict__ out_idx,
                  float* __restrict__ out_dist, const FitOutputs out, const uint32_t* __restrict__ queue,
-                 const unsigned int* __restrict__ queue_count, unsigned int* __restrict__ unresolved_count) {
+                 const unsigned int* __restrict__ queue_count, unsigned int* __restrict__ unresolved_count,
+                 uint32_t* __restrict__ rankq, unsigned int* __restrict__ rank_count) {
     extern __shared__ uint32_t smem_rows[];  // [kExactWarps][k]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* mine = smem_rows + warp * k;
@@ -161,8 +164,11 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
             nb.src = &src; nb.list.base = mine; nb.list.stride = 1; nb.list.rows = k; nb.count = k; nb.q = q; nb.first = mine[0]; nb.last = mine[k - 1];
             FitResult r;
             r.status = ST_EXACT_PATH;
-            fit_neighbourhood<false>(nb, r);
-            store_fit(out, qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx), r);
+            fit_neighbourhood<MINNORM>(nb, r);
+            if (!MINNORM && (r.status & ST_RANK) && rankq)
+                rankq[atomicAdd(rank_count, 1u)] = i;
+            else
+                store_fit(out, qr.layout == kLayoutList ? (long long)w : out_row(qr, i, q.idx), r);
         }
         __syncwarp();
     }
@@ -175,6 +181,7 @@ __global__ void publish_stats_kernel(const unsigned int* counters, unsigned int*
     stats[3] = queries;
     stats[4] = counters[2];
     stats[5] = counters[3];
+    stats[6] = counters[4];
 }
 
 // ---- epsilon ball ----------------------------------------------------------
@@ -185,11 +192,13 @@ struct CountOnly {
     __device__ __forceinline__ void add(float, float, float) { ++n; }
 };
 
-template <int MODE>
+// MINNORM (fused mode): the instance that redoes the rank-deficient balls the others queue in `rankq`
+template <int MODE, bool MINNORM = false>
 __global__ void __launch_bounds__(kBlock)
 ball_kernel(const IndexView ix, const int level, const QueryRange qr, const double radius, int32_t* __restrict__ counts,
             const long long* __restrict__ offsets, int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
-            double* __restrict__ scratch_d2, const FitOutputs out) {
+            double* __restrict__ scratch_d2, const FitOutputs out, uint32_t* __restrict__ rankq = nullptr,
+            unsigned int* __restrict__ rank_count = nullptr) {
     const long long total = qr.list ? (long long)*qr.count : qr.q_end - qr.q_begin;
     for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += (long long)gridDim.x * kBlock) {
         const uint32_t i = qr.list ? qr.list[t] : (uint32_t)(qr.q_begin + t);
@@ -209,8 +218,12 @@ ball_kernel(const IndexView ix, const int level, const QueryRange qr, const doub
         } else if (MODE == BALL_FUSED) {
             FitResult r;
             r.status = 0;
-            fit_neighbourhood<false>(nb, r);
+            fit_neighbourhood<MINNORM>(nb, r);
             if (counts) counts[row] = nb.count;
+            if (!MINNORM && (r.status & ST_RANK) && rankq) {
+                rankq[atomicAdd(rank_count, 1u)] = i;
+                continue;
+            }
             store_fit(out, row, r);
         } else {
             // CSR fill: members in walk order, then insertion sort of the row by (d2, index)
@@ -256,12 +269,14 @@ __global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
 ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius, const int cap_pts,
                    int32_t* __restrict__ counts, const FitOutputs out, const long long* __restrict__ offsets,
                    int32_t* __restrict__ out_idx, float* __restrict__ out_dist, uint32_t* __restrict__ fallback,
-                   unsigned int* __restrict__ fallback_count) {
-    StagedQuery sq;
-    if (!stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sq)) return;
-    const Pt q = sq.q;
+                   unsigned int* __restrict__ fallback_count, uint32_t* __restrict__ rankq) {
+    StagedBlock<U> sb;
+    uint32_t qi;
+    Pt q;
+    if (stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sb, qi, q) != STAGE_QUERY) return;  // (no barrier follows)
+    const StagedSource src = sb.source(threadIdx.x);
     ListRef<uint16_t> list;
-    list.base = reinterpret_cast<uint16_t*>(sq.scratch) + 2 * threadIdx.x;
+    list.base = reinterpret_cast<uint16_t*>(sb.scratch) + 2 * threadIdx.x;
     list.stride = 2 * kStagedBlock;
     list.rows = kBallListSlots / 2;  // both halves of every row are used
     struct Collect {
@@ -277,12 +292,12 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
     } col;
     col.list = list; col.q = q; col.n = 0;
     col.test.set(radius);
-    sq.src.scan(col);
+    src.scan(col);
     if (col.n > kBallListSlots) {  // a ball larger than the list: streamed by ball_kernel
-        fallback[atomicAdd(fallback_count, 1u)] = sq.i;
+        fallback[atomicAdd(fallback_count, 1u)] = qi;
         return;
     }
-    const long long row = out_row(qr, sq.i, q.idx);
+    const long long row = out_row(qr, qi, q.idx);
     if (MODE == BALL_FILL) {
         // CSR row ordered by (d2, index): successive minima over the listed members
         const long long o = offsets[row];
@@ -292,7 +307,7 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
             double bd = 1.0e300;
             uint32_t bi = 0xffffffffu;
             for (int c = 0; c < col.n; ++c) {
-                const Pt p = sq.src.load(list.at(c));
+                const Pt p = src.load(list.at(c));
                 const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
                 if (key_less(pd, pi, d, p.idx) && key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; }
             }
@@ -305,10 +320,14 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
     FitResult r;
     r.status = 0;
     ListNeighbourhood<StagedSource, false> nb;
-    nb.src = &sq.src; nb.list = list; nb.count = col.n; nb.q = q; nb.first = 0; nb.last = 0;
-    if (col.n >= 2) list_extremes(sq.src, list, col.n, q, nb.first, nb.last);
+    nb.src = &src; nb.list = list; nb.count = col.n; nb.q = q; nb.first = 0; nb.last = 0;
+    if (col.n >= 2) list_extremes(src, list, col.n, q, nb.first, nb.last);
     fit_neighbourhood<false>(nb, r);
     if (counts) counts[row] = col.n;
+    if ((r.status & ST_RANK) && rankq) {
+        rankq[atomicAdd(fallback_count + 1, 1u)] = qi;  // redone by ball_kernel<BALL_FUSED, true>
+        return;
+    }
     store_fit(out, row, r);
 }
 
@@ -332,32 +351,40 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
     const long long nq = q_end - q_begin;
     if (nq == 0) return PCT_OK;
     const int cap = k + PCT_TIE_SLACK;
-    // three work queues of up to nq entries each, from the stream's scratch arena
-    ScratchSession scratch(s, sizeof(uint32_t) * 3 * (size_t)nq + 4096);
-    uint32_t* queues = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * 3 * (size_t)nq));
-    unsigned int* counters = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
+    // four work queues of up to nq entries each, from the stream's scratch arena
+    ScratchSession scratch(s, sizeof(uint32_t) * 4 * (size_t)nq + 4096);
+    uint32_t* queues = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * 4 * (size_t)nq));
+    unsigned int* counters = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 8));
     const bool pooled = !queues || !counters;
     if (pooled) {
-        PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 3 * (size_t)nq, s));
-        PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 4, s));
+        PCT_CUDA(cudaMallocAsync(&queues, sizeof(uint32_t) * 4 * (size_t)nq, s));
+        PCT_CUDA(cudaMallocAsync(&counters, sizeof(unsigned int) * 8, s));
     }
-    PCT_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, s));
+    PCT_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 8, s));
     uint32_t* retry1 = queues;
     uint32_t* exactq = queues + nq;
     uint32_t* fallback0 = queues + 2 * nq;
+    uint32_t* rankq = fused ? queues + 3 * nq : nullptr;
     QueryRange qr{q_begin, q_end, nullptr, nullptr, layout, ix->row_map};
     unsigned int launches = 0;
-    FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, fallback0, counters, s};
+    FastLaunch fl{ix, qr, k, cap, fused, idx, dist, out, retry1, exactq, fallback0, rankq, counters, s};
     int rc = PCT_OK;
     rc = launch_fast(fl, &launches);
     if (rc != PCT_OK) return rc;
 
     const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
     const int grid_exact = ix->sm_count * 4;
-    if (fused)
-        knn_exact_kernel<true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3);
-    else
-        knn_exact_kernel<false><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3);
+    if (fused) {
+        knn_exact_kernel<true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3,
+                                                                               rankq, counters + 4);
+        // rank-deficient neighbourhoods (collinear / duplicated / lattice points): lstsq's minimum-norm solution
+        knn_exact_kernel<true, true><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, rankq, counters + 4, counters + 3,
+                                                                                     nullptr, nullptr);
+        ++launches;
+    } else {
+        knn_exact_kernel<false><<<grid_exact, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, out, exactq, counters + 1, counters + 3,
+                                                                                nullptr, nullptr);
+    }
     ++launches;
     publish_stats_kernel<<<1, 1, 0, s>>>(counters, ix->stats, (unsigned int)nq, launches);
     PCT_CUDA(cudaGetLastError());
@@ -384,9 +411,11 @@ int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const i
     const size_t smem_exact = sizeof(uint32_t) * (size_t)k * kExactWarps;
     const int grid = (int)std::min<long long>((nq + kExactWarps - 1) / kExactWarps, (long long)ix->sm_count * 8);
     if (records)
-        knn_exact_kernel<true><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, nullptr, nullptr, outs, positions, counters, nullptr);
+        knn_exact_kernel<true, true><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, nullptr, nullptr, outs, positions, counters, nullptr,
+                                                                               nullptr, nullptr);
     else
-        knn_exact_kernel<false><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, outs, positions, counters, nullptr);
+        knn_exact_kernel<false><<<grid, kExactWarps * 32, smem_exact, s>>>(v, qr, k, idx, dist, outs, positions, counters, nullptr,
+                                                                          nullptr, nullptr);
     PCT_CUDA(cudaGetLastError());
     unsigned int h_missing = 0;
     PCT_CUDA(cudaMemcpyAsync(&h_missing, counters + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -413,12 +442,13 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
     } else {
         constexpr int U = 2;
-        const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, 0, false);
+        const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2, 0);
         const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
         const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
         const size_t d2_bytes = mode == BALL_FILL ? sizeof(double) * (size_t)std::max<long long>(nnz, 1) : 0;
-        ScratchSession scratch(s, sizeof(uint32_t) * (size_t)nq + 8192 + d2_bytes);
+        ScratchSession scratch(s, sizeof(uint32_t) * 2 * (size_t)nq + 8192 + d2_bytes);
         uint32_t* fallback = static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * (size_t)nq));
+        uint32_t* rankq = mode == BALL_FUSED ? static_cast<uint32_t*>(scratch.take(sizeof(uint32_t) * (size_t)nq)) : nullptr;
         unsigned int* fb_count = static_cast<unsigned int*>(scratch.take(sizeof(unsigned int) * 4));
         // squared distances of the rows ball_kernel<fill> sorts by insertion
         double* scratch_d2 = d2_bytes ? static_cast<double*>(scratch.take(d2_bytes)) : nullptr;
@@ -429,7 +459,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         }
         if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
             // staged kernel over the whole range, L1/L2 kernel over the chunks and balls that did not fit
-            const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, cap_pts, false);
+            const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2, cap_pts);
             PCT_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int) * 4, s));
             const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
             QueryRange ql = qr;
@@ -439,16 +469,24 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
             if (mode == BALL_FUSED) {
                 PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U, BALL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ball_staged_kernel<U, BALL_FUSED><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(
-                    v, qr, radius, cap_pts, counts, out, nullptr, nullptr, nullptr, fallback, fb_count);
-                ball_kernel<BALL_FUSED><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+                    v, qr, radius, cap_pts, counts, out, nullptr, nullptr, nullptr, fallback, fb_count, rankq);
+                ball_kernel<BALL_FUSED><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, counts, nullptr, nullptr, nullptr, nullptr, out,
+                                                                     rankq, fb_count + 1);
+                if (rankq) {  // rank-deficient balls: lstsq's minimum-norm solution
+                    QueryRange qk = qr;
+                    qk.list = rankq;
+                    qk.count = fb_count + 1;
+                    ball_kernel<BALL_FUSED, true><<<grid_list, kBlock, 0, s>>>(v, level, qk, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+                }
             } else {
                 PCT_CUDA(cudaFuncSetAttribute(ball_staged_kernel<U, BALL_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ball_staged_kernel<U, BALL_FILL><<<(unsigned int)chunks, kStagedBlock, smem, s>>>(
-                    v, qr, radius, cap_pts, nullptr, out, offsets, idx, dist, fallback, fb_count);
+                    v, qr, radius, cap_pts, nullptr, out, offsets, idx, dist, fallback, fb_count, nullptr);
                 ball_kernel<BALL_FILL><<<grid_list, kBlock, 0, s>>>(v, level, ql, radius, nullptr, offsets, idx, dist, scratch_d2, out);
             }
         } else if (mode == BALL_FUSED) {
-            ball_kernel<BALL_FUSED><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
+            // (coarser levels / no staging: one kernel that carries the minimum-norm solver itself)
+            ball_kernel<BALL_FUSED, true><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
         } else {
             ball_kernel<BALL_FILL><<<grid, kBlock, 0, s>>>(v, level, qr, radius, nullptr, offsets, idx, dist, scratch_d2, out);
         }

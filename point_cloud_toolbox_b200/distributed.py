@@ -297,64 +297,219 @@ def shared_cloud_from_text(path, name: str, group=None) -> SharedHostArray:
     return shared
 
 
-def exchange_by_owner(ids: torch.Tensor, rows: torch.Tensor, n: int, group=None):
-    """All-to-all of per-point rows to the ranks that own their ORIGINAL index ranges.
+# ---------------------------------------------------------------------------
+# slab exchange: the cloud is never replicated
+# ---------------------------------------------------------------------------
+PLAN_SAMPLE = 1 << 18  # rows of the sample the ranks agree on cell size and cut planes from
 
-    ``ids`` ascending original indices this rank computed, ``rows`` their rows.  Rank r owns original
-    indices ``shard_bounds(n, world, r)``; returns that range filled, ``(end - begin, ...)``.
-    Ascending ids make every destination a contiguous segment, so no sort is needed."""
+
+class SlabPlan:
+    """What every rank derives, identically, from the gathered sample: cell edge, slab axis, bounds of all slabs."""
+
+    def __init__(self, h, axis, cuts, bounds, bbox):
+        self.h, self.axis, self.cuts, self.bounds, self.bbox = h, axis, cuts, bounds, bbox
+
+
+class Stages:
+    """Optional stage timer of the exchange path: CUDA events on the current stream between named stages."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled and torch.cuda.is_available()
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def durations_ms(self):
+        """{stage name: ms} -- the time between the previous mark and this one (call after a synchronize)."""
+        out = {}
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def plan_slabs(share: torch.Tensor, n_total: int, k: int, group=None, cell_fn=None) -> SlabPlan:
+    """Collective.  Every rank contributes the bounding box of its share and a strided sample of it in ONE
+    all-gather; all ranks then compute the same cell edge (density pilot on the sample), the same slab axis
+    (longest box axis) and the same cut planes (quantiles of the sample, so slabs hold equal numbers of points)."""
+    from . import engine
+
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    edges = torch.tensor([shard_bounds(n, world, r)[0] for r in range(world)] + [n], dtype=ids.dtype, device=ids.device)
-    cuts = torch.searchsorted(ids.contiguous(), edges)
-    send = (cuts[1:] - cuts[:-1]).to(torch.int64)
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
-    send_l, recv_l = [int(v) for v in send.tolist()], [int(v) for v in recv.tolist()]
-    total = sum(recv_l)
-    ids_in = torch.empty((total,), dtype=ids.dtype, device=ids.device)
-    rows_in = torch.empty((total,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
-    dist.all_to_all_single(ids_in, ids.contiguous(), recv_l, send_l, group=group)
-    dist.all_to_all_single(rows_in, rows.contiguous(), recv_l, send_l, group=group)
-    begin, end = shard_bounds(n, world, rank)
-    out = torch.empty((end - begin,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
-    out[(ids_in - begin).long()] = rows_in
+    per = max(1, min(-(-PLAN_SAMPLE // world), padded_rows(n_total, world)))
+    n = int(share.shape[0])
+    payload = torch.full((per + 2, 3), float("nan"), dtype=torch.float32, device=share.device)
+    if n:
+        xyz = share[:, :3]
+        payload[0] = xyz.min(0).values
+        payload[1] = xyz.max(0).values
+        step = max(1, n // per)
+        smp = xyz[::step][:per]
+        payload[2:2 + smp.shape[0]] = smp
+    parts = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(parts, payload, group=group)
+    allp = torch.stack(parts)                                   # (world, per + 2, 3)
+    lo = torch.nan_to_num(allp[:, 0], nan=float("inf")).min(0).values
+    hi = torch.nan_to_num(allp[:, 1], nan=float("-inf")).max(0).values
+    sample = allp[:, 2:].reshape(-1, 3)
+    sample = sample[~torch.isnan(sample[:, 0])].contiguous()
+    if not bool(torch.isfinite(sample).all()) or not bool(torch.isfinite(lo).all() & torch.isfinite(hi).all()):
+        raise ValueError("Non-finite values in input points")    # ref :273-274
+    bbox = [float(v) for v in lo] + [float(v) for v in hi]
+    h = (cell_fn or engine.estimate_cell_size_sample)(sample, n_total, bbox, k)
+    axis = max(range(3), key=lambda a: bbox[3 + a] - bbox[a])
+    cuts = slab_cuts(sample[:, axis], world, sample=1 << 62)
+    bounds = [slab_bounds(cuts, r, SLAB_MARGIN_CELLS * h) for r in range(world)]
+    return SlabPlan(h, axis, cuts, bounds, bbox)
+
+
+def _all_to_all_rows(send: torch.Tensor, send_counts, recv_counts, group=None):
+    """all_to_all_single of rows with per-rank row counts (lists of ints)."""
+    out = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(out, send.contiguous(), list(recv_counts), list(send_counts), group=group)
     return out
 
 
-def curvature_knn_shared(points: SharedHostArray, out: SharedHostArray, k: int, group=None, device=None):
+class ExchangeFit:
+    """Result of one rank of the exchange path.
+
+    ``rows``: (n_share, C) result columns of this rank's OWN share of the cloud, share order;
+    ``index`` / ``local_ids`` / ``records`` / ``own_ids``: the slab this rank answered -- its index, the original index
+    of every indexed point, the packed records of the points it owns and their original indices (ascending)."""
+
+    def __init__(self, rows, plan, index, local_ids, records, own_ids, unresolved, indexed):
+        self.rows, self.plan, self.index, self.local_ids = rows, plan, index, local_ids
+        self.records, self.own_ids, self.unresolved, self.indexed = records, own_ids, unresolved, indexed
+
+    def close(self):
+        if self.index is not None:
+            self.index.close()
+            self.index = None
+
+
+def answer_slab(recv: torch.Tensor, plan: SlabPlan, rank: int, k: int, n_own: int):
+    """Index over the received slab cloud (x, y, z, original-index bits) and the fused kernel on the points it owns.
+    Returns (records (n_own, 8), index, unresolved count)."""
+    from . import engine
+
+    c_lo, c_hi, own_lo, own_hi = plan.bounds[rank]
+    if n_own == 0 or int(recv.shape[0]) == 0:
+        return torch.empty((0, 8), dtype=torch.float32, device=recv.device), None, 0
+    index = engine.GridIndex(recv, cell_hint=plan.h, k_hint=k)
+    row_map = engine.slab_rows(recv, plan.axis, own_lo, own_hi)
+    index.set_slab(plan.axis, c_lo, c_hi, own_lo, own_hi, row_map=row_map, mapped_rows=n_own)
+    if int(recv.shape[0]) <= k:
+        # fewer points than a neighbourhood needs: nothing can be resolved inside this slab
+        rec = torch.full((n_own, 8), float("nan"), dtype=torch.float32, device=recv.device)
+        return rec, index, n_own
+    rec = index.curvature_knn(k, want_coeffs=False).records
+    return rec, index, int(index.last_stats().unresolved)
+
+
+def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: int, group=None, columns=(3, 4),
+                           stages: Stages = None, bin_fn=None, answer_fn=None, cell_fn=None, redo_fn=None) -> ExchangeFit:
+    """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() of a cloud DISTRIBUTED over the ranks.
+
+    ``share``: this rank's contiguous rows ``[id_base, id_base + len(share))`` of the cloud, (n, 3) float32 on the
+    device (rank order = index order).  Collective over ``group``:
+
+      1. one small all-gather (boxes + sample) -> cell edge, axis, cut planes        (plan_slabs)
+      2. every rank bins its share by destination slab (owner + margins)             (pct_slab_bin_*)
+      3. one all-to-all of counts, one all-to-all of 16-byte point records: each rank now holds its slab + margin,
+         in ascending original index (ties keep the whole cloud's order)
+      4. slab index + fused kernel on the owned points                               (answer_slab)
+      5. one all-to-all returns the rows to the ranks whose share the points came from -- no ids travel: a slab
+         returns rows in the order it received the points, which the sender remembers (``owned_local``)
+
+    Queries a slab cannot resolve inside its margin (isolated points) are redone on a whole-cloud index after an
+    all-gather of the shares; that collective only happens when some rank reports such a query.
+    ``columns``: record columns returned (3 = K, 4 = H).  The ``*_fn`` hooks exist for the gloo tests, which have no GPU.
+    """
+    from . import engine
+
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    st = stages or Stages(False)
+    st.mark("start")
+    plan = plan_slabs(share, n_total, k, group, cell_fn)
+    st.mark("plan")
+    records, complete, owned, owned_local = (bin_fn or engine.slab_bin)(share, plan.axis, plan.bounds, id_base)
+    st.mark("bin")
+    send = torch.tensor([complete, owned], dtype=torch.int64, device=share.device).t().contiguous()    # (world, 2)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_l = recv.tolist()                                      # the one host sync of the exchange
+    recv_complete, recv_owned = [int(r[0]) for r in recv_l], [int(r[1]) for r in recv_l]
+    slab = _all_to_all_rows(records, complete, recv_complete, group)                                # (m, 4)
+    st.mark("exchange")
+    n_own = sum(recv_owned)
+    rec, index, n_bad = (answer_fn or answer_slab)(slab, plan, rank, k, n_own)
+    st.mark("answer")
+    local_ids = slab[:, 3].contiguous().view(torch.int32)
+    c_lo, c_hi, own_lo, own_hi = plan.bounds[rank]
+    xs = slab[:, plan.axis]
+    own_ids = local_ids[(xs >= own_lo) & (xs < own_hi)]
+    bad_total = torch.tensor([n_bad], dtype=torch.int64, device=share.device)
+    dist.all_reduce(bad_total, group=group)
+    if int(bad_total.item()):
+        # rare: some k-th neighbour lies beyond a margin -- replicate the cloud and redo those queries
+        rows = padded_rows(n_total, world)
+        padded = torch.zeros((rows, 3), dtype=torch.float32, device=share.device)
+        padded[: share.shape[0]] = share[:, :3]
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded, group=group)
+        if n_bad:
+            cloud = torch.cat([parts[r][: shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0]]
+                               for r in range(world)], 0)
+            rec = (redo_fn or _redo_unresolved)(cloud, rec, own_ids, plan, k)
+        del parts
+    st.mark("unresolved")
+    cols = rec[:, list(columns)].contiguous()
+    back = _all_to_all_rows(cols, recv_owned, owned, group)     # rows of MY share, grouped by the slab that answered
+    out = torch.empty((int(share.shape[0]), len(columns)), dtype=rec.dtype, device=share.device)
+    out[owned_local.long()] = back
+    st.mark("return")
+    return ExchangeFit(out, plan, index, local_ids, rec, own_ids, n_bad, int(slab.shape[0]))
+
+
+def _redo_unresolved(cloud, rec, own_ids, plan, k):
+    from . import engine
+    from ._lib import STATUS_UNRESOLVED
+
+    bad = (rec[:, 7].contiguous().view(torch.int32) & STATUS_UNRESOLVED) != 0
+    whole = engine.GridIndex(cloud, cell_hint=plan.h, k_hint=k)
+    redo = whole.curvature_points(own_ids[bad], k)
+    rec[bad] = redo.records
+    whole.close()
+    return rec
+
+
+def curvature_knn_shared(points: SharedHostArray, out: SharedHostArray, k: int, group=None, device=None, stages: Stages = None):
     """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() of a cloud in shared host memory.
 
     ``points`` (N, 3) and ``out`` (2, N) = [K; H] are mapped by every rank.  Rank r copies rows
-    ``shard_bounds(N, world, r)`` of the cloud to its GPU, an all-gather over NVLink replicates the cloud,
-    every rank answers its slab, an all-to-all returns the rows to the ranks owning their original index
-    ranges, and each rank writes its range of ``out``.  Collective: returns after a barrier, when
-    ``out`` is complete on the host."""
+    ``shard_bounds(N, world, r)`` of the cloud to its GPU over its own PCIe link, the ranks trade slabs
+    (``curvature_knn_exchange``: the cloud is never replicated), and each rank writes the K and H of its own rows
+    to ``out``.  Collective: returns after a barrier, when ``out`` is complete on the host."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     n = int(points.tensor.shape[0])
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    rows = padded_rows(n, world)
+    st = stages or Stages(False)
+    st.mark("begin")
     begin, end = shard_bounds(n, world, rank)
-    padded = torch.empty((world * rows, 3), dtype=torch.float32, device=device)
-    mine = padded[rank * rows: rank * rows + (end - begin)]
-    mine.copy_(points.tensor[begin:end], non_blocking=True)                      # this rank's share, its own PCIe link
-    dist.all_gather_into_tensor(padded, padded[rank * rows:(rank + 1) * rows], group=group)
-    if n == world * rows:
-        cloud = padded
-    else:
-        cloud = torch.cat([padded[r * rows: r * rows + (shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0])]
-                           for r in range(world)], 0)
-    part = curvature_knn_slab(cloud, k, rank, world)
-    kh = part.records[:, 3:5].contiguous()
-    own = exchange_by_owner(part.ids.to(torch.int32), kh, n, group)                              # (end - begin, 2) in original order
-    khT = own.t().contiguous()
+    share = torch.empty((end - begin, 3), dtype=torch.float32, device=device)
+    share.copy_(points.tensor[begin:end], non_blocking=True)                     # this rank's share, its own PCIe link
+    st.mark("h2d")
+    part = curvature_knn_exchange(share, begin, n, k, group, stages=st)
+    khT = part.rows.t().contiguous()
     out.tensor[0, begin:end].copy_(khT[0], non_blocking=True)
     out.tensor[1, begin:end].copy_(khT[1], non_blocking=True)
+    st.mark("d2h")
     torch.cuda.current_stream(device).synchronize()
-    if part.index is not None:
-        part.index.close()
     dist.barrier(group=group)
     return part
 

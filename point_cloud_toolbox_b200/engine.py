@@ -353,6 +353,54 @@ def slab_select(points_dev, axis, bounds):
     return sel, local, row_map, int(n_own.value)
 
 
+def estimate_cell_size_sample(sample_dev, n_total, bbox, k_hint=20):
+    """Cell edge the index build would choose for a cloud of ``n_total`` points given a sample of it and the whole
+    cloud's bounding box ``bbox`` = [min xyz, max xyz] (pct_estimate_cell_size_sample)."""
+    h = ctypes.c_float()
+    box = (ctypes.c_float * 6)(*[float(v) for v in bbox])
+    with torch.cuda.device(sample_dev.device):
+        check(lib.pct_estimate_cell_size_sample(ptr(sample_dev), int(sample_dev.shape[0]), int(sample_dev.shape[1]), int(n_total),
+                                                box, int(k_hint), _stream(), ctypes.byref(h)))
+    return float(h.value)
+
+
+def slab_bin(share_dev, axis, bounds, id_base):
+    """Bins a contiguous share of the cloud by destination slab (pct_slab_bin_count + pct_slab_bin_fill).
+
+    ``bounds``: per slab (complete_lo, complete_hi, own_lo, own_hi).  Returns ``(records (T, 4) float32 {x, y, z,
+    original index bits} grouped by destination, complete counts, owned counts, owned_local int32 (n,))``."""
+    n, stride = int(share_dev.shape[0]), int(share_dev.shape[1])
+    world = len(bounds)
+    dev = share_dev.device
+    flat = (ctypes.c_float * (4 * world))(*[float(v) for b in bounds for v in b])
+    if n == 0:
+        return (torch.empty((0, 4), dtype=torch.float32, device=dev), [0] * world, [0] * world,
+                torch.empty((0,), dtype=torch.int32, device=dev))
+    blocks = int(lib.pct_slab_bin_blocks(n))
+    block_pos = torch.empty((2 * world * blocks + 1,), dtype=torch.int32, device=dev)
+    counts = (ctypes.c_int64 * (2 * world))()
+    with torch.cuda.device(dev):
+        check(lib.pct_slab_bin_count(ptr(share_dev), n, stride, int(axis), world, flat, ptr(block_pos), counts, _stream()))
+        complete = [int(counts[d]) for d in range(world)]
+        owned = [int(counts[world + d]) for d in range(world)]
+        total = sum(complete)
+        records = torch.empty((max(total, 1), 4), dtype=torch.float32, device=dev)
+        owned_local = torch.empty((n,), dtype=torch.int32, device=dev)
+        check(lib.pct_slab_bin_fill(ptr(share_dev), n, stride, int(axis), world, flat, ptr(block_pos), total, int(id_base),
+                                    ptr(records), ptr(owned_local), _stream()))
+    return records[:total], complete, owned, owned_local[:sum(owned)]
+
+
+def slab_rows(cloud_dev, axis, own_lo, own_hi):
+    """row_map of GridIndex.set_slab for a slab cloud: rank of every owned point among the owned ones (pct_slab_rows)."""
+    m = int(cloud_dev.shape[0])
+    row_map = torch.empty((m,), dtype=torch.int32, device=cloud_dev.device)
+    with torch.cuda.device(cloud_dev.device):
+        check(lib.pct_slab_rows(ptr(cloud_dev), m, int(cloud_dev.shape[1]), int(axis), float(own_lo), float(own_hi), ptr(row_map),
+                                _stream()))
+    return row_map
+
+
 def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:
     """Fit rows of original-index neighbour lists (nq, k) on an (N, 3) cloud."""
     if points_dev.shape[1] != 3 or not points_dev.is_contiguous():

@@ -10,10 +10,7 @@
 #include <cstring>
 #include <vector>
 
-static long long g_twopass;  // one-pass selections whose cut missed (redone with both passes)
-static int g_onepass;       // knn_impl uses knn_select<true, true> on the staged source
-static long long g_pass2[2];  // [0] = pass 2 walked all candidates, [1] = pass 2 read the pre-collected list
-#define PCT_SELECT_TRACE(used_list) (++g_pass2[(used_list) ? 1 : 0])
+static long long g_listed[4];  // listed selection: [0] attempts, [1] re-cuts, [2] queries handed to the two-pass selection, [3] queries
 #include "pct_grid.cuh"
 #include "pct_dispatch.h"
 
@@ -54,7 +51,7 @@ void* h_build(const float* xyz, long long n, float h) {
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
     v.volumetric = 0;
-    v.cut_gain = 6.5f;
+    v.cut_gain = 3.3f;
     v.slab_axis = -1;
     std::vector<std::pair<unsigned long long, uint32_t>> keyed(n);
     for (long long i = 0; i < n; ++i) {
@@ -97,9 +94,8 @@ void h_set_slab(void* p, int axis, float complete_lo, float complete_hi, float o
     IndexView& v = ((HostIndex*)p)->view;
     v.slab_axis = axis; v.complete_lo = complete_lo; v.complete_hi = complete_hi; v.own_lo = own_lo; v.own_hi = own_hi;
 }
-void h_pass2_counts(long long* out, int reset) {
-    out[0] = g_pass2[0]; out[1] = g_pass2[1];
-    if (reset) g_pass2[0] = g_pass2[1] = 0;
+void h_listed_stats(long long* out, int reset) {
+    for (int i = 0; i < 4; ++i) { out[i] = g_listed[i]; if (reset) g_listed[i] = 0; }
 }
 void h_perm(void* p, int32_t* perm) {
     HostIndex* ix = (HostIndex*)p;
@@ -168,18 +164,21 @@ struct HostStage {
 // kNN lists (original indices, sorted by key) + per-query path code:
 // 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback, +50 = staged source.
 // staged_u: 0 = candidates straight from the sorted cloud, 1 / 2 = staged regions of (1 << U)^3 cells
+// listed: the staged source is searched with knn_select_listed() (the staged kernel's selection: its attempts with
+//   re-scaled cuts, then the two-pass selection, exactly the hand-overs of csrc/pct_knn_fast.cuh); the first cut is
+//   multiplied by cut_scale so that tests can make it miss
 template <int U>
-static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int coll_extra, int32_t* idx, float* dist, int32_t* code,
+static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int listed, float cut_scale, int32_t* idx, float* dist, int32_t* code,
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
-    const int cap = k + PCT_TIE_SLACK + coll_extra;  // coll_extra > 0 switches the pre-collection of pass 1 on
+    const int cap = k + PCT_TIE_SLACK;
+    const int rows = k > 12 ? k : 12;  // staged_list_rows()
     std::vector<uint32_t> list(cap), runs(54);
-    std::vector<uint16_t> list16(2 * cap + 2);
+    std::vector<uint16_t> list16(2 * (cap > rows ? cap : rows) + 2);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
     SelectScratch<uint32_t> sc{{list.data(), 1, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};
     SelectScratch<uint16_t> sc16{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // 16-bit: two slots per row
-    SelectScratch<uint16_t, true> sc16p{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // packed rows (one-pass experiment)
-    const bool collect = coll_extra > 0;
+    ListRef<uint16_t> listed_rows{list16.data(), 2, rows};
     GlobalSource gsrc;
     gsrc.pts = v.pts;
     gsrc.runs.buf = runs.data();
@@ -209,29 +208,35 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
-                bool packed = false;
-                if (collect && g_onepass) {
-                    rc = knn_select<true, true>(v, st, level, ssrc, q, k, sc16p, f16, l16, d2_last);
-                    packed = rc == SEL_OK;
-                    if (rc == SEL_TWOPASS) {  // what the L1/L2 kernel does with the queued query
-                        ++g_twopass;
-                        rc = knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                bool from_rows = false;
+                if (listed) {
+                    ++g_listed[3];
+                    const int target = listed_target(k, 2 * rows);
+                    float cut2 = listed_first_cut(v, target, ssrc.count()) * cut_scale;
+                    rc = SEL_RECUT;
+                    for (int round = 0; round < 4 && rc == SEL_RECUT; ++round) {  // kStagedRounds
+                        ++g_listed[0];
+                        rc = knn_select_listed(v, st, ssrc, q, k, target, listed_rows, cut2, f16, l16);
+                        if (rc == SEL_RECUT) ++g_listed[1];
+                    }
+                    from_rows = rc == SEL_OK;
+                    if (rc == SEL_RECUT || rc == SEL_TWOPASS) {  // what the L1/L2 kernel does with the queued query
+                        ++g_listed[2];
+                        rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
                     }
                 } else {
-                    rc = collect ? knn_select<true>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last)
-                                 : knn_select<false>(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
+                    rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
                 }
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
-                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[packed ? sc16p.list.lo(m) : sc16.list.lo(m)].idx];
+                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[from_rows ? listed_rows.lo(m) : sc16.list.lo(m)].idx];
                     first = ix->pos_of[stage.pts[f16].idx];
                     last = ix->pos_of[stage.pts[l16].idx];
                     staged = true;
                 }
             } else {
                 gsrc.runs.collect(st);
-                rc = collect ? knn_select<true>(v, st, level, gsrc, q, k, sc, first, last, d2_last)
-                             : knn_select<false>(v, st, level, gsrc, q, k, sc, first, last, d2_last);
+                rc = knn_select(v, st, level, gsrc, q, k, sc, first, last, d2_last);
             }
             if (rc != SEL_RETRY_COARSER) break;
         }
@@ -271,23 +276,19 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
 
 extern "C" {
 
-// one-pass selection on the staged source (with coll_extra > 0 and a cut_gain); returns the number of redone queries so far
-long long h_set_onepass(int on) { g_onepass = on; const long long r = g_twopass; if (on) g_twopass = 0; return r; }
-
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    knn_impl<0>(ix, k, max_fast_level, 0, 0, idx, dist, code, normals, coeffs, curv, status);
+    knn_impl<0>(ix, k, max_fast_level, 0, 0, 1.f, idx, dist, code, normals, coeffs, curv, status);
 }
 
 // same through the staged source (level 0), staging buffer of cap_pts points
-void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int coll_extra, float cut_gain, int32_t* idx, float* dist, int32_t* code,
+void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int listed, float cut_scale, int32_t* idx, float* dist, int32_t* code,
                   float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    ix->view.cut_gain = cut_gain;
-    if (staged_u == 0) knn_impl<0>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
-    else if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
-    else knn_impl<2>(ix, k, max_fast_level, cap_pts, coll_extra, idx, dist, code, normals, coeffs, curv, status);
+    if (staged_u == 0) knn_impl<0>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
+    else if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
+    else knn_impl<2>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
 }
 
 void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,

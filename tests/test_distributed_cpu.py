@@ -97,12 +97,8 @@ def _worker(rank, world, port, n, out_path):
             assert torch.equal(full, want)
         else:
             assert full is None
-        # shared-host mode: rows go back to the ranks that own their original index ranges
-        mine = pdist.exchange_by_owner(ids, rows, n, None)
+        # the host arrays of the end-to-end path are one segment mapped by every rank
         b, e = pdist.shard_bounds(n, world, rank)
-        want = torch.stack((torch.arange(b, e).float() * 3.0, cloud[b:e, 2]), 1)
-        assert torch.equal(mine, want)
-        # ... and the host arrays are one segment mapped by every rank
         name = f"pct_test_{port}"
         if rank == 0:
             shared = pdist.SharedHostArray(name, (2, n), create=True)
@@ -110,8 +106,8 @@ def _worker(rank, world, port, n, out_path):
         dist.barrier()
         if rank != 0:
             shared = pdist.SharedHostArray(name, (2, n), create=False)
-        shared.tensor[0, b:e] = mine[:, 0]
-        shared.tensor[1, b:e] = mine[:, 1]
+        shared.tensor[0, b:e] = torch.arange(b, e).float() * 3.0
+        shared.tensor[1, b:e] = cloud[b:e, 2]
         dist.barrier()
         if rank == 0:
             assert np.array_equal(shared.array[0], np.arange(n, dtype=np.float32) * 3.0)
@@ -159,3 +155,91 @@ def test_shared_cloud_from_text_world2(tmp_path, cols):
     mp.spawn(_text_worker, args=(2, _free_port(), path, out), nprocs=2, join=True)
     for rank in range(2):
         assert np.array_equal(np.load(out + f".{rank}.npy"), g["points"])
+
+
+# ---------------------------------------------------------------------------
+# slab exchange (the cloud is never replicated): protocol, ordering and margins, with CPU stand-ins for the kernels
+# ---------------------------------------------------------------------------
+def _ref_bin(share, axis, bounds, id_base):
+    """What pct_slab_bin_count / pct_slab_bin_fill compute, in torch (test stand-in, no GPU here)."""
+    x = share[:, axis]
+    recs, complete, owned, owned_local = [], [], [], []
+    for c_lo, c_hi, own_lo, own_hi in bounds:
+        idx = ((x >= c_lo) & (x <= c_hi)).nonzero().squeeze(1)
+        ids = (idx + id_base).to(torch.int32).view(torch.float32)
+        recs.append(torch.cat((share[idx, :3], ids[:, None]), 1))
+        complete.append(int(idx.numel()))
+        own = ((x >= own_lo) & (x < own_hi)).nonzero().squeeze(1)
+        owned.append(int(own.numel()))
+        owned_local.append(own.to(torch.int32))
+    return torch.cat(recs), complete, owned, torch.cat(owned_local)
+
+
+def _brute_rows(cloud, ids, queries, k):
+    """Row per query: [sum of the k nearest other points' ORIGINAL indices, k-th distance]; ties by original index."""
+    d = torch.cdist(cloud[queries].double(), cloud.double())
+    order = torch.argsort(d * 1e6 + ids[None, :].double() * 1e-6, dim=1)[:, 1:k + 1]      # self first (distance 0)
+    return torch.stack((ids[order].sum(1).float(), torch.gather(d, 1, order)[:, -1].float()), 1)
+
+
+def _exchange_worker(rank, world, port, n, k, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        u, v = torch.rand(n, generator=g) * 6.283, torch.rand(n, generator=g) * 6.283
+        cloud = torch.stack(((1 + 0.3 * torch.cos(v)) * torch.cos(u), (1 + 0.3 * torch.cos(v)) * torch.sin(u), 0.3 * torch.sin(v)), 1)
+        cloud[5] = torch.tensor([0.0, 0.0, 0.0])                                   # isolated, on the cut plane of two slabs: unresolved there
+        b, e = pdist.shard_bounds(n, world, rank)
+        share = cloud[b:e].contiguous()
+        h = 0.08
+
+        def answer(slab, plan, r, kk, n_own):
+            c_lo, c_hi, own_lo, own_hi = plan.bounds[r]
+            ids = slab[:, 3].contiguous().view(torch.int32).long()
+            assert bool((ids[1:] > ids[:-1]).all())                                # ascending original index at the receiver
+            xs = slab[:, plan.axis]
+            assert bool(((xs >= c_lo) & (xs <= c_hi)).all())
+            own = ((xs >= own_lo) & (xs < own_hi)).nonzero().squeeze(1)
+            assert own.numel() == n_own
+            rows = _brute_rows(slab[:, :3], ids, own, kk)
+            rec = torch.zeros((n_own, 8))
+            rec[:, 3:5] = rows
+            # a query is resolved when its k-th neighbour is closer than the slab's knowledge ends
+            reach = torch.minimum(xs[own] - c_lo, c_hi - xs[own])
+            bad = rows[:, 1] > reach
+            rec[bad, 3:5] = float("nan")
+            rec[:, 7] = torch.where(bad, torch.tensor(16, dtype=torch.int32), torch.tensor(0, dtype=torch.int32)).view(torch.float32)
+            return rec, None, int(bad.sum())
+
+        def redo(whole, rec, own_ids, plan, kk):
+            assert whole.shape[0] == n and torch.equal(whole, cloud)
+            bad = rec[:, 7].contiguous().view(torch.int32) != 0
+            rec[bad, 3:5] = _brute_rows(whole, torch.arange(n), own_ids[bad].long(), kk)
+            return rec
+
+        part = pdist.curvature_knn_exchange(share, b, n, k, bin_fn=_ref_bin, answer_fn=answer, redo_fn=redo,
+                                            cell_fn=lambda sample, n_total, bbox, kk: h)
+        want = _brute_rows(cloud, torch.arange(n), torch.arange(b, e), k)
+        ok = torch.equal(part.rows, want)
+        # every rank derived the same plan, slabs own every point exactly once
+        owned_total = torch.tensor([int(part.own_ids.numel())])
+        dist.all_reduce(owned_total)
+        np.save(out_path + f".{rank}.npy", np.array([float(ok), float(owned_total.item()), float(part.unresolved), part.plan.h,
+                                                    part.plan.axis] + list(part.plan.cuts[1:-1])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1500), (3, 2000)])
+def test_slab_exchange_protocol(tmp_path, world, n):
+    out = str(tmp_path / "ex")
+    mp.spawn(_exchange_worker, args=(world, _free_port(), n, 12, out), nprocs=world, join=True)
+    res = [np.load(out + f".{r}.npy") for r in range(world)]
+    for r in res:
+        assert r[0] == 1.0, "rows differ from the whole-cloud brute force"
+        assert r[1] == n
+        assert np.array_equal(r[3:], res[0][3:])           # same plan on every rank
+    if world == 2:
+        assert sum(r[2] for r in res) >= 1                  # the isolated point went through the whole-cloud redo

@@ -345,36 +345,100 @@ def test_unresolved_slab_queries_fall_back_to_the_whole_cloud(pct):
     whole.close()
 
 
-def test_shared_host_path_single_rank_group(pct):
-    """curvature_knn_shared (share-wise H2D, all-gather, slab, all-to-all by owner, share-wise D2H) on a
-    one-rank NCCL group: same K, H as the PointCloud call."""
-    import socket
-
+def _exchange_rank(rank, world, port, n, k, out_path):
+    """One NCCL rank of the slab-exchange path: its rows against the oracle, and a sampled parity block."""
     import torch.distributed as dist
+
+    from oracle import sample_parity
     from point_cloud_toolbox_b200 import distributed as pdist
 
-    pts, _, _ = datasets.torus_random(150_000, seed=6)
-    k = 20
-    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
-    pc.plant_kdtree(k)
-    K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    try:
+        pts, _, _ = datasets.torus_random(n, seed=6)
+        pts[7] = (0.0, 0.0, 0.9)                          # isolated: its neighbours lie beyond any margin
+        cloud = torch.from_numpy(pts).to(dev)
+        b, e = pdist.shard_bounds(n, world, rank)
+        part = pdist.curvature_knn_exchange(cloud[b:e].contiguous(), b, n, k, columns=(3, 4, 5, 6))
+        rows = np.arange(b, e, 37)
+        ref = oracle.knn_curvature(pts, k, rows=rows)
+        got_all = part.rows.cpu().numpy()
+        sel = rows - b
+        rec = part.records
+        own_ids = part.own_ids.long()
+        # curvature of the rows that came back to this rank (answered by whichever slab owns them)
+        dummy_n = ref["normal"]
+        got = dict(normal=dummy_n, K=got_all[sel, 0], H=got_all[sel, 1], k1=got_all[sel, 2], k2=got_all[sel, 3])
+        rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
+        # neighbour rows + records of the slab this rank answered, on Morton runs incl. the cut planes
+        c_lo, c_hi, own_lo, own_hi = part.plan.bounds[rank]
+        axis = part.plan.axis
+        runs = sample_parity.choose_runs(part.index, 4, 2048, seed=rank, planes=(own_lo, own_hi), axis=axis)
+        par = sample_parity.check_runs(part.index, cloud, k, runs, local_to_orig=part.local_ids,
+                                       owned=lambda c: (c[:, axis] >= own_lo) & (c[:, axis] < own_hi),
+                                       records_of=lambda ids: rec[torch.searchsorted(own_ids, ids)])
+        # the host-array form: every rank moves its share
+        name = f"pct_gpu_test_{port}"
+        if rank == 0:
+            cin = pdist.SharedHostArray(name + "_in", pts.shape, create=True)
+            cout = pdist.SharedHostArray(name + "_out", (2, n), create=True)
+            cin.array[:] = pts
+            cout.array[:] = np.nan
+        dist.barrier()
+        if rank != 0:
+            cin = pdist.SharedHostArray(name + "_in", pts.shape, create=False)
+            cout = pdist.SharedHostArray(name + "_out", (2, n), create=False)
+        st = pdist.Stages()
+        pdist.curvature_knn_shared(cin, cout, k, stages=st).close()
+        host_ok = bool(np.array_equal(cout.array[0, b:e], got_all[:, 0]) and np.array_equal(cout.array[1, b:e], got_all[:, 1]))
+        all_written = bool(np.isfinite(cout.array).mean() > 0.999)
+        stages = st.durations_ms()
+        unresolved = torch.tensor([part.unresolved], device=dev)
+        dist.all_reduce(unresolved)
+        dist.barrier()
+        cin.close()
+        cout.close()
+        part.close()
+        np.save(out_path + f".{rank}.npy", np.array([rep["violations"], rep["rows"], par["rows_differing"], par["dist_differing"],
+                                                    par["violations"], par["rows"], float(host_ok), float(all_written),
+                                                    float(unresolved.item()), float(len(stages))]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_exchange(tmp_path, world, n, k):
+    import socket
+
+    import torch.multiprocessing as mp
+
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
-                            device_id=torch.device("cuda", torch.cuda.current_device()))
-    try:
-        cloud = pdist.SharedHostArray(f"pct_gpu_test_{port}_in", pts.shape, create=True)
-        out = pdist.SharedHostArray(f"pct_gpu_test_{port}_out", (2, len(pts)), create=True)
-        cloud.array[:] = pts
-        out.array[:] = np.nan
-        pdist.curvature_knn_shared(cloud, out, k)
-        assert np.allclose(out.array[0], K, rtol=1e-5, atol=1e-6, equal_nan=True)
-        assert np.allclose(out.array[1], H, rtol=1e-5, atol=1e-6, equal_nan=True)
-        cloud.close()
-        out.close()
-    finally:
-        dist.destroy_process_group()
+    out = str(tmp_path / "ex")
+    mp.spawn(_exchange_rank, args=(world, port, n, k, out), nprocs=world, join=True)
+    for r in range(world):
+        res = np.load(out + f".{r}.npy")
+        assert res[0] == 0 and res[1] > 100, res          # curvature of the returned rows within tolerance
+        assert res[2] == 0 and res[3] == 0 and res[5] > 1000, res   # neighbour rows and distances bit-exact
+        assert res[4] == 0, res                           # records of the slab within tolerance
+        assert res[6] == 1.0 and res[7] == 1.0, res       # host arrays = device rows, everything written
+        assert res[9] >= 6
+    return res
+
+
+def test_exchange_path_single_rank_group(pct, tmp_path):
+    """curvature_knn_exchange / curvature_knn_shared on a one-rank NCCL group (any box)."""
+    _run_exchange(tmp_path, 1, 150_000, 20)
+
+
+@pytest.mark.parametrize("k", [20, 32])
+def test_exchange_path_two_ranks_nccl(pct, tmp_path, k):
+    """Two real NCCL ranks on two GPUs: bins, all-to-all, slab margins, return order, unresolved redo."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    res = _run_exchange(tmp_path, 2, 400_000, k)
+    assert res[8] >= 1                                    # the isolated point went through the whole-cloud redo
 
 
 def test_tiny_and_degenerate_clouds(pct):

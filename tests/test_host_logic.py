@@ -40,7 +40,7 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, coll_extra=0, cut_gain=6.5, slab=None):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, listed=0, cut_scale=1.0, slab=None):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
@@ -50,8 +50,8 @@ def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, coll_ext
                normal=np.zeros((n, 3), np.float32), coeffs=np.zeros((n, 6), np.float32), curv=np.zeros((n, 5), np.float32),
                status=np.zeros(n, np.uint8))
     args = (P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]), P(out["curv"]), P(out["status"]))
-    if staged_u or coll_extra:
-        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, coll_extra, cut_gain, *args)
+    if staged_u:
+        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, listed, cut_scale, *args)
     else:
         lib.h_knn(ix, k, max_fast_level, *args)
     lib.h_destroy(ix)
@@ -92,18 +92,6 @@ def test_staged_source_gives_the_same_rows(harness, bunny, staged_u):
     small = run_knn(harness, pts, k, h, staged_u=staged_u, cap_pts=1200)
     assert 0.0 < np.mean(small["code"] == 50) < np.mean(got["code"] == 50)
     assert np.array_equal(small["idx"], got["idx"])
-    # pre-collection during pass 1: the estimate of the k-th distance (any gain, any list size) only
-    # changes how much work is done
-    counts = (ctypes.c_longlong * 2)()
-    for gain, extra in ((6.5, 2 * k), (1.0, 2 * k), (40.0, 2 * k), (6.5, 5), (40.0, 200)):
-        harness.h_pass2_counts(counts, 1)
-        coll = run_knn(harness, pts, k, h, staged_u=staged_u, coll_extra=extra, cut_gain=gain)
-        harness.h_pass2_counts(counts, 0)
-        if (gain, extra) == (6.5, 2 * k):  # the shipped setting: most queries never walk the candidates twice
-            assert counts[1] > 0.8 * (counts[0] + counts[1]), list(counts)
-        assert np.array_equal(coll["idx"], got["idx"]), (gain, extra)
-        assert np.array_equal(coll["dist"], got["dist"]), (gain, extra)
-        assert np.array_equal(coll["code"], got["code"]), (gain, extra)
 
 
 def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
@@ -115,10 +103,10 @@ def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
     tiny = rng.normal(size=(23, 3)).astype(np.float32)
     for name, pts, k, h in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
         ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
-        for u, extra in ((1, 0), (2, 0), (2, 3 * k), (0, 3 * k)):
-            got = run_knn(harness, pts, k, h, staged_u=u, coll_extra=extra)
-            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u, extra)
-            assert np.array_equal(got["dist"], ref_dist), (name, u, extra)
+        for u, listed in ((1, 0), (2, 0), (2, 1), (1, 1)):
+            got = run_knn(harness, pts, k, h, staged_u=u, listed=listed)
+            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u, listed)
+            assert np.array_equal(got["dist"], ref_dist), (name, u, listed)
 
 
 @pytest.mark.parametrize("axis", [0, 2])
@@ -564,11 +552,9 @@ def test_io_code_under_address_and_ub_sanitizers(tmp_path):
     assert run.returncode == 0 and "asan run done" in run.stdout, (run.stdout[-500:], run.stderr[-3000:])
 
 
-def test_one_pass_selection_gives_the_same_rows(harness, bunny):
-    """knn_select<COLLECT, ONEPASS> (the experiment behind PCT_ONEPASS): rows equal the oracle's whatever the cut --
-    the margin of DESIGN.md 7, a cut that misses often (redone with both passes), a list too short for the cut."""
-    harness.h_set_onepass.restype = ctypes.c_longlong
-    harness.h_set_onepass.argtypes = [ctypes.c_int]
+def test_listed_selection_gives_the_same_rows(harness, bunny):
+    """knn_select_listed (the staged kernel's selection): rows equal the oracle's whatever the cut -- the shipped
+    first cut, cuts that miss low or high (re-cut inside the block, then handed to the two-pass selection)."""
     pts = bunny[::3]
     k = 20
     ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
@@ -576,36 +562,37 @@ def test_one_pass_selection_gives_the_same_rows(harness, bunny):
     base = run_knn(harness, pts, k, h, staged_u=2)
     staged = np.mean(base["code"] == 50)
     assert staged > 0.8
+    stats = (ctypes.c_longlong * 4)()
     seen = {}
-    for gain, extra in ((6.3, 48), (2.5, 48), (12.0, 12)):
-        harness.h_set_onepass(1)
-        try:
-            got = run_knn(harness, pts, k, h, staged_u=2, coll_extra=extra, cut_gain=gain)
-        finally:
-            redone = harness.h_set_onepass(0)
-        assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (gain, extra)
-        assert np.array_equal(got["dist"], ref_dist), (gain, extra)
-        # (a k-th neighbour in the last 0.1 % of the certain radius is found one level coarser: the list's
-        # histogram stops at 0.999 of the cut)
+    for scale in (1.0, 0.2, 8.0, 1e-4, 1e4):
+        harness.h_listed_stats(stats, 1)
+        got = run_knn(harness, pts, k, h, staged_u=2, listed=1, cut_scale=scale)
+        harness.h_listed_stats(stats, 0)
+        assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, scale
+        assert np.array_equal(got["dist"], ref_dist), scale
+        # (a k-th neighbour in the last 0.1 % of the certain radius is found one level coarser by the two-pass selection)
         moved = got["code"] != base["code"]
-        assert moved.mean() < 1e-3 and (got["code"][moved] == 1).all() and (base["code"][moved] == 50).all(), (gain, extra)
-        seen[(gain, extra)] = redone / (staged * len(pts))
-    assert seen[(6.3, 48)] < 0.02, seen            # the cut rarely misses ...
-    assert seen[(2.5, 48)] > 0.2, seen             # ... a tight one often does ...
-    assert seen[(12.0, 12)] > 0.2, seen            # ... and a generous one overflows a short list
-    # ties, duplicates of the query, tiny clouds
-    rng = np.random.default_rng(5)
-    g = np.arange(9, dtype=np.float32)
-    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
-    cloud = rng.normal(size=(1200, 3)).astype(np.float32)
-    dup = np.concatenate((cloud, cloud[:150]))
-    tiny = rng.normal(size=(23, 3)).astype(np.float32)
-    for name, p3, kk, hh in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
-        want_idx, want_dist, _ = oracle.knn_canonical(p3, kk)
-        harness.h_set_onepass(1)
-        try:
-            got = run_knn(harness, p3, kk, hh, staged_u=2, coll_extra=3 * kk, cut_gain=6.3)
-        finally:
-            harness.h_set_onepass(0)
-        assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0, name
-        assert np.array_equal(got["dist"], want_dist), name
+        assert moved.mean() < 2e-3, (scale, moved.mean())
+        attempts, recuts, handed, queries = list(stats)
+        seen[scale] = (attempts / queries, handed / queries)
+    assert seen[1.0][0] < 1.5 and seen[1.0][1] < 0.03, seen        # the first cut usually holds ...
+    assert seen[0.2][0] > 1.5 and seen[8.0][0] > 1.5, seen         # ... bad ones are re-cut with the count they produced ...
+    assert seen[0.2][1] < 0.05 and seen[8.0][1] < 0.05, seen       # ... which settles nearly all of them inside the block
+    # fit out of the listed rows
+    ref = oracle.knn_curvature(pts, k)
+    got = run_knn(harness, pts, k, h, staged_u=2, listed=1)
+    rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
+    assert rep["violations"] == 0 and rep["tight_fraction"] > 0.999, rep
+    # other k, incl. the smallest lists and the largest
+    for kk in (1, 6, 32, 50, 100):
+        want_idx, want_dist, _ = oracle.knn_canonical(pts, kk)
+        hh = 1.25 * float(np.median(want_dist[:, -1]))
+        got = run_knn(harness, pts, kk, hh, staged_u=2, listed=1, cap_pts=60000)
+        assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0, kk
+        assert np.array_equal(got["dist"], want_dist), kk
+    # a volumetric cloud (the cut scales with the 2/3 power of the count)
+    rng = np.random.default_rng(8)
+    vol = rng.uniform(0, 1, size=(6000, 3)).astype(np.float32)
+    want_idx, want_dist, _ = oracle.knn_canonical(vol, 16)
+    got = run_knn(harness, vol, 16, 1.1 * float(np.median(want_dist[:, -1])), staged_u=2, listed=1, cap_pts=60000)
+    assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0 and np.array_equal(got["dist"], want_dist)
