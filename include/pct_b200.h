@@ -18,6 +18,10 @@
  *   - the library owns only `pct_index` (opaque; immutable after build)
  *   - per-point failures are reported in `status[]` bits, never as an error
  *     code; outputs of a failed point are NaN
+ *   - threading: calls on ONE stream must come from one host thread at a time
+ *     (the temporaries of a call live in a scratch arena keyed by the stream,
+ *     which the next call on that stream reuses); different streams may be
+ *     driven from different threads concurrently
  *
  * Query ranges and output layout
  *   The index keeps the cloud Morton-sorted.  Queries are addressed by SORTED
@@ -38,7 +42,7 @@
 extern "C" {
 #endif
 
-#define PCT_VERSION 100
+#define PCT_VERSION 200
 
 #define PCT_OK 0
 #define PCT_ERR_INVALID_ARGUMENT (-1)
@@ -54,8 +58,9 @@ extern "C" {
 #define PCT_STATUS_OK 0u
 #define PCT_STATUS_EXACT_PATH 1u     /* informational: resolved by the exact tie/expansion path */
 #define PCT_STATUS_FEW_NEIGHBORS 2u  /* < 2 neighbours (no covariance) -> NaN */
-#define PCT_STATUS_RANK_DEFICIENT 4u /* 6x6 normal equations not positive definite -> NaN */
+#define PCT_STATUS_RANK_DEFICIENT 4u /* rank-deficient design: the coefficients are lstsq's minimum-norm solution (ref :359), finite */
 #define PCT_STATUS_NONFINITE 8u      /* non-finite intermediate: ref :318-319 / :356-357 ValueError */
+#define PCT_STATUS_BAD_INDEX 32u     /* rows entry points: a caller-provided index lies outside [-N, N) -> NaN */
 #define PCT_STATUS_UNRESOLVED 16u    /* slab index only (pct_index_set_slab): the k-th neighbour may lie outside the slab */
 
 typedef struct pct_index pct_index;
@@ -168,6 +173,14 @@ int pct_knn(const pct_index* index, int64_t q_begin, int64_t q_end, int k,
 int pct_knn_points(const pct_index* index, const float* xyz, int stride, const int32_t* query_ids,
                    int64_t nq, int k, int32_t* idx, float* dist, void* stream);
 
+/* kNN of ARBITRARY coordinates: `self.kdtree.query(x, k)` as scipy defines it (the reference only passes cloud points,
+ * ref :83, :759).  queries: nq x 3 fp32 on the device.  Row r = the k nearest cloud points of queries[r] ordered by
+ * (fp64 squared distance, index) -- a query that is a cloud point finds itself first, at distance 0; nothing is dropped.
+ * idx nq x k int32, dist nq x k fp64 (scipy returns float64).  Whole-cloud indexes only.  A query outside the cloud's
+ * bounding box is answered by a scan of the whole cloud (correct, slow for large clouds). */
+int pct_knn_query(const pct_index* index, const float* queries, int64_t nq, int k, int32_t* idx, double* dist,
+                  void* stream);
+
 /* fused search + fit for selected cloud points (same addressing as pct_knn_points), packed records nq x 8 */
 int pct_curvature_points_records(const pct_index* index, const float* xyz, int stride,
                                  const int32_t* query_ids, int64_t nq, int k, float* records, void* stream);
@@ -227,7 +240,7 @@ int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uin
 int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream);
 
 /* Text loader: replaces `np.loadtxt(file_path)` of read_from_file (ref :51) with a memory-mapped,
- * multi-threaded parser (host code).  One row per line; values separated by blanks, tabs or commas; '#'
+ * multi-threaded parser (host code).  One row per line; values separated by blanks or tabs (np.loadtxt's default delimiter: a comma is an error); '#'
  * starts a comment; empty lines are skipped; every row has the same number of columns
  * (PCT_ERR_INVALID_ARGUMENT otherwise, np.loadtxt raises ValueError).  Values are converted like Python's
  * float() (correctly rounded), so the table equals np.loadtxt's bit for bit.

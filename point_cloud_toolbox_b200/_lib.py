@@ -27,6 +27,7 @@ STATUS_FEW_NEIGHBORS = 2
 STATUS_RANK_DEFICIENT = 4
 STATUS_NONFINITE = 8
 STATUS_UNRESOLVED = 16
+STATUS_BAD_INDEX = 32
 
 MAX_K = 128
 
@@ -70,6 +71,7 @@ SIGNATURES = {
     "pct_index_last_stats": (c_int, [c_void_p, c_void_p, POINTER(QueryStats)]),
     "pct_knn": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_knn_points": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "pct_knn_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pct_curvature_points_records": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "pct_estimate_cell_size": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
     "pct_index_set_slab": (c_int, [c_void_p, c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p]),

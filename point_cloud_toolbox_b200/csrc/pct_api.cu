@@ -88,6 +88,14 @@ int pct_knn_points(const pct_index* ix, const float* xyz, int stride, const int3
     return launch_knn_points(ix, xyz, stride, query_ids, nq, k, idx, dist, nullptr, (cudaStream_t)stream);
 }
 
+int pct_knn_query(const pct_index* ix, const float* queries, int64_t nq, int k, int32_t* idx, double* dist, void* stream) {
+    PCT_REQUIRE(ix && nq >= 0 && (queries || nq == 0) && (idx || nq == 0) && (dist || nq == 0), "pct_knn_query: bad argument");
+    PCT_REQUIRE(ix->view.slab_axis < 0, "pct_knn_query: not available on a slab index");
+    PCT_REQUIRE(k >= 1 && k <= PCT_MAX_K, "pct_knn_query: k must be in [1, 128]");
+    if ((long long)k > ix->view.n) { set_error("pct_knn_query: k exceeds the number of points"); return PCT_ERR_K_TOO_LARGE; }
+    return launch_knn_query(ix, queries, nq, k, idx, dist, (cudaStream_t)stream);
+}
+
 int pct_curvature_points_records(const pct_index* ix, const float* xyz, int stride, const int32_t* query_ids, int64_t nq,
                                  int k, float* records, void* stream) {
     PCT_REQUIRE(ix && xyz && (stride == 3 || stride == 4) && nq >= 0 && (query_ids || nq == 0) &&
@@ -218,6 +226,7 @@ int pct_curvature_knn_host(const float* xyz_host, int64_t n, int k, float* K_hos
         if (d_xyz) cudaFree(d_xyz);
         if (d_curv) cudaFree(d_curv);
         if (h_curv) cudaFreeHost(h_curv);
+        release_scratch_of(s);  // the build's and the query's temporaries live in an arena keyed by this stream
         cudaStreamDestroy(s);
     };
 #define PCT_TRY(call)                                                        \

@@ -20,12 +20,14 @@ namespace {
 constexpr int kBlock = 128;
 
 __global__ void __launch_bounds__(kBlock)
-fit_rows_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, long long nq, int k,
+fit_rows_kernel(const float* __restrict__ xyz, const long long n, const int32_t* __restrict__ idx, long long nq, int k,
                 const int32_t* __restrict__ qids, const long long* __restrict__ offsets, FitOutputs out) {
     for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < nq; r += (long long)gridDim.x * kBlock) {
-        const long long qi = qids ? (long long)qids[r] : r;
+        long long qi = qids ? (long long)qids[r] : r;
+        qi += qi < 0 ? n : 0;
         RowNeighbourhood nb;
         nb.xyz = xyz;
+        nb.n = n;
         if (offsets) {
             nb.row = idx + offsets[r];
             nb.count = (int)(offsets[r + 1] - offsets[r]);
@@ -33,9 +35,21 @@ fit_rows_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx, 
             nb.row = idx + r * k;
             nb.count = k;
         }
-        nb.qx = __ldg(xyz + 3 * qi); nb.qy = __ldg(xyz + 3 * qi + 1); nb.qz = __ldg(xyz + 3 * qi + 2);
         FitResult res;
         res.status = 0;
+        // caller-provided indices: negative ones count from the end like numpy's (ref :640 is fancy indexing), anything
+        // else outside the cloud is an error of the row, never an address
+        bool valid = qi >= 0 && qi < n;
+        for (int m = 0; m < nb.count && valid; ++m) {
+            const long long j = nb.row[m];
+            valid = j >= -n && j < n;
+        }
+        if (!valid) {
+            fit_fail(res, ST_BAD_INDEX);
+            store_fit(out, r, res);
+            continue;
+        }
+        nb.qx = __ldg(xyz + 3 * qi); nb.qy = __ldg(xyz + 3 * qi + 1); nb.qz = __ldg(xyz + 3 * qi + 2);
         fit_neighbourhood<true>(nb, res);
         store_fit(out, r, res);
     }
@@ -185,18 +199,18 @@ int grid_for(long long n) {
 
 }  // namespace
 
-int launch_fit_rows(const float* xyz, long long, const int32_t* idx, long long nq, int k, const int32_t* qids,
+int launch_fit_rows(const float* xyz, long long n, const int32_t* idx, long long nq, int k, const int32_t* qids,
                     FitOutputs out, cudaStream_t s) {
     if (nq == 0) return PCT_OK;
-    fit_rows_kernel<<<grid_for(nq), kBlock, 0, s>>>(xyz, idx, nq, k, qids, nullptr, out);
+    fit_rows_kernel<<<grid_for(nq), kBlock, 0, s>>>(xyz, n, idx, nq, k, qids, nullptr, out);
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
 }
 
-int launch_fit_csr(const float* xyz, long long, const long long* offsets, const int32_t* idx, long long nq,
+int launch_fit_csr(const float* xyz, long long n, const long long* offsets, const int32_t* idx, long long nq,
                    const int32_t* qids, FitOutputs out, cudaStream_t s) {
     if (nq == 0) return PCT_OK;
-    fit_rows_kernel<<<grid_for(nq), kBlock, 0, s>>>(xyz, idx, nq, 0, qids, offsets, out);
+    fit_rows_kernel<<<grid_for(nq), kBlock, 0, s>>>(xyz, n, idx, nq, 0, qids, offsets, out);
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
 }

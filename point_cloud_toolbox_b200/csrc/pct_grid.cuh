@@ -61,7 +61,6 @@ struct IndexView {
     int bits;          // bits per axis of the Morton key
     int num_levels;    // tables for levels 0 .. num_levels-1 (last one: a single cell)
     int volumetric;    // density pilot saw a space-filling cloud (intrinsic dimension > 2.5), not a surface
-    float cut_gain;    // head-room of the k-th-distance estimate used to pre-collect candidates
     // Slab of a spatially partitioned cloud (multi-GPU): the index holds every cloud point whose
     // coordinate on `slab_axis` lies in [complete_lo, complete_hi] and nothing is known about the rest,
     // so no search radius may reach beyond those planes; only queries in [own_lo, own_hi) are answered.
@@ -319,9 +318,7 @@ struct CellRuns {
 // ---------------------------------------------------------------------------
 // kNN selection, thread per query
 // ---------------------------------------------------------------------------
-enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2,
-                        SEL_RECUT = 3,    // listed selection only: the cut missed, `cut2` holds the cut to try next
-                        SEL_TWOPASS = 4 };  // listed selection only: hand the query to the two-pass selection
+enum SelectCode : int { SEL_OK = 0, SEL_RETRY_COARSER = 1, SEL_EXACT = 2 };
 
 // Selection scratch of one query (two-pass selection).  On the GPU all of it lives in shared memory:
 //   runs  54 words, word w at runs[w * stride]           (27 cell runs, GlobalSource only)
@@ -475,8 +472,10 @@ struct SelectScratch {
 };
 
 // Two-pass selection: finds the exact k nearest neighbours (scipy order, self excluded) of query `q` inside the
-// level-`level` stencil, in O(candidates) work.  The L1/L2 kernel runs it (queued queries); the staged kernel
-// uses knn_select_listed() below.
+// level-`level` stencil, in O(candidates) work.  Measured against it on B200 and removed (profiles/README.md, r02):
+// one-pass variants that list the candidates below a cut from the local density and select from the list (13.0 /
+// 19.3 ms against 11.4 / 16.0 ms at 20 M points, k = 20 / 32: the listing pass costs as many instructions per
+// candidate as the histogram pass, and the list walks are chains of dependent shared-memory loads).
 //
 //   pass 1  histogram of the fp32 squared distances over kHistBins equal bins of
 //           [0, range2) (squared distance is uniform in area on a surface, so the
@@ -654,198 +653,6 @@ PCT_HD int knn_select(const IndexView& ix, const Stencil& st, int level, const S
     return SEL_OK;
 }
 
-// ---------------------------------------------------------------------------
-// listed selection (the staged kernel): ONE pass over the candidates
-// ---------------------------------------------------------------------------
-// The two-pass selection visits every candidate twice and updates a shared-memory histogram per visit; of the
-// ~150 candidates of a query only k + 1 matter.  Here one pass lists the candidates below a CUT and everything
-// else runs over the list:
-//
-//   cut     squared radius expected to hold `target` candidates, from the population C of the query's 27 cells
-//           (a surface: C = density * 9 cell^2 * tilt; a volume: density * 27 cell^3).  The caller keeps it per
-//           query: a cut that lists fewer than k + 1 or more than the list holds is rescaled with the count it
-//           produced (count ~ cut2 on a surface) and the query is tried again -- by whichever thread of the
-//           block is free (the block compacts its retries, so a warp does not pay a second pass for one lane).
-//   pass 1  lists every candidate with d32 < cut2 (the query itself among them).  cut2 never exceeds the certain
-//           radius of the stencil, so everything closer than the cut IS listed.
-//   list    16-bin byte histogram of the listed distances over [0, 0.999 cut2), kept in registers -> bin b of
-//           the (k + 1)-th entry; in-place partition of the list into the front (d32 < lo, certain neighbours)
-//           and the boundary zone (bin b widened by 1e-5: at most 8 positions, in registers); the same walk
-//           finds the nearest entry and the front / zone gap.  The zone is resolved with the fp64 key.
-//
-// Exactness is the two-pass argument with range2 replaced by cut2: every candidate below cut2 is listed, the
-// boundary bin ends below cut2 (the histogram stops at 0.999 cut2), so every true neighbour is in front or zone.
-// The cut only decides how much work is done, never the result.
-//
-// Slots: the list has 2 * list.rows 16-bit slots (low halves, then high halves of its rows); the k neighbours
-// end up in the low slots, where the fit reads them.
-static constexpr int kListedBins = 16;
-static constexpr int kListedZone = 8;
-
-// entries a cut should list: the geometric middle of what is needed and what fits
-PCT_HD int listed_target(int k, int slots) {
-    const float t = sqrtf((float)(k + 1) * (float)slots);
-    const int ti = (int)t;
-    return ti < k + 2 ? k + 2 : ti;
-}
-
-// first cut of a query whose 27 cells hold `population` points
-PCT_HD float listed_first_cut(const IndexView& ix, int target, uint32_t population) {
-    const float cell2 = ix.h * ix.h;
-    const float frac = (float)target / (float)(population + 1u);
-    // surface: count = C * pi cut2 / (9 cell2 tilt); volume: count = C * (4/3) pi cut^3 / (27 cell^3)
-    return ix.volumetric ? cbrtf(frac * frac) * 3.46f * cell2 : ix.cut_gain * frac * cell2;
-}
-
-template <class Source, class List>
-PCT_HD int knn_select_listed(const IndexView& ix, const Stencil& st, const Source& src, const Pt& q, int k, int target,
-                             const List& list, float& cut2, typename Source::Pos& first, typename Source::Pos& last) {
-    typedef typename Source::Pos Pos;
-    static_assert(sizeof(Pos) == 2, "zone positions are packed four to a 64-bit register");
-    const uint32_t self = q.idx;
-    const int slots = 2 * list.rows;
-    const float cell = ix.h;
-    const float range2 = (st.safe2 < 1.0e37f ? st.safe2 : 27.f * cell * cell) * 0.999f;
-    if (!(range2 > 1.0e-30f)) return SEL_EXACT;
-    const bool at_range = !(cut2 < range2);
-    if (at_range) cut2 = range2;   // never beyond the radius within which every cloud point has been visited
-    if (!(cut2 > 1.0e-30f)) return SEL_EXACT;
-
-    struct P1 {
-        List list;
-        uint32_t n, slots;
-        float qx, qy, qz, cut2;
-        PCT_HD void operator()(Pos j, const Pt& p, bool valid) {
-            const float d = valid ? dist2_f32(qx, qy, qz, p.x, p.y, p.z) : 3.4e38f;
-            const bool in = d < cut2;
-            if (in && n < slots) list.at((int)n) = j;
-            n += in ? 1u : 0u;
-        }
-    } p1;
-    p1.list = list; p1.n = 0; p1.slots = (uint32_t)slots;
-    p1.qx = q.x; p1.qy = q.y; p1.qz = q.z; p1.cut2 = cut2;
-    src.scan(p1);
-    const int n = (int)p1.n;
-    if (n > slots || n < k + 1) {
-        if (n < k + 1 && at_range) return SEL_RETRY_COARSER;   // fewer than k + 1 points within the certain radius
-        float ratio = (float)target / (float)(n > 0 ? n : 1);
-        if (ix.volumetric) ratio = cbrtf(ratio * ratio);
-        ratio = fminf(fmaxf(ratio, 0.2f), 6.f);
-        cut2 *= ratio;
-        return SEL_RECUT;
-    }
-
-    // histogram of the n listed entries: bin = d / (0.999 cut2 / 16); entries in the last 0.1 % below the cut
-    // land in no bin, so the boundary bin (widened by 1e-5) always ends below cut2
-    const float inv_w = (float)kListedBins / (cut2 * 0.999f) * 0.99999f;
-    if (!(inv_w < 3.0e38f)) return SEL_EXACT;
-    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-#pragma unroll 1
-    for (int s = 0; s < n; ++s) {
-        const Pt p = src.load(list.at(s));
-        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
-        const int b = (int)fminf(d * inv_w, (float)kListedBins);
-        const uint32_t inc = 1u << ((b & 3) * 8);
-        const int w = b >> 2;
-        h0 += w == 0 ? inc : 0u;
-        h1 += w == 1 ? inc : 0u;
-        h2 += w == 2 ? inc : 0u;
-        h3 += w == 3 ? inc : 0u;
-    }
-    int b = -1;
-    uint32_t cum = 0, cum_before = 0;
-    {
-        const uint32_t words[4] = {h0, h1, h2, h3};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const uint32_t c = (words[w] >> (8 * t)) & 255u;
-                if (b < 0 && cum + c > (uint32_t)k) { b = 4 * w + t; cum_before = cum; }
-                cum += c;
-            }
-        }
-    }
-    if (cum > (uint32_t)n) return SEL_EXACT;   // (cannot happen: a byte only wraps at 256 entries in one bin)
-    if (b < 0) {
-        // the (k + 1)-th entry lies in the last 0.1 % below the cut: a slightly larger cut settles it
-        if (at_range) return SEL_TWOPASS;
-        cut2 *= 1.05f;
-        return SEL_RECUT;
-    }
-    const float bin_w = 1.f / inv_w;
-    const float hi = (float)(b + 1) * bin_w * 1.00001f;
-    const float lo = b == 0 ? -1.f : (float)b * bin_w * 0.99999f;
-
-    // in-place partition: front entries move to the low slots 0 .. n_front-1 (the write position never passes
-    // the read position, and high slots are only read), zone entries into two registers of four positions
-    unsigned long long za = 0ull, zb = 0ull;
-    int n_front = 0, n_zone = 0;
-    float d_min = 3.4e38f, d_min2 = 3.4e38f, front_max = 0.f, zone_min = 3.4e38f;
-    Pos j_min = 0;
-#pragma unroll 1
-    for (int s = 0; s < n; ++s) {
-        const Pos j = list.at(s);
-        const Pt p = src.load(j);
-        const float d = dist2_f32(q.x, q.y, q.z, p.x, p.y, p.z);
-        const bool in = d <= hi && p.idx != self, front = d < lo;
-        const bool is_front = in && front, is_zone = in && !front;
-        if (is_front) list.lo(n_front) = j;
-        if (is_zone) {
-            const unsigned long long e = (unsigned long long)j << (16 * (n_zone & 3));
-            za |= n_zone < 4 ? e : 0ull;
-            zb |= (n_zone >= 4 && n_zone < kListedZone) ? e : 0ull;
-        }
-        n_front += is_front ? 1 : 0;
-        n_zone += is_zone ? 1 : 0;
-        front_max = is_front ? fmaxf(front_max, d) : front_max;
-        zone_min = is_zone ? fminf(zone_min, d) : zone_min;
-        const bool closer = in && d < d_min;
-        d_min2 = closer ? d_min : (in ? fminf(d_min2, d) : d_min2);
-        j_min = closer ? j : j_min;
-        d_min = closer ? d : d_min;
-    }
-    if (n_zone > kListedZone) return SEL_TWOPASS;      // a crowded boundary bin: the two-pass selection has 16 slots, then the exact kernel
-    if (!(d_min > 1.0e-30f)) return SEL_EXACT;         // duplicates of the query / denormal range: fp64 only
-    if (n_front > 0 && !(zone_min > front_max * 1.000002f)) return SEL_EXACT;
-    const int need = k - n_front;
-    if (need < 1 || need > n_zone) return SEL_EXACT;
-
-    // exact choice inside the boundary zone: `need` successive minima of (d2, index)
-    unsigned int taken = 0u;
-    for (int t = 0; t < need; ++t) {
-        double bd = 0.0;
-        uint32_t bi = 0;
-        Pos bj = 0;
-        int bm = -1;
-        for (int m = 0; m < n_zone; ++m) {
-            if ((taken >> m) & 1u) continue;
-            const Pos j = (Pos)(((m < 4 ? za : zb) >> (16 * (m & 3))) & 0xffffull);
-            const Pt p = src.load(j);
-            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (bm < 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; bj = j; bm = m; }
-        }
-        taken |= 1u << bm;
-        list.lo(n_front + t) = bj;
-        last = bj;
-    }
-
-    // nearest neighbour: decided in fp32 when the runner-up is clearly farther
-    if (d_min2 > d_min * 1.00001f) {
-        first = j_min;
-    } else {
-        double bd = 0.0;
-        uint32_t bi = 0;
-        for (int m = 0; m < k; ++m) {
-            const Pos j = list.lo(m);
-            const Pt p = src.load(j);
-            const double d = dist2_f64(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (m == 0 || key_less(d, p.idx, bd, bi)) { bd = d; bi = p.idx; first = j; }
-        }
-    }
-    return SEL_OK;
-}
-
 // Neighbourhood adaptor over a list of candidate positions (fused kNN path: the neighbours sit in
 // the low slots; the ball path fills low and high slots, LOW_ONLY = false).
 template <class Source, bool LOW_ONLY = true, class List = ListRef<typename Source::Pos>>
@@ -1003,18 +810,23 @@ PCT_HD void list_extremes(const Source& src, const ListRef<typename Source::Pos>
 struct RowNeighbourhood {
     const float* xyz;
     const int32_t* row;
+    long long n;  // points in the cloud: a negative index counts from the end (the caller has checked the range)
     int count;
     float qx, qy, qz;
+    PCT_HD const float* point(int m) const {
+        const long long j = row[m];
+        return xyz + 3 * (size_t)(j < 0 ? j + n : j);
+    }
     template <class F>
     PCT_HD void pass(F& fn) const {
         for (int m = 0; m < count; ++m) {
-            const float* p = xyz + 3 * (size_t)row[m];
+            const float* p = point(m);
             fn.add(fsub_rn(p[0], qx), fsub_rn(p[1], qy), fsub_rn(p[2], qz));
         }
     }
     PCT_HD void reference(float& rx, float& ry, float& rz) const {
-        const float* a = xyz + 3 * (size_t)row[0];
-        const float* b = xyz + 3 * (size_t)row[count - 1];
+        const float* a = point(0);
+        const float* b = point(count - 1);
         rx = fsub_rn(fsub_rn(b[0], qx), fsub_rn(a[0], qx));
         ry = fsub_rn(fsub_rn(b[1], qy), fsub_rn(a[1], qy));
         rz = fsub_rn(fsub_rn(b[2], qz), fsub_rn(a[2], qz));

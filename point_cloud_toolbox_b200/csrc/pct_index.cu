@@ -322,15 +322,8 @@ static int build_impl(const float* xyz, long long n, int stride, float cell_hint
     while ((1 << v.bits) < maxdim) ++v.bits;
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
-    // first cut of the listed selection (knn_select_listed): cut2 = gain * (target / C) cell^2 on a surface, where
-    // C = population of the 3x3x3 block = density * 9 cell^2 * tilt: gain = 9 tilt / pi.  Performance only.
     v.slab_axis = -1;
     v.volumetric = est_dim > 2.5f ? 1 : 0;
-    v.cut_gain = 3.3f;
-    if (const char* g = std::getenv("PCT_CUT_GAIN")) {  // tuning knob of scripts/tune.py
-        const float gv = (float)std::atof(g);
-        if (gv > 0.f) v.cut_gain = gv;
-    }
 
     // 3. keys, sort, gather
     DeviceTemp keys_a(s, &scratch), keys_b(s, &scratch), vals_a(s, &scratch), vals_b(s, &scratch), sort_tmp(s, &scratch), hist(s, &scratch);

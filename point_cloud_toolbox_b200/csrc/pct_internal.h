@@ -58,6 +58,7 @@ class ScratchSession {
     size_t left_ = 0;
 };
 void release_scratch();
+void release_scratch_of(cudaStream_t s);  // one stream of the current device; call before destroying a library-owned stream
 void release_upload_stage();  // pct_transfer.cu
 
 // per-row output pointers of the fit (any may be null)
@@ -99,6 +100,7 @@ int launch_knn(const pct_index* ix, long long q_begin, long long q_end, int k, b
                int32_t* idx, float* dist, FitOutputs out, int layout, cudaStream_t s);
 int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const int32_t* ids, long long nq, int k,
                       int32_t* idx, float* dist, float* records, cudaStream_t s);
+int launch_knn_query(const pct_index* ix, const float* queries, long long nq, int k, int32_t* idx, double* dist, cudaStream_t s);
 int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode,
                 int32_t* counts, const long long* offsets, long long nnz, int32_t* idx, float* dist,
                 FitOutputs out, int layout, cudaStream_t s);

@@ -3,7 +3,7 @@
 // itself takes a tenth of a second.  Host code only: the file is
 // memory-mapped, cut at line boundaries into one piece per thread, and every token is converted with
 // std::from_chars -- correctly rounded like Python's float(), so the table equals np.loadtxt's bit for
-// bit.  Format = what the reference's scans use: numbers separated by blanks, tabs or commas, one row per
+// bit.  Format = what the reference's scans use: numbers separated by blanks or tabs (np.loadtxt's default delimiter), one row per
 // line, '#' starts a comment, empty lines are skipped, every row has the same number of columns.
 #include <fcntl.h>
 #include <sys/mman.h>

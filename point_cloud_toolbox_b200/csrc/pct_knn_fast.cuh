@@ -138,7 +138,6 @@ knn_fast_kernel(const IndexView ix, const int level, const QueryRange qr, const 
 // ---------------------------------------------------------------------------
 constexpr int kStagedBlock = PCT_STAGED_BLOCK;  // queries (= threads) of one CTA
 constexpr int kStagedWarps = kStagedBlock / 32;
-constexpr int kStagedRoundsMax = 4;             // attempts of a query inside its CTA (first cut + rescaled cuts)
 
 template <int U>
 struct StageShape : RegionShape<U> {
@@ -146,13 +145,9 @@ struct StageShape : RegionShape<U> {
     static constexpr int kMaxRegions = U >= 2 ? 2 + kStagedBlock / 64 : 4 + kStagedBlock / 16;
     static constexpr int kTable = kMaxRegions * RegionShape<U>::kCells;
     static constexpr int kItemsPerThread = (kTable + kStagedBlock - 1) / kStagedBlock;
-    // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, the two retry-queue
-    // lengths, then the region origins
-    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrRetry = kHdrFlag + 2, kHdrOrg = kHdrFlag + 4;
+    // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, then the region origins
+    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrOrg = kHdrFlag + 2;
     static constexpr int kHdrWords = (kHdrOrg + 3 * kMaxRegions + 3) & ~3;
-    // per-query words that outlive staging: cut of the next attempt (float), region | block corner (uint16),
-    // two retry queues of query numbers (uint16)
-    static constexpr int kQueryBytes = kStagedBlock * (4 + 2 + 2 + 2);
 };
 
 struct StagedCell {
@@ -161,69 +156,51 @@ struct StagedCell {
     uint16_t count;
 };
 
-// dynamic shared memory of the staged kernels, in this order (every part 16-byte aligned):
+// dynamic shared memory of the staged kernel, in this order (every part 16-byte aligned):
 //   Pt       pts[cap_pts]
 //   uint32   tab[kTable + 4]         shared address of the first record of every region cell
 //   int      hdr[kHdrWords]          block-scan partials, flags, region origins
-//   query    float cut[B], uint16 where[B], uint16 retry[2][B]      (kQueryBytes)
 //   scratch  max(per-query scratch, staging temporaries)
-//       per query  : uint16 list[2 * rows][kStagedBlock] as `rows` 32-bit rows
+//       per query  : uint16 list[cap][kStagedBlock], uint32 hist[17][kStagedBlock]; the list is first written
+//                    after the histogram has been read, so the two share their memory
 //       temporaries: uint32 first[kTable], StagedCell cells[kTable], uint16 count[kTable]
 template <int U>
-__host__ __device__ inline size_t staged_smem_bytes(int rows, int cap_pts) {
-    const size_t per_query = (size_t)4 * rows * kStagedBlock;
+__host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
+    const size_t list = ListRef<uint16_t>::bytes(cap - PCT_TIE_SLACK, cap);
+    const size_t hist = kHistRowBytes;
+    const size_t per_query = (list > hist ? list : hist) * kStagedBlock;
     const size_t temps = (size_t)StageShape<U>::kTable * (sizeof(uint32_t) + sizeof(uint16_t) + sizeof(StagedCell)) + 64;
     const size_t scratch = per_query > temps ? per_query : temps;
     const size_t tab = (size_t)(StageShape<U>::kTable + 4) * sizeof(uint32_t);
-    return sizeof(Pt) * (size_t)cap_pts + tab + StageShape<U>::kHdrWords * sizeof(int) + StageShape<U>::kQueryBytes +
-           ((scratch + 15) & ~(size_t)15);
+    return sizeof(Pt) * (size_t)cap_pts + tab + StageShape<U>::kHdrWords * sizeof(int) + ((scratch + 15) & ~(size_t)15);
 }
 
-// list rows of the staged kNN kernel: 2 * rows slots for the listed candidates, the k neighbours end up in the low ones
-__host__ __device__ inline int staged_list_rows(int k) { return k > 12 ? k : 12; }
-
 #if defined(__CUDACC__)
-// What staging leaves a block with.
-template <int U>
-struct StagedBlock {
-    uint32_t tab;      // shared address of the cell table (region r starts at tab + 4 * r * kCells)
-    float* cut;        // [B] cut of the query's next attempt
-    uint16_t* where;   // [B] region * 256 + raster index of the lowest cell of the query's 3x3x3 block
-    uint16_t* retry;   // [2][B] retry queues
-    int* hdr;
-    char* scratch;     // start of the block's per-query scratch area
-    __device__ __forceinline__ StagedSource source(int t) const {
-        const uint32_t w = where[t];
-        StagedSource src;
-        src.tab = tab + 4u * (w >> 8) * (uint32_t)StageShape<U>::kCells;
-        src.corner = (int)(w & 255u);
-        src.side = StageShape<U>::kSide;
-        return src;
-    }
+// What staging leaves a thread with: its query, the staged source positioned on the query's region,
+// and the block's per-query scratch area (the staging temporaries in it are dead).
+struct StagedQuery {
+    uint32_t i;      // sorted position of the query
+    Pt q;
+    StagedSource src;
+    char* scratch;   // start of the block's scratch area
 };
 
-enum StageCode : int { STAGE_QUERY = 0,     // this thread's query is staged
-                       STAGE_IDLE = 1,      // no query (beyond the range, or another slab owns it); the thread still joins the block's barriers
-                       STAGE_UNSTAGED = 2 };  // the whole chunk went to the fallback queue: every thread of the block gets this
-
 // Steps A-D of the staged kernels: block-cooperative copy of the cells the chunk's queries can reach.
-// All threads of the block must call it; the return value is STAGE_UNSTAGED for all of them or for none.
+// Returns false for threads that have nothing to do afterwards: threads beyond the range, queries the
+// index does not own (slabs), and every thread of a chunk that does not fit the staging buffer (its
+// queries are appended to `fallback`).  All threads of the block must call it.
 template <int U>
-__device__ __forceinline__ int stage_chunk(const IndexView& ix, const QueryRange& qr, const int cap_pts,
-                                           uint32_t* __restrict__ fallback, unsigned int* __restrict__ fallback_count,
-                                           StagedBlock<U>& sb, uint32_t& query, Pt& q_out) {
+__device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRange& qr, const int cap_pts,
+                                            uint32_t* __restrict__ fallback, unsigned int* __restrict__ fallback_count,
+                                            StagedQuery& sq) {
     typedef StageShape<U> Shape;
     constexpr int S = Shape::kSide, C = Shape::kCells, B = kStagedBlock, W = kStagedWarps;
-    static_assert(C <= 256 && Shape::kMaxRegions <= 255, "`where` packs region and corner into 16 bits");
     extern __shared__ uint4 smem_u4[];
     Pt* const pts_s = reinterpret_cast<Pt*>(smem_u4);
     uint32_t* const tab = reinterpret_cast<uint32_t*>(pts_s + cap_pts);
     int* const hdr = reinterpret_cast<int*>(tab + Shape::kTable + 4);
     const uint32_t pts_addr = (uint32_t)__cvta_generic_to_shared(pts_s);
-    float* const cut = reinterpret_cast<float*>(hdr + Shape::kHdrWords);
-    uint16_t* const where = reinterpret_cast<uint16_t*>(cut + B);
-    uint16_t* const retry = where + B;
-    char* const scratch = reinterpret_cast<char*>(retry + 2 * B);
+    char* const scratch = reinterpret_cast<char*>(hdr + Shape::kHdrWords);
     int* const org = hdr + Shape::kHdrOrg;
     // staging temporaries (dead before the per-query scratch is first written)
     uint32_t* const t_first = reinterpret_cast<uint32_t*>(scratch);
@@ -244,7 +221,7 @@ __device__ __forceinline__ int stage_chunk(const IndexView& ix, const QueryRange
     const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
                                       ((unsigned long long)(cz >> U) << 42);
     t_parent[t] = parent;
-    if (t == 0) { hdr[Shape::kHdrFlag] = 0; hdr[Shape::kHdrRetry] = 0; hdr[Shape::kHdrRetry + 1] = 0; }
+    if (t == 0) hdr[Shape::kHdrFlag] = 0;
     __syncthreads();
     const bool head = t == 0 || t_parent[t - 1] != parent;
     const unsigned int heads = __ballot_sync(0xffffffffu, head);
@@ -319,7 +296,7 @@ __device__ __forceinline__ int stage_chunk(const IndexView& ix, const QueryRange
         if (t == 0) hdr[Shape::kHdrQueue] = (int)atomicAdd(fallback_count, n_active);
         __syncthreads();
         if (active) fallback[(unsigned int)hdr[Shape::kHdrQueue] + (unsigned int)t] = i;
-        return STAGE_UNSTAGED;
+        return false;
     }
 #pragma unroll
     for (int u = 0; u < Shape::kItemsPerThread; ++u) {
@@ -346,91 +323,54 @@ __device__ __forceinline__ int stage_chunk(const IndexView& ix, const QueryRange
             reinterpret_cast<float4*>(pts_s)[sc.slot + m] = v;
         }
     }
-    const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
-    where[t] = (uint16_t)((region << 8) | ((lx - 1) + S * (ly - 1) + S * S * (lz - 1)));
     __syncthreads();  // temporaries are dead, the per-query scratch may be written
-    sb.tab = (uint32_t)__cvta_generic_to_shared(tab);
-    sb.cut = cut; sb.where = where; sb.retry = retry; sb.hdr = hdr; sb.scratch = scratch;
-    query = i;
-    q_out = q;
-    return active && query_owned(ix, q.x, q.y, q.z) ? STAGE_QUERY : STAGE_IDLE;
-}
-
-// One attempt at one query of the block (any thread may run it): listed selection with the cut stored for the
-// query, then the fit / the ordered rows.  Returns false when the query wants another attempt with the cut it left
-// in sb.cut[tq].
-template <int U, bool FUSED>
-__device__ __forceinline__ bool staged_attempt(const IndexView& ix, const QueryRange& qr, const StagedBlock<U>& sb, const int tq,
-                                               const uint32_t i, const Pt& q, const int k, const int rows, const int target, const bool last_round,
-                                               int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs& out,
-                                               const Queues& qu) {
-    const StagedSource src = sb.source(tq);
-    ListRef<uint16_t> list;
-    list.base = reinterpret_cast<uint16_t*>(sb.scratch) + 2 * tq;
-    list.stride = 2 * kStagedBlock;
-    list.rows = rows;
-    Stencil st;
-    make_stencil(ix, 0, q.x, q.y, q.z, st);
-    float cut2 = sb.cut[tq];
-    if (!(cut2 > 0.f)) cut2 = listed_first_cut(ix, target, src.count());
-    uint16_t first = 0, last = 0;
-    const int rc = knn_select_listed(ix, st, src, q, k, target, list, cut2, first, last);
-    if (rc == SEL_OK) {
-        emit_query<FUSED>(src, list, k, i, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out, qu);
-        return true;
-    }
-    if (rc == SEL_RECUT && !last_round) {
-        sb.cut[tq] = cut2;
-        return false;
-    }
-    if (rc == SEL_RECUT || rc == SEL_TWOPASS) {
-        qu.fallback[atomicAdd(&qu.counters[2], 1u)] = i;  // the L1/L2 kernel redoes it with the two-pass selection
-    } else if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
-        qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
-    } else {
-        qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
-    }
+    if (!active || !query_owned(ix, q.x, q.y, q.z)) return false;
+    const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
+    sq.i = i;
+    sq.q = q;
+    sq.src.tab = (uint32_t)__cvta_generic_to_shared(tab + region * C);
+    sq.src.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
+    sq.src.side = S;
+    sq.scratch = scratch;
     return true;
 }
 
 template <int U, bool FUSED>
 __global__ void __launch_bounds__(kStagedBlock, PCT_STAGED_CTAS)
-knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int rows, const int target, const int rounds, const int cap_pts,
+knn_staged_kernel(const IndexView ix, const QueryRange qr, const int k, const int cap, const int cap_pts,
                   int32_t* __restrict__ out_idx, float* __restrict__ out_dist, const FitOutputs out, const Queues qu) {
     constexpr int B = kStagedBlock;
-    typedef StageShape<U> Shape;
-    StagedBlock<U> sb;
-    uint32_t i;
-    Pt q;  // (the rounds below reload the query they work on)
-    const int code = stage_chunk<U>(ix, qr, cap_pts, qu.fallback, qu.counters + 2, sb, i, q);
-    if (code == STAGE_UNSTAGED) return;  // (the whole block)
+    StagedQuery sq;
+    if (!stage_chunk<U>(ix, qr, cap_pts, qu.fallback, qu.counters + 2, sq)) return;
     const int t = threadIdx.x;
-    const uint32_t chunk0 = (uint32_t)(qr.q_begin + (long long)blockIdx.x * B);  // sorted position of the block's first query
+    const uint32_t i = sq.i;
+    const Pt q = sq.q;
+    const StagedSource& src = sq.src;
+    char* const scratch = sq.scratch;
 
-    // ---- E, F. round 0: every thread its own query with the cut from the local density; rounds 1..: the queries
-    // whose cut missed, compacted over the threads of the block, with the cut rescaled by the count it produced
-    sb.cut[t] = 0.f;
-    int n_items = B;
-#pragma unroll 1
-    for (int round = 0; round < rounds; ++round) {
-        const int from = (round - 1) & 1, to = round & 1;
-        if (round > 0) {
-            __syncthreads();
-            n_items = sb.hdr[Shape::kHdrRetry + from];
-            if (n_items == 0) return;  // (uniform)
-            __syncthreads();           // everybody has read the count before it is reset
-            if (t == 0) sb.hdr[Shape::kHdrRetry + from] = 0;  // it becomes the queue of round + 1, written after the next barrier
+    // ---- E. select out of the staged copy (two passes over the candidates, see knn_select)
+    SelectScratch<uint16_t> sel;
+    sel.list.base = reinterpret_cast<uint16_t*>(scratch) + 2 * t;
+    sel.list.stride = 2 * B;
+    sel.list.rows = cap - PCT_TIE_SLACK;
+    sel.hist = reinterpret_cast<uint32_t*>(scratch) + t;
+    sel.hist_stride = B;
+    sel.cap = cap;
+    Stencil st;
+    make_stencil(ix, 0, q.x, q.y, q.z, st);
+    uint16_t first = 0, last = 0;
+    double d2_last = 0.0;
+    const int rc = knn_select(ix, st, 0, src, q, k, sel, first, last, d2_last);
+    if (rc != SEL_OK) {
+        if (rc == SEL_RETRY_COARSER && qu.retry && ix.num_levels > 1) {
+            qu.retry[atomicAdd(&qu.counters[0], 1u)] = i;
+        } else {
+            qu.exact[atomicAdd(&qu.counters[1], 1u)] = i;
         }
-#pragma unroll 1
-        for (int item = t; item < n_items; item += B) {
-            const int tq = round == 0 ? t : (int)sb.retry[from * B + item];
-            if (round == 0 && code != STAGE_QUERY) continue;
-            const uint32_t iq = chunk0 + (uint32_t)tq;
-            const Pt qq = load_pt(ix.pts + iq);
-            if (!staged_attempt<U, FUSED>(ix, qr, sb, tq, iq, qq, k, rows, target, round + 1 == rounds, out_idx, out_dist, out, qu))
-                sb.retry[to * B + atomicAdd(&sb.hdr[Shape::kHdrRetry + to], 1)] = (uint16_t)tq;
-        }
+        return;
     }
+    // ---- F. fit (or ordered rows) out of the staged copy
+    emit_query<FUSED>(src, sel.list, k, i, q, first, last, out_row(qr, i, q.idx), out_idx, out_dist, out, qu);
 }
 #endif
 
@@ -467,13 +407,9 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
     // to be larger than that share (large k: cells hold 0.4 k points), fewer, larger CTAs are resident.
     constexpr int U = 2;
     auto staged = knn_staged_kernel<U, FUSED>;
-    int rows = staged_list_rows(a.k);
-    if (const char* e = std::getenv("PCT_LIST_ROWS")) rows = std::max(a.k, std::min(128, std::atoi(e)));        // experiments
-    int target = listed_target(a.k, 2 * rows);
-    if (const char* e = std::getenv("PCT_LIST_TARGET")) target = std::max(a.k + 1, std::min(2 * rows, std::atoi(e)));  // experiments
-    int rounds = 2;
-    if (const char* e = std::getenv("PCT_STAGED_ROUNDS")) rounds = std::max(1, std::min(kStagedRoundsMax, std::atoi(e)));  // experiments
-    const size_t fixed = staged_smem_bytes<U>(rows, 0);
+    // at least PCT_TIE_SLACK low slots: the zone lives in the upper halves of the first rows
+    const int cap_staged = std::max(a.k, PCT_TIE_SLACK) + PCT_TIE_SLACK;
+    const size_t fixed = staged_smem_bytes<U>(cap_staged, 0);
     // a chunk covers (points of one parent cube + chunk) * halo growth points on average; the spread is wide:
     // with a buffer of 2.1 times that mean about 4 % of the chunks do not fit, which still beats giving up a
     // third of the resident warps; below that the unstaged share explodes (k = 40: 26 %; scripts/qbench.py)
@@ -490,11 +426,11 @@ static int launch_fast_impl(const FastLaunch& a, unsigned int* launches) {
         if ((double)cap_pts >= wanted) break;
     }
     if (cap_pts > 0xffff) cap_pts = 0xffff;
-    const size_t smem_staged = staged_smem_bytes<U>(rows, cap_pts);
+    const size_t smem_staged = staged_smem_bytes<U>(cap_staged, cap_pts);
     if (cap_pts >= 512 && smem_staged <= (size_t)a.ix->smem_per_block_optin) {
         PCT_CUDA(cudaFuncSetAttribute(staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
-        staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, rows, target, rounds, cap_pts, a.idx, a.dist, a.out, q0);
+        staged<<<(unsigned int)chunks, kStagedBlock, smem_staged, a.s>>>(v, a.qr, a.k, cap_staged, cap_pts, a.idx, a.dist, a.out, q0);
         ++*launches;
         QueryRange qf = a.qr;
         qf.list = a.fallback0;

@@ -622,7 +622,7 @@ PCT_HD void fit_fail(FitResult& o, uint32_t status) {
 }
 
 // status bits (mirrors include/pct_b200.h)
-enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u, ST_UNRESOLVED = 16u };
+enum : uint32_t { ST_EXACT_PATH = 1u, ST_FEW = 2u, ST_RANK = 4u, ST_NONFINITE = 8u, ST_UNRESOLVED = 16u, ST_BAD_INDEX = 32u };
 
 // minimum-norm solution of a design that has no unique least-squares solution: fewer rows than coefficients, or
 // rows that are linearly dependent (kept out of line, it is rare and needs a stack frame)

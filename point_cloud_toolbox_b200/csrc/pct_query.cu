@@ -174,6 +174,70 @@ knn_exact_kernel(const IndexView ix, const QueryRange qr, const int k, int32_t* 
     }
 }
 
+// ---- kdtree.query(x, k) for ARBITRARY coordinates (ref :83, :759 only ever pass cloud points, scipy takes any x) ----
+// One warp per query point: smallest level whose 3x3x3 block provably holds the k nearest cloud points, then k
+// successive minima of (d2 fp64, original index).  Nothing is dropped: a query that is a cloud point finds itself
+// first, at distance 0, like scipy.  A query outside the grid's box is answered at the top level (the block is
+// the whole cloud): correct, and slow for large clouds.
+__global__ void __launch_bounds__(kExactWarps * 32)
+knn_query_kernel(const IndexView ix, const float* __restrict__ queries, const long long nq, const int k,
+                 int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long w = (long long)blockIdx.x * kExactWarps + warp; w < nq; w += (long long)gridDim.x * kExactWarps) {
+        const float qx = __ldg(queries + 3 * w), qy = __ldg(queries + 3 * w + 1), qz = __ldg(queries + 3 * w + 2);
+        const float ux = cell_coord(qx, ix.ox, ix.inv_h), uy = cell_coord(qy, ix.oy, ix.inv_h), uz = cell_coord(qz, ix.oz, ix.inv_h);
+        const bool inside = ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)ix.dims[0] && uy < (float)ix.dims[1] && uz < (float)ix.dims[2];
+        Stencil st;
+        uint32_t cs = 0, ce = 0;
+        int level = inside ? 0 : ix.num_levels - 1;
+        for (;; ++level) {
+            make_stencil(ix, level, qx, qy, qz, st);
+            if (!inside) { st.lx = st.ly = st.lz = 0; }   // top level: one cell
+            cs = ce = 0;
+            if (lane < 27) {
+                const int cx = st.lx + lane % 3 - 1, cy = st.ly + (lane / 3) % 3 - 1, cz = st.lz + lane / 9 - 1;
+                if (cx >= 0 && cx < st.dx && cy >= 0 && cy < st.dy && cz >= 0 && cz < st.dz)
+                    if (!lookup_cell(*st.table, morton3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), cs, ce)) cs = ce = 0;
+            }
+            if (level + 1 >= ix.num_levels) break;  // the block is the whole grid
+            const double safe2 = (double)st.safe2;
+            unsigned int in_safe = 0;
+            for (int c = 0; c < 27; ++c) {
+                const uint32_t s = __shfl_sync(0xffffffffu, cs, c), e = __shfl_sync(0xffffffffu, ce, c);
+                for (uint32_t j = s + lane; j < e; j += 32) {
+                    const Pt p = load_pt(ix.pts + j);
+                    in_safe += dist2_f64(qx, qy, qz, p.x, p.y, p.z) < safe2 ? 1u : 0u;
+                }
+            }
+            in_safe = __reduce_add_sync(0xffffffffu, in_safe);
+            if (in_safe >= (unsigned int)k) break;
+        }
+        const double bound = level + 1 >= ix.num_levels ? 1.0e300 : (double)st.safe2;
+        Key prev;
+        prev.d = -1.0; prev.idx = 0; prev.pos = 0;
+        for (int m = 0; m < k; ++m) {
+            Key best;
+            best.d = 1.0e301; best.idx = 0xffffffffu; best.pos = 0;
+            for (int c = 0; c < 27; ++c) {
+                const uint32_t s = __shfl_sync(0xffffffffu, cs, c), e = __shfl_sync(0xffffffffu, ce, c);
+                for (uint32_t j = s + lane; j < e; j += 32) {
+                    const Pt p = load_pt(ix.pts + j);
+                    const double d = dist2_f64(qx, qy, qz, p.x, p.y, p.z);
+                    if (d < bound && key_less(prev.d, prev.idx, d, p.idx) && key_less(d, p.idx, best.d, best.idx)) {
+                        best.d = d; best.idx = p.idx; best.pos = j;
+                    }
+                }
+            }
+            best = warp_min_key(best);
+            if (lane == 0) {
+                out_idx[w * k + m] = (int32_t)best.idx;
+                out_dist[w * k + m] = sqrt(best.d);
+            }
+            prev = best;
+        }
+    }
+}
+
 __global__ void publish_stats_kernel(const unsigned int* counters, unsigned int* stats, unsigned int queries, unsigned int launches) {
     stats[0] = counters[0];
     stats[1] = counters[1];
@@ -270,13 +334,13 @@ ball_staged_kernel(const IndexView ix, const QueryRange qr, const double radius,
                    int32_t* __restrict__ counts, const FitOutputs out, const long long* __restrict__ offsets,
                    int32_t* __restrict__ out_idx, float* __restrict__ out_dist, uint32_t* __restrict__ fallback,
                    unsigned int* __restrict__ fallback_count, uint32_t* __restrict__ rankq) {
-    StagedBlock<U> sb;
-    uint32_t qi;
-    Pt q;
-    if (stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sb, qi, q) != STAGE_QUERY) return;  // (no barrier follows)
-    const StagedSource src = sb.source(threadIdx.x);
+    StagedQuery sq;
+    if (!stage_chunk<U>(ix, qr, cap_pts, fallback, fallback_count, sq)) return;
+    const Pt q = sq.q;
+    const uint32_t qi = sq.i;
+    const StagedSource& src = sq.src;
     ListRef<uint16_t> list;
-    list.base = reinterpret_cast<uint16_t*>(sb.scratch) + 2 * threadIdx.x;
+    list.base = reinterpret_cast<uint16_t*>(sq.scratch) + 2 * threadIdx.x;
     list.stride = 2 * kStagedBlock;
     list.rows = kBallListSlots / 2;  // both halves of every row are used
     struct Collect {
@@ -429,6 +493,14 @@ int launch_knn_points(const pct_index* ix, const float* xyz, int stride, const i
     return PCT_OK;
 }
 
+int launch_knn_query(const pct_index* ix, const float* queries, long long nq, int k, int32_t* idx, double* dist, cudaStream_t s) {
+    if (nq == 0) return PCT_OK;
+    const int grid = (int)std::min<long long>((nq + kExactWarps - 1) / kExactWarps, (long long)ix->sm_count * 8);
+    knn_query_kernel<<<grid, kExactWarps * 32, 0, s>>>(ix->view, queries, nq, k, idx, dist);
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
 int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double radius, int mode, int32_t* counts,
                 const long long* offsets, long long nnz, int32_t* idx, float* dist, FitOutputs out, int layout,
                 cudaStream_t s) {
@@ -442,7 +514,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         ball_kernel<BALL_COUNT><<<grid, kBlock, 0, s>>>(v, level, qr, radius, counts, nullptr, nullptr, nullptr, nullptr, out);
     } else {
         constexpr int U = 2;
-        const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2, 0);
+        const size_t fixed = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, 0);
         const size_t budget = std::min((size_t)ix->smem_per_sm / PCT_STAGED_CTAS - 1024, (size_t)ix->smem_per_block_optin);
         const int cap_pts = (int)std::min<size_t>(budget > fixed ? (budget - fixed) / sizeof(Pt) : 0, 0xffff);
         const size_t d2_bytes = mode == BALL_FILL ? sizeof(double) * (size_t)std::max<long long>(nnz, 1) : 0;
@@ -459,7 +531,7 @@ int launch_ball(const pct_index* ix, long long q_begin, long long q_end, double 
         }
         if (level == 0 && cap_pts >= 512 && fallback && fb_count) {
             // staged kernel over the whole range, L1/L2 kernel over the chunks and balls that did not fit
-            const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2, cap_pts);
+            const size_t smem = staged_smem_bytes<U>(kBallListSlots / 2 + PCT_TIE_SLACK, cap_pts);
             PCT_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(unsigned int) * 4, s));
             const long long chunks = (nq + kStagedBlock - 1) / kStagedBlock;
             QueryRange ql = qr;

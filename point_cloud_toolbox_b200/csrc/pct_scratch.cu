@@ -69,11 +69,31 @@ void release_scratch() {
     for (auto& kv : g_arenas) {
         if (!kv.second.base) continue;
         cudaSetDevice(kv.first.first);
-        cudaStreamSynchronize(kv.first.second);
+        // the stream belongs to the caller and may be gone by now (an invalid handle is an error code, not a fault;
+        // whoever destroys a stream should call release_scratch_of first): fall back to a device synchronisation
+        if (cudaStreamSynchronize(kv.first.second) != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+        }
         cudaFree(kv.second.base);
     }
     g_arenas.clear();
     cudaSetDevice(cur);
+}
+
+// frees the arena of ONE stream of the current device (synchronises that stream): for library-owned streams that
+// are about to be destroyed -- an arena keyed by a dead stream handle would never be reused or freed
+void release_scratch_of(cudaStream_t s) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_arenas.find(std::make_pair(device, s));
+    if (it == g_arenas.end()) return;
+    if (it->second.base) {
+        cudaStreamSynchronize(s);
+        cudaFree(it->second.base);
+    }
+    g_arenas.erase(it);
 }
 
 }  // namespace pct

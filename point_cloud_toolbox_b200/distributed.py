@@ -87,7 +87,8 @@ def slab_cuts(axis_coords: torch.Tensor, world: int, sample: int = 1 << 20):
     step = max(1, n // sample)
     s = axis_coords[::step].to(torch.float32).sort().values
     m = int(s.numel())
-    inner = [float(s[min(m - 1, (m * g) // world)]) for g in range(1, world)]
+    picks = torch.tensor([min(m - 1, (m * g) // world) for g in range(1, world)], dtype=torch.int64, device=s.device)
+    inner = [float(v) for v in s[picks].tolist()] if world > 1 else []      # one host transfer for all cuts
     return [float("-inf")] + inner + [float("inf")]
 
 
@@ -343,7 +344,7 @@ def plan_slabs(share: torch.Tensor, n_total: int, k: int, group=None, cell_fn=No
     payload = torch.full((per + 2, 3), float("nan"), dtype=torch.float32, device=share.device)
     if n:
         xyz = share[:, :3]
-        payload[0] = xyz.min(0).values
+        payload[0] = xyz.min(0).values               # NaN propagates: the receivers see a non-finite box
         payload[1] = xyz.max(0).values
         step = max(1, n // per)
         smp = xyz[::step][:per]
@@ -355,9 +356,11 @@ def plan_slabs(share: torch.Tensor, n_total: int, k: int, group=None, cell_fn=No
     hi = torch.nan_to_num(allp[:, 1], nan=float("-inf")).max(0).values
     sample = allp[:, 2:].reshape(-1, 3)
     sample = sample[~torch.isnan(sample[:, 0])].contiguous()
-    if not bool(torch.isfinite(sample).all()) or not bool(torch.isfinite(lo).all() & torch.isfinite(hi).all()):
+    # (a NaN / Inf coordinate anywhere in a share shows in that share's box; one host transfer for box + flag)
+    head = torch.cat((lo, hi, torch.isfinite(allp[:, :2]).all().reshape(1).to(lo.dtype))).tolist()
+    bbox = [float(v) for v in head[:6]]
+    if not head[6] or not all(abs(v) <= 3.0e38 for v in bbox):
         raise ValueError("Non-finite values in input points")    # ref :273-274
-    bbox = [float(v) for v in lo] + [float(v) for v in hi]
     h = (cell_fn or engine.estimate_cell_size_sample)(sample, n_total, bbox, k)
     axis = max(range(3), key=lambda a: bbox[3 + a] - bbox[a])
     cuts = slab_cuts(sample[:, axis], world, sample=1 << 62)
@@ -379,9 +382,22 @@ class ExchangeFit:
     ``index`` / ``local_ids`` / ``records`` / ``own_ids``: the slab this rank answered -- its index, the original index
     of every indexed point, the packed records of the points it owns and their original indices (ascending)."""
 
-    def __init__(self, rows, plan, index, local_ids, records, own_ids, unresolved, indexed):
-        self.rows, self.plan, self.index, self.local_ids = rows, plan, index, local_ids
-        self.records, self.own_ids, self.unresolved, self.indexed = records, own_ids, unresolved, indexed
+    def __init__(self, rows, plan, index, slab, rank, records, unresolved):
+        self.rows, self.plan, self.index, self.slab, self.rank = rows, plan, index, slab, rank
+        self.records, self.unresolved, self.indexed = records, unresolved, int(slab.shape[0])
+        self._own_ids = None
+
+    @property
+    def local_ids(self):
+        """original index of every point of the slab cloud (int32)"""
+        return self.slab[:, 3].contiguous().view(torch.int32)
+
+    @property
+    def own_ids(self):
+        """original indices of the points this rank answered, ascending (= the rows of ``records``)"""
+        if self._own_ids is None:
+            self._own_ids = _owned_ids(self.slab, self.plan, self.rank)
+        return self._own_ids
 
     def close(self):
         if self.index is not None:
@@ -447,10 +463,6 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
     n_own = sum(recv_owned)
     rec, index, n_bad = (answer_fn or answer_slab)(slab, plan, rank, k, n_own)
     st.mark("answer")
-    local_ids = slab[:, 3].contiguous().view(torch.int32)
-    c_lo, c_hi, own_lo, own_hi = plan.bounds[rank]
-    xs = slab[:, plan.axis]
-    own_ids = local_ids[(xs >= own_lo) & (xs < own_hi)]
     bad_total = torch.tensor([n_bad], dtype=torch.int64, device=share.device)
     dist.all_reduce(bad_total, group=group)
     if int(bad_total.item()):
@@ -463,15 +475,21 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
         if n_bad:
             cloud = torch.cat([parts[r][: shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0]]
                                for r in range(world)], 0)
-            rec = (redo_fn or _redo_unresolved)(cloud, rec, own_ids, plan, k)
+            rec = (redo_fn or _redo_unresolved)(cloud, rec, _owned_ids(slab, plan, rank), plan, k)
         del parts
     st.mark("unresolved")
     cols = rec[:, list(columns)].contiguous()
     back = _all_to_all_rows(cols, recv_owned, owned, group)     # rows of MY share, grouped by the slab that answered
     out = torch.empty((int(share.shape[0]), len(columns)), dtype=rec.dtype, device=share.device)
-    out[owned_local.long()] = back
+    out[owned_local] = back          # (int32 indices: no 64-bit copy of the index list)
     st.mark("return")
-    return ExchangeFit(out, plan, index, local_ids, rec, own_ids, n_bad, int(slab.shape[0]))
+    return ExchangeFit(out, plan, index, slab, rank, rec, n_bad)
+
+
+def _owned_ids(slab, plan, rank):
+    c_lo, c_hi, own_lo, own_hi = plan.bounds[rank]
+    xs = slab[:, plan.axis]
+    return slab[:, 3].contiguous().view(torch.int32)[(xs >= own_lo) & (xs < own_hi)]
 
 
 def _redo_unresolved(cloud, rec, own_ids, plan, k):

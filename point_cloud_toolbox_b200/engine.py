@@ -48,43 +48,48 @@ def to_device_points(points, device=None):
     return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
 
 
-def _storage_refs(buf):
-    return torch._C._storage_Use_Count(buf.untyped_storage()._cdata)
-
-
 class _PinnedPool:
     """Recycles pinned host buffers behind the numpy arrays handed to the caller.
 
-    ``cudaHostAlloc`` costs about as much as copying the data it will hold, so result
-    buffers are reused -- but only once every numpy array (and view of it) that was made
-    from a buffer is gone: those arrays keep the buffer's storage alive, so the storage's
-    reference count is back at its idle value exactly when nobody can see the old data.
+    ``cudaHostAlloc`` costs about as much as copying the data it will hold, so result buffers are reused -- but
+    only once the numpy array that was made from a buffer, and every view of it, is gone.  A buffer is LEASED to
+    the array ``to_host`` returns: ``weakref.finalize`` on that array gives the lease back.  Views keep their
+    parent alive through ``.base`` (numpy stops collapsing base chains at the array whose own base is not an
+    ndarray -- the tensor's buffer object here), so the finalizer runs exactly when nobody can see the old data.
     """
 
     def __init__(self, max_bytes=16 << 30):
-        self.entries = []  # [pinned uint8 tensor, idle reference count of its storage]
+        self.entries = []  # [pinned uint8 tensor, leased?]
         self.max_bytes = max_bytes
         self.allocations = 0
 
     def take(self, shape, dtype):
+        """(tensor view of a free buffer, its pool entry); the entry is leased until ``release(entry)``."""
         nbytes = 1
         for d in shape:
             nbytes *= int(d)
         nbytes *= torch.empty((), dtype=dtype).element_size()
-        for buf, idle in self.entries:
-            if nbytes <= buf.numel() <= 2 * nbytes + 4096 and _storage_refs(buf) == idle:
-                return buf[:nbytes].view(dtype).view(shape)
-        held = sum(b.numel() for b, _ in self.entries)
+        for ent in self.entries:
+            buf, leased = ent
+            if not leased and nbytes <= buf.numel() <= 2 * nbytes + 4096:
+                ent[1] = True
+                return buf[:nbytes].view(dtype).view(shape), ent
+        held = sum(e[0].numel() for e in self.entries)
         for ent in list(self.entries):
             if held + nbytes <= self.max_bytes:
                 break
-            if _storage_refs(ent[0]) == ent[1]:
+            if not ent[1]:
                 self.entries.remove(ent)
                 held -= ent[0].numel()
         self.allocations += 1
         buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
-        self.entries.append([buf, _storage_refs(buf)])
-        return buf[:nbytes].view(dtype).view(shape)
+        ent = [buf, True]
+        self.entries.append(ent)
+        return buf[:nbytes].view(dtype).view(shape), ent
+
+    @staticmethod
+    def release(ent):
+        ent[1] = False
 
 
 _PINNED = _PinnedPool()
@@ -92,13 +97,17 @@ _PINNED = _PinnedPool()
 
 def to_host(t: torch.Tensor):
     """Device tensor -> numpy array backed by (recycled) pinned host memory; synchronises the stream."""
+    import weakref
+
     if not t.is_cuda:
         return t.numpy()
     t = t.contiguous()
-    h = _PINNED.take(tuple(t.shape), t.dtype)
+    h, lease = _PINNED.take(tuple(t.shape), t.dtype)
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return h.numpy()
+    arr = h.numpy()
+    weakref.finalize(arr, _PinnedPool.release, lease)
+    return arr
 
 
 def load_text_f32(path, threads=0) -> torch.Tensor:
@@ -274,6 +283,18 @@ class GridIndex:
             check(lib.pct_knn_points(self._handle, ptr(self.points), int(self.points.shape[1]), ptr(ids), nq, int(k),
                                      ptr(idx), ptr(dist), _stream()))
         return idx, dist
+
+    def query(self, x_dev, k):
+        """k nearest cloud points of arbitrary coordinates ``x_dev`` (m, 3) float32 on the device (pct_knn_query):
+        ``(dist float64 (m, k), idx int32 (m, k))`` ordered by (distance, index); a query that is a cloud point
+        finds itself first."""
+        x = x_dev.to(device=self.device, dtype=torch.float32).contiguous()
+        m = int(x.shape[0])
+        idx = torch.empty((m, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((m, k), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pct_knn_query(self._handle, ptr(x), m, int(k), ptr(idx), ptr(dist), _stream()))
+        return dist, idx
 
     def curvature_knn(self, k, q_begin=None, q_end=None, layout=LAYOUT_ORIGINAL, want_normals=True, want_coeffs=True,
                       want_status=True) -> FitOutputs:

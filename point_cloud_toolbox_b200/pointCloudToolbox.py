@@ -33,7 +33,7 @@ import numpy as np
 import torch
 
 from . import engine, trace
-from ._lib import STATUS_NONFINITE, MAX_K
+from ._lib import STATUS_FEW_NEIGHBORS, STATUS_NONFINITE, MAX_K
 
 
 class _Tree:
@@ -46,24 +46,26 @@ class _Tree:
         self.m = 3
 
     def query(self, x, k=1):
-        """k nearest cloud points of query point(s) ``x`` that ARE cloud points.
-
-        The reference only ever queries the tree with points of the cloud itself
-        (ref :83, :759).  Returns ``(dists, indices)`` like scipy: float64
-        distances and int64 indices, the query point itself first.
-        """
+        """``scipy.spatial.cKDTree.query(x, k)`` for the uses of the reference (ref :83, :759) and beyond: ``x`` is one
+        point (3,) or an array (m, 3) of ARBITRARY coordinates; returns ``(dists float64, indices int64)`` of the k
+        nearest cloud points, nearest first -- a query that is a cloud point finds itself first, at distance 0.
+        Shapes follow scipy: (k,) / (m, k), and the last axis is dropped for ``k == 1``.  Equal distances are ordered
+        by index (scipy's order is an artefact of its tree traversal)."""
         x = np.asarray(x, dtype=np.float32)
         single = x.ndim == 1
-        rows = self._cloud_ref()._locate(np.atleast_2d(x))
-        if k < 2:
-            d = np.zeros((len(rows), 1))
-            i = rows[:, None].astype(np.int64)
-        else:
-            idx, dist = self.index.knn(k - 1)
-            torch.cuda.synchronize()
-            sel = torch.from_numpy(rows).to(idx.device)
-            i = torch.cat((sel[:, None], idx[sel].long()), 1).cpu().numpy()
-            d = np.concatenate((np.zeros((len(rows), 1)), dist[sel].double().cpu().numpy()), 1)
+        pts = np.ascontiguousarray(np.atleast_2d(x))
+        if pts.shape[1] != 3:
+            raise ValueError(f"x must be of shape (3,) or (m, 3), got {x.shape}")
+        kk = int(k)
+        if kk < 1:
+            raise ValueError("k must be at least 1")
+        if kk > self.n:
+            raise IndexError(f"index {self.n} is out of bounds for axis 0 with size {self.n}")  # scipy pads with N, the reference trips over it
+        d, i = self.index.query(torch.from_numpy(pts).to(self.index.device), kk)
+        d = engine.to_host(d)
+        i = engine.to_host(i).astype(np.int64)
+        if kk == 1:
+            d, i = d[:, 0], i[:, 0]
         return (d[0], i[0]) if single else (d, i)
 
 
@@ -114,19 +116,6 @@ class PointCloud:
     def _upload(self):
         self._d_points = engine.to_device_points(self.points, self._device)
         return self._d_points
-
-    def _locate(self, x):
-        """Row numbers of query points that are members of the cloud."""
-        pts = self._host_points().astype(np.float32, copy=False)
-        view = np.ascontiguousarray(pts).view([("", np.float32)] * 3).ravel()
-        order = np.argsort(view, kind="stable")
-        keys = np.ascontiguousarray(x.astype(np.float32)).view([("", np.float32)] * 3).ravel()
-        pos = np.searchsorted(view[order], keys)
-        pos = np.clip(pos, 0, len(order) - 1)
-        rows = order[pos]
-        if not np.array_equal(pts[rows], x.astype(np.float32)):
-            raise NotImplementedError("kdtree.query is implemented for query points that belong to the cloud")
-        return rows
 
     # ------------------------------------------------------------------
     # loading                                                   ref :50-66
@@ -268,10 +257,21 @@ class PointCloud:
             # rows were read or assigned: fit exactly those rows (ref :640)
             d_points = self._d_points if self._d_points is not None else self._upload()
             idx = self._lists_dev
+            n = len(self.points)
             if idx is None:
-                idx = torch.from_numpy(np.ascontiguousarray(self._lists[0], dtype=np.int32)).to(d_points.device)
-            if idx.numel() and (int(idx.max()) >= len(self.points) or int(idx.min()) < -len(self.points)):
-                raise IndexError(f"index {int(idx.max())} is out of bounds for axis 0 with size {len(self.points)}")
+                rows = np.asarray(self._lists[0])
+                if rows.ndim != 2:
+                    raise ValueError("neighbor_indices must have shape (num_points, k)")
+                if rows.shape[0] < n:
+                    # the reference loops over all points and indexes row i (ref :638-640)
+                    raise IndexError(f"index {rows.shape[0]} is out of bounds for axis 0 with size {rows.shape[0]}")
+                idx = torch.from_numpy(np.ascontiguousarray(rows[:n], dtype=np.int32)).to(d_points.device)
+                if idx.numel():
+                    lo, hi = int(idx.min()), int(idx.max())
+                    if hi >= n or lo < -n:
+                        raise IndexError(f"index {hi if hi >= n else lo} is out of bounds for axis 0 with size {n}")
+                    if lo < 0:
+                        idx = torch.where(idx < 0, idx + n, idx)   # numpy's negative indices (ref :640 is plain fancy indexing)
             fit = engine.fit_from_neighbors(d_points, idx)
         else:
             fit = self._fused_fit(want_coeffs=True)
@@ -293,14 +293,12 @@ class PointCloud:
     # curvature                                                 ref :657-674, :505-509
     # ------------------------------------------------------------------
     def calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points(self):
-        stored = self.quadratic_coefficients
-        if self._fit is not None and stored is self.__dict__.get("_coeffs_of_fit"):
-            curv = self._fit.curv  # the fused kernel already turned exactly these coefficients into curvature
-        else:
-            coeffs = np.ascontiguousarray(np.asarray(stored, dtype=np.float32)).reshape(-1, 6)
-            engine.require_cuda()
-            dev = self._d_points.device if self._d_points is not None else "cuda"
-            curv = engine.quadric_curvature(torch.from_numpy(coeffs).to(dev))
+        # always from the STORED coefficients, like the reference (ref :663-672): an in-place edit such as
+        # pc.quadratic_coefficients[i] = 0 (the pattern of ref :768-769) must show in K and H
+        coeffs = np.ascontiguousarray(np.asarray(self.quadratic_coefficients, dtype=np.float32)).reshape(-1, 6)
+        engine.require_cuda()
+        dev = self._d_points.device if self._d_points is not None else "cuda"
+        curv = engine.quadric_curvature(torch.from_numpy(coeffs).to(dev))
         c = engine.to_host(curv)
         self.K_quadratic = c[:, 0].copy()
         self.H_quadratic = c[:, 1].copy()
@@ -386,7 +384,7 @@ class PointCloud:
         K = engine.to_host(fit.curv[:, 0]).reshape(S, P)
         st = engine.to_host(fit.status).reshape(S, P)
         # ref :768-769: a failed fit becomes coefficients (0,...,0), i.e. K = 0
-        K = np.where((st & ~np.uint8(1)) != 0, np.float32(0), K)
+        K = np.where((st & np.uint8(STATUS_NONFINITE | STATUS_FEW_NEIGHBORS)) != 0, np.float32(0), K)
         converged = []
         for s_row in inverse:                                                    # ref :794-795, one search per sampled point
             lo, hi, best = lower, upper, None

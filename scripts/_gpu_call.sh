@@ -1,15 +1,6 @@
 set -x
-L=gpurun_out/sweep_r02d.log
-: > $L
-run() { echo "== $*" >> $L; env "$@" python scripts/qbench.py 2e7 20,32 6 >> $L 2>&1; }
-run PCT_STAGED_ROUNDS=1
-run PCT_STAGED_ROUNDS=2
-run PCT_STAGED_ROUNDS=1 PCT_LIST_ROWS=24
-run PCT_STAGED_ROUNDS=1 PCT_LIST_ROWS=26
-run PCT_STAGED_ROUNDS=1 PCT_LIST_ROWS=30
-run PCT_STAGED_ROUNDS=1 PCT_LIST_ROWS=30 PCT_LIST_TARGET=38
-run PCT_STAGED_ROUNDS=1 PCT_LIST_ROWS=40
-run PCT_STAGED_ROUNDS=1 PCT_CUT_GAIN=3.0
-run PCT_STAGED_ROUNDS=1 PCT_CUT_GAIN=3.6
-grep -v "^+" $L | cut -c1-230
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02d.log 2>&1; tail -15 gpurun_out/pytest_r02d.log
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu_r02g.txt
+python scripts/qbench.py 2e7 20,32 6 > gpurun_out/qbench_r02g.log 2>&1; cat gpurun_out/qbench_r02g.log | cut -c1-200
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02g.log 2>&1; tail -15 gpurun_out/pytest_r02g.log
+PCT_B200_TRACE=1 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_1gpu_r02g.json 2> gpurun_out/bench_1gpu_r02g.err; tail -5 gpurun_out/bench_1gpu_r02g.err; cut -c1-1500 gpurun_out/bench_1gpu_r02g.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu_r02g.json 2> gpurun_out/bench_2gpu_r02g.err; tail -5 gpurun_out/bench_2gpu_r02g.err; cat gpurun_out/bench_2gpu_r02g.json

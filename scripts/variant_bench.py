@@ -1,4 +1,4 @@
-"""Compare compile-time variants of the library on one GPU box, one index, one command.
+"""Compare compile-time variants of the library on one GPU box, one index, one command (results of round 2: profiles/variants_r02a.txt).
 
 Here (no GPU needed):   python scripts/variant_bench.py build red=-DPCT_HIST_RED=1 cull=-DPCT_CULL_PASS2=1 ...
     builds point_cloud_toolbox_b200/build/variants/<name>.so for every NAME=FLAGS (FLAGS: nvcc flags joined by ','),

@@ -10,7 +10,6 @@
 #include <cstring>
 #include <vector>
 
-static long long g_listed[4];  // listed selection: [0] attempts, [1] re-cuts, [2] queries handed to the two-pass selection, [3] queries
 #include "pct_grid.cuh"
 #include "pct_dispatch.h"
 
@@ -51,7 +50,6 @@ void* h_build(const float* xyz, long long n, float h) {
     v.num_levels = v.bits + 1;
     v.slack = 4.0f * 1.1920929e-7f * (float)maxdim + 1e-6f;
     v.volumetric = 0;
-    v.cut_gain = 3.3f;
     v.slab_axis = -1;
     std::vector<std::pair<unsigned long long, uint32_t>> keyed(n);
     for (long long i = 0; i < n; ++i) {
@@ -93,9 +91,6 @@ void h_destroy(void* p) { delete (HostIndex*)p; }
 void h_set_slab(void* p, int axis, float complete_lo, float complete_hi, float own_lo, float own_hi) {
     IndexView& v = ((HostIndex*)p)->view;
     v.slab_axis = axis; v.complete_lo = complete_lo; v.complete_hi = complete_hi; v.own_lo = own_lo; v.own_hi = own_hi;
-}
-void h_listed_stats(long long* out, int reset) {
-    for (int i = 0; i < 4; ++i) { out[i] = g_listed[i]; if (reset) g_listed[i] = 0; }
 }
 void h_perm(void* p, int32_t* perm) {
     HostIndex* ix = (HostIndex*)p;
@@ -164,21 +159,16 @@ struct HostStage {
 // kNN lists (original indices, sorted by key) + per-query path code:
 // 0..levels-1 = level at which the fast path succeeded, 100 = exact fallback, +50 = staged source.
 // staged_u: 0 = candidates straight from the sorted cloud, 1 / 2 = staged regions of (1 << U)^3 cells
-// listed: the staged source is searched with knn_select_listed() (the staged kernel's selection: its attempts with
-//   re-scaled cuts, then the two-pass selection, exactly the hand-overs of csrc/pct_knn_fast.cuh); the first cut is
-//   multiplied by cut_scale so that tests can make it miss
 template <int U>
-static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int listed, float cut_scale, int32_t* idx, float* dist, int32_t* code,
+static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int32_t* idx, float* dist, int32_t* code,
                      float* normals, float* coeffs, float* curv, uint8_t* status) {
     const IndexView& v = ix->view;
     const int cap = k + PCT_TIE_SLACK;
-    const int rows = k > 12 ? k : 12;  // staged_list_rows()
     std::vector<uint32_t> list(cap), runs(54);
-    std::vector<uint16_t> list16(2 * (cap > rows ? cap : rows) + 2);
+    std::vector<uint16_t> list16(2 * cap + 2);
     std::vector<uint32_t> hist(kHistRowBytes / 4);
     SelectScratch<uint32_t> sc{{list.data(), 1, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};
     SelectScratch<uint16_t> sc16{{list16.data(), 2, cap - PCT_TIE_SLACK}, hist.data(), 1, cap};  // 16-bit: two slots per row
-    ListRef<uint16_t> listed_rows{list16.data(), 2, rows};
     GlobalSource gsrc;
     gsrc.pts = v.pts;
     gsrc.runs.buf = runs.data();
@@ -208,28 +198,10 @@ static void knn_impl(HostIndex* ix, int k, int max_fast_level, int cap_pts, int 
                 ssrc.corner = (lx - 1) + S * (ly - 1) + S * S * (lz - 1);
                 ssrc.side = S;
                 uint16_t f16 = 0, l16 = 0;
-                bool from_rows = false;
-                if (listed) {
-                    ++g_listed[3];
-                    const int target = listed_target(k, 2 * rows);
-                    float cut2 = listed_first_cut(v, target, ssrc.count()) * cut_scale;
-                    rc = SEL_RECUT;
-                    for (int round = 0; round < 4 && rc == SEL_RECUT; ++round) {  // kStagedRounds
-                        ++g_listed[0];
-                        rc = knn_select_listed(v, st, ssrc, q, k, target, listed_rows, cut2, f16, l16);
-                        if (rc == SEL_RECUT) ++g_listed[1];
-                    }
-                    from_rows = rc == SEL_OK;
-                    if (rc == SEL_RECUT || rc == SEL_TWOPASS) {  // what the L1/L2 kernel does with the queued query
-                        ++g_listed[2];
-                        rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
-                    }
-                } else {
-                    rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
-                }
+                rc = knn_select(v, st, level, ssrc, q, k, sc16, f16, l16, d2_last);
                 if (rc == SEL_OK) {
                     // staged slots -> sorted positions, so that the rest of this routine is shared
-                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[from_rows ? listed_rows.lo(m) : sc16.list.lo(m)].idx];
+                    for (int m = 0; m < k; ++m) list[m] = ix->pos_of[stage.pts[sc16.list.lo(m)].idx];
                     first = ix->pos_of[stage.pts[f16].idx];
                     last = ix->pos_of[stage.pts[l16].idx];
                     staged = true;
@@ -279,16 +251,16 @@ extern "C" {
 void h_knn(void* p, int k, int max_fast_level, int32_t* idx, float* dist, int32_t* code,
            float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    knn_impl<0>(ix, k, max_fast_level, 0, 0, 1.f, idx, dist, code, normals, coeffs, curv, status);
+    knn_impl<0>(ix, k, max_fast_level, 0, idx, dist, code, normals, coeffs, curv, status);
 }
 
 // same through the staged source (level 0), staging buffer of cap_pts points
-void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int listed, float cut_scale, int32_t* idx, float* dist, int32_t* code,
+void h_knn_staged(void* p, int k, int max_fast_level, int staged_u, int cap_pts, int32_t* idx, float* dist, int32_t* code,
                   float* normals, float* coeffs, float* curv, uint8_t* status) {
     HostIndex* ix = (HostIndex*)p;
-    if (staged_u == 0) knn_impl<0>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
-    else if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
-    else knn_impl<2>(ix, k, max_fast_level, cap_pts, listed, cut_scale, idx, dist, code, normals, coeffs, curv, status);
+    if (staged_u == 0) knn_impl<0>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
+    else if (staged_u == 1) knn_impl<1>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
+    else knn_impl<2>(ix, k, max_fast_level, cap_pts, idx, dist, code, normals, coeffs, curv, status);
 }
 
 void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const int32_t* qids,
@@ -296,7 +268,7 @@ void h_fit_rows(const float* xyz, const int32_t* idx, long long nq, int k, const
     for (long long r = 0; r < nq; ++r) {
         const long long qi = qids ? qids[r] : r;
         RowNeighbourhood nb;
-        nb.xyz = xyz; nb.row = idx + r * k; nb.count = k;
+        nb.xyz = xyz; nb.row = idx + r * k; nb.count = k; nb.n = 1ll << 40;  // (rows of the tests hold valid non-negative indices)
         nb.qx = xyz[3 * qi]; nb.qy = xyz[3 * qi + 1]; nb.qz = xyz[3 * qi + 2];
         FitResult o;
         o.status = 0;

@@ -443,7 +443,8 @@ def test_exchange_path_two_ranks_nccl(pct, tmp_path, k):
 
 def test_tiny_and_degenerate_clouds(pct):
     """Edge cases of the staged kernel: clouds smaller than a chunk, k = 1, k = N - 1, coincident points,
-    points on a line and on a plane.  Neighbour rows stay bit-exact; fits of degenerate geometry are NaN + status."""
+    points on a line and on a plane.  Neighbour rows stay bit-exact; fits of rank-deficient neighbourhoods are lstsq's
+    minimum-norm solution (ref :359), finite like the reference's, with the status bit as information."""
     rng = np.random.default_rng(12)
     cases = {
         "seven": (rng.normal(size=(7, 3)).astype(np.float32), [1, 5, 6]),
@@ -467,11 +468,128 @@ def test_tiny_and_degenerate_clouds(pct):
                 ok = np.isfinite(K)
                 assert ok.mean() > 0.99 and np.abs(K[ok]).max() < 1e-3 and np.abs(H[ok]).max() < 1e-2
             if name in ("line", "coincident"):
-                assert not np.isfinite(K).any()                              # rank-deficient designs: NaN, like a failed lstsq
-                assert (pc2.fit_status != 0).all()
+                # rank-deficient designs with z = 0: the minimum-norm solution is w = 0, like the reference's
+                assert np.isfinite(K).all() and np.abs(K).max() < 1e-6 and np.abs(H).max() < 1e-4, (name, np.abs(K).max(), np.abs(H).max())
+                assert ((pc2.fit_status & pct._lib.STATUS_RANK_DEFICIENT) != 0).mean() > 0.9
+                assert int(pc2.kdtree.index.last_stats().rank_deficient) > 0
     with pytest.raises(IndexError):
         pc = pct.PointCloud(points=cases["seven"][0], normals=_empty_normals(7), k_neighbors=7)
         pc.plant_kdtree(7)
+
+
+def test_degenerate_goldens_of_the_reference(pct):
+    """tests/golden/degenerate.npz: what the UNMODIFIED reference returns for collinear, coincident, planar-lattice and
+    two-parallel-lines clouds (oracle/make_golden_degenerate.py) -- finite numbers from lstsq's minimum-norm solution.
+    Fused path (own neighbours; the clouds are full of ties, so rows differ from scipy's traversal order and only
+    tie-free quantities are compared) and rows path (the reference's own rows: coefficient by coefficient)."""
+    g = load_golden("degenerate")
+    for name in ("line", "coincident", "plane_grid", "two_lines"):
+        pts, k = np.ascontiguousarray(g[name + "_points"]), int(g[name + "_k"])
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+        pc.plant_kdtree(k)
+        K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+        assert np.isfinite(K).all() and np.isfinite(H).all(), name
+        if name != "two_lines":   # z = 0 in the tangent frame whatever the tie order: all zeros
+            assert np.abs(K).max() < 1e-6 and np.abs(H).max() < 1e-4, (name, np.abs(K).max(), np.abs(H).max())
+        # the reference's rows through the rows path
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=k)
+        pc.neighbor_indices = g[name + "_neighbor_indices"]
+        pc.fit_explicit_quadratic_surfaces_to_neighborhoods()
+        K, H = pc.calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points()
+        assert np.allclose(K, g[name + "_K"], rtol=1e-4, atol=1e-7), (name, np.abs(K - g[name + "_K"]).max())
+        assert np.allclose(H, g[name + "_H"], rtol=1e-4, atol=1e-6), (name, np.abs(H - g[name + "_H"]).max())
+        scale = np.maximum(np.abs(g[name + "_coeffs"]).max(axis=1, keepdims=True), 1e-6)
+        assert (np.abs(np.asarray(pc.quadratic_coefficients) - g[name + "_coeffs"]) / scale).max() < 1e-3, name
+
+
+def test_kdtree_query_is_scipy_query(pct, bunny):
+    """self.kdtree.query(x, k) (ref :83, :759) for cloud points AND arbitrary coordinates, against scipy itself."""
+    from scipy.spatial import cKDTree
+
+    pts = np.ascontiguousarray(bunny[::2])
+    tree = cKDTree(pts)
+    pc = pct.PointCloud(points=pts, normals=_empty_normals(len(pts)), k_neighbors=20)
+    pc.plant_kdtree(20)
+    rng = np.random.default_rng(1)
+    members = pts[rng.integers(0, len(pts), 200)]
+    lo, hi = pts.min(0), pts.max(0)
+    inside = (lo + rng.uniform(size=(200, 3)) * (hi - lo)).astype(np.float32)
+    outside = (hi + rng.uniform(0.01, 0.3, size=(20, 3)) * (hi - lo)).astype(np.float32)
+    for name, x in (("members", members), ("inside", inside), ("outside", outside)):
+        for k in (1, 21, 101):
+            d_ref, i_ref = tree.query(x, k)
+            d, i = pc.kdtree.query(x, k)
+            assert d.dtype == np.float64 and i.dtype == np.int64 and d.shape == d_ref.shape and i.shape == i_ref.shape
+            assert np.array_equal(i, i_ref), (name, k)               # (bunny has no exact distance ties)
+            assert np.allclose(d, d_ref, rtol=1e-12, atol=0), (name, k)
+    # one point in, one row out; the point itself comes first (what ref :83-85 drops)
+    d, i = pc.kdtree.query(pts[17], 21)
+    assert d.shape == (21,) and i[0] == 17 and d[0] == 0.0
+    assert np.array_equal(i[1:], pc.neighbor_indices[17])
+    d1, i1 = pc.kdtree.query(pts[17])
+    assert np.ndim(d1) == 0 and int(i1) == 17
+    with pytest.raises(IndexError):
+        pc.kdtree.query(pts[0], len(pts) + 1)
+
+
+def test_assigned_rows_follow_numpy_indexing(pct, bunny):
+    """user-assigned neighbor_indices -- negative indices count from the end, rows beyond the cloud are
+    ignored, too few rows or an index outside [-N, N) raise IndexError like ref :638-640; nothing reaches the kernel
+    unchecked, and the C entry flags bad rows instead of dereferencing them."""
+    pts = np.ascontiguousarray(bunny[::7])
+    n, k = len(pts), 12
+    idx, _, _ = oracle.knn_canonical(pts, k)
+    a = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+    a.neighbor_indices = idx
+    a.fit_explicit_quadratic_surfaces_to_neighborhoods()
+    want = np.asarray(a.quadratic_coefficients).copy()
+    neg = idx.astype(np.int64).copy()
+    neg[::2] -= n                                                       # the same points, addressed from the end
+    b = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+    b.neighbor_indices = np.concatenate((neg, neg[:5]))                 # extra rows: the reference never reads them
+    b.fit_explicit_quadratic_surfaces_to_neighborhoods()
+    assert np.array_equal(np.asarray(b.quadratic_coefficients), want, equal_nan=True)
+    for bad in (idx[: n - 3], np.where(idx == idx[0, 0], n, idx), np.where(idx == idx[0, 0], -n - 1, idx)):
+        c = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+        c.neighbor_indices = bad
+        with pytest.raises(IndexError):
+            c.fit_explicit_quadratic_surfaces_to_neighborhoods()
+    # the C ABI itself: a bad row comes back NaN with PCT_STATUS_BAD_INDEX
+    from point_cloud_toolbox_b200 import engine
+
+    d_pts = torch.from_numpy(pts).cuda()
+    rows = torch.from_numpy(idx[:4].copy()).cuda()
+    rows[1, 3] = n + 5
+    rows[2, 0] = -n - 9
+    fit = engine.fit_from_neighbors(d_pts, rows, query_ids=torch.arange(4, dtype=torch.int32, device="cuda"))
+    st = fit.status.cpu().numpy()
+    assert (st[[1, 2]] & pct._lib.STATUS_BAD_INDEX).all() and not (st[[0, 3]] & pct._lib.STATUS_BAD_INDEX).any()
+    assert torch.isnan(fit.curv[[1, 2]]).all() and torch.isfinite(fit.curv[[0, 3]]).all()
+    # in-place edits of the stored coefficients show in K and H (ref :663-672 reads them on every call)
+    K0, H0 = a.calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points()
+    a.quadratic_coefficients[5] = 0
+    K1, H1 = a.calculate_curvatures_of_explicit_quadratic_surfaces_for_all_points()
+    assert K1[5] == 0 and H1[5] == 0 and np.array_equal(np.delete(K1, 5), np.delete(K0, 5), equal_nan=True)
+
+
+def test_host_entry_does_not_strand_scratch_memory(pct):
+    """pct_curvature_knn_host runs on a private stream; its scratch arena goes with the stream."""
+    import ctypes
+
+    pts, _, _ = datasets.torus_random(300_000, seed=2)
+    n = len(pts)
+    K = np.empty(n, np.float32)
+    H = np.empty(n, np.float32)
+    lib = pct._lib.lib
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(6):
+        pct._lib.check(lib.pct_curvature_knn_host(pts.ctypes.data_as(ctypes.c_void_p), n, 20, K.ctypes.data_as(ctypes.c_void_p),
+                                                  H.ctypes.data_as(ctypes.c_void_p)))
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, (free0 - free1) >> 20      # (six stranded arenas would be > 200 MB)
+    assert np.isfinite(K).mean() > 0.999
 
 
 def test_errors_mirror_reference(pct):

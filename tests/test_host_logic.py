@@ -29,7 +29,7 @@ def harness():
     lib.h_build.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float]
     lib.h_destroy.argtypes = [ctypes.c_void_p]
     lib.h_knn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
-    lib.h_knn_staged.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_float] + [ctypes.c_void_p] * 7
+    lib.h_knn_staged.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 7
     lib.h_set_slab.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_float] * 4
     lib.h_fit_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5
     lib.h_ball.argtypes = [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 5
@@ -40,7 +40,7 @@ def P(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, listed=0, cut_scale=1.0, slab=None):
+def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, slab=None):
     n = len(pts)
     pts = np.ascontiguousarray(pts, np.float32)
     ix = lib.h_build(P(pts), n, float(h))
@@ -51,7 +51,7 @@ def run_knn(lib, pts, k, h, max_fast_level=1, staged_u=0, cap_pts=4096, listed=0
                status=np.zeros(n, np.uint8))
     args = (P(out["idx"]), P(out["dist"]), P(out["code"]), P(out["normal"]), P(out["coeffs"]), P(out["curv"]), P(out["status"]))
     if staged_u:
-        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, listed, cut_scale, *args)
+        lib.h_knn_staged(ix, k, max_fast_level, staged_u, cap_pts, *args)
     else:
         lib.h_knn(ix, k, max_fast_level, *args)
     lib.h_destroy(ix)
@@ -103,10 +103,10 @@ def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
     tiny = rng.normal(size=(23, 3)).astype(np.float32)
     for name, pts, k, h in (("lattice", lattice, 12, 1.3), ("dup", dup, 10, 0.3), ("tiny", tiny, 5, 0.7)):
         ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
-        for u, listed in ((1, 0), (2, 0), (2, 1), (1, 1)):
-            got = run_knn(harness, pts, k, h, staged_u=u, listed=listed)
-            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u, listed)
-            assert np.array_equal(got["dist"], ref_dist), (name, u, listed)
+        for u in (1, 2):
+            got = run_knn(harness, pts, k, h, staged_u=u)
+            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, (name, u)
+            assert np.array_equal(got["dist"], ref_dist), (name, u)
 
 
 @pytest.mark.parametrize("axis", [0, 2])
@@ -200,6 +200,43 @@ def test_fewer_rows_than_coefficients_give_lstsq_minimum_norm(harness, bunny, k)
     assert np.quantile(err[ok], 0.99) < 1e-4, np.quantile(err[ok], [0.5, 0.9, 0.99, 1.0])
 
 
+def test_rank_deficient_rows_give_lstsq_minimum_norm(harness):
+    """Collinear, coincident, planar-lattice and two-parallel-lines neighbourhoods: the reference's lstsq (ref :359)
+    returns the minimum-norm solution; fit_min_norm (Givens QR + Jacobi SVD, rcond = eps * max(M, N)) must land on the
+    reference's own numbers (tests/golden/degenerate.npz, made by oracle/make_golden_degenerate.py)."""
+    g = load_golden("degenerate")
+    for name in ("line", "coincident", "plane_grid", "two_lines"):
+        pts = np.ascontiguousarray(g[name + "_points"])
+        k = int(g[name + "_k"])
+        idx = np.ascontiguousarray(g[name + "_neighbor_indices"].astype(np.int32))
+        n = len(pts)
+        normal = np.zeros((n, 3), np.float32); coeffs = np.zeros((n, 6), np.float32)
+        curv = np.zeros((n, 5), np.float32); status = np.zeros(n, np.uint8)
+        harness.h_fit_rows(P(pts), P(idx), n, k, None, P(normal), P(coeffs), P(curv), P(status))
+        assert np.isfinite(curv).all(), name
+        assert np.allclose(curv[:, 0], g[name + "_K"], rtol=1e-4, atol=1e-7), name
+        assert np.allclose(curv[:, 1], g[name + "_H"], rtol=1e-4, atol=1e-6), name
+        scale = np.maximum(np.abs(g[name + "_coeffs"]).max(axis=1, keepdims=True), 1e-6)
+        assert (np.abs(coeffs - g[name + "_coeffs"]) / scale).max() < 1e-3, name
+        if name in ("line", "coincident"):
+            assert (status == 4).all()       # informational bit: the design was rank deficient
+    # random rank-deficient designs against numpy's lstsq on the same rows (the normal is not at stake: planar rows)
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        k = 12
+        a = rng.integers(-4, 5, size=k).astype(np.float32)
+        b = rng.integers(0, 2, size=k).astype(np.float32)          # b^2 = b: rank 5
+        z = np.zeros(k, np.float32)
+        rows_pts = np.stack((a, b, z), 1)
+        pts = np.concatenate((np.zeros((1, 3), np.float32), rows_pts))
+        idx = np.arange(1, k + 1, dtype=np.int32)[None]
+        normal = np.zeros((1, 3), np.float32); coeffs = np.zeros((1, 6), np.float32)
+        curv = np.zeros((1, 5), np.float32); status = np.zeros(1, np.uint8)
+        qids = np.zeros(1, np.int32)
+        harness.h_fit_rows(P(pts), P(idx), 1, k, P(qids), P(normal), P(coeffs), P(curv), P(status))
+        assert np.isfinite(coeffs).all() and np.abs(coeffs).max() < 1e-6    # z = 0 in the plane: w = 0
+
+
 def test_ball_logic(harness, bunny):
     pts = np.ascontiguousarray(bunny[::4])
     n = len(pts)
@@ -235,7 +272,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/pct_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib.pct_version() == 100
+    assert _lib.lib.pct_version() == 200
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -516,7 +553,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     src.write_text('#include "pct_b200.h"\n#include <stdio.h>\n'
                    'int main(void) {\n'
                    '    long long rows = -1, cols = -1;\n'
-                   '    if (pct_version() != 100) return 1;\n'
+                   '    if (pct_version() != 200) return 1;\n'
                    '    if (pct_text_shape("/nonexistent/file", (int64_t*)&rows, (int64_t*)&cols) == PCT_OK) return 2;\n'
                    '    printf("%s\\n", pct_last_error());\n'
                    '    return 0;\n}\n')
@@ -552,47 +589,31 @@ def test_io_code_under_address_and_ub_sanitizers(tmp_path):
     assert run.returncode == 0 and "asan run done" in run.stdout, (run.stdout[-500:], run.stderr[-3000:])
 
 
-def test_listed_selection_gives_the_same_rows(harness, bunny):
-    """knn_select_listed (the staged kernel's selection): rows equal the oracle's whatever the cut -- the shipped
-    first cut, cuts that miss low or high (re-cut inside the block, then handed to the two-pass selection)."""
-    pts = bunny[::3]
-    k = 20
-    ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
-    h = 1.25 * float(np.median(ref_dist[:, -1]))
-    base = run_knn(harness, pts, k, h, staged_u=2)
-    staged = np.mean(base["code"] == 50)
-    assert staged > 0.8
-    stats = (ctypes.c_longlong * 4)()
-    seen = {}
-    for scale in (1.0, 0.2, 8.0, 1e-4, 1e4):
-        harness.h_listed_stats(stats, 1)
-        got = run_knn(harness, pts, k, h, staged_u=2, listed=1, cut_scale=scale)
-        harness.h_listed_stats(stats, 0)
-        assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, scale
-        assert np.array_equal(got["dist"], ref_dist), scale
-        # (a k-th neighbour in the last 0.1 % of the certain radius is found one level coarser by the two-pass selection)
-        moved = got["code"] != base["code"]
-        assert moved.mean() < 2e-3, (scale, moved.mean())
-        attempts, recuts, handed, queries = list(stats)
-        seen[scale] = (attempts / queries, handed / queries)
-    assert seen[1.0][0] < 1.5 and seen[1.0][1] < 0.03, seen        # the first cut usually holds ...
-    assert seen[0.2][0] > 1.5 and seen[8.0][0] > 1.5, seen         # ... bad ones are re-cut with the count they produced ...
-    assert seen[0.2][1] < 0.05 and seen[8.0][1] < 0.05, seen       # ... which settles nearly all of them inside the block
-    # fit out of the listed rows
-    ref = oracle.knn_curvature(pts, k)
-    got = run_knn(harness, pts, k, h, staged_u=2, listed=1)
-    rep = compare.curvature_report(got, ref, ref["dist"][:, -1])
-    assert rep["violations"] == 0 and rep["tight_fraction"] > 0.999, rep
-    # other k, incl. the smallest lists and the largest
-    for kk in (1, 6, 32, 50, 100):
-        want_idx, want_dist, _ = oracle.knn_canonical(pts, kk)
-        hh = 1.25 * float(np.median(want_dist[:, -1]))
-        got = run_knn(harness, pts, kk, hh, staged_u=2, listed=1, cap_pts=60000)
-        assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0, kk
-        assert np.array_equal(got["dist"], want_dist), kk
-    # a volumetric cloud (the cut scales with the 2/3 power of the count)
-    rng = np.random.default_rng(8)
-    vol = rng.uniform(0, 1, size=(6000, 3)).astype(np.float32)
-    want_idx, want_dist, _ = oracle.knn_canonical(vol, 16)
-    got = run_knn(harness, vol, 16, 1.1 * float(np.median(want_dist[:, -1])), staged_u=2, listed=1, cap_pts=60000)
-    assert compare.neighbor_rows_differing(got["idx"], want_idx) == 0 and np.array_equal(got["dist"], want_dist)
+def test_pinned_result_buffers_are_leased_until_every_view_is_gone(monkeypatch):
+    """engine._PinnedPool: a recycled host buffer must never be handed out while an array (or a view of a view)
+    of the previous result is alive; the lease is tied to the numpy array with weakref.finalize."""
+    import gc
+    import weakref
+
+    import torch
+
+    from point_cloud_toolbox_b200 import engine
+
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"}))
+    pool = engine._PinnedPool()
+    h, lease = pool.take((10, 2), torch.float32)
+    arr = h.numpy()
+    weakref.finalize(arr, engine._PinnedPool.release, lease)
+    view = arr[:, 0]
+    inner = view[2:5]
+    del arr, h
+    gc.collect()
+    assert lease[1] and pool.take((10, 2), torch.float32)[1] is not lease      # a second buffer, not the leased one
+    del view
+    gc.collect()
+    assert lease[1]                                                             # a view of a view still sees the data
+    del inner
+    gc.collect()
+    assert not lease[1]
+    assert pool.take((10, 2), torch.float32)[1] is lease                        # recycled now
