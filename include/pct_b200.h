@@ -239,6 +239,19 @@ int pct_quadric_fit(const double* rotated, int64_t nq, int k, float* coeffs, uin
                     void* stream);
 int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* stream);
 
+/* Implicit 10-coefficient quadric A x^2 + B y^2 + C z^2 + D xy + E xz + F yz + G x + H y + I z + J = 0 (ref :363-396,
+ * :435-480, :617-633, :676-689).
+ * pct_implicit_quadric_fit: the minimiser of |A c|^2 on the unit sphere -- the problem the reference hands to SLSQP
+ *   from the all-ones start, which stops far from the minimiser: coefficients are NOT comparable
+ *   with the reference's ("parity unpinned").  Neighbourhoods either as rows of original indices (nq x k, centred on
+ *   point query_ids[r] in fp32 like ref :627) or, when `centered` != NULL, as nq x k x 3 centred fp32 points.
+ *   coeffs nq x 10 fp64, unit norm, signed so that (G, H, I) points away from the neighbours' centroid.
+ * pct_implicit_quadric_curvature: calculate_implicit_quadric_curvatures (ref :435-480) as written, fp64:
+ *   curv nq x 4 = [K_g = det(Hess) / |g|^4, K_h, k1, k2] at the origin. */
+int pct_implicit_quadric_fit(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k,
+                             const int32_t* query_ids, const float* centered, double* coeffs, void* stream);
+int pct_implicit_quadric_curvature(const double* coeffs, int64_t nq, double* curv, void* stream);
+
 /* Text loader: replaces `np.loadtxt(file_path)` of read_from_file (ref :51) with a memory-mapped,
  * multi-threaded parser (host code).  One row per line; values separated by blanks or tabs (np.loadtxt's default delimiter: a comma is an error); '#'
  * starts a comment; empty lines are skipped; every row has the same number of columns

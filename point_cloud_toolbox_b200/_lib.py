@@ -105,6 +105,8 @@ SIGNATURES = {
     "pct_curvature_fused_ball_records": (c_int, [c_void_p, c_int64, c_int64, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "pct_plane_rotate": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pct_quadric_fit": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "pct_implicit_quadric_fit": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pct_implicit_quadric_curvature": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pct_quadric_curvature": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pct_curvature_knn_host": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
 }

@@ -206,6 +206,17 @@ int pct_quadric_curvature(const float* coeffs, int64_t nq, float* curv, void* st
     return launch_quadric_curvature(coeffs, nq, curv, (cudaStream_t)stream);
 }
 
+int pct_implicit_quadric_fit(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, const int32_t* query_ids,
+                              const float* centered, double* coeffs, void* stream) {
+    PCT_REQUIRE(coeffs && nq >= 0 && k >= 1 && ((xyz && idx && n >= 1) || centered), "pct_implicit_quadric_fit: bad argument");
+    return launch_implicit_fit(xyz, n, idx, nq, k, query_ids, centered, coeffs, (cudaStream_t)stream);
+}
+
+int pct_implicit_quadric_curvature(const double* coeffs, int64_t nq, double* curv, void* stream) {
+    PCT_REQUIRE(coeffs && curv && nq >= 0, "pct_implicit_quadric_curvature: bad argument");
+    return launch_implicit_curvature(coeffs, nq, curv, (cudaStream_t)stream);
+}
+
 int pct_pca_from_neighbors(const float* xyz, int64_t n, const int32_t* idx, int64_t nq, int k, int include_self,
                            const int32_t* query_ids, double* values, double* directions, void* stream) {
     PCT_REQUIRE(xyz && idx && values && n >= 1 && nq >= 0 && k >= 1, "pct_pca_from_neighbors: bad argument");

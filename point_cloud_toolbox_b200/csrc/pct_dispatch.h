@@ -15,3 +15,9 @@
 #ifndef PCT_STAGED_CTAS
 #define PCT_STAGED_CTAS 3
 #endif
+
+// staging copy of the staged kernels: 1 = TMA bulk copies (cp.async.bulk global -> shared, one per cell run, completion
+// on an mbarrier), 0 = 16-byte loads through registers
+#ifndef PCT_TMA_STAGE
+#define PCT_TMA_STAGE 1
+#endif

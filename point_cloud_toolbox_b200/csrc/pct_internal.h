@@ -114,6 +114,9 @@ int launch_plane_rotate(const float* centered, long long nq, int k, double* rota
                         uint8_t* status, cudaStream_t s);
 int launch_quadric_fit(const double* rotated, long long nq, int k, float* coeffs, uint8_t* status, cudaStream_t s);
 int launch_quadric_curvature(const float* coeffs, long long nq, float* curv, cudaStream_t s);
+int launch_implicit_fit(const float* xyz, long long n, const int32_t* idx, long long nq, int k, const int32_t* qids,
+                        const float* centered, double* coeffs, cudaStream_t s);
+int launch_implicit_curvature(const double* coeffs, long long nq, double* out, cudaStream_t s);
 int launch_pca_rows(const float* xyz, const int32_t* idx, long long nq, int k, int include_self, const int32_t* qids,
                     double* values, double* directions, cudaStream_t s);
 

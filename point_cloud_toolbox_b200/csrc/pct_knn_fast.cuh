@@ -146,7 +146,8 @@ struct StageShape : RegionShape<U> {
     static constexpr int kTable = kMaxRegions * RegionShape<U>::kCells;
     static constexpr int kItemsPerThread = (kTable + kStagedBlock - 1) / kStagedBlock;
     // header words: [0, W) and [W, 2W) block-scan partials, then regions-flag-queue base, then the region origins
-    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrOrg = kHdrFlag + 2;
+    static constexpr int kHdrFlag = 2 * kStagedWarps, kHdrQueue = kHdrFlag + 1, kHdrMbar = kHdrFlag + 2 /* even: 8-byte aligned */,
+                         kHdrOrg = kHdrFlag + 4;
     static constexpr int kHdrWords = (kHdrOrg + 3 * kMaxRegions + 3) & ~3;
 };
 
@@ -176,6 +177,33 @@ __host__ __device__ inline size_t staged_smem_bytes(int cap, int cap_pts) {
 }
 
 #if defined(__CUDACC__)
+// ---- TMA bulk copies for the staging phase (sm_90+: cp.async.bulk global -> shared, completion on an mbarrier) ----
+// One cell run = one contiguous, 16-byte aligned piece of the sorted cloud = one bulk copy; no register round trip.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// bounded: a lost transaction must not hang the GPU (returns false after ~2^22 polls)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 // What staging leaves a thread with: its query, the staged source positioned on the query's region,
 // and the block's per-query scratch area (the staging temporaries in it are dead).
 struct StagedQuery {
@@ -221,7 +249,11 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
     const unsigned long long parent = (unsigned long long)(cx >> U) | ((unsigned long long)(cy >> U) << 21) |
                                       ((unsigned long long)(cz >> U) << 42);
     t_parent[t] = parent;
-    if (t == 0) hdr[Shape::kHdrFlag] = 0;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(hdr + Shape::kHdrMbar);
+    if (t == 0) {
+        hdr[Shape::kHdrFlag] = 0;
+        mbar_init(mbar, 1);
+    }
     __syncthreads();
     const bool head = t == 0 || t_parent[t - 1] != parent;
     const unsigned int heads = __ballot_sync(0xffffffffu, head);
@@ -312,10 +344,29 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
             run += n;
         }
     }
-    if (t == 0) tab[n_table] = pts_addr + 16u * staged;
+    if (t == 0) {
+        tab[n_table] = pts_addr + 16u * staged;
+#if PCT_TMA_STAGE
+        mbar_arrive_expect_tx(mbar, 16u * staged);  // the one arrival of the phase; the copies below bring the bytes
+#endif
+    }
     __syncthreads();
 
-    // ---- D. copy the non-empty cells, eight lanes per cell
+#if PCT_TMA_STAGE
+    // ---- D. copy the non-empty cells: one TMA bulk copy per cell run (global -> shared, no registers in between),
+    // all of them in flight at once, completion counted in bytes on the block's mbarrier
+    for (int e = t; e < n_cells; e += B) {
+        const StagedCell sc = t_cells[e];
+        bulk_copy_g2s(pts_addr + 16u * sc.slot, ix.pts + sc.first, 16u * sc.count, mbar);
+    }
+    const bool landed = staged == 0 || mbar_wait(mbar, 0);
+    __syncthreads();  // temporaries are dead, the per-query scratch may be written
+    if (!landed) {    // (never observed; a lost transaction sends the chunk to the L1/L2 kernel instead of hanging)
+        if (active) fallback[atomicAdd(fallback_count, 1u)] = i;
+        return false;
+    }
+#else
+    // ---- D. copy the non-empty cells, eight lanes per cell (through registers)
     for (int e = t >> 3; e < n_cells; e += B / 8) {
         const StagedCell sc = t_cells[e];
         for (uint32_t m = t & 7; m < sc.count; m += 8) {
@@ -324,6 +375,7 @@ __device__ __forceinline__ bool stage_chunk(const IndexView& ix, const QueryRang
         }
     }
     __syncthreads();  // temporaries are dead, the per-query scratch may be written
+#endif
     if (!active || !query_owned(ix, q.x, q.y, q.z)) return false;
     const int lx = cx - org[3 * region], ly = cy - org[3 * region + 1], lz = cz - org[3 * region + 2];
     sq.i = i;

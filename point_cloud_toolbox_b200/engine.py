@@ -477,6 +477,36 @@ def quadric_curvature(coeffs_dev):
     return curv
 
 
+def implicit_quadric_fit(points_dev=None, idx_dev=None, query_ids=None, centered_dev=None):
+    """Unit-norm minimiser of |A c|^2 per neighbourhood (pct_implicit_quadric_fit): rows of original indices on an
+    (N, 3) cloud, or ``centered_dev`` (nq, k, 3) float32.  Returns (nq, 10) float64."""
+    if centered_dev is not None:
+        c = centered_dev.to(torch.float32).contiguous()
+        nq, k, _ = c.shape
+        out = torch.empty((nq, 10), dtype=torch.float64, device=c.device)
+        with torch.cuda.device(c.device):
+            check(lib.pct_implicit_quadric_fit(None, 0, None, nq, k, None, ptr(c), ptr(out), _stream()))
+        return out
+    if points_dev.shape[1] != 3 or not points_dev.is_contiguous():
+        raise ValueError("implicit_quadric_fit needs packed (N, 3) points")
+    idx_dev = idx_dev.to(torch.int32).contiguous()
+    nq, k = idx_dev.shape
+    out = torch.empty((nq, 10), dtype=torch.float64, device=points_dev.device)
+    with torch.cuda.device(points_dev.device):
+        check(lib.pct_implicit_quadric_fit(ptr(points_dev), int(points_dev.shape[0]), ptr(idx_dev), nq, k, ptr(query_ids), None,
+                                           ptr(out), _stream()))
+    return out
+
+
+def implicit_quadric_curvature(coeffs_dev):
+    """(nq, 10) float64 -> (nq, 4) float64 [K_g, K_h, k1, k2] by the reference's formulas (ref :435-480)."""
+    c = coeffs_dev.to(torch.float64).contiguous()
+    out = torch.empty((c.shape[0], 4), dtype=torch.float64, device=c.device)
+    with torch.cuda.device(c.device):
+        check(lib.pct_implicit_quadric_curvature(ptr(c), int(c.shape[0]), ptr(out), _stream()))
+    return out
+
+
 def pca_from_neighbors(points_dev, idx_dev, include_self=False, query_ids=None, want_directions=True):
     """PCA of the neighbourhood rows (nq, k): ``values (nq, 6)`` float64 = [l1, l2, l3, l1*l2, (l1+l2)/2,
     l3/(l1+l2+l3+1e-10)] and ``directions (nq, 3, 2)`` float64 (ref :901-945)."""

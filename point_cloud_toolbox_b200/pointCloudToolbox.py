@@ -437,6 +437,51 @@ class PointCloud:
         self.pca_K_values = v[:, 3].copy()
         self.pca_H_values = v[:, 4].copy()
 
+    # ------------------------------------------------------------------
+    # implicit 10-coefficient quadric              ref :363-396, :435-480, :617-633, :676-689
+    # ------------------------------------------------------------------
+    def fit_implicit_quadric_surfaces_all_points(self):
+        """``quadric_coefficients`` (N, 10) float64 of every point's neighbourhood -- the point itself and its
+        k - 1 nearest, centred on the point (ref :617-633 queries the tree with k, not k + 1).
+
+        PARITY UNPINNED: the reference minimises |A c|^2 on the unit sphere with SLSQP from the all-ones start and
+        stops far from the minimiser; this returns the minimiser itself (smallest eigenvector of A^T A), signed so
+        that the gradient at the point looks away from the neighbours' centroid.  Returns what the reference
+        returns: ``(self.K_quadratic, self.H_quadratic)`` (sic, ref :633)."""
+        if self.kdtree is None:
+            raise AttributeError("'PointCloud' object has no attribute 'kdtree'")
+        k = int(self.k_neighbors)
+        index = self.kdtree.index
+        d_points = index.points if index.points.shape[1] == 3 else index.points[:, :3].contiguous()
+        n = len(self.points)
+        if k > n:
+            raise IndexError(f"index {n} is out of bounds for axis 0 with size {n}")
+        me = torch.arange(n, dtype=torch.int32, device=d_points.device)[:, None]
+        if k > 1:
+            others, _ = index.knn(k - 1, want_dist=False)
+            rows = torch.cat((me, others), 1)
+        else:
+            rows = me
+        coeffs = engine.implicit_quadric_fit(d_points, rows)
+        self._implicit_dev = coeffs
+        self.quadric_coefficients = engine.to_host(coeffs)
+        return self.K_quadratic, self.H_quadratic                       # ref :633
+
+    def calculate_curvatures_of_implicit_quadric_surfaces_for_all_points(self):
+        """``K_quadric`` / ``H_quadric`` from the stored ``quadric_coefficients`` by the reference's formulas (ref :676-689)."""
+        coeffs = np.ascontiguousarray(np.asarray(self.quadric_coefficients, dtype=np.float64)).reshape(-1, 10)
+        engine.require_cuda()
+        dev = self._d_points.device if self._d_points is not None else "cuda"
+        curv = engine.to_host(engine.implicit_quadric_curvature(torch.from_numpy(coeffs).to(dev)))
+        self.K_quadric = curv[:, 0].copy()
+        self.H_quadric = curv[:, 1].copy()
+
+    def compute_pointwise_implicit_quadric_curvature(self):
+        """ref :511-515"""
+        self.fit_implicit_quadric_surfaces_all_points()
+        self.calculate_curvatures_of_implicit_quadric_surfaces_for_all_points()
+        return np.array(self.K_quadric), np.array(self.H_quadric)
+
     def __getattr__(self, name):
         # outputs of the fused call are copied to the host only when somebody asks for them
         lazy = ("quadratic_coefficients", "normals_quadratic", "fit_status", "K_H_sq_quadratic", "k1_quadratic", "k2_quadratic")
@@ -483,6 +528,24 @@ class PointCloud:
         engine.require_cuda()
         coeffs, _ = engine.quadric_fit(torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64)[None]).cuda())
         return coeffs[0].cpu().numpy()
+
+    @staticmethod
+    def fit_implicit_quadric_surface(points):
+        """(k, 3) centred points -> 10 coefficients of unit norm minimising |A c|^2 (ref :363-396; see
+        fit_implicit_quadric_surfaces_all_points for how this differs from the reference's SLSQP result)."""
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float32))
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError("Input points must have shape (N, 3)")
+        engine.require_cuda()
+        return engine.implicit_quadric_fit(centered_dev=torch.from_numpy(pts[None]).cuda())[0].cpu().numpy()
+
+    @staticmethod
+    def calculate_implicit_quadric_curvatures(coefficients):
+        """(K_g, K_h, k1, k2) of the implicit quadric at the origin, exactly the reference's formulas (ref :435-480)."""
+        c = np.asarray(coefficients, dtype=np.float64).reshape(1, 10)
+        engine.require_cuda()
+        out = engine.implicit_quadric_curvature(torch.from_numpy(c).cuda())[0].cpu().numpy()
+        return out[0], out[1], out[2], out[3]
 
     @staticmethod
     def calculate_explicit_quadratic_curvatures(coefficients):

@@ -133,13 +133,17 @@ def load_mesh_compute_energies(mesh, device=None):
     return compute_energies(verts, tris, None, None, device)
 
 
-def estimate_curvature(points, k_fraction=0.025, max_neighbors=100, device=None):
+def estimate_curvature(points, k_fraction=0.025, max_neighbors=100, device=None, reference_compatible=False):
     """Surface variation l3 / (l1 + l2 + l3 + 1e-10) of every point's k-neighbourhood (itself included, as
     sklearn's ``kneighbors(points)`` lists it), float64 -- the quantity utils.py:778-829 documents.
 
-    Deviation: the reference's ``einsum('nik,njk->nij')`` contracts over the coordinate axis, so it actually
-    diagonalises the k x k Gram matrix, whose smallest eigenvalue is rounding noise; this returns the
-    documented ratio of the 3 x 3 covariance instead.  Points must be three-dimensional.
+    Deviation, and the switch that undoes it: the reference's ``einsum('nik,njk->nij')`` contracts over the
+    COORDINATE axis, so what it diagonalises is the k x k Gram matrix of the centred neighbourhood, whose k - 3
+    smallest eigenvalues are exactly zero in exact arithmetic; its return value ``eigenvalues[:, 0] / (sum + 1e-10)``
+    is therefore rounding noise around 0 (|value| ~ 1e-17, either sign).  ``reference_compatible=True`` computes
+    exactly that -- the Gram matrix, ``eigvalsh`` (batched, on the device), the same ratio -- so a caller gets the
+    reference's numbers up to that noise; the default returns the documented ratio of the 3 x 3 covariance.
+    Points must be three-dimensional.
     """
     import torch
 
@@ -156,5 +160,19 @@ def estimate_curvature(points, k_fraction=0.025, max_neighbors=100, device=None)
     d = engine.to_device_points(pts, device)
     index = engine.GridIndex(d, k_hint=k - 1)
     idx, _ = index.knn(k - 1, want_dist=False)
+    if reference_compatible:
+        out = torch.empty(n, dtype=torch.float64, device=d.device)
+        me = torch.arange(n, device=d.device)
+        chunk = max(1, (64 << 20) // (k * k * 8))
+        src = d.double() if pts.dtype == np.float64 else d                         # the reference computes in the input's dtype
+        for b in range(0, n, chunk):
+            e = min(n, b + chunk)
+            rows = torch.cat((me[b:e, None], idx[b:e].long()), 1)                  # kneighbors(points): the point itself first
+            nb = src[rows]                                                         # (m, k, 3)            utils.py:815
+            c = nb - nb.mean(1, keepdim=True)                                      # utils.py:818-819
+            gram = torch.einsum("nik,njk->nij", c, c) / (k - 1)                    # utils.py:822 (k x k, as written)
+            ev = torch.linalg.eigvalsh(gram.double())                              # utils.py:825, ascending
+            out[b:e] = ev[:, 0] / (ev.sum(1) + 1e-10)                              # utils.py:827-828
+        return out.cpu().numpy()
     values, _ = engine.pca_from_neighbors(d, idx, include_self=True, want_directions=False)
     return values[:, 5].cpu().numpy()

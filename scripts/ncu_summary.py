@@ -22,9 +22,12 @@ KEEP = [
 ]
 
 
-def launches(path):
+def launches(path, exclude=()):
+    """`exclude`: substrings of kernel names left out of the total (diagnostics that run after the timed regions of the
+    profiled command, e.g. the FMA peak measurement and the generation of the synthetic cloud)."""
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.OrderedDict()
+    skipped = collections.OrderedDict()
     for row in csv.DictReader(lines):
         try:
             v = float(row["Metric Value"].replace(",", ""))
@@ -32,11 +35,14 @@ def launches(path):
             continue
         unit = row["Metric Unit"]
         v = v / 1e3 if unit == "ns" else v * 1e3 if unit == "ms" else v * 1e6 if unit == "s" else v
-        a = agg.setdefault(row["Kernel Name"][:110], [0, 0.0])
+        name = row["Kernel Name"][:110]
+        a = (skipped if any(x in name for x in exclude) else agg).setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     print(f"# per-kernel device time (us), cold-cache serialised launches under ncu; total {tot:.1f} us")
+    for k, (c, t) in skipped.items():
+        print(f"# not in the total (runs outside the timed regions): {t:10.1f} us {c:4d}x  {k[:80]}")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{t:12.1f} us {c:5d}x {100 * t / tot:6.2f}%  {k}")
 
@@ -55,4 +61,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], tuple(sys.argv[3:]))
+    else:
+        full(sys.argv[2])

@@ -592,6 +592,67 @@ def test_host_entry_does_not_strand_scratch_memory(pct):
     assert np.isfinite(K).mean() > 0.999
 
 
+def test_implicit_quadric(pct):
+    """Implicit 10-coefficient quadric (ref :363-396, :435-480, :617-633, :676-689): the curvature formulas are pinned
+    to the unmodified reference (tests/golden/implicit.npz), the fit is the minimiser of the reference's own problem
+    (unpinned: SLSQP does not reach it, tests/test_oracle.py) and recovers a sphere exactly."""
+    g = load_golden("implicit")
+    for c, want in zip(g["coeffs"][:64], g["curv"][:64]):
+        got = np.array(pct.PointCloud.calculate_implicit_quadric_curvatures(c))
+        assert np.allclose(got, want, rtol=1e-11, atol=0, equal_nan=True), (got, want)
+    from point_cloud_toolbox_b200 import engine
+
+    got = engine.implicit_quadric_curvature(torch.from_numpy(g["coeffs"]).cuda()).cpu().numpy()
+    assert np.allclose(got, g["curv"], rtol=1e-11, atol=0, equal_nan=True)
+    # the fit minimises |A c|^2 on the unit sphere: compare with the spectrum numpy found for the stored neighbourhoods
+    for pts, w, obj_slsqp in zip(g["neighbourhoods"], g["eigenvalues"], g["slsqp_objective"]):
+        c = pct.PointCloud.fit_implicit_quadric_surface(pts)
+        p = pts.astype(np.float32)
+        A = np.column_stack((p[:, 0] ** 2, p[:, 1] ** 2, p[:, 2] ** 2, p[:, 0] * p[:, 1], p[:, 0] * p[:, 2], p[:, 1] * p[:, 2],
+                             p[:, 0], p[:, 1], p[:, 2], np.ones(len(p))))
+        obj = float(np.sum((A @ c) ** 2))
+        assert abs(np.linalg.norm(c) - 1) < 1e-12
+        assert obj <= 2 * w[0] + 1e-17 and obj < 1e-6 * obj_slsqp, (obj, w[0], obj_slsqp)
+    # a sphere is an exact quadric: x^2 + y^2 + z^2 - 2 R n.x = 0 in coordinates centred on a surface point
+    R = 2.0
+    sph, _, _ = datasets.sphere_fibonacci(20000, radius=R)
+    pc = pct.PointCloud(points=sph, normals=_empty_normals(len(sph)), k_neighbors=30)
+    pc.plant_kdtree(30)
+    pc.K_quadratic, pc.H_quadratic = None, None                  # (ref :633 returns these attributes)
+    K, H = pc.compute_pointwise_implicit_quadric_curvature()
+    coef = np.asarray(pc.quadric_coefficients)
+    assert coef.shape == (len(sph), 10) and np.allclose(np.linalg.norm(coef, axis=1), 1, atol=1e-12)
+    s = coef[:, 0]
+    assert np.allclose(coef[:, 1], s, rtol=1e-3) and np.allclose(coef[:, 2], s, rtol=1e-3)       # A = B = C
+    assert np.abs(coef[:, 3:6]).max() < 1e-3 * np.abs(s).min()                                    # no mixed terms
+    n_out = sph / R                                                                               # outward normal
+    assert np.allclose(coef[:, 6:9], 2 * R * s[:, None] * n_out, rtol=2e-3, atol=1e-4)          # gradient along the normal, away from the neighbours
+    assert np.allclose(np.abs(H), 1 / R, rtol=2e-3)                                               # K_h = -+ 1 / R, scale invariant
+    assert np.allclose(K, 8 * s ** 3 / (2 * R * np.abs(s)) ** 4, rtol=1e-2)                       # the reference's K_g = det(Hess) / |g|^4 (not scale invariant)
+
+
+def test_estimate_curvature_reference_compatible(pct, bunny):
+    """utils.estimate_curvature(reference_compatible=True) computes what utils.py:778-829 computes as written: the
+    smallest eigenvalue of the k x k Gram matrix over the eigenvalue sum -- rounding noise around zero."""
+    from point_cloud_toolbox_b200 import utils as U
+
+    pts = np.ascontiguousarray(bunny[::12])
+    got = U.estimate_curvature(pts, k_fraction=0.004, reference_compatible=True)
+    n = len(pts)
+    k = min(max(5, int(0.004 * n)), 100)
+    from scipy.spatial import cKDTree
+
+    _, idx = cKDTree(pts).query(pts, k)                                  # sklearn's kneighbors(points): self first
+    nb = pts[idx]
+    c = nb - nb.mean(axis=1, keepdims=True)
+    cov = np.einsum("nik,njk->nij", c, c) / (k - 1)                      # utils.py:822
+    ev = np.linalg.eigh(cov)[0]
+    want = ev[:, 0] / (ev.sum(axis=1) + 1e-10)                           # utils.py:827-828
+    assert got.shape == want.shape and np.abs(want).max() < 1e-5
+    assert np.abs(got - want).max() < 1e-5 and np.abs(got).max() < 1e-5  # noise on both sides, nothing else
+    assert U.estimate_curvature(pts, k_fraction=0.004).min() > 1e-6       # the documented quantity is not noise
+
+
 def test_errors_mirror_reference(pct):
     with pytest.raises(ValueError, match="Either file_path or points and normals"):
         pct.PointCloud()

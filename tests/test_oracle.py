@@ -184,3 +184,21 @@ def test_around_path_oracle_is_pinned_to_the_reference():
     vals, dirs = ap.pca_from_rows(g["pca_points"], idx)
     assert np.allclose(vals[:, 0], l1, rtol=1e-9, atol=1e-18) and np.allclose(vals[:, 1], l2, rtol=1e-9, atol=1e-18)
     assert np.allclose(vals[:, 3], K, rtol=1e-9, atol=1e-30) and np.allclose(vals[:, 4], H, rtol=1e-9, atol=1e-18)
+
+
+def test_slsqp_does_not_reach_the_minimiser():
+    """Why the implicit quadric fit is "parity unpinned" (DESIGN.md section 9): on bunny neighbourhoods the
+    UNMODIFIED reference's fit_implicit_quadric_surface (SLSQP from the all-ones start, ref :363-396; outputs stored by
+    oracle/make_golden_implicit.py) ends with an objective 1e7 .. 1e11 times the minimum of the problem it poses and
+    with a small overlap with the minimiser, the smallest eigenvector of A^T A."""
+    g = load_golden("implicit")
+    for pts, c, obj, w, v in zip(g["neighbourhoods"], g["slsqp_coeffs"], g["slsqp_objective"], g["eigenvalues"], g["minimiser"]):
+        p = pts.astype(np.float32)
+        A = np.column_stack((p[:, 0] ** 2, p[:, 1] ** 2, p[:, 2] ** 2, p[:, 0] * p[:, 1], p[:, 0] * p[:, 2], p[:, 1] * p[:, 2],
+                             p[:, 0], p[:, 1], p[:, 2], np.ones(len(p))))
+        assert abs(np.linalg.norm(c) - 1) < 1e-6                       # the constraint holds ...
+        assert np.isclose(np.sum((A @ c) ** 2), obj, rtol=1e-9)
+        assert np.allclose(np.linalg.eigvalsh(A.T @ A), w, rtol=1e-3, atol=1e-15 * w[-1])   # (tiny eigenvalues sit at the accuracy limit of eigh: eps * the largest)
+        assert obj > 1e6 * max(w[0], 1e-300)                           # ... but the objective is nowhere near its minimum
+        assert abs(np.dot(c, v)) < 0.6                                 # and the direction is another one
+        assert w[3] < 1e-9 * w[-1]                                     # four nearly flat directions: (n.x) * (a.x + b) vanishes near a plane
