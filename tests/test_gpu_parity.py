@@ -622,13 +622,26 @@ def test_implicit_quadric(pct):
     K, H = pc.compute_pointwise_implicit_quadric_curvature()
     coef = np.asarray(pc.quadric_coefficients)
     assert coef.shape == (len(sph), 10) and np.allclose(np.linalg.norm(coef, axis=1), 1, atol=1e-12)
+    # the definition, row by row: |A c| equals the smallest singular value of the neighbourhood's own design matrix
+    # (ref :617-633 fits the point and its k - 1 nearest, centred on the point)
+    nb = np.concatenate((np.arange(len(sph))[:, None], np.asarray(pc.neighbor_indices)[:, :29]), axis=1)
+    P = (sph[nb] - sph[:, None, :]).astype(np.float32)
+    x, y, z = P[..., 0], P[..., 1], P[..., 2]
+    A = np.stack((x * x, y * y, z * z, x * y, x * z, y * z, x, y, z, np.ones_like(x)), -1).astype(np.float64)
+    sv = np.linalg.svd(A, compute_uv=False)
+    res = np.linalg.norm(np.einsum("nkj,nj->nk", A, coef), axis=1)
+    assert np.all(res <= sv[:, -1] * (1 + 1e-6) + 1e-13 * sv[:, 0]), float((res / sv[:, -1]).max())
+    # geometry, as far as fp32 coordinates condition it (the second smallest singular value is only 100 times the
+    # smallest: numpy's own SVD has B / A - 1 up to 3.4e-2 on these rows, median 2e-3)
     s = coef[:, 0]
-    assert np.allclose(coef[:, 1], s, rtol=1e-3) and np.allclose(coef[:, 2], s, rtol=1e-3)       # A = B = C
-    assert np.abs(coef[:, 3:6]).max() < 1e-3 * np.abs(s).min()                                    # no mixed terms
+    assert np.median(np.abs(coef[:, 1] / s - 1)) < 5e-3 and np.abs(coef[:, 1] / s - 1).max() < 0.1       # A = B = C
+    assert np.median(np.abs(coef[:, 2] / s - 1)) < 5e-3 and np.abs(coef[:, 2] / s - 1).max() < 0.1
+    assert np.abs(coef[:, 3:6]).max() < 0.1 * np.abs(s).min()                                     # no mixed terms
     n_out = sph / R                                                                               # outward normal
-    assert np.allclose(coef[:, 6:9], 2 * R * s[:, None] * n_out, rtol=2e-3, atol=1e-4)          # gradient along the normal, away from the neighbours
-    assert np.allclose(np.abs(H), 1 / R, rtol=2e-3)                                               # K_h = -+ 1 / R, scale invariant
-    assert np.allclose(K, 8 * s ** 3 / (2 * R * np.abs(s)) ** 4, rtol=1e-2)                       # the reference's K_g = det(Hess) / |g|^4 (not scale invariant)
+    assert np.allclose(coef[:, 6:9], 2 * R * s[:, None] * n_out, rtol=0.1, atol=0.05)           # gradient along the normal, away from the neighbours
+    assert np.all(np.einsum("ij,ij->i", coef[:, 6:9], n_out) * np.sign(s) > 0)
+    assert np.allclose(np.abs(H), 1 / R, rtol=2e-4)                                               # K_h = -+ 1 / R, scale invariant
+    assert np.allclose(K, 8 * s ** 3 / (2 * R * np.abs(s)) ** 4, rtol=0.15)                       # the reference's K_g = det(Hess) / |g|^4 (not scale invariant)
 
 
 def test_estimate_curvature_reference_compatible(pct, bunny):
