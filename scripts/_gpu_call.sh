@@ -1,2 +1,3 @@
 set -x
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02j.log 2>&1; tail -8 gpurun_out/pytest_r02j.log
+PCT_KNN_KERNEL=warp timeout 900 ncu --set full --import-source on --clock-control none -k regex:knn_warp -c 1 -o gpurun_out/prof_warp_r02k -f python scripts/qbench.py 1e7 20 1 > gpurun_out/ncu_warpfull_r02k.log 2>&1
+tail -3 gpurun_out/ncu_warpfull_r02k.log
