@@ -557,6 +557,12 @@ def ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    near = None
+    if world > 1:
+        # host threads and the host pages this rank touches stay on the GPU's socket (no effect on one-socket hosts)
+        from point_cloud_toolbox_b200.distributed import bind_near_gpu
+
+        near = bind_near_gpu(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -604,22 +610,15 @@ def ours(args):
     # (a one-node job's ranks see the same input), so each rank moves its share over its own PCIe link
     shared_in = shared_out = None
     if world > 1:
+        # NUMA placement: every rank touches the rows it will move from a thread bound next to its GPU, page-locks
+        # afterwards, and fills its share of the input (every rank holds the cloud for the parity crops)
         tag = f"pct_bench_{os.environ.get('MASTER_PORT', '0')}"
-        ok = torch.ones(1, device=dev)
         try:
-            if rank == 0:
-                shared_in = pdist.SharedHostArray(tag + "_in", (n, 3), create=True)
-                shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=True)
-                shared_in.array[:] = host_pts
+            shared_in, shared_out = pdist.shared_arrays_placed(tag, [(n, 3), (2, n)], n)
         except Exception as exc:  # pragma: no cover
-            print(f"shared host memory unavailable ({exc!r})", file=sys.stderr)
-            ok.zero_()
-        dist.broadcast(ok, 0)
-        if not bool(ok.item()):
-            raise RuntimeError("the multi-GPU end-to-end path needs /dev/shm room for the cloud and the result")
-        if rank != 0:
-            shared_in = pdist.SharedHostArray(tag + "_in", (n, 3), create=False)
-            shared_out = pdist.SharedHostArray(tag + "_out", (2, n), create=False)
+            raise RuntimeError(f"the multi-GPU end-to-end path needs /dev/shm room for the cloud and the result ({exc!r})")
+        shared_in.tensor[begin:end].copy_(pts[begin:end])
+        torch.cuda.synchronize()
         dist.barrier()
 
     def e2e_step(stages=None):
@@ -825,7 +824,9 @@ def ours(args):
         },
         "e2e": {"value": n / (e2e_step_ms * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
                 "ms_per_step": e2e_step_ms, "step_wall_ms": step_walls,
-                "host_io": "one rank" if world == 1 else "every rank its share (shared host memory)"},
+                "host_io": "one rank" if world == 1 else
+                "every rank its share (shared host memory, pages first-touched by the rank that moves them" +
+                (f", ranks bound to their GPU's {len(near)} local CPUs)" if near else ", no CPU binding: topology not visible)")},
         "gpu_launches": launches_step * args.steps * 2,
         "gpu_launches_source": "pct_index_info.build_launches + pct_query_stats.kernel_launches of the last timed step (+ 7 slab-exchange kernels at N > 1), x steps x 2 timed loops",
         "clocks": clocks,

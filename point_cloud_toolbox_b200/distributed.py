@@ -205,9 +205,14 @@ class SharedHostArray:
     with the cloud and the result in shared host memory each rank copies only ITS share in and out,
     over its own PCIe link, instead of rank 0 moving everything.  ``create=True`` on exactly one rank
     (which also unlinks the segment on ``close``), ``create=False`` on the others after a barrier.
+
+    Page placement: a page of the segment lands on the NUMA node of the thread that first touches it, and page-locking
+    touches every page.  With ``register=False`` nothing is touched: every rank then writes (``first_touch``) the rows
+    it will move, from a thread bound near its GPU (``bind_near_gpu``), and page-locks afterwards (``register``) --
+    ``shared_arrays_placed`` does exactly that.  On a two-socket host the copies of a rank then stay on its socket.
     """
 
-    def __init__(self, name: str, shape, create: bool):
+    def __init__(self, name: str, shape, create: bool, register: bool = True):
         import numpy as np
         from multiprocessing import shared_memory
 
@@ -234,9 +239,20 @@ class SharedHostArray:
         self.array = np.ndarray(tuple(shape), dtype=np.float32, buffer=self._shm.buf)
         self.tensor = torch.from_numpy(self.array)
         self._registered = False
-        if torch.cuda.is_available() and nbytes:
-            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+        self._nbytes = nbytes
+        if register:
+            self.register()
+
+    def first_touch(self, index):
+        """Zero ``array[index]`` from the calling thread: its pages are allocated on that thread's NUMA node."""
+        self.array[index] = 0.0
+
+    def register(self):
+        """Page-lock the whole segment for this process's CUDA context (idempotent)."""
+        if not self._registered and torch.cuda.is_available() and self._nbytes:
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self._nbytes, 0)
             self._registered = int(rc) == 0
+        return self._registered
 
     def close(self):
         if self._registered:
@@ -250,6 +266,66 @@ class SharedHostArray:
                 self._shm.unlink()
         except (BufferError, FileNotFoundError):
             pass
+
+
+def gpu_local_cpus(device_index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs ``local_cpulist`` of its PCI function), or None."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+    except (OSError, AttributeError, RuntimeError):
+        return None
+    cpus = set()
+    for part in text.split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus or None
+
+
+def bind_near_gpu(device_index: int):
+    """Restrict the calling process to the CPUs next to its GPU (intersected with what it may already use), so that
+    the host pages it touches and its staging threads sit on the GPU's socket.  Returns the CPU set, or None when the
+    topology is not visible (containers without sysfs, one-socket hosts report everything: harmless)."""
+    import os
+
+    cpus = gpu_local_cpus(device_index)
+    if not cpus or not hasattr(os, "sched_setaffinity"):
+        return None
+    allowed = os.sched_getaffinity(0) & cpus
+    if not allowed:
+        return None
+    os.sched_setaffinity(0, allowed)
+    return allowed
+
+
+def shared_arrays_placed(name: str, shapes, n: int, group=None, row_axis=None):
+    """Collective.  One shared host array per entry of ``shapes``, each with an axis of length ``n`` (``row_axis[i]``,
+    default: the first axis of that length) along which the ranks split the cloud: rank r first-touches its
+    ``shard_bounds(n, world, r)`` part of every array, then all ranks page-lock.  Returns the list of arrays
+    (zero-filled); rank 0 owns the segments."""
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    arrays = []
+    if rank == 0:
+        arrays = [SharedHostArray(f"{name}_{i}", shp, create=True, register=False) for i, shp in enumerate(shapes)]
+    dist.barrier(group=group)
+    if rank != 0:
+        arrays = [SharedHostArray(f"{name}_{i}", shp, create=False, register=False) for i, shp in enumerate(shapes)]
+    begin, end = shard_bounds(n, world, rank)
+    for i, (arr, shp) in enumerate(zip(arrays, shapes)):
+        axis = row_axis[i] if row_axis is not None else list(shp).index(n)
+        index = [slice(None)] * len(shp)
+        index[axis] = slice(begin, end)
+        arr.first_touch(tuple(index))
+    dist.barrier(group=group)
+    for arr in arrays:
+        arr.register()
+    dist.barrier(group=group)
+    return arrays
 
 
 def shared_cloud_from_text(path, name: str, group=None) -> SharedHostArray:

@@ -1,3 +1,2 @@
 set -x
-PCT_KNN_KERNEL=warp timeout 900 ncu --set full --import-source on --clock-control none -k regex:knn_warp -c 1 -o gpurun_out/prof_warp_r02k -f python scripts/qbench.py 1e7 20 1 > gpurun_out/ncu_warpfull_r02k.log 2>&1
-tail -3 gpurun_out/ncu_warpfull_r02k.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/pcie_probe.py 128 > gpurun_out/pcie_probe_r02n.txt 2> gpurun_out/pcie_probe_r02n.err; cat gpurun_out/pcie_probe_r02n.txt; tail -3 gpurun_out/pcie_probe_r02n.err

@@ -56,6 +56,12 @@ def test_slabs_partition_the_cloud():
     assert sum(sizes) == n
 
 
+def test_gpu_local_cpus_parses_sysfs_or_gives_up():
+    """No GPU here: the topology helpers must return None instead of raising."""
+    assert pdist.gpu_local_cpus(0) is None or isinstance(pdist.gpu_local_cpus(0), set)
+    assert pdist.bind_near_gpu(0) is None or isinstance(pdist.bind_near_gpu(0), set)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -114,6 +120,19 @@ def _worker(rank, world, port, n, out_path):
             assert np.array_equal(shared.array[1], cloud[:, 2].numpy())
         dist.barrier()
         shared.close()
+        # the placed form: every rank first-touches the part it will move, then all page-lock (a no-op without CUDA)
+        a_in, a_out = pdist.shared_arrays_placed(f"pct_place_{port}", [(n, 3), (2, n)], n)
+        assert a_in.array.shape == (n, 3) and a_out.array.shape == (2, n)
+        a_in.array[b:e] = cloud[b:e].numpy()
+        a_out.array[:, b:e] = float(rank + 1)
+        dist.barrier()
+        assert np.array_equal(a_in.array, cloud.numpy())
+        for r in range(world):
+            rb, re_ = pdist.shard_bounds(n, world, r)
+            assert np.all(a_out.array[:, rb:re_] == float(r + 1))
+        dist.barrier()
+        a_in.close()
+        a_out.close()
     finally:
         dist.destroy_process_group()
 
