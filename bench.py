@@ -41,9 +41,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="torus", choices=["torus", "c3_sphere", "bunny_ball", "sheet_ball"])
+    ap.add_argument("--workload", default="torus", choices=["torus", "c3_sphere", "bunny_ball", "sheet_ball", "c1_torus", "bunny_knn"])
     ap.add_argument("--points", type=int, default=100_000_000)
-    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--k", type=int, default=None, help="neighbours (default 20; 30 for bunny_knn, BASELINE.json config 2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of each cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
@@ -51,7 +51,10 @@ def parse_args():
     ap.add_argument("--parity-k", default="20,32", help="k values of the parity block (torus workload)")
     ap.add_argument("--parity-rows", type=int, default=100_000, help="queries checked per k, over all ranks")
     ap.add_argument("--clock-interval-ms", type=int, default=200)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.k is None:
+        args.k = 30 if args.workload == "bunny_knn" else 20
+    return args
 
 
 # --------------------------------------------------------------------------
@@ -65,6 +68,13 @@ def workload_config(args):
     if args.workload == "c3_sphere":
         return {"workload": f"C3: Fibonacci sphere R=1, N=1000000, k={k} kNN, closed-form K=1, |H|=1", "k": k, "points": 1_000_000,
                 "l2": "28 MB of inputs fit the L2: a 256 MB buffer is written between timed steps"}
+    if args.workload == "c1_torus":
+        return {"workload": f"C1 stand-in: torus R=1, r=1/3 on the reference's 317 x 317 (theta, phi) grid, through %.6f text and the "
+                            f"loader's fp32 max-shift, N=100489, k={k} kNN; CPU arm = the unmodified reference on the WHOLE cloud, one thread",
+                "k": k, "points": 100_489, "l2": "inputs fit the L2: a 256 MB buffer is written between timed steps"}
+    if args.workload == "bunny_knn":
+        return {"workload": f"C2: sample_scans/bunny.txt (35947 points), k={k} kNN; CPU arm = the unmodified reference on the WHOLE cloud, one thread",
+                "k": k, "points": 35947, "l2": "inputs fit the L2: a 256 MB buffer is written between timed steps"}
     if args.workload == "bunny_ball":
         return {"workload": "C2: sample_scans/bunny.txt (35947 points), epsilon-ball radius 3.8e-3 (mean ~30 members)", "k": 0,
                 "points": 35947, "radius": 3.8e-3, "l2": "inputs fit the L2: a 256 MB buffer is written between timed steps"}
@@ -82,6 +92,26 @@ def host_sample(n_sample, seed=3):
     v = rng.uniform(0, 2 * np.pi, n_sample)
     R, r = 1.0, 1.0 / 3.0
     return np.stack(((R + r * np.cos(v)) * np.cos(u), (R + r * np.cos(v)) * np.sin(u), r * np.sin(v)), 1).astype(np.float32)
+
+
+def c1_torus_cloud(grid=317, R=1.0, r=1.0 / 3.0):
+    """C1 stand-in: the reference's torus generator (utils.py:883-896) on a grid x grid lattice, written
+    as 3-column %.6f text and read back the way PointCloud(file_path) conditions a scan (ref :51-57)."""
+    import io
+
+    import numpy as np
+
+    t = np.linspace(0, 2 * np.pi, grid, endpoint=False)
+    U, V = np.meshgrid(t, t)
+    u, v = U.ravel(), V.ravel()
+    p64 = np.stack(((R + r * np.cos(v)) * np.cos(u), (R + r * np.cos(v)) * np.sin(u), r * np.sin(v)), 1)
+    buf = io.StringIO()
+    np.savetxt(buf, p64, fmt="%.6f")
+    buf.seek(0)
+    pts = np.loadtxt(buf)[:, 0:3].astype(np.float32)
+    pts[:, 0] -= np.max(pts[:, 0])
+    pts[:, 1] -= np.max(pts[:, 1])
+    return np.ascontiguousarray(pts)
 
 
 def sphere_sample(n_sample, seed=0):
@@ -118,9 +148,11 @@ def small_workload_cloud(args):
 
     if args.workload == "c3_sphere":
         return sphere_sample(1_000_000), None
-    if args.workload == "bunny_ball":
+    if args.workload == "c1_torus":
+        return c1_torus_cloud(), None
+    if args.workload in ("bunny_ball", "bunny_knn"):
         pts = np.load(os.path.join(ROOT, "tests", "golden", "bunny_points.npz"))["points"].astype(np.float32)
-        return np.ascontiguousarray(pts), 3.8e-3
+        return np.ascontiguousarray(pts), (3.8e-3 if args.workload == "bunny_ball" else None)
     pts = sheet_cloud()
     from scipy.spatial import cKDTree  # input preparation only: the radius is defined from the data's spacing
 
@@ -148,6 +180,8 @@ def reference_leg(args, seconds, with_fan_out=True):
 
     if args.workload in ("bunny_ball", "sheet_ball"):
         return ball_port_leg(args, seconds)
+    if args.workload in ("c1_torus", "bunny_knn"):
+        return reference_full_leg(args)[0]
     if not ref_arm.available():
         ref_arm.install()
     if not ref_arm.available():
@@ -166,6 +200,35 @@ def reference_leg(args, seconds, with_fan_out=True):
                             "sample": (f"the same unmodified call sequence in {fan['cores']} processes, each on its own "
                                        f"{fan['rows'] // fan['cores']}-point sample cloud, {fan['seconds']:.1f} s wall")}
     return out
+
+
+def reference_full_leg(args):
+    """c1_torus / bunny_knn: the unmodified reference on the WHOLE cloud, one thread (CPU baseline (1)).
+    Returns the cpu_baseline object and the reference's own K, H for the parity figure of the run."""
+    import numpy as np
+
+    from oracle import ref_arm
+
+    if not ref_arm.available():
+        ref_arm.install()
+    if not ref_arm.available():
+        return {"unavailable": "baseline/_ref/pointCloudToolbox.py is missing (run __graft_entry__.build() in the dev container)"}, None
+    try:
+        from threadpoolctl import threadpool_limits
+
+        limits = threadpool_limits(1)
+    except Exception:
+        limits = None
+    pts, _ = small_workload_cloud(args)
+    K, H, secs = ref_arm._silenced(ref_arm.run_reference, pts, args.k)
+    del limits
+    n = len(pts)
+    return ({"value": n / secs, "unit": "points/s", "cores": 1, "kind": "reference", "rows": n, "seconds": secs,
+             "per_point_us_single_core": 1e6 * secs / n,
+             "sample": (f"the WHOLE cloud ({n} points): PointCloud(points) -> plant_kdtree({args.k}) -> "
+                        f"compute_pointwise_explicit_quadratic_curvature() of the UNMODIFIED reference (baseline/_ref/pointCloudToolbox.py, "
+                        f"sha256 {ref_arm.sha256()[:12]}) on one thread, {secs:.1f} s")},
+            (np.asarray(K, np.float32), np.asarray(H, np.float32)))
 
 
 def ball_port_leg(args, seconds):
@@ -191,7 +254,9 @@ def reference_arm(args):
         return
     step_seconds = max(2.0, min(15.0, 90.0 / max(1, args.steps + args.warmup)))
     legs = []
-    for s in range(args.warmup + args.steps):
+    full = args.workload in ("c1_torus", "bunny_knn")   # a step = the whole cloud (10-30 s): one untimed + two timed runs at most
+    plan = ([0] * min(1, args.warmup) + [args.warmup] * min(2, args.steps)) if full else range(args.warmup + args.steps)
+    for s in plan:
         leg = reference_leg(args, step_seconds, with_fan_out=False)
         if "unavailable" in leg:
             print(json.dumps({"impl": "reference", "unavailable": leg["unavailable"]}), flush=True)
@@ -208,7 +273,7 @@ def reference_arm(args):
         ms = 1e3 * secs / len(legs)
     cpu = dict(legs[-1])
     cpu["value"] = value
-    if args.workload not in ("bunny_ball", "sheet_ball"):
+    if args.workload not in ("bunny_ball", "sheet_ball", "c1_torus", "bunny_knn"):
         from oracle import ref_arm
 
         fan = ref_arm.fan_out(cpu_cloud_maker(args), args.k, step_seconds, cpu["per_point_us_single_core"] * 1e-6)
@@ -217,7 +282,8 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 inputs, f64 LAPACK", "data": "synthetic", "config": workload_config(args),
+        "dtype": "f32 inputs, f64 LAPACK",
+        "data": "synthetic" if not args.workload.startswith("bunny") else "sample_scans/bunny.txt (fixture copy)", "config": workload_config(args),
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -431,9 +497,12 @@ def small_workload(args):
     import torch
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    cpu = None
+    cpu, ref_kh = None, None
     if not args.no_cpu_baseline:
-        cpu = reference_leg(args, args.cpu_seconds, with_fan_out=False)
+        if args.workload in ("c1_torus", "bunny_knn"):
+            cpu, ref_kh = reference_full_leg(args)
+        else:
+            cpu = reference_leg(args, args.cpu_seconds, with_fan_out=False)
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     from point_cloud_toolbox_b200 import GridIndex, PointCloud
@@ -472,7 +541,9 @@ def small_workload(args):
         else:
             pc.plant_ball(radius)
         K, H = pc.compute_pointwise_explicit_quadratic_curvature()
-        return K, H, time.perf_counter() - t
+        wall = time.perf_counter() - t
+        e2e_step.r_k = np.asarray(pc.dists)[:, -1].astype(np.float64) if (radius is None and ref_kh is not None) else None
+        return K, H, wall
 
     for _ in range(args.warmup):
         index, fit, _ = device_step()
@@ -512,13 +583,30 @@ def small_workload(args):
     if radius is not None:
         details["radius"] = radius
         details["count_min_max"] = [int(fit.counts.min().item()), int(fit.counts.max().item())]
-    else:
+    elif args.workload == "c3_sphere":
         Kd = np.asarray(K, np.float64)
         details["closed_form"] = {"K_abs_err_median": float(np.median(np.abs(Kd - 1.0))), "H_abs_err_median": float(np.median(np.abs(np.abs(H) - 1.0)))}
+    parity = None
+    if ref_kh is not None:
+        # the K, H this run wrote to the host against the K, H the unmodified reference produced for the same cloud in the
+        # same run, with the stated tolerance (oracle/compare.py): |dK| <= 1e-3 |K| + 1e-5 / r_k^2, |dH| <= 1e-3 |H| + 1e-5 / r_k
+        Kr, Hr = (a.astype(np.float64) for a in ref_kh)
+        Kg, Hg = np.asarray(K, np.float64), np.asarray(H, np.float64)
+        r_k = e2e_step.r_k
+        ok = np.isfinite(Kr) & np.isfinite(Hr)
+        k_bad = (np.abs(Kg - Kr) > 1e-3 * np.abs(Kr) + 1e-5 / r_k ** 2) & ok
+        h_bad = (np.abs(Hg - Hr) > 1e-3 * np.abs(Hr) + 1e-5 / r_k) & ok
+        parity = {"rows": int(ok.sum()), "K_violations": int(k_bad.sum()), "H_violations": int(h_bad.sum()),
+                  "violations": int((k_bad | h_bad).sum()), "nan_rows": int((~np.isfinite(Kg) & ok).sum()),
+                  "bit_identical_K": int((np.asarray(K, np.float32).view(np.uint32) == ref_kh[0].view(np.uint32)).sum()),
+                  "checker": "K, H of baseline/_ref/pointCloudToolbox.py (unmodified) on the whole cloud in this run; signed, tolerance of oracle/compare.py"
+                             + ("; a lattice cloud has exact distance ties at the k-th neighbour, where scipy's traversal order and the (d, index) "
+                                "rule pick different, equally valid neighbourhoods: those rows may differ (tests/test_oracle.py pins the rule)"
+                                if args.workload == "c1_torus" else "")}
     line = {
         "metric": METRIC, "value": n / ((build_ms + query_ms) * 1e-3), "unit": "points/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": build_ms + query_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 search keys, f64 re-rank and fit, f32 outputs", "data": "synthetic" if args.workload != "bunny_ball" else "sample_scans/bunny.txt (fixture copy)",
+        "dtype": "f32 search keys, f64 re-rank and fit, f32 outputs", "data": "synthetic" if not args.workload.startswith("bunny") else "sample_scans/bunny.txt (fixture copy)",
         "config": workload_config(args), "details": details,
         "roofline": {"bound": "hbm", "kernel": "ball_staged_kernel<2, fused>" if radius is not None else "knn_staged_kernel<2, fused>",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -530,6 +618,8 @@ def small_workload(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity"] = parity
     print(json.dumps(line), flush=True)
 
 

@@ -1,2 +1,10 @@
 set -x
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 scripts/pcie_probe.py 128 > gpurun_out/pcie_probe_r02n.txt 2> gpurun_out/pcie_probe_r02n.err; cat gpurun_out/pcie_probe_r02n.txt; tail -3 gpurun_out/pcie_probe_r02n.err
+for w in bunny_knn c1_torus; do
+  timeout 600 python bench.py --workload $w > gpurun_out/bench_${w}_r02p.json 2> gpurun_out/bench_${w}_r02p.err; tail -c 400 gpurun_out/bench_${w}_r02p.err; python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_${w}_r02p.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step")}, d["e2e"], d.get("parity"), d["cpu_baseline"]["value"], d["cpu_baseline"]["seconds"])
+PY
+done
+timeout 300 python bench.py --impl reference --workload bunny_knn --steps 2 --warmup 1 > gpurun_out/bench_bunny_knn_ref_r02p.json 2>/dev/null; cut -c1-300 gpurun_out/bench_bunny_knn_ref_r02p.json
+timeout 900 python bench.py > gpurun_out/bench_1gpu_r02p.json 2> gpurun_out/bench_1gpu_r02p.err; tail -c 300 gpurun_out/bench_1gpu_r02p.err; cut -c1-700 gpurun_out/bench_1gpu_r02p.json
