@@ -762,6 +762,7 @@ def ours(args):
     barrier()
     total_ms = t_start.elapsed_time(t_end)
     launches_step = 0
+    peer_return = False
     if world == 1:
         build_steps = [round(a.elapsed_time(b), 2) for a, b, _ in events]
         build_ms = sum(build_steps) / len(events)
@@ -780,8 +781,10 @@ def ours(args):
         nan_rows = int(torch.isnan(rec[:, 3]).sum().item())
         pts_per_launch, indexed, unresolved = int(fit.own_ids.numel()), int(fit.indexed), int(fit.unresolved)
         build_steps, build_ms, query_ms = [], None, None
-        # bbox/sample torch kernels are not ours; pilot (2), bin count + fill + row starts (3), own flags + rows (2)
-        launches_step = int(info.build_launches) + int(stats.kernel_launches) + 7
+        # bbox/sample torch kernels are not ours; pilot (2), bin count + fill + row starts (3), own flags + rows (2),
+        # and with the return fused into the kernel: row ids + peer route (2)
+        launches_step = int(info.build_launches) + int(stats.kernel_launches) + 7 + (2 if getattr(fit, "peer_return", False) else 0)
+        peer_return = bool(getattr(fit, "peer_return", False))
     last[0].close()
     del last
     torch.cuda.empty_cache()
@@ -856,6 +859,8 @@ def ours(args):
     if not args.no_parity:
         parity = parity_block(args, world, rank, dev, pts, shared_in, shared_out, host_pts)
 
+    if world > 1:
+        pdist.PeerResults.release()
     for sh in (shared_in, shared_out):
         if sh is not None:
             sh.close()
@@ -889,7 +894,10 @@ def ours(args):
     details = {
         "parallelism": ("one GPU" if world == 1 else
                         f"{world} slabs across the longest axis; every rank starts with 1/{world} of the cloud, one all-to-all delivers each slab "
-                        f"(+ margin) to its rank, one returns the rows (rank 0: {indexed} indexed, {pts_per_launch} answered, {unresolved} redone)"),
+                        f"(+ margin) to its rank, "
+                        + ("the fused kernel stores K, H straight into the owner rank's array over NVLink peer memory (no return collective)"
+                           if peer_return else "one all-to-all returns the rows")
+                        + f" (rank 0: {indexed} indexed, {pts_per_launch} answered, {unresolved} redone)"),
         "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
         "level1_retries": stats.level1_retries, "exact_path": stats.exact_path, "unstaged": stats.unstaged,
         "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": roof_query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
@@ -918,7 +926,7 @@ def ours(args):
                 "every rank its share (shared host memory, pages first-touched by the rank that moves them" +
                 (f", ranks bound to their GPU's {len(near)} local CPUs)" if near else ", no CPU binding: topology not visible)")},
         "gpu_launches": launches_step * args.steps * 2,
-        "gpu_launches_source": "pct_index_info.build_launches + pct_query_stats.kernel_launches of the last timed step (+ 7 slab-exchange kernels at N > 1), x steps x 2 timed loops",
+        "gpu_launches_source": "pct_index_info.build_launches + pct_query_stats.kernel_launches of the last timed step (+ 7 slab-exchange kernels at N > 1, + 2 when the return is fused into the kernel), x steps x 2 timed loops",
         "clocks": clocks,
     }
     if world > 1:

@@ -138,7 +138,21 @@ int pct_slab_gather(const float* xyz, int stride, int axis, const int32_t* sel, 
  *   destination slab, ascending index inside a group (distance ties keep the whole cloud's order at the receiver);
  *   owned_local (device, n int32): the share's local indices grouped by OWNER slab, ascending -- the order in which the
  *   owners return their rows.
- * pct_slab_rows: row_map of pct_index_set_slab for a received slab cloud (m rows): rank of every owned point. */
+ * pct_slab_rows: row_map of pct_index_set_slab for a received slab cloud (m rows): rank of every owned point.
+ * pct_slab_row_ids: row_ids (device, owned-rows int32) = the original index of every output row of that slab (the id
+ *   column of the owned points in row order), which pct_index_set_peers needs. */
+int pct_slab_row_ids(const float* xyz4, int64_t m, int axis, float own_lo, float own_hi, const int32_t* row_map,
+                     int32_t* row_ids, void* stream);
+/* Return fused into the kernel (new, multi-GPU; replaces the gather SURVEY.md 8(e) puts after the queries): rank r of
+ * `world` holds the original indices begins[r] .. begins[r + 1] - 1 and a result array of (its rows) x {K, H} floats
+ * that the other ranks have mapped (CUDA IPC / NVLink peer memory); peer_rows[r] (host array of `world` device
+ * pointers) is that array as THIS process sees it.  After this call pct_curvature_fused_knn_records on the slab index
+ * stores K and H of every answered query with one 8-byte store into the array of the rank that holds the query's
+ * point (besides its local record), so no all-to-all and no scatter follow the kernel -- the ranks only need a
+ * barrier before they read their arrays.  row_ids: pct_slab_row_ids (caller keeps it alive).  begins: host, world + 1.
+ * world = 0 removes the routing.  Asynchronous on the stream the index was built on. */
+int pct_index_set_peers(pct_index* index, int world, const int64_t* begins, void* const* peer_rows,
+                        const int32_t* row_ids);
 int pct_estimate_cell_size_sample(const float* sample, int64_t n_sample, int stride, int64_t n_total,
                                   const float* bbox_min_max, int k_hint, void* stream, float* cell_size);
 int64_t pct_slab_bin_blocks(int64_t n);

@@ -2,6 +2,7 @@
 // error strings, launches.  No C++ exception crosses this file.
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "pct_internal.h"
@@ -118,6 +119,40 @@ int pct_index_set_slab(pct_index* ix, int axis, float complete_lo, float complet
     return PCT_OK;
 }
 
+}  // extern "C"
+namespace {
+__global__ void store_peers_kernel(const pct::PeerRoute route, pct::PeerRoute* dst) { *dst = route; }
+}  // namespace
+extern "C" {
+
+int pct_index_set_peers(pct_index* ix, int world, const int64_t* begins, void* const* peer_rows, const int32_t* row_ids) {
+    PCT_REQUIRE(ix != nullptr, "pct_index_set_peers: index is NULL");
+    cudaStream_t s = ix->stream;
+    if (world <= 0) {  // removes the routing
+        if (ix->peers) PCT_CUDA(cudaFreeAsync(ix->peers, s));
+        ix->peers = nullptr;
+        return PCT_OK;
+    }
+    PCT_REQUIRE(world <= pct::kPeerMax && begins && peer_rows && row_ids, "pct_index_set_peers: bad argument");
+    PCT_REQUIRE(ix->view.slab_axis >= 0 && ix->row_map, "pct_index_set_peers: the index must be a slab with a row map (pct_index_set_slab)");
+    pct::PeerRoute h;
+    std::memset(&h, 0, sizeof(h));
+    for (int r = 0; r < world; ++r) {
+        PCT_REQUIRE(begins[r] <= begins[r + 1], "pct_index_set_peers: share bounds must ascend");
+        PCT_REQUIRE(peer_rows[r] != nullptr && (reinterpret_cast<uintptr_t>(peer_rows[r]) & 7) == 0 || begins[r] == begins[r + 1],
+                    "pct_index_set_peers: peer arrays must be non-NULL and 8-byte aligned");
+        h.base[r] = static_cast<float*>(peer_rows[r]);
+        h.begin[r] = begins[r];
+    }
+    h.begin[world] = begins[world];
+    h.row_ids = row_ids;
+    h.world = world;
+    if (!ix->peers) PCT_CUDA(cudaMallocAsync(&ix->peers, sizeof(pct::PeerRoute), s));
+    store_peers_kernel<<<1, 1, 0, s>>>(h, ix->peers);  // by value through the parameter space: no host synchronisation
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
 int pct_curvature_fused_knn(const pct_index* ix, int64_t q_begin, int64_t q_end, int k, float* normals, float* coeffs,
                             float* curv, uint8_t* status, int layout, void* stream) {
     int rc = check_range(ix, q_begin, q_end, layout, "pct_curvature_fused_knn");
@@ -137,6 +172,10 @@ int pct_curvature_fused_knn_records(const pct_index* ix, int64_t q_begin, int64_
     PCT_REQUIRE(records != nullptr && (reinterpret_cast<uintptr_t>(records) & 31) == 0,
                 "pct_curvature_fused_knn_records: records must be non-NULL and 32-byte aligned");
     FitOutputs out{nullptr, nullptr, nullptr, nullptr, records};
+    if (ix->peers) {
+        PCT_REQUIRE(layout == PCT_LAYOUT_ORIGINAL, "pct_curvature_fused_knn_records: peer routing needs PCT_LAYOUT_ORIGINAL");
+        out.peers = ix->peers;
+    }
     return launch_knn(ix, q_begin, q_end, k, true, nullptr, nullptr, out, layout, (cudaStream_t)stream);
 }
 

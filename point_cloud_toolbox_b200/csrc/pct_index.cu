@@ -451,6 +451,7 @@ int pct_index_destroy(pct_index* ix) {
     if (ix->pts) cudaFreeAsync(ix->pts, ix->stream);
     if (ix->table_mem) cudaFreeAsync(ix->table_mem, ix->stream);
     if (ix->stats) cudaFreeAsync(ix->stats, ix->stream);
+    if (ix->peers) cudaFreeAsync(ix->peers, ix->stream);
     if (cur != ix->device) cudaSetDevice(cur);
     delete ix;
     return PCT_OK;
@@ -491,6 +492,16 @@ __global__ void slab_gather_kernel(const float* __restrict__ xyz, int stride, in
     local[3 * r] = x; local[3 * r + 1] = y; local[3 * r + 2] = z;
     const float v = axis == 0 ? x : (axis == 1 ? y : z);
     own_flag[r] = v >= own_lo && v < own_hi ? 1 : 0;
+}
+
+// original (whole-cloud) index of every output row: the id column of the owned points, in row order
+__global__ void slab_row_ids_kernel(const float* __restrict__ xyz4, long long m, int axis, float own_lo, float own_hi,
+                                    const int32_t* __restrict__ row_map, int32_t* __restrict__ row_ids) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const float4 p = __ldg(reinterpret_cast<const float4*>(xyz4) + r);
+    const float v = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    if (v >= own_lo && v < own_hi) row_ids[row_map[r]] = __float_as_int(p.w);
 }
 
 __global__ void slab_rows_kernel(const int32_t* __restrict__ incl, long long m, int32_t* __restrict__ row_map) {
@@ -762,6 +773,15 @@ int pct_slab_bin_fill(const float* xyz, int64_t n, int stride, int axis, int wor
     pct::slab_bin_kernel<true><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, nullptr, block_pos,
                                                                                  total_complete, id_base,
                                                                                  reinterpret_cast<float4*>(records), owned_local);
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+int pct_slab_row_ids(const float* xyz4, int64_t m, int axis, float own_lo, float own_hi, const int32_t* row_map,
+                     int32_t* row_ids, void* stream) {
+    PCT_REQUIRE(xyz4 && row_map && row_ids && m >= 1 && axis >= 0 && axis <= 2 && (reinterpret_cast<uintptr_t>(xyz4) & 15) == 0,
+                "pct_slab_row_ids: bad argument");
+    pct::slab_row_ids_kernel<<<(int)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz4, m, axis, own_lo, own_hi, row_map, row_ids);
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
 }

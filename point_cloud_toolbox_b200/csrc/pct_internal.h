@@ -10,11 +10,14 @@
 #include "pct_dispatch.h"
 #include "pct_grid.cuh"
 
+namespace pct { struct PeerRoute; }
+
 struct pct_index {
     pct::IndexView view;       // device pointers inside
     pct::Pt* pts = nullptr;    // N sorted records
     pct::HashSlot* table_mem = nullptr;  // all level tables, one allocation
     const int32_t* row_map = nullptr;    // caller-owned (pct_index_set_slab): output row per original index
+    pct::PeerRoute* peers = nullptr;  // device copy of the peer routing (pct_index_set_peers), owned by the index
     unsigned int* stats = nullptr;       // device: [retries, exact, launches, queries, unstaged, -, -, -]
     pct_index_info info{};
     int device = 0;
@@ -61,6 +64,17 @@ void release_scratch();
 void release_scratch_of(cudaStream_t s);  // one stream of the current device; call before destroying a library-owned stream
 void release_upload_stage();  // pct_transfer.cu
 
+// Multi-GPU return fused into the fit's store (pct_index_set_peers): the K, H of an answered query go straight to the
+// rank that holds the query's share of the cloud -- an 8-byte store into that rank's result array through NVLink peer
+// memory -- instead of a local write, a column extraction, an all-to-all and a scatter after the kernel.
+constexpr int kPeerMax = 32;
+struct PeerRoute {
+    float* base[kPeerMax];            // (rows of rank r) x {K, H}: rank r's result array, mapped into this process
+    long long begin[kPeerMax + 1];    // rank r holds the original indices begin[r] .. begin[r + 1] - 1
+    const int32_t* row_ids;           // original (whole-cloud) index of output row r of this index (owned points, row order)
+    int world;
+};
+
 // per-row output pointers of the fit (any may be null)
 struct FitOutputs {
     float* normals;
@@ -68,6 +82,7 @@ struct FitOutputs {
     float* curv;
     uint8_t* status;
     float* records;  // rows x 8 floats {nx, ny, nz, K, H, k1, k2, status bits}: one aligned 32-byte sector per point
+    const PeerRoute* peers = nullptr;  // device pointer; when set, K and H of a row also go to the rank that owns its point
 };
 
 __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, const FitResult& r) {
@@ -92,6 +107,13 @@ __device__ __forceinline__ void store_fit(const FitOutputs& o, long long row, co
         float4* p = reinterpret_cast<float4*>(o.records + 8 * row);
         p[0] = make_float4(r.normal[0], r.normal[1], r.normal[2], r.curv[0]);
         p[1] = make_float4(r.curv[1], r.curv[2], r.curv[3], __uint_as_float(r.status));
+    }
+    if (o.peers) {
+        const PeerRoute& pr = *o.peers;
+        const long long g = pr.row_ids[row];
+        int owner = 0;
+        for (int t = 1; t < pr.world; ++t) owner += g >= pr.begin[t] ? 1 : 0;
+        reinterpret_cast<float2*>(pr.base[owner])[g - pr.begin[owner]] = make_float2(r.curv[0], r.curv[1]);
     }
 }
 

@@ -481,9 +481,88 @@ class ExchangeFit:
             self.index = None
 
 
-def answer_slab(recv: torch.Tensor, plan: SlabPlan, rank: int, k: int, n_own: int):
+class PeerResults:
+    """The K, H arrays of all ranks of a one-node job, mapped into every rank (CUDA IPC; NVLink peer memory).
+
+    Rank r's array has ``padded_rows(n_total, world)`` rows of {K, H}; row i belongs to original index
+    ``shard_bounds(n_total, world, r)[0] + i``.  The fused kernel of every rank stores results straight into the array
+    of the rank that holds the point (``GridIndex.set_peers``), so the exchange path needs no return all-to-all.
+    Built once per (group, device, cloud size) and reused: opening IPC handles costs milliseconds."""
+
+    _cache = {}
+
+    def __init__(self, n_total: int, group, device):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        self.rows = padded_rows(n_total, world)
+        self.local = torch.zeros((max(self.rows, 1), 2), dtype=torch.float32, device=device)
+        handles = [None] * world
+        dist.all_gather_object(handles, reduce_tensor(self.local), group=group)
+        self.views = []
+        for r, (fn, args) in enumerate(handles):
+            if r == rank:
+                self.views.append(self.local)
+                continue
+            args = list(args)
+            args[6] = device.index if device.index is not None else torch.cuda.current_device()   # storage_device: map it here
+            self.views.append(fn(*args))
+        self.ptrs = [int(v.data_ptr()) for v in self.views]
+        self.begins = [shard_bounds(n_total, world, r)[0] for r in range(world)] + [n_total]
+
+    @classmethod
+    def release(cls, group=None):
+        """Collective: unmap the peers' arrays, then free the own ones (a producer must outlive its consumers' mappings)."""
+        for made in cls._cache.values():
+            if made is not None:
+                made.views = []
+                made.ptrs = []
+        if dist.is_initialized():
+            if torch.cuda.is_available():
+                import gc
+
+                torch.cuda.synchronize()
+                gc.collect()
+                torch.cuda.ipc_collect()      # closes the mappings whose tensors are gone
+            dist.barrier(group=group)
+        cls._cache.clear()
+        if torch.cuda.is_available():
+            torch.cuda.ipc_collect()
+
+    @classmethod
+    def get(cls, n_total: int, group, device):
+        """Collective on first use.  None when the job cannot share device memory (every rank then agrees on that)."""
+        import os
+
+        key = (id(group) if group is not None else 0, str(device), int(n_total), dist.get_world_size(group))
+        if key in cls._cache:
+            return cls._cache[key]
+        ok, made = 1, None
+        if os.environ.get("PCT_PEER_RETURN", "1") == "0" or dist.get_backend(group) != "nccl" or device.type != "cuda":
+            ok = 0
+        flags = [None] * dist.get_world_size(group)
+        dist.all_gather_object(flags, ok, group=group)
+        if all(flags):
+            try:
+                made = cls(n_total, group, device)
+                ok = 1
+            except Exception as exc:  # pragma: no cover  (no IPC between these processes: fall back to the all-to-all)
+                import warnings
+
+                warnings.warn(f"peer result arrays unavailable ({exc!r}); results return through NCCL")
+                ok = 0
+            dist.all_gather_object(flags, ok, group=group)
+            if not all(flags):
+                made = None
+        cls._cache[key] = made
+        return made
+
+
+def answer_slab(recv: torch.Tensor, plan: SlabPlan, rank: int, k: int, n_own: int, peers: PeerResults = None):
     """Index over the received slab cloud (x, y, z, original-index bits) and the fused kernel on the points it owns.
-    Returns (records (n_own, 8), index, unresolved count)."""
+    With ``peers`` the kernel also stores K, H of every answered query into the array of the rank that holds the
+    query's point.  Returns (records (n_own, 8), index, unresolved count)."""
     from . import engine
 
     c_lo, c_hi, own_lo, own_hi = plan.bounds[rank]
@@ -492,6 +571,8 @@ def answer_slab(recv: torch.Tensor, plan: SlabPlan, rank: int, k: int, n_own: in
     index = engine.GridIndex(recv, cell_hint=plan.h, k_hint=k)
     row_map = engine.slab_rows(recv, plan.axis, own_lo, own_hi)
     index.set_slab(plan.axis, c_lo, c_hi, own_lo, own_hi, row_map=row_map, mapped_rows=n_own)
+    if peers is not None:
+        index.set_peers(peers.begins, peers.ptrs, engine.slab_row_ids(recv, plan.axis, own_lo, own_hi, row_map, n_own))
     if int(recv.shape[0]) <= k:
         # fewer points than a neighbourhood needs: nothing can be resolved inside this slab
         rec = torch.full((n_own, 8), float("nan"), dtype=torch.float32, device=recv.device)
@@ -537,11 +618,17 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
     slab = _all_to_all_rows(records, complete, recv_complete, group)                                # (m, 4)
     st.mark("exchange")
     n_own = sum(recv_owned)
-    rec, index, n_bad = (answer_fn or answer_slab)(slab, plan, rank, k, n_own)
+    # results return inside the kernel (peer stores over NVLink) when the ranks can map each other's memory
+    peers = PeerResults.get(n_total, group, share.device) if (answer_fn is None and tuple(columns) == (3, 4)) else None
+    if peers is not None:
+        rec, index, n_bad = answer_slab(slab, plan, rank, k, n_own, peers)
+    else:
+        rec, index, n_bad = (answer_fn or answer_slab)(slab, plan, rank, k, n_own)
     st.mark("answer")
     bad_total = torch.tensor([n_bad], dtype=torch.int64, device=share.device)
     dist.all_reduce(bad_total, group=group)
-    if int(bad_total.item()):
+    any_bad = int(bad_total.item())
+    if any_bad:
         # rare: some k-th neighbour lies beyond a margin -- replicate the cloud and redo those queries
         rows = padded_rows(n_total, world)
         padded = torch.zeros((rows, 3), dtype=torch.float32, device=share.device)
@@ -554,12 +641,19 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
             rec = (redo_fn or _redo_unresolved)(cloud, rec, _owned_ids(slab, plan, rank), plan, k)
         del parts
     st.mark("unresolved")
-    cols = rec[:, list(columns)].contiguous()
-    back = _all_to_all_rows(cols, recv_owned, owned, group)     # rows of MY share, grouped by the slab that answered
-    out = torch.empty((int(share.shape[0]), len(columns)), dtype=rec.dtype, device=share.device)
-    out[owned_local] = back          # (int32 indices: no 64-bit copy of the index list)
+    if peers is not None and not any_bad:
+        # every rank's kernel has finished (the all-reduce above is the barrier): my rows are complete in my array.
+        # A copy, because the array is written again by the next call.
+        out = peers.local[: int(share.shape[0])].clone()
+    else:
+        cols = rec[:, list(columns)].contiguous()
+        back = _all_to_all_rows(cols, recv_owned, owned, group)     # rows of MY share, grouped by the slab that answered
+        out = torch.empty((int(share.shape[0]), len(columns)), dtype=rec.dtype, device=share.device)
+        out[owned_local] = back          # (int32 indices: no 64-bit copy of the index list)
     st.mark("return")
-    return ExchangeFit(out, plan, index, slab, rank, rec, n_bad)
+    fit = ExchangeFit(out, plan, index, slab, rank, rec, n_bad)
+    fit.peer_return = peers is not None
+    return fit
 
 
 def _owned_ids(slab, plan, rank):

@@ -261,6 +261,21 @@ class GridIndex:
         check(lib.pct_index_set_slab(self._handle, int(axis), float(complete_lo), float(complete_hi), float(own_lo),
                                      float(own_hi), ptr(row_map)))
 
+    def set_peers(self, begins, peer_ptrs, row_ids):
+        """Multi-GPU return fused into the kernel (pct_index_set_peers): ``begins`` (world + 1 original-index bounds of the
+        ranks' shares), ``peer_ptrs`` (device address of every rank's (rows, 2) K, H array as this process maps it),
+        ``row_ids`` (device int32: original index of every output row, ``slab_row_ids``).  ``begins=None`` removes it."""
+        if begins is None:
+            self._peer_keep = None
+            check(lib.pct_index_set_peers(self._handle, 0, None, None, None))
+            return
+        world = len(peer_ptrs)
+        b = (ctypes.c_int64 * (world + 1))(*[int(v) for v in begins])
+        p = (ctypes.c_void_p * world)(*[int(v) for v in peer_ptrs])
+        self._peer_keep = row_ids
+        with torch.cuda.device(self.device):
+            check(lib.pct_index_set_peers(self._handle, world, b, p, ptr(row_ids)))
+
     def curvature_points(self, query_ids, k) -> "FitOutputs":
         """Fused search + fit for the cloud points named by original index; packed records, row r = query r."""
         ids = torch.as_tensor(query_ids, device=self.device).to(torch.int32).contiguous()
@@ -420,6 +435,17 @@ def slab_rows(cloud_dev, axis, own_lo, own_hi):
         check(lib.pct_slab_rows(ptr(cloud_dev), m, int(cloud_dev.shape[1]), int(axis), float(own_lo), float(own_hi), ptr(row_map),
                                 _stream()))
     return row_map
+
+
+def slab_row_ids(cloud_dev, axis, own_lo, own_hi, row_map, n_own):
+    """Original (whole-cloud) index of every output row of a slab cloud (x, y, z, id bits): pct_slab_row_ids."""
+    if cloud_dev.shape[1] != 4 or not cloud_dev.is_contiguous():
+        raise ValueError("slab_row_ids needs the packed (m, 4) slab records")
+    row_ids = torch.empty((int(n_own),), dtype=torch.int32, device=cloud_dev.device)
+    with torch.cuda.device(cloud_dev.device):
+        check(lib.pct_slab_row_ids(ptr(cloud_dev), int(cloud_dev.shape[0]), int(axis), float(own_lo), float(own_hi), ptr(row_map),
+                                   ptr(row_ids), _stream()))
+    return row_ids
 
 
 def fit_from_neighbors(points_dev, idx_dev, query_ids=None) -> FitOutputs:

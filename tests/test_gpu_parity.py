@@ -5,6 +5,8 @@ Tolerances are the policy of oracle/compare.py (relative 1e-3 + absolute floor s
 r_k, neighbour sets bit-exact); the observed agreement is asserted much tighter where the
 path is expected to reproduce the reference's fp64 steps (tight_fraction).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -400,9 +402,26 @@ def _exchange_rank(rank, world, port, n, k, out_path):
         cin.close()
         cout.close()
         part.close()
+        # the return fused into the kernel (K, H stored straight into the owner rank's array over peer memory) against
+        # the NCCL return, on a cloud without the isolated point (an unresolved query sends everything through NCCL)
+        clean = torch.from_numpy(datasets.torus_random(n, seed=6)[0]).to(dev)
+        fused = pdist.curvature_knn_exchange(clean[b:e].contiguous(), b, n, k)
+        again = pdist.curvature_knn_exchange(clean[b:e].contiguous(), b, n, k)      # the peer arrays are reused
+        os.environ["PCT_PEER_RETURN"] = "0"
+        pdist.PeerResults._cache.clear()
+        plain = pdist.curvature_knn_exchange(clean[b:e].contiguous(), b, n, k)
+        del os.environ["PCT_PEER_RETURN"]
+        pdist.PeerResults._cache.clear()
+        same = bool(torch.equal(fused.rows.view(torch.int32), plain.rows.view(torch.int32)) and
+                    torch.equal(again.rows.view(torch.int32), plain.rows.view(torch.int32)))
+        modes = (bool(fused.peer_return), bool(plain.peer_return), int(fused.unresolved) + int(plain.unresolved))
+        for f in (fused, again, plain):
+            f.close()
+        pdist.PeerResults.release()
         np.save(out_path + f".{rank}.npy", np.array([rep["violations"], rep["rows"], par["rows_differing"], par["dist_differing"],
                                                     par["violations"], par["rows"], float(host_ok), float(all_written),
-                                                    float(unresolved.item()), float(len(stages))]))
+                                                    float(unresolved.item()), float(len(stages)), float(same), float(modes[0]),
+                                                    float(modes[1]), float(modes[2])]))
     finally:
         dist.destroy_process_group()
 
@@ -424,6 +443,8 @@ def _run_exchange(tmp_path, world, n, k):
         assert res[4] == 0, res                           # records of the slab within tolerance
         assert res[6] == 1.0 and res[7] == 1.0, res       # host arrays = device rows, everything written
         assert res[9] >= 6
+        # fused peer return = NCCL return bit for bit; the fused mode was really on; nothing unresolved on the clean cloud
+        assert res[10] == 1.0 and res[11] == 1.0 and res[12] == 0.0 and res[13] == 0.0, res
     return res
 
 
