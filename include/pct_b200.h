@@ -161,6 +161,14 @@ int pct_slab_bin_count(const float* xyz, int64_t n, int stride, int axis, int wo
 int pct_slab_bin_fill(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
                       const int32_t* block_pos, int64_t total_complete, int64_t id_base, float* records,
                       int32_t* owned_local, void* stream);
+/* The forward exchange fused into the binning kernel (new, multi-GPU): like pct_slab_bin_fill, but the records of
+ * destination d are stored straight into rank d's slab buffer -- peer_slabs[d] (host array of `world` device pointers:
+ * the buffer as THIS process maps it, CUDA IPC / NVLink peer memory), from row dest_rows[d] on (host; the number of
+ * records the lower ranks send to d, so that the received slab is in ascending original index).  complete_counts:
+ * the first `world` counts of pct_slab_bin_count.  The ranks need a barrier before they read their buffers. */
+int pct_slab_bin_fill_peers(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                            const int32_t* block_pos, const int64_t* complete_counts, int64_t id_base,
+                            void* const* peer_slabs, const int64_t* dest_rows, int32_t* owned_local, void* stream);
 int pct_slab_rows(const float* xyz, int64_t m, int stride, int axis, float own_lo, float own_hi, int32_t* row_map,
                   void* stream);
 /* frees the index in the order of the stream it was built on (no device synchronisation);

@@ -94,6 +94,8 @@ SIGNATURES = {
     "pct_slab_bin_blocks": (c_int64, [c_int64]),
     "pct_slab_bin_count": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(ctypes.c_float), c_void_p, POINTER(c_int64), c_void_p]),
     "pct_slab_bin_fill": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, POINTER(ctypes.c_float), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "pct_slab_bin_fill_peers": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "pct_slab_row_ids": (c_int, [c_void_p, c_int64, c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p]),
     "pct_index_set_peers": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pct_slab_rows": (c_int, [c_void_p, c_int64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_void_p, c_void_p]),

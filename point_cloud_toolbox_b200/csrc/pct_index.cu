@@ -592,11 +592,19 @@ namespace {
 
 constexpr int kBinThreads = 256, kBinItems = 4, kBinWarps = kBinThreads / 32;
 constexpr int kBinBlockPoints = kBinThreads * kBinItems;
+constexpr int kBinStage = kBinBlockPoints + kBinBlockPoints / 2;  // records of one block staged in shared memory (24 KB)
 constexpr int kMaxWorld = 32;
 
 struct SlabBounds {
     float c_lo[kMaxWorld], c_hi[kMaxWorld], own_lo[kMaxWorld], own_hi[kMaxWorld];
     int world;
+};
+
+// Where the records of destination d go: dest.base[d] + (position in the concatenated local order), or the local
+// `records` array when dest.base[d] is null.  A peer pointer (the slab buffer of rank d, mapped over NVLink) arrives
+// already shifted by (first row this rank may write there) - (first position of bin d).
+struct SlabDest {
+    float4* base[kMaxWorld];
 };
 
 // bit d of the result: the point belongs to slab d's complete range; `owner` = the slab that answers it (-1: none)
@@ -617,7 +625,7 @@ __global__ void __launch_bounds__(kBinThreads)
 slab_bin_kernel(const float* __restrict__ xyz, const long long n, const int stride, const int axis, const SlabBounds b,
                 const long long blocks, int32_t* __restrict__ counts, const int32_t* __restrict__ pos,
                 const long long total_complete, const long long id_base, float4* __restrict__ records,
-                int32_t* __restrict__ owned_local) {
+                int32_t* __restrict__ owned_local, const SlabDest dest) {
     __shared__ int cnt[2 * kMaxWorld][kBinItems * kBinWarps + 1];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const long long base = (long long)blockIdx.x * kBinBlockPoints;
@@ -656,8 +664,22 @@ slab_bin_kernel(const float* __restrict__ xyz, const long long n, const int stri
     if (!FILL) return;
     __syncthreads();
     const unsigned int lt = (1u << lane) - 1u;
+    // The block's records are first grouped by destination in shared memory and then copied out destination by
+    // destination, so that a destination receives the block's share as ONE contiguous piece (about 2 KB at 8 slabs)
+    // instead of a few 16-byte records per warp: what a peer buffer behind NVLink needs, and kinder to local DRAM too.
+    // A block whose records do not fit (margins that cover most of the cloud: tiny clouds) writes them directly.
+    __shared__ float4 staged[kBinStage];
+    __shared__ int dest_off[kMaxWorld + 1];
+    if (t == 0) {
+        int run = 0;
+        for (int d = 0; d < b.world; ++d) { dest_off[d] = run; run += cnt[d][kBinItems * kBinWarps]; }
+        dest_off[b.world] = run;
+    }
+    __syncthreads();
+    const bool stage = dest_off[b.world] <= kBinStage;
     for (int d = 0; d < b.world; ++d) {
         const long long p_c = pos[(long long)d * blocks + blockIdx.x];
+        float4* const out_d = dest.base[d] ? dest.base[d] : records;
         const long long p_o = (long long)pos[(long long)(b.world + d) * blocks + blockIdx.x] - total_complete;
 #pragma unroll
         for (int j = 0; j < kBinItems; ++j) {
@@ -670,10 +692,20 @@ slab_bin_kernel(const float* __restrict__ xyz, const long long n, const int stri
                 float4 r;
                 r.x = __ldg(p); r.y = __ldg(p + 1); r.z = __ldg(p + 2);
                 r.w = __int_as_float((int)(id_base + i));
-                records[p_c + cnt[d][j * kBinWarps + warp] + __popc(bc & lt)] = r;
+                const int within = cnt[d][j * kBinWarps + warp] + __popc(bc & lt);
+                if (stage) staged[dest_off[d] + within] = r;
+                else out_d[p_c + within] = r;
             }
             if (fo) owned_local[p_o + cnt[b.world + d][j * kBinWarps + warp] + __popc(bo & lt)] = (int32_t)i;
         }
+    }
+    if (!stage) return;
+    __syncthreads();
+    for (int d = 0; d < b.world; ++d) {
+        const long long p_c = pos[(long long)d * blocks + blockIdx.x];
+        float4* const out_d = dest.base[d] ? dest.base[d] : records;
+        const int first = dest_off[d], count = dest_off[d + 1] - first;
+        for (int e = t; e < count; e += kBinThreads) out_d[p_c + e] = staged[first + e];
     }
 }
 
@@ -733,7 +765,7 @@ int pct_slab_bin_count(const float* xyz, int64_t n, int stride, int axis, int wo
     const long long cells = 2ll * world * blocks;
     PCT_REQUIRE(cells + 1 < (1ll << 31), "pct_slab_bin_count: share too large");
     pct::slab_bin_kernel<false><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, block_pos, nullptr, 0, 0,
-                                                                                  nullptr, nullptr);
+                                                                                  nullptr, nullptr, pct::SlabDest{});
     // exclusive scan of the flattened counts in place (+ one closing entry = grand total)
     size_t tmp_bytes = 0;
     PCT_CUDA(cudaMemsetAsync(block_pos + cells, 0, sizeof(int32_t), s));
@@ -772,7 +804,32 @@ int pct_slab_bin_fill(const float* xyz, int64_t n, int stride, int axis, int wor
     const long long blocks = pct_slab_bin_blocks(n);
     pct::slab_bin_kernel<true><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, nullptr, block_pos,
                                                                                  total_complete, id_base,
-                                                                                 reinterpret_cast<float4*>(records), owned_local);
+                                                                                 reinterpret_cast<float4*>(records), owned_local, pct::SlabDest{});
+    PCT_CUDA(cudaGetLastError());
+    return PCT_OK;
+}
+
+int pct_slab_bin_fill_peers(const float* xyz, int64_t n, int stride, int axis, int world, const float* bounds,
+                            const int32_t* block_pos, const int64_t* complete_counts, int64_t id_base,
+                            void* const* peer_slabs, const int64_t* dest_rows, int32_t* owned_local, void* stream) {
+    PCT_REQUIRE(xyz && block_pos && complete_counts && peer_slabs && dest_rows && owned_local && n >= 1 && (stride == 3 || stride == 4) &&
+                    axis >= 0 && axis <= 2 && id_base >= 0 && id_base + n <= (1ll << 31),
+                "pct_slab_bin_fill_peers: bad argument");
+    pct::SlabBounds b;
+    PCT_REQUIRE(pct::fill_bounds(b, world, bounds) == PCT_OK, "pct_slab_bin_fill_peers: world must be in [1, 32]");
+    pct::SlabDest dest{};
+    long long bin_start = 0;
+    for (int d = 0; d < world; ++d) {
+        PCT_REQUIRE(complete_counts[d] == 0 || (peer_slabs[d] && (reinterpret_cast<uintptr_t>(peer_slabs[d]) & 15) == 0 && dest_rows[d] >= 0),
+                    "pct_slab_bin_fill_peers: every destination needs a 16-byte aligned slab buffer");
+        dest.base[d] = peer_slabs[d] ? static_cast<float4*>(peer_slabs[d]) + (dest_rows[d] - bin_start) : nullptr;
+        bin_start += complete_counts[d];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long blocks = pct_slab_bin_blocks(n);
+    // (a destination without a buffer holds no record of this share: its null base is never dereferenced)
+    pct::slab_bin_kernel<true><<<(unsigned int)blocks, pct::kBinThreads, 0, s>>>(xyz, n, stride, axis, b, blocks, nullptr, block_pos,
+                                                                                 bin_start, id_base, nullptr, owned_local, dest);
     PCT_CUDA(cudaGetLastError());
     return PCT_OK;
 }

@@ -456,7 +456,9 @@ class ExchangeFit:
 
     ``rows``: (n_share, C) result columns of this rank's OWN share of the cloud, share order;
     ``index`` / ``local_ids`` / ``records`` / ``own_ids``: the slab this rank answered -- its index, the original index
-    of every indexed point, the packed records of the points it owns and their original indices (ascending)."""
+    of every indexed point, the packed records of the points it owns and their original indices (ascending).
+    When the exchanges run over peer memory (``peer_return``), ``slab`` is a view of this rank's persistent slab buffer:
+    it (and ``local_ids``) is valid until the next exchange call on the group; ``rows`` is always a private copy."""
 
     def __init__(self, rows, plan, index, slab, rank, records, unresolved):
         self.rows, self.plan, self.index, self.slab, self.rank = rows, plan, index, slab, rank
@@ -482,11 +484,16 @@ class ExchangeFit:
 
 
 class PeerResults:
-    """The K, H arrays of all ranks of a one-node job, mapped into every rank (CUDA IPC; NVLink peer memory).
+    """Two arrays per rank of a one-node job, mapped into every rank (CUDA IPC; NVLink peer memory), so that the two
+    exchanges of the slab path happen INSIDE kernels instead of after them:
 
-    Rank r's array has ``padded_rows(n_total, world)`` rows of {K, H}; row i belongs to original index
-    ``shard_bounds(n_total, world, r)[0] + i``.  The fused kernel of every rank stores results straight into the array
-    of the rank that holds the point (``GridIndex.set_peers``), so the exchange path needs no return all-to-all.
+    * ``local`` / ``ptrs``: the K, H array -- ``padded_rows(n_total, world)`` rows of {K, H}; row i belongs to original
+      index ``shard_bounds(n_total, world, r)[0] + i``.  The fused kernel of every rank stores results straight into the
+      array of the rank that holds the point (``GridIndex.set_peers``): no return all-to-all.
+    * ``slab_local`` / ``slab_ptrs``: the slab buffer -- ``slab_cap`` rows of {x, y, z, original index}.  The binning
+      kernel of every rank stores its records straight into the buffer of the destination slab
+      (``SlabBinCount.fill_peers``): no all-to-all of the points.
+
     Built once per (group, device, cloud size) and reused: opening IPC handles costs milliseconds."""
 
     _cache = {}
@@ -498,17 +505,24 @@ class PeerResults:
         rank = dist.get_rank(group)
         self.rows = padded_rows(n_total, world)
         self.local = torch.zeros((max(self.rows, 1), 2), dtype=torch.float32, device=device)
+        # a slab = the points it owns (about 1 / world of the cloud) + its margins; clouds whose slabs outgrow the
+        # buffer take the all-to-all instead
+        self.slab_cap = int(min(n_total, self.rows + self.rows // 2 + 65536))
+        self.slab_local = torch.zeros((max(self.slab_cap, 1), 4), dtype=torch.float32, device=device)
         handles = [None] * world
-        dist.all_gather_object(handles, reduce_tensor(self.local), group=group)
-        self.views = []
-        for r, (fn, args) in enumerate(handles):
-            if r == rank:
-                self.views.append(self.local)
-                continue
-            args = list(args)
-            args[6] = device.index if device.index is not None else torch.cuda.current_device()   # storage_device: map it here
-            self.views.append(fn(*args))
+        dist.all_gather_object(handles, (reduce_tensor(self.local), reduce_tensor(self.slab_local)), group=group)
+        here = device.index if device.index is not None else torch.cuda.current_device()
+        self.views, self.slab_views = [], []
+        for r, pair in enumerate(handles):
+            for (fn, args), mine, views in zip(pair, (self.local, self.slab_local), (self.views, self.slab_views)):
+                if r == rank:
+                    views.append(mine)
+                    continue
+                args = list(args)
+                args[6] = here                                   # storage_device: map the peer's memory into THIS device
+                views.append(fn(*args))
         self.ptrs = [int(v.data_ptr()) for v in self.views]
+        self.slab_ptrs = [int(v.data_ptr()) for v in self.slab_views]
         self.begins = [shard_bounds(n_total, world, r)[0] for r in range(world)] + [n_total]
 
     @classmethod
@@ -516,8 +530,8 @@ class PeerResults:
         """Collective: unmap the peers' arrays, then free the own ones (a producer must outlive its consumers' mappings)."""
         for made in cls._cache.values():
             if made is not None:
-                made.views = []
-                made.ptrs = []
+                made.views, made.slab_views = [], []
+                made.ptrs, made.slab_ptrs = [], []
         if dist.is_initialized():
             if torch.cuda.is_available():
                 import gc
@@ -608,18 +622,43 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
     st.mark("start")
     plan = plan_slabs(share, n_total, k, group, cell_fn)
     st.mark("plan")
-    records, complete, owned, owned_local = (bin_fn or engine.slab_bin)(share, plan.axis, plan.bounds, id_base)
-    st.mark("bin")
-    send = torch.tensor([complete, owned], dtype=torch.int64, device=share.device).t().contiguous()    # (world, 2)
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)
-    recv_l = recv.tolist()                                      # the one host sync of the exchange
-    recv_complete, recv_owned = [int(r[0]) for r in recv_l], [int(r[1]) for r in recv_l]
-    slab = _all_to_all_rows(records, complete, recv_complete, group)                                # (m, 4)
+    # both exchanges happen inside kernels (peer stores over NVLink) when the ranks can map each other's memory
+    peers = None
+    if bin_fn is None and answer_fn is None and tuple(columns) == (3, 4):
+        peers = PeerResults.get(n_total, group, share.device)
+    slab = None
+    if peers is not None:
+        binc = engine.SlabBinCount(share, plan.axis, plan.bounds)
+        complete, owned = binc.complete, binc.owned
+        mine = torch.tensor(complete + owned, dtype=torch.int64, device=share.device)
+        table = torch.empty((world, 2 * world), dtype=torch.int64, device=share.device)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        table = table.tolist()                                   # the one host sync of the exchange
+        recv_complete = [int(table[src][rank]) for src in range(world)]
+        recv_owned = [int(table[src][world + rank]) for src in range(world)]
+        if all(sum(table[src][d] for src in range(world)) <= peers.slab_cap for d in range(world)):
+            # rank d receives the records of the lower ranks first: its slab is in ascending original index
+            dest_rows = [sum(table[src][d] for src in range(rank)) for d in range(world)]
+            owned_local = binc.fill_peers(id_base, peers.slab_ptrs, dest_rows)
+            st.mark("bin")
+            landed = torch.zeros(1, dtype=torch.int32, device=share.device)
+            dist.all_reduce(landed, group=group)                 # barrier: every rank's records are in place
+            slab = peers.slab_local[: sum(recv_complete)]
+        else:
+            records, owned_local = binc.fill(id_base)
+            st.mark("bin")
+            slab = _all_to_all_rows(records, complete, recv_complete, group)
+    else:
+        records, complete, owned, owned_local = (bin_fn or engine.slab_bin)(share, plan.axis, plan.bounds, id_base)
+        st.mark("bin")
+        send = torch.tensor([complete, owned], dtype=torch.int64, device=share.device).t().contiguous()    # (world, 2)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        recv_l = recv.tolist()                                      # the one host sync of the exchange
+        recv_complete, recv_owned = [int(r[0]) for r in recv_l], [int(r[1]) for r in recv_l]
+        slab = _all_to_all_rows(records, complete, recv_complete, group)                                # (m, 4)
     st.mark("exchange")
     n_own = sum(recv_owned)
-    # results return inside the kernel (peer stores over NVLink) when the ranks can map each other's memory
-    peers = PeerResults.get(n_total, group, share.device) if (answer_fn is None and tuple(columns) == (3, 4)) else None
     if peers is not None:
         rec, index, n_bad = answer_slab(slab, plan, rank, k, n_own, peers)
     else:
@@ -653,6 +692,8 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
     st.mark("return")
     fit = ExchangeFit(out, plan, index, slab, rank, rec, n_bad)
     fit.peer_return = peers is not None
+    if peers is not None and index is not None and getattr(index, "_peer_keep", None) is not None:
+        fit._own_ids = index._peer_keep        # the row ids the kernel routed by = the owned original indices, ascending
     return fit
 
 

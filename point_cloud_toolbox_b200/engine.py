@@ -400,31 +400,61 @@ def estimate_cell_size_sample(sample_dev, n_total, bbox, k_hint=20):
     return float(h.value)
 
 
+class SlabBinCount:
+    """First half of the binning (pct_slab_bin_count): how many of the share's points go to every slab."""
+
+    def __init__(self, share_dev, axis, bounds):
+        self.share, self.axis, self.bounds = share_dev, int(axis), bounds
+        n, world = int(share_dev.shape[0]), len(bounds)
+        self.flat = (ctypes.c_float * (4 * world))(*[float(v) for b in bounds for v in b])
+        self.complete, self.owned, self.block_pos = [0] * world, [0] * world, None
+        if n == 0:
+            return
+        blocks = int(lib.pct_slab_bin_blocks(n))
+        self.block_pos = torch.empty((2 * world * blocks + 1,), dtype=torch.int32, device=share_dev.device)
+        counts = (ctypes.c_int64 * (2 * world))()
+        with torch.cuda.device(share_dev.device):
+            check(lib.pct_slab_bin_count(ptr(share_dev), n, int(share_dev.shape[1]), self.axis, world, self.flat, ptr(self.block_pos),
+                                         counts, _stream()))
+        self.complete = [int(counts[d]) for d in range(world)]
+        self.owned = [int(counts[world + d]) for d in range(world)]
+
+    def fill(self, id_base):
+        """Second half into a local array (pct_slab_bin_fill): ``(records (T, 4) grouped by destination, owned_local)``."""
+        dev, n = self.share.device, int(self.share.shape[0])
+        total = sum(self.complete)
+        if n == 0:
+            return torch.empty((0, 4), dtype=torch.float32, device=dev), torch.empty((0,), dtype=torch.int32, device=dev)
+        records = torch.empty((max(total, 1), 4), dtype=torch.float32, device=dev)
+        owned_local = torch.empty((n,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pct_slab_bin_fill(ptr(self.share), n, int(self.share.shape[1]), self.axis, len(self.bounds), self.flat,
+                                        ptr(self.block_pos), total, int(id_base), ptr(records), ptr(owned_local), _stream()))
+        return records[:total], owned_local[:sum(self.owned)]
+
+    def fill_peers(self, id_base, peer_ptrs, dest_rows):
+        """Second half straight into the destination ranks' slab buffers (pct_slab_bin_fill_peers); returns owned_local."""
+        dev, n, world = self.share.device, int(self.share.shape[0]), len(self.bounds)
+        if n == 0:
+            return torch.empty((0,), dtype=torch.int32, device=dev)
+        owned_local = torch.empty((n,), dtype=torch.int32, device=dev)
+        comp = (ctypes.c_int64 * world)(*self.complete)
+        p = (ctypes.c_void_p * world)(*[int(v) for v in peer_ptrs])
+        rows = (ctypes.c_int64 * world)(*[int(v) for v in dest_rows])
+        with torch.cuda.device(dev):
+            check(lib.pct_slab_bin_fill_peers(ptr(self.share), n, int(self.share.shape[1]), self.axis, world, self.flat,
+                                              ptr(self.block_pos), comp, int(id_base), p, rows, ptr(owned_local), _stream()))
+        return owned_local[:sum(self.owned)]
+
+
 def slab_bin(share_dev, axis, bounds, id_base):
     """Bins a contiguous share of the cloud by destination slab (pct_slab_bin_count + pct_slab_bin_fill).
 
     ``bounds``: per slab (complete_lo, complete_hi, own_lo, own_hi).  Returns ``(records (T, 4) float32 {x, y, z,
     original index bits} grouped by destination, complete counts, owned counts, owned_local int32 (n,))``."""
-    n, stride = int(share_dev.shape[0]), int(share_dev.shape[1])
-    world = len(bounds)
-    dev = share_dev.device
-    flat = (ctypes.c_float * (4 * world))(*[float(v) for b in bounds for v in b])
-    if n == 0:
-        return (torch.empty((0, 4), dtype=torch.float32, device=dev), [0] * world, [0] * world,
-                torch.empty((0,), dtype=torch.int32, device=dev))
-    blocks = int(lib.pct_slab_bin_blocks(n))
-    block_pos = torch.empty((2 * world * blocks + 1,), dtype=torch.int32, device=dev)
-    counts = (ctypes.c_int64 * (2 * world))()
-    with torch.cuda.device(dev):
-        check(lib.pct_slab_bin_count(ptr(share_dev), n, stride, int(axis), world, flat, ptr(block_pos), counts, _stream()))
-        complete = [int(counts[d]) for d in range(world)]
-        owned = [int(counts[world + d]) for d in range(world)]
-        total = sum(complete)
-        records = torch.empty((max(total, 1), 4), dtype=torch.float32, device=dev)
-        owned_local = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(lib.pct_slab_bin_fill(ptr(share_dev), n, stride, int(axis), world, flat, ptr(block_pos), total, int(id_base),
-                                    ptr(records), ptr(owned_local), _stream()))
-    return records[:total], complete, owned, owned_local[:sum(owned)]
+    c = SlabBinCount(share_dev, axis, bounds)
+    records, owned_local = c.fill(id_base)
+    return records, c.complete, c.owned, owned_local
 
 
 def slab_rows(cloud_dev, axis, own_lo, own_hi):
