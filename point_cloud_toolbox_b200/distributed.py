@@ -552,6 +552,8 @@ class PeerResults:
         key = (id(group) if group is not None else 0, str(device), int(n_total), dist.get_world_size(group))
         if key in cls._cache:
             return cls._cache[key]
+        if cls._cache:
+            cls.release(group)        # another cloud size: the old buffers go first (every rank takes this branch together)
         ok, made = 1, None
         if os.environ.get("PCT_PEER_RETURN", "1") == "0" or dist.get_backend(group) != "nccl" or device.type != "cuda":
             ok = 0

@@ -462,6 +462,72 @@ def test_exchange_path_two_ranks_nccl(pct, tmp_path, k):
     assert res[8] >= 1                                    # the isolated point went through the whole-cloud redo
 
 
+def _fuzz_cloud(rng, case):
+    """Random small clouds with the traits that stress the search: scale, offset, anisotropy, clusters, duplicates."""
+    n = int(rng.integers(40, 3500))
+    kind = case % 6
+    if kind == 0:      # volumetric blob
+        p = rng.normal(size=(n, 3))
+    elif kind == 1:    # noisy sheet
+        p = np.stack((rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 0.02 * rng.normal(size=n)), 1)
+    elif kind == 2:    # thin filament: cells mostly empty, long search radii
+        t = rng.uniform(0, 6, n)
+        p = np.stack((np.cos(t), np.sin(t), 0.3 * t), 1) + 0.01 * rng.normal(size=(n, 3))
+    elif kind == 3:    # clusters of very different density
+        c = rng.normal(size=(5, 3)) * 3
+        s = np.array([0.01, 0.05, 0.2, 0.5, 1.0])
+        w = rng.integers(0, 5, n)
+        p = c[w] + rng.normal(size=(n, 3)) * s[w, None]
+    elif kind == 4:    # surface of a sphere with a few exact duplicates
+        v = rng.normal(size=(n, 3))
+        p = v / np.linalg.norm(v, axis=1, keepdims=True)
+        p[rng.integers(0, n, n // 20)] = p[rng.integers(0, n, n // 20)]
+    else:              # jittered lattice: many near-ties
+        g = int(round(n ** (1 / 3))) + 1
+        m = np.stack(np.meshgrid(*(np.arange(g),) * 3, indexing="ij"), -1).reshape(-1, 3)[:n].astype(np.float64)
+        p = m + 1e-4 * rng.normal(size=m.shape)
+    scale = 10.0 ** rng.integers(-4, 5)
+    offset = rng.normal(size=3) * scale * 10.0 ** rng.integers(0, 3)
+    return (p * scale + offset).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_clouds_against_the_oracle(pct, seed):
+    """Randomised clouds (sizes 40 .. 3500, k 1 .. 64, scales 1e-4 .. 1e4, offsets up to 1000 extents, sheets, filaments,
+    clusters, duplicates, jittered lattices): neighbour rows and distances bit-exact, curvature within the tolerance,
+    through both the list kernels and the fused kernel."""
+    rng = np.random.default_rng(1000 + seed)
+    for case in range(12):
+        pts = _fuzz_cloud(rng, case)
+        n = len(pts)
+        k = int(min(n - 2, rng.choice([1, 3, 7, 12, 20, 33, 64])))
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(n), k_neighbors=k)
+        pc.plant_kdtree(k)
+        tag = (seed, case, n, k)
+        assert compare.neighbor_rows_differing(pc.neighbor_indices, ref_idx) == 0, tag
+        assert np.array_equal(pc.dists, ref_dist), tag
+        if k >= 6:     # (fewer rows than coefficients: lstsq's minimum-norm answer, covered by the degenerate goldens)
+            K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+            ref = oracle.knn_curvature(pts, k)
+            ok = np.isfinite(ref["K"]) & (np.asarray(pc.fit_status) & 4 == 0)      # rank-deficient rows: see test_tiny_and_degenerate_clouds
+            # The reference hands the UNSCALED design [a^2, b^2, ab, a, b, 1] to lstsq (ref :358-359): its condition
+            # number grows like sqrt(k) / r_k^2, so for neighbourhood radii below ~1e-4 (absolute units) the reference's
+            # own coefficients carry a relative error of ~2e3 * eps / r_k^2 -- 0.1 % at r_k = 7e-7 -- before they drop to
+            # zero altogether near 1e-7 (rcond).  The scaled solve here does not; such rows get the reference's noise as
+            # extra tolerance (observed on the harness: (|dK| / |K|) * r_k^2 <= 4.8e-13).
+            r_k = ref["dist"][:, -1].astype(np.float64)
+            tiny = r_k < 1e-4
+            rep = compare.curvature_report(_gpu_dict(pc), ref, r_k, rows_ok=ok & ~tiny)
+            assert rep["violations"] == 0, (tag, rep)
+            if (ok & tiny).any():
+                m = ok & tiny
+                rel = 1e-3 + 2e-12 / r_k[m] ** 2
+                Kr, Hr = ref["K"][m].astype(np.float64), ref["H"][m].astype(np.float64)
+                assert np.all(np.abs(np.asarray(pc.K_quadratic, np.float64)[m] - Kr) <= rel * np.abs(Kr) + 1e-5 / r_k[m] ** 2), tag
+                assert np.all(np.abs(np.abs(np.asarray(pc.H_quadratic, np.float64)[m]) - np.abs(Hr)) <= rel * np.abs(Hr) + 1e-5 / r_k[m]), tag
+
+
 def test_tiny_and_degenerate_clouds(pct):
     """Edge cases of the staged kernel: clouds smaller than a chunk, k = 1, k = N - 1, coincident points,
     points on a line and on a plane.  Neighbour rows stay bit-exact; fits of rank-deficient neighbourhoods are lstsq's
