@@ -528,6 +528,34 @@ def test_random_clouds_against_the_oracle(pct, seed):
                 assert np.all(np.abs(np.abs(np.asarray(pc.H_quadratic, np.float64)[m]) - np.abs(Hr)) <= rel * np.abs(Hr) + 1e-5 / r_k[m]), tag
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_clouds_ball_against_scipy(pct, seed):
+    """The same randomised clouds through the epsilon-ball entry: the CSR rows (members ordered by (d, index), the radius
+    test inclusive in fp64) equal scipy's query_ball_point bit for bit, empty and huge balls included; the fused ball fit
+    stays inside the tolerance wherever a ball holds enough members."""
+    rng = np.random.default_rng(2000 + seed)
+    for case in range(12):
+        pts = _fuzz_cloud(rng, case)
+        n = len(pts)
+        _, d1, _ = oracle.knn_canonical(pts, 8)
+        radius = float(np.quantile(d1[:, -1], rng.choice([0.05, 0.5, 0.95])) * rng.choice([0.5, 1.0, 2.0]))
+        if not radius > 0:
+            continue
+        tag = (seed, case, n, radius)
+        pc = pct.PointCloud(points=pts, normals=_empty_normals(n))
+        pc.plant_ball(radius)
+        off, idx, dist = pc.ball_neighbors()
+        roff, ridx, rdist = oracle.ball_canonical(pts, radius)
+        assert compare.csr_equal(off, idx, roff, ridx), tag
+        assert np.array_equal(dist, rdist), tag
+        K, H = pc.compute_pointwise_explicit_quadratic_curvature()
+        ref = oracle.curvature_from_csr(pts, roff, ridx)
+        enough = (np.diff(roff) >= 10) & (np.asarray(pc.fit_status) & 4 == 0) & np.isfinite(ref["K"])
+        if radius >= 1e-4 and enough.any():            # (below: the reference's own lstsq noise, see the kNN test above)
+            rep = compare.curvature_report(_gpu_dict(pc), ref, np.full(n, radius), rows_ok=enough)
+            assert rep["violations"] == 0, (tag, rep)
+
+
 def test_tiny_and_degenerate_clouds(pct):
     """Edge cases of the staged kernel: clouds smaller than a chunk, k = 1, k = N - 1, coincident points,
     points on a line and on a plane.  Neighbour rows stay bit-exact; fits of rank-deficient neighbourhoods are lstsq's
