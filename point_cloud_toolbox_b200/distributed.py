@@ -509,18 +509,31 @@ class PeerResults:
         # buffer take the all-to-all instead
         self.slab_cap = int(min(n_total, self.rows + self.rows // 2 + 65536))
         self.slab_local = torch.zeros((max(self.slab_cap, 1), 4), dtype=torch.float32, device=device)
+        # every rank takes part in the one collective below whatever happens to it: a rank that cannot export its
+        # arrays sends None, a rank that cannot map a peer's remembers why -- ``get`` then lets the ranks agree
+        self.error = None
+        try:
+            mine = (reduce_tensor(self.local), reduce_tensor(self.slab_local))
+        except Exception as exc:      # e.g. an allocator configuration whose blocks cannot be exported
+            mine, self.error = None, exc
         handles = [None] * world
-        dist.all_gather_object(handles, (reduce_tensor(self.local), reduce_tensor(self.slab_local)), group=group)
+        dist.all_gather_object(handles, mine, group=group)
         here = device.index if device.index is not None else torch.cuda.current_device()
         self.views, self.slab_views = [], []
-        for r, pair in enumerate(handles):
-            for (fn, args), mine, views in zip(pair, (self.local, self.slab_local), (self.views, self.slab_views)):
-                if r == rank:
-                    views.append(mine)
-                    continue
-                args = list(args)
-                args[6] = here                                   # storage_device: map the peer's memory into THIS device
-                views.append(fn(*args))
+        try:
+            for r, pair in enumerate(handles):
+                if pair is None:
+                    raise RuntimeError(f"rank {r} could not export its arrays")
+                for (fn, args), own, views in zip(pair, (self.local, self.slab_local), (self.views, self.slab_views)):
+                    if r == rank:
+                        views.append(own)
+                        continue
+                    args = list(args)
+                    args[6] = here                                   # storage_device: map the peer's memory into THIS device
+                    views.append(fn(*args))
+        except Exception as exc:
+            self.error = self.error or exc
+            self.views, self.slab_views = [], []
         self.ptrs = [int(v.data_ptr()) for v in self.views]
         self.slab_ptrs = [int(v.data_ptr()) for v in self.slab_views]
         self.begins = [shard_bounds(n_total, world, r)[0] for r in range(world)] + [n_total]
@@ -560,16 +573,14 @@ class PeerResults:
         flags = [None] * dist.get_world_size(group)
         dist.all_gather_object(flags, ok, group=group)
         if all(flags):
-            try:
-                made = cls(n_total, group, device)
-                ok = 1
-            except Exception as exc:  # pragma: no cover  (no IPC between these processes: fall back to the all-to-all)
+            made = cls(n_total, group, device)
+            if made.error is not None:  # pragma: no cover  (no IPC between these processes: fall back to the all-to-alls)
                 import warnings
 
-                warnings.warn(f"peer result arrays unavailable ({exc!r}); results return through NCCL")
-                ok = 0
-            dist.all_gather_object(flags, ok, group=group)
+                warnings.warn(f"peer arrays unavailable ({made.error!r}); the exchanges go through NCCL")
+            dist.all_gather_object(flags, 0 if made.error is not None else 1, group=group)
             if not all(flags):
+                made.views, made.slab_views = [], []
                 made = None
         cls._cache[key] = made
         return made

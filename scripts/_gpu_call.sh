@@ -1,8 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02y.log 2>&1; tail -4 gpurun_out/pytest_r02y.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/bench_1gpu_r02y.json 2> gpurun_out/bench_1gpu_r02y.err; tail -c 300 gpurun_out/bench_1gpu_r02y.err; python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_1gpu_r02y.json").read().strip().splitlines()[-1])
-print({k:d[k] for k in ("value","ms_per_step","gpu_launches")}, d["e2e"]["ms_per_step"], {k:v for k,v in d["parity"].items() if k not in ("per_k","checker")}, d["roofline"]["frac"], d["clocks"])
-PY
+timeout 900 python -m pytest tests -m gpu -x -q -k "exchange" > gpurun_out/pytest_peer_r03a.log 2>&1; tail -5 gpurun_out/pytest_peer_r03a.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus 2 --steps 3 --warmup 3 --no-parity > gpurun_out/bench_2gpu_r03a.json 2> gpurun_out/bench_2gpu_r03a.err; tail -c 300 gpurun_out/bench_2gpu_r03a.err; cut -c1-200 gpurun_out/bench_2gpu_r03a.json

@@ -133,6 +133,9 @@ def _worker(rank, world, port, n, out_path):
         dist.barrier()
         a_in.close()
         a_out.close()
+        # the peer-memory exchanges need NCCL and CUDA: on this backend every rank agrees to use the all-to-alls
+        assert pdist.PeerResults.get(n, None, torch.device("cpu")) is None
+        pdist.PeerResults.release()
     finally:
         dist.destroy_process_group()
 
