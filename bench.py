@@ -645,14 +645,22 @@ def ours(args):
         cpu = reference_leg(args, args.cpu_seconds)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # Ranks are spread over the box: neighbouring GPU indices of an HGX board share a PCIe uplink towards the host
+    # (profiles/pcie_probe_8gpu_r02n.txt: GPUs 0 and 1 together 72 GB/s D2H, GPUs 0 and 4 together 106 GB/s), so a job
+    # of 2 or 4 ranks on 8 visible GPUs takes every 4th / 2nd device.  One rank per GPU either way.
+    gpu_stride = 1
+    visible = torch.cuda.device_count()
+    if world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world and visible >= 2 * world:
+        gpu_stride = visible // world
+    gpu_index = local_rank * gpu_stride
+    torch.cuda.set_device(gpu_index)
+    dev = torch.device("cuda", gpu_index)
     near = None
     if world > 1:
         # host threads and the host pages this rank touches stay on the GPU's socket (no effect on one-socket hosts)
         from point_cloud_toolbox_b200.distributed import bind_near_gpu
 
-        near = bind_near_gpu(local_rank)
+        near = bind_near_gpu(gpu_index)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -720,7 +728,7 @@ def ours(args):
         pdist.curvature_knn_shared(shared_in, shared_out, k, device=dev, stages=stages).close()
         return (shared_out.array[0], shared_out.array[1]) if rank == 0 else (None, None)
 
-    sampler = ClockSampler(local_rank, args.clock_interval_ms, not args.no_clocks)
+    sampler = ClockSampler(gpu_index, args.clock_interval_ms, not args.no_clocks)
     if rank == 0:
         sampler.prepare()
 
@@ -898,6 +906,7 @@ def ours(args):
                         + ("the fused kernel stores K, H straight into the owner rank's array over NVLink peer memory (no return collective)"
                            if peer_return else "one all-to-all returns the rows")
                         + f" (rank 0: {indexed} indexed, {pts_per_launch} answered, {unresolved} redone)"),
+        "gpu_of_rank": [r * gpu_stride for r in range(world)],
         "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
         "level1_retries": stats.level1_retries, "exact_path": stats.exact_path, "unstaged": stats.unstaged,
         "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": roof_query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,
