@@ -648,11 +648,11 @@ def ours(args):
     # Ranks are spread over the box: neighbouring GPU indices of an HGX board share a PCIe uplink towards the host
     # (profiles/pcie_probe_8gpu_r02n.txt: GPUs 0 and 1 together 72 GB/s D2H, GPUs 0 and 4 together 106 GB/s), so a job
     # of 2 or 4 ranks on 8 visible GPUs takes every 4th / 2nd device.  One rank per GPU either way.
-    gpu_stride = 1
-    visible = torch.cuda.device_count()
-    if world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world and visible >= 2 * world:
-        gpu_stride = visible // world
-    gpu_index = local_rank * gpu_stride
+    from point_cloud_toolbox_b200.distributed import device_for_rank
+
+    one_node = int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world
+    gpu_of_rank = [device_for_rank(r, world) if (world > 1 and one_node) else r for r in range(max(world, local_rank + 1))]
+    gpu_index = gpu_of_rank[local_rank]
     torch.cuda.set_device(gpu_index)
     dev = torch.device("cuda", gpu_index)
     near = None
@@ -906,7 +906,7 @@ def ours(args):
                         + ("the fused kernel stores K, H straight into the owner rank's array over NVLink peer memory (no return collective)"
                            if peer_return else "one all-to-all returns the rows")
                         + f" (rank 0: {indexed} indexed, {pts_per_launch} answered, {unresolved} redone)"),
-        "gpu_of_rank": [r * gpu_stride for r in range(world)],
+        "gpu_of_rank": gpu_of_rank[:world],
         "cell_size": info.cell_size, "cells_level0": info.cells_level0, "index_bytes": info.device_bytes,
         "level1_retries": stats.level1_retries, "exact_path": stats.exact_path, "unstaged": stats.unstaged,
         "build_ms": build_ms, "build_ms_steps": build_steps, "query_ms": roof_query_ms, "status_nonzero": status_bad, "nan_rows": nan_rows,

@@ -268,6 +268,17 @@ class SharedHostArray:
             pass
 
 
+def device_for_rank(local_rank: int, local_world: int, visible: int = None) -> int:
+    """GPU index of a rank of a one-node job: the ranks are spread over the visible devices (rank r takes device
+    r * (visible // local_world)) so that a job smaller than the box does not crowd the GPUs of one PCIe uplink --
+    on an HGX board neighbouring indices share a switch towards the host (profiles/pcie_probe_8gpu_r02n.txt: two
+    neighbours together move 72 GB/s to the host, two GPUs of different halves 106 GB/s).  One rank per GPU either way."""
+    if visible is None:
+        visible = torch.cuda.device_count()
+    stride = visible // local_world if local_world >= 1 and visible >= 2 * local_world else 1
+    return int(local_rank) * max(1, stride)
+
+
 def gpu_local_cpus(device_index: int):
     """CPUs of the NUMA node the GPU hangs off (sysfs ``local_cpulist`` of its PCI function), or None."""
     try:

@@ -56,6 +56,16 @@ def test_slabs_partition_the_cloud():
     assert sum(sizes) == n
 
 
+def test_ranks_are_spread_over_the_visible_gpus():
+    assert [pdist.device_for_rank(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [pdist.device_for_rank(r, 4, 8) for r in range(4)] == [0, 2, 4, 6]
+    assert [pdist.device_for_rank(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [pdist.device_for_rank(r, 2, 2) for r in range(2)] == [0, 1]       # exactly as many devices as ranks
+    assert [pdist.device_for_rank(r, 3, 8) for r in range(3)] == [0, 2, 4]
+    assert pdist.device_for_rank(0, 1, 8) == 0
+    assert len({pdist.device_for_rank(r, 4, 5) for r in range(4)}) == 4        # never two ranks on one device
+
+
 def test_gpu_local_cpus_parses_sysfs_or_gives_up():
     """No GPU here: the topology helpers must return None instead of raising."""
     assert pdist.gpu_local_cpus(0) is None or isinstance(pdist.gpu_local_cpus(0), set)
