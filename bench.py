@@ -914,6 +914,9 @@ def ours(args):
     if world > 1:
         details["value_stages_ms"] = value_stages
         details["e2e_stages_ms"] = e2e_stages
+        details["host_copy_rounds"] = {"h2d_d2h": [list(v) for v in pdist.CopyRounds._cache.values()], "probe_ms": pdist.CopyRounds.timings,
+                                       "note": "ranks copy to / from the host in this many rounds (measured on the first call: "
+                                               "the GPUs of the box share PCIe uplinks)"}
         details["stage_note"] = "max over ranks of CUDA-event times of one instrumented pass after the timed region; a stage ends where it is named"
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -739,31 +739,118 @@ def _redo_unresolved(cloud, rec, own_ids, plan, k):
     return rec
 
 
+class CopyRounds:
+    """How many ranks of a one-node job should copy to / from the host AT ONCE.
+
+    The GPUs of a box share PCIe uplinks: on the HGX boards measured (profiles/pcie_probe_8gpu_r02n.txt) eight
+    concurrent D2H copies move 96 GB/s in aggregate, four (every second GPU) 108 GB/s, and eight concurrent H2D copies
+    187 GB/s against 217 GB/s for four.  So a host copy of all ranks can be faster in ROUNDS -- round p: the ranks with
+    rank % R == p copy, a stream-ordered barrier (4-byte all-reduce) separates the rounds, no host synchronisation.
+    R is not assumed: the first call on a group times R = 1, 2 and 4 on a 32 MB piece of the caller's own arrays and
+    keeps the fastest (a smaller R wins ties within 5 %)."""
+
+    _cache = {}
+    timings = []          # [{rounds: ms} of the H2D probe, {rounds: ms} of the D2H probe] of the last calibration
+    PROBE_ROWS = 1 << 22
+
+    @staticmethod
+    def run(rounds, rank, copy_fn, token, group):
+        """The copy of every rank in ``rounds`` rounds; ``token``: a 1-element device tensor for the barriers."""
+        for phase in range(rounds):
+            if rank % rounds == phase:
+                copy_fn()
+            if phase + 1 < rounds:
+                dist.all_reduce(token, group=group)
+
+    @classmethod
+    def get(cls, points, out, begin, end, group, device):
+        """(rounds H2D, rounds D2H) of this group; collective on first use."""
+        import os
+
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        key = (id(group) if group is not None else 0, world, str(device))
+        if key in cls._cache:
+            return cls._cache[key]
+        fixed = os.environ.get("PCT_COPY_ROUNDS")       # "h2d,d2h": skips the probe (experiments)
+        if fixed or world < 4 or device.type != "cuda":
+            got = tuple(int(v) for v in fixed.split(",")) if fixed else (1, 1)
+            cls._cache[key] = got
+            return got
+        rows = max(1, min(cls.PROBE_ROWS, end - begin))
+        dev_in = torch.empty((rows, 3), dtype=torch.float32, device=device)
+        dev_out = torch.zeros((rows,), dtype=torch.float32, device=device)
+        token = torch.zeros(1, dtype=torch.int32, device=device)
+        src = points.tensor[begin:begin + rows]
+        dst0, dst1 = out.tensor[0, begin:begin + rows], out.tensor[1, begin:begin + rows]
+
+        def probe_out():
+            dst0.copy_(dev_out, non_blocking=True)
+            dst1.copy_(dev_out, non_blocking=True)
+
+        best = []
+        for copy_fn in (lambda: dev_in.copy_(src, non_blocking=True), probe_out):
+            times = {}
+            for rounds in (1, 2, 4):
+                if world % rounds:
+                    continue
+                t_best = None
+                for rep in range(3):
+                    dist.all_reduce(token, group=group)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    cls.run(rounds, rank, copy_fn, token, group)
+                    dist.all_reduce(token, group=group)
+                    e1.record()
+                    e1.synchronize()
+                    t = torch.tensor([e0.elapsed_time(e1)], device=device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                    if rep and (t_best is None or t.item() < t_best):
+                        t_best = t.item()
+                times[rounds] = t_best
+            pick = 1
+            for rounds in sorted(times):
+                if times[rounds] < 0.95 * times[pick]:
+                    pick = rounds
+            best.append(pick)
+            cls.timings.append(times)
+        cls._cache[key] = tuple(best)
+        return cls._cache[key]
+
+
 def curvature_knn_shared(points: SharedHostArray, out: SharedHostArray, k: int, group=None, device=None, stages: Stages = None):
     """plant_kdtree(k) + compute_pointwise_explicit_quadratic_curvature() of a cloud in shared host memory.
 
     ``points`` (N, 3) and ``out`` (2, N) = [K; H] are mapped by every rank.  Rank r copies rows
     ``shard_bounds(N, world, r)`` of the cloud to its GPU over its own PCIe link, the ranks trade slabs
     (``curvature_knn_exchange``: the cloud is never replicated), and each rank writes the K and H of its own rows
-    to ``out``.  Collective: returns after a barrier, when ``out`` is complete on the host."""
+    to ``out``.  The host copies run in as many rounds as ``CopyRounds`` measured to be fastest on this box.
+    Collective: returns after a barrier, when ``out`` is complete on the host."""
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
     n = int(points.tensor.shape[0])
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
+    begin, end = shard_bounds(n, world, rank)
+    r_in, r_out = CopyRounds.get(points, out, begin, end, group, device)
+    token = torch.zeros(1, dtype=torch.int32, device=device) if max(r_in, r_out) > 1 else None
     st = stages or Stages(False)
     st.mark("begin")
-    begin, end = shard_bounds(n, world, rank)
     share = torch.empty((end - begin, 3), dtype=torch.float32, device=device)
-    share.copy_(points.tensor[begin:end], non_blocking=True)                     # this rank's share, its own PCIe link
+    CopyRounds.run(r_in, rank, lambda: share.copy_(points.tensor[begin:end], non_blocking=True), token, group)   # this rank's share
     st.mark("h2d")
     part = curvature_knn_exchange(share, begin, n, k, group, stages=st)
     khT = part.rows.t().contiguous()
-    out.tensor[0, begin:end].copy_(khT[0], non_blocking=True)
-    out.tensor[1, begin:end].copy_(khT[1], non_blocking=True)
+
+    def to_host():
+        out.tensor[0, begin:end].copy_(khT[0], non_blocking=True)
+        out.tensor[1, begin:end].copy_(khT[1], non_blocking=True)
+
+    CopyRounds.run(r_out, rank, to_host, token, group)
     st.mark("d2h")
     torch.cuda.current_stream(device).synchronize()
     dist.barrier(group=group)
+    part.copy_rounds = (r_in, r_out)
     return part
 
 
