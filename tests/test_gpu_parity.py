@@ -395,6 +395,16 @@ def _exchange_rank(rank, world, port, n, k, out_path):
         pdist.curvature_knn_shared(cin, cout, k, stages=st).close()
         host_ok = bool(np.array_equal(cout.array[0, b:e], got_all[:, 0]) and np.array_equal(cout.array[1, b:e], got_all[:, 1]))
         all_written = bool(np.isfinite(cout.array).mean() > 0.999)
+        # the host copies in rounds (what CopyRounds picks on boxes whose GPUs share PCIe uplinks): same arrays
+        first = cout.array.copy()
+        dist.barrier()
+        cout.array[:, b:e] = np.nan
+        os.environ["PCT_COPY_ROUNDS"] = "2,2" if world % 2 == 0 else "1,1"
+        pdist.CopyRounds._cache.clear()
+        pdist.curvature_knn_shared(cin, cout, k).close()
+        del os.environ["PCT_COPY_ROUNDS"]
+        pdist.CopyRounds._cache.clear()
+        host_ok = host_ok and bool(np.array_equal(cout.array, first, equal_nan=True))
         stages = st.durations_ms()
         unresolved = torch.tensor([part.unresolved], device=dev)
         dist.all_reduce(unresolved)
