@@ -505,7 +505,9 @@ class PeerResults:
       kernel of every rank stores its records straight into the buffer of the destination slab
       (``SlabBinCount.fill_peers``): no all-to-all of the points.
 
-    Built once per (group, device, cloud size) and reused: opening IPC handles costs milliseconds."""
+    Built once per (group, device, cloud size) and reused: opening IPC handles costs milliseconds.  A job that tears its
+    process group down and builds another calls ``PeerResults.release()`` first (collective): the mappings belong to the
+    processes of the group they were made in."""
 
     _cache = {}
 
