@@ -526,7 +526,9 @@ class PeerResults:
         # arrays sends None, a rank that cannot map a peer's remembers why -- ``get`` then lets the ranks agree
         self.error = None
         try:
-            mine = (reduce_tensor(self.local), reduce_tensor(self.slab_local))
+            # one export per consumer: torch counts the references of an exported block per export, and every peer
+            # releases the one it received
+            mine = [(reduce_tensor(self.local), reduce_tensor(self.slab_local)) if r != rank else None for r in range(world)]
         except Exception as exc:      # e.g. an allocator configuration whose blocks cannot be exported
             mine, self.error = None, exc
         handles = [None] * world
@@ -534,13 +536,14 @@ class PeerResults:
         here = device.index if device.index is not None else torch.cuda.current_device()
         self.views, self.slab_views = [], []
         try:
-            for r, pair in enumerate(handles):
-                if pair is None:
+            for r, per_consumer in enumerate(handles):
+                if r == rank:
+                    self.views.append(self.local)
+                    self.slab_views.append(self.slab_local)
+                    continue
+                if per_consumer is None:
                     raise RuntimeError(f"rank {r} could not export its arrays")
-                for (fn, args), own, views in zip(pair, (self.local, self.slab_local), (self.views, self.slab_views)):
-                    if r == rank:
-                        views.append(own)
-                        continue
+                for (fn, args), views in zip(per_consumer[rank], (self.views, self.slab_views)):
                     args = list(args)
                     args[6] = here                                   # storage_device: map the peer's memory into THIS device
                     views.append(fn(*args))
