@@ -94,6 +94,53 @@ def test_staged_source_gives_the_same_rows(harness, bunny, staged_u):
     assert np.array_equal(small["idx"], got["idx"])
 
 
+def _random_cloud(rng, case):
+    """Small clouds with the traits that stress the search (the GPU suite runs the same families at larger sizes)."""
+    n = int(rng.integers(30, 1200))
+    kind = case % 5
+    if kind == 0:
+        p = rng.normal(size=(n, 3))
+    elif kind == 1:
+        p = np.stack((rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 0.02 * rng.normal(size=n)), 1)
+    elif kind == 2:
+        t = rng.uniform(0, 6, n)
+        p = np.stack((np.cos(t), np.sin(t), 0.3 * t), 1) + 0.01 * rng.normal(size=(n, 3))
+    elif kind == 3:
+        c = rng.normal(size=(4, 3)) * 3
+        s = np.array([0.01, 0.1, 0.5, 1.0])
+        w = rng.integers(0, 4, n)
+        p = c[w] + rng.normal(size=(n, 3)) * s[w, None]
+    else:
+        v = rng.normal(size=(n, 3))
+        p = v / np.linalg.norm(v, axis=1, keepdims=True)
+        p[rng.integers(0, n, n // 15)] = p[rng.integers(0, n, n // 15)]
+    scale = 10.0 ** rng.integers(-3, 4)
+    offset = rng.normal(size=3) * scale * 10.0 ** rng.integers(0, 3)
+    return (p * scale + offset).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_clouds_host_logic(harness, seed):
+    """The device code's selection on randomised clouds (scales 1e-3 .. 1e3, offsets, sheets, filaments, clusters,
+    duplicates), from the sorted cloud and from staged regions, with cell sizes from far too small to far too large:
+    rows and distances bit-exact whatever path answers."""
+    rng = np.random.default_rng(300 + seed)
+    for case in range(10):
+        pts = _random_cloud(rng, case)
+        n = len(pts)
+        k = int(min(n - 2, rng.choice([1, 4, 9, 20, 33])))
+        ref_idx, ref_dist, _ = oracle.knn_canonical(pts, k)
+        r_k = float(np.median(ref_dist[:, -1]))
+        if not r_k > 0:
+            continue
+        for factor, staged_u in ((1.25, 0), (1.25, 2), (0.4, 2), (4.0, 1)):
+            got = run_knn(harness, pts, k, factor * r_k, max_fast_level=2, staged_u=staged_u)
+            tag = (seed, case, n, k, factor, staged_u)
+            assert (got["code"] >= 0).all(), tag
+            assert compare.neighbor_rows_differing(got["idx"], ref_idx) == 0, tag
+            assert np.array_equal(got["dist"], ref_dist), tag
+
+
 def test_staged_source_on_ties_duplicates_and_tiny_clouds(harness):
     rng = np.random.default_rng(5)
     g = np.arange(9, dtype=np.float32)
