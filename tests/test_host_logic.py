@@ -305,6 +305,28 @@ def test_ball_logic(harness, bunny):
     assert rep["violations"] == 0, rep
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_clouds_ball_host_logic(harness, seed):
+    """The device code's inclusive radius test (fp32 brackets, fp64 inside them) on randomised clouds: member counts
+    equal scipy's query_ball_point at any grid level, empty and crowded balls included."""
+    rng = np.random.default_rng(400 + seed)
+    for case in range(10):
+        pts = _random_cloud(rng, case)
+        n = len(pts)
+        _, d8, _ = oracle.knn_canonical(pts, min(8, n - 2))
+        radius = float(np.quantile(d8[:, -1], rng.choice([0.1, 0.5, 0.9])) * rng.choice([0.5, 1.0, 2.0]))
+        if not radius > 0:
+            continue
+        roff, _, _ = oracle.ball_canonical(pts, radius)
+        for h in (radius * 1.001, radius / 2.5):
+            ix = harness.h_build(P(pts), n, float(h))
+            counts = np.zeros(n, np.int32); normal = np.zeros((n, 3), np.float32); coeffs = np.zeros((n, 6), np.float32)
+            curv = np.zeros((n, 5), np.float32); status = np.zeros(n, np.uint8)
+            harness.h_ball(ix, radius, P(counts), P(normal), P(coeffs), P(curv), P(status))
+            harness.h_destroy(ix)
+            assert np.array_equal(counts, np.diff(roff)), (seed, case, n, radius, h)
+
+
 # ---------------------------------------------------------------------------
 # C ABI: the shipped library loads here (no GPU) and exports what the header declares
 # ---------------------------------------------------------------------------
