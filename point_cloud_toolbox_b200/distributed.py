@@ -1,22 +1,29 @@
-"""Multi-GPU form of the path: replicate the cloud, shard the queries, gather the results.
+"""Multi-GPU forms of the path.  One process per GPU (torchrun), ``torch.distributed`` for the plumbing.
 
-One process per GPU (torchrun), ``torch.distributed`` for the plumbing:
+The throughput form is the SLAB EXCHANGE (``curvature_knn_exchange``, ``curvature_knn_shared``): every rank starts with
+a contiguous share of the cloud and the cloud is never replicated.
 
-  1. rank 0 holds the cloud; ``broadcast`` puts the raw xyz on every GPU (NVLink / NVSwitch)
-  2. the queries are divided
-       "slab" (default)   by position: the ranks agree on cut planes across the longest axis of the
-                          bounding box (quantiles, so the slabs hold equal numbers of points); rank g
-                          builds an index over ITS slab plus a margin of 4.5 cells only and answers the
-                          points of its slab.  The index knows where its knowledge ends
-                          (pct_index_set_slab): no search radius crosses the margin, and a query whose
-                          k-th neighbour could lie beyond it comes back PCT_STATUS_UNRESOLVED and is
-                          answered from a whole-cloud index built on demand.  The build, the serial
-                          fraction of the replicated form, shrinks with the number of ranks.
-       "replicated"       (kept for comparison) every rank builds the same whole-cloud index; rank g answers Morton-sorted
-                          positions [g*N/G, (g+1)*N/G) in slice layout (PCT_LAYOUT_SLICE)
-  3. ``gather`` to rank 0, which puts the rows in original order
+  1. plan      one small all-gather (bounding boxes + a strided sample): every rank derives the same cell edge, slab
+               axis and cut planes (quantiles: slabs hold equal numbers of points)
+  2. bin       every rank bins its share by destination slab -- the owner, and the neighbours whose margin of 4.5
+               cells holds the point
+  3. exchange  INSIDE the binning kernel: the records {x, y, z, original index} are stored straight into the slab
+               buffer of the destination rank over NVLink peer memory (``PeerResults``, CUDA IPC); the received slab
+               is in ascending original index, so distance ties keep the whole cloud's order
+  4. answer    slab index + fused kernel.  The index knows where its knowledge ends (pct_index_set_slab): no search
+               radius crosses the margin, a query whose k-th neighbour could lie beyond it comes back
+               PCT_STATUS_UNRESOLVED and is redone on a whole-cloud index (only then are the shares all-gathered)
+  5. return    INSIDE the fused kernel: K, H of every answered query are stored straight into the result array of
+               the rank that holds the query's point
+  Without peer mapping (other backends, processes that cannot share device memory) steps 3 and 5 are one
+  all-to-all each.  ``curvature_knn_shared`` wraps this for host arrays in shared memory: every rank moves its own
+  share over its own PCIe link, in as many rounds as ``CopyRounds`` measures to be fastest on the box.
 
-There is no exchange step between 1 and 3, so no other collective is involved.
+Kept beside it: ``curvature_knn_slab`` / ``curvature_knn_sharded`` -- round 1's forms, which broadcast the whole cloud
+to every GPU and either let rank g select and answer its slab ("slab") or build the same whole-cloud index everywhere
+and answer Morton slices ("replicated"), then gather to rank 0.  ``bench.py`` reports the former as the comparison
+figure ``value_replicated_no_collective``.
+
 The reference has no distributed code at all; this is new.
 """
 from __future__ import annotations
@@ -633,11 +640,13 @@ def curvature_knn_exchange(share: torch.Tensor, id_base: int, n_total: int, k: i
 
       1. one small all-gather (boxes + sample) -> cell edge, axis, cut planes        (plan_slabs)
       2. every rank bins its share by destination slab (owner + margins)             (pct_slab_bin_*)
-      3. one all-to-all of counts, one all-to-all of 16-byte point records: each rank now holds its slab + margin,
+      3. the 16-byte point records reach their slab's rank -- stored there by the binning kernel itself over NVLink peer
+         memory (``PeerResults``), else one all-to-all of counts and one of the records: each rank now holds its slab + margin,
          in ascending original index (ties keep the whole cloud's order)
       4. slab index + fused kernel on the owned points                               (answer_slab)
-      5. one all-to-all returns the rows to the ranks whose share the points came from -- no ids travel: a slab
-         returns rows in the order it received the points, which the sender remembers (``owned_local``)
+      5. the rows return to the ranks whose share the points came from -- stored there by the fused kernel itself
+         (``GridIndex.set_peers``), else by one all-to-all in which no ids travel: a slab returns rows in the order it
+         received the points, which the sender remembers (``owned_local``)
 
     Queries a slab cannot resolve inside its margin (isolated points) are redone on a whole-cloud index after an
     all-gather of the shares; that collective only happens when some rank reports such a query.
